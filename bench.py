@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the natural-gradient solve (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload mlp64|arm|...] [--impl reference]
+
+A "step" is one 10-iteration conjugate-gradient solve (ResidualTh = 0, so exactly 10 Fisher-vector products,
+TRPO_CG.c:45-107) over the whole rollout batch. Default workload = BASELINE.json configs[2], the configuration the
+metric is quoted on: the 17-64-64-6 tanh Gaussian policy over 1M synthetic states, sharded over the N ranks
+(total work fixed => "strong" scaling; one NCCL all-reduce of the P-length FVP sum per CG iteration).
+
+value    FVP samples/s with the batch already resident in HBM (10 * N_states / step time; CUDA events on the
+         launching stream, L2 flushed between steps, max over ranks)
+e2e      the same metric through the C-ABI with HOST buffers (trpo_ctx_set_batch + trpo_ctx_cg from pinned memory:
+         H2D of the batch and b, D2H of x every step)
+roofline the dominant kernel (per-sample FVP sum) against the measured FP64 DMMA peak
+cpu_baseline / --impl reference: the reference's own CPU CG (oracle/_ref, unmodified sources) on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CG_ITERS = 10
+DAMPING = 0.1
+# measured on this pool's B200 with tools/fp64_peak.cu (profiles/fp64_peak_r01.txt): DMMA.8x8x4 and DFMA share one
+# FP64 pipe, 37.1 TFLOP/s = 148 SMs x 64 FMA/clk x 2 x 1.96 GHz. MEASURED_PEAKS.json has no FP64 entry.
+FP64_PEAK_TFLOPS = 37.1
+WORKLOAD_INDEX = {"arm": 1, "mlp64": 2, "pendulum64": 2, "humanoid64": 2, "humanoid256": 3}
+
+
+def shard_bounds(n, world, rank):
+    """Contiguous block of samples owned by `rank` (sizes differ by at most one)."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def flops_min_per_sample(layers):
+    """Algorithmic flops of one per-sample FVP: 6*L0*L1 + 10*sum_{i>=1} L_i*L_{i+1}."""
+    return 6 * layers[0] * layers[1] + 10 * sum(layers[i] * layers[i + 1] for i in range(1, len(layers) - 1))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v == "Active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def make_workload(pkg, name, n_states):
+    layers, ac, default_n = pkg.synth.SHAPES[name]
+    n = n_states or default_n
+    seed = pkg.synth.SEED_BASE + WORKLOAD_INDEX.get(name, 9)
+    theta = pkg.synth.make_model(layers, seed)
+    batch = pkg.synth.make_batch(layers, ac, theta, n, seed)
+    vec = pkg.synth.make_vectors(layers, seed)
+    return layers, ac, n, theta, batch, vec
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU reference arm: the unmodified reference CG() (oracle/_ref) on text files in a tmpfs directory
+def reference_cg_rate(pkg, layers, ac, theta, batch, vec, n_sample, steps, warmup, tmpdir):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_lib import Oracle, Reference
+    sl = {k: (v[:n_sample] if k != "Std" else v) for k, v in batch.items()}
+    use_ref = Reference.available()
+    times = []
+    if use_ref:
+        ref = Reference(fast=True)
+        mf, df = os.path.join(tmpdir, "model.txt"), os.path.join(tmpdir, "data.txt")
+        pkg.textio.write_model(mf, theta)
+        pkg.textio.write_data(df, sl["Mean"], sl["Std"], sl["Observ"], sl["Action"], sl["Advantage"])
+        devnull = os.open(os.devnull, os.O_WRONLY)
+        saved = os.dup(1)
+        sys.stdout.flush()
+        os.dup2(devnull, 1)                      # the reference printf's a CG trace per call
+        try:
+            for i in range(warmup + steps):
+                _, t = ref.cg(mf, df, layers, ac, n_sample, DAMPING, vec["b"], CG_ITERS, 0.0, 1)
+                if i >= warmup:
+                    times.append(t)              # the function's own returned compute seconds (file parsing excluded)
+        finally:
+            os.dup2(saved, 1)
+            os.close(devnull)
+    else:
+        orc = Oracle(fast=True)
+        obs = np.ascontiguousarray(sl["Observ"])
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            orc.cg(layers, ac, theta, sl["Std"], obs, DAMPING, vec["b"], CG_ITERS, 0.0)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    t = float(np.mean(times))
+    return CG_ITERS * n_sample / t, t, ("reference" if use_ref else "port")
+
+
+def run_reference_arm(args, pkg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    layers, ac, n, theta, batch, vec = make_workload(pkg, args.workload, args.states)
+    # bounded sample: about 8 s of CPU work per step (the reference needs ~ 1.3 ns per flop_ref single-threaded)
+    flops_ref = 10 * sum(layers[i] * layers[i + 1] for i in range(len(layers) - 1))
+    n_sample = int(min(n, max(512, 8.0 / (CG_ITERS * flops_ref * 1.3e-9))))
+    with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as tmp:
+        rate, t_step, kind = reference_cg_rate(pkg, layers, ac, theta, batch, vec, n_sample, args.steps, max(1, min(args.warmup, 1)), tmp)
+    line = {
+        "impl": "reference", "metric": "fvp_samples_per_sec", "value": rate, "unit": "samples/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {'-'.join(map(str, layers))} policy, {n} synthetic states, "
+                               f"{CG_ITERS}-iteration CG (ResidualTh=0), damping {DAMPING}"},
+        "cpu_baseline": {"value": rate, "unit": "samples/s", "cores": 1, "kind": kind,
+                         "sample": f"CG() of the unmodified reference on the first {n_sample} states, NumThreads=1 "
+                                   f"(its OpenMP sits inside the 64-wide layer loops and anti-scales, SURVEY.md section 6)"},
+        "e2e": {"value": rate, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def run_gpu_arm(args, pkg):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU path; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    layers, ac, n_total, theta, batch, vec = make_workload(pkg, args.workload, args.states)
+    lo, hi = shard_bounds(n_total, world, rank)
+    n_local = hi - lo
+    P = len(theta)
+
+    # pinned host staging buffers (the e2e leg copies from these every step)
+    obs_pin = torch.from_numpy(np.ascontiguousarray(batch["Observ"][lo:hi])).pin_memory()
+    b_pin = torch.from_numpy(vec["b"].copy()).pin_memory()
+    x_pin = torch.zeros(P, dtype=torch.float64).pin_memory()
+
+    stream = torch.cuda.Stream(device=dev)
+    ctx = pkg.Context(layers, ac, device=local_rank)
+    ctx.set_stream(stream.cuda_stream)
+    if args.path:
+        ctx.set_path({"chain": pkg.api.PATH_GEMM_CHAIN, "fused": pkg.api.PATH_FUSED}[args.path])
+    if world > 1:
+        uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(pkg.api.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        ctx.init_comm(bytes(uid.cpu().numpy().tobytes()), rank, world)
+    ctx.set_model(theta)
+    ctx.set_batch(obs_pin.numpy(), batch["Std"])
+    assert ctx.global_samples() == n_total
+
+    d_b = torch.from_numpy(vec["b"]).to(dev)
+    d_x = torch.zeros(P, dtype=torch.float64, device=dev)
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_loop(step_fn, steps, warmup, count_launches=False):
+        with torch.cuda.stream(stream):
+            for _ in range(warmup):
+                flush_buf.zero_()
+                step_fn()
+            barrier()
+            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+            l0 = ctx.launch_count()
+            t_wall = time.perf_counter()
+            for e0, e1 in evs:
+                flush_buf.zero_()              # L2 flush between timed steps (outside the event pair)
+                e0.record(stream)
+                step_fn()
+                e1.record(stream)
+            barrier()
+            t_wall = time.perf_counter() - t_wall
+            l1 = ctx.launch_count()
+        ms = sum(e0.elapsed_time(e1) for e0, e1 in evs)
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / steps, (l1 - l0), t_wall
+
+    # ---- leg 1: device-resident (value) -------------------------------------------------------------------------
+    def step_resident():
+        ctx.cg_device(d_b.data_ptr(), d_x.data_ptr(), CG_ITERS, 0.0, DAMPING)
+
+    sampler = ClockSampler(local_rank)
+    ctx.kernel_timing(True)
+    ctx.kernel_time_ms()
+    # warm-up first, then start sampling clocks for the timed region only
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            step_resident()
+        torch.cuda.synchronize()
+    ctx.kernel_time_ms()
+    sampler.start()
+    ms_step, launches, _ = timed_loop(step_resident, args.steps, 0)
+    clocks = sampler.stop()
+    k_ms, k_n = ctx.kernel_time_ms()
+    ctx.kernel_timing(False)
+    value = CG_ITERS * n_total / (ms_step * 1e-3)
+
+    # ---- leg 2: end to end through the host-buffer C-ABI (e2e) ---------------------------------------------------
+    def step_e2e():
+        ctx.set_batch(obs_pin.numpy(), batch["Std"])                                  # H2D of the rollout batch
+        x, _ = ctx_cg_host()
+
+    def ctx_cg_host():
+        import ctypes as C
+        L = pkg.api.lib()
+        rc = L.trpo_ctx_cg(ctx.h, C.cast(b_pin.data_ptr(), pkg.api.c_double_p), C.cast(x_pin.data_ptr(), pkg.api.c_double_p),
+                           CG_ITERS, 0.0, DAMPING)
+        if rc:
+            raise RuntimeError(pkg.api.last_error())
+        return x_pin, None
+
+    ms_e2e, _, wall_e2e = timed_loop(step_e2e, args.steps, max(1, args.warmup // 2))
+    # the host-buffer calls synchronise internally, so wall clock per step is the honest end-to-end figure
+    e2e_ms = max(ms_e2e, wall_e2e * 1e3 / args.steps)
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    e2e_value = CG_ITERS * n_total / (e2e_ms * 1e-3)
+    A = layers[-1]
+    h2d = n_local * layers[0] * 8 + 2 * A * 8 + P * 8
+    d2h = P * 8 + 576
+
+    path_used = {1: "gemm_chain", 2: "fused_dmma"}.get(ctx.path_used(), "?")
+    x_dev = d_x.cpu().numpy()
+    assert np.isfinite(x_dev).all() and np.isfinite(x_pin.numpy()).all()
+
+    if rank == 0:
+        fl = flops_min_per_sample(layers)
+        k_avg_ms = k_ms / max(k_n, 1)
+        achieved = fl * n_local / (k_avg_ms * 1e-3) / 1e12 if k_n else None
+        line = {
+            "metric": "fvp_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "cg_solve_ms": ms_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {'-'.join(map(str, layers))} policy, {n_total} synthetic states, "
+                                   f"{CG_ITERS}-iteration CG (ResidualTh=0), damping {DAMPING}",
+                       "kernel_path": path_used, "l2": "flushed between steps (256 MiB write); 1M-state shard is 136 MB > L2",
+                       "parallelism": f"samples sharded over {world} GPU(s), 1 all-reduce of P={P} doubles per FVP"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
+                         "frac": (achieved / FP64_PEAK_TFLOPS) if achieved else None, "traffic": None,
+                         "kernel": path_used, "kernel_avg_ms": k_avg_ms, "kernel_launches_timed": k_n,
+                         "flops_per_sample": fl,
+                         "peak_source": "measured FP64 DMMA/DFMA pipe, profiles/fp64_peak_r01.txt (MEASURED_PEAKS.json has no FP64 entry)"},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            flops_ref = 10 * sum(layers[i] * layers[i + 1] for i in range(len(layers) - 1))
+            n_sample = int(min(n_total, max(512, 12.0 / (CG_ITERS * flops_ref * 1.3e-9))))
+            with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as tmp:
+                rate, t_step, kind = reference_cg_rate(pkg, layers, ac, theta, batch, vec, n_sample, 1, 0, tmp)
+            line["cpu_baseline"] = {"value": rate, "unit": "samples/s", "cores": 1, "kind": kind,
+                                    "sample": f"one {CG_ITERS}-iteration CG() of the unmodified reference on the first {n_sample} "
+                                              f"states ({t_step:.1f} s), NumThreads=1 of {os.cpu_count()} host cores"}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="mlp64")
+    ap.add_argument("--states", type=int, default=0, help="override the number of synthetic states")
+    ap.add_argument("--path", default="", choices=["", "chain", "fused"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    from __graft_entry__ import load_package
+    pkg = load_package()
+    if args.impl == "reference":
+        run_reference_arm(args, pkg)
+    else:
+        run_gpu_arm(args, pkg)
+
+
+if __name__ == "__main__":
+    main()

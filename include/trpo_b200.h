@@ -1,0 +1,160 @@
+/*
+ * trpo_b200.h -- C-ABI of the B200-native natural-gradient solve (FVP + CG + TRPO update).
+ *
+ * Drop-in boundary for the reference's FPGA host files:
+ *   FVP_FPGA  /root/reference/src/TRPO_FVP_FPGA.c:13   (prototype /root/reference/src/include/TRPO.h:98)
+ *   CG_FPGA   /root/reference/src/TRPO_CG_FPGA.c:13    (prototype TRPO.h:101)
+ * and GPU counterparts of the CPU entry points they are tested against:
+ *   FVP / FVPFast  /root/reference/src/TRPO_FVP.c:11,548   (TRPO.h:88,92)
+ *   CG             /root/reference/src/TRPO_CG.c:11        (TRPO.h:95)
+ *   TRPO_Update    /root/reference/src/TRPO_Update.c:10    (TRPO.h:104)
+ *
+ * Everything here is plain C: pointers, sizes and doubles. No torch / C++ types cross the boundary.
+ * All functions return the reference's convention where they mirror a reference function
+ * (elapsed compute seconds >= 0, or -1.0 after printing "[ERROR] ..." on stderr), and
+ * 0 / negative error code for the context API (trpo_last_error() gives the message).
+ */
+#ifndef TRPO_B200_H
+#define TRPO_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------------
+ * TRPOparam: identical field order and ABI to /root/reference/src/include/TRPO.h:6-49
+ * (11 x 8 bytes on LP64, passed BY VALUE). If the reference header was included first, reuse its type.
+ * The FPGA-only fields PaddedLayerSize / NumBlocks are ignored (callers leave them uninitialised).
+ * ---------------------------------------------------------------------------------------------- */
+#ifndef TRPO_H
+typedef struct {
+    char   *ModelFile;        /* W, B per layer then LogStd: text, TRPO_FVP.c:677-696 */
+    char   *BaselineFile;     /* unused on this path */
+    char   *ResultFile;       /* unused on this path */
+    char   *DataFile;         /* rows Mean[A] Std[A] Observ[O] Action[A] Advantage: TRPO_FVP.c:740-759 */
+    size_t  NumLayers;        /* input + hidden + output, e.g. 4 */
+    char   *AcFunc;           /* NumLayers chars, AcFunc[0] unused: 'l','t','o','s' (TRPO_FVP.c:806-834) */
+    size_t *LayerSize;        /* NumLayers entries */
+    size_t  NumSamples;
+    double  CG_Damping;
+    size_t *PaddedLayerSize;  /* FPGA only -- ignored */
+    size_t *NumBlocks;        /* FPGA only -- ignored */
+} TRPOparam;
+#endif
+
+/* ------------------------------------------------------------------------------------------------
+ * File-based drop-in entry points (reference signatures). Each call loads ModelFile / DataFile, stages the
+ * batch on the GPU, runs, copies the P-length result back and releases everything, like the FPGA hosts
+ * (max_load ... max_unload, TRPO_FVP_FPGA.c:197-198,370-371). Return: seconds spent in the device compute
+ * section (file parsing excluded, as in TRPO_FVP.c:768-769,933-934), or -1.0 on failure.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Replaces FVP_FPGA (TRPO_FVP_FPGA.c:13). Result = (1/N) sum_n F_n * Input + CG_Damping * Input. */
+double FVP_GPU(TRPOparam param, double *Result, double *Input);
+
+/* Replaces CG_FPGA (TRPO_CG_FPGA.c:13). Solves (F + damping I) x = b; prints the reference's
+ * "CG Iter[%zu] Residual Norm=%.12e, Soln Norm=%.12e" lines (TRPO_CG.c:56). NumThreads is accepted and ignored. */
+double CG_GPU(TRPOparam param, double *Result, double *b, size_t MaxIter, double ResidualTh, size_t NumThreads);
+
+/* GPU counterpart of TRPO_Update (TRPO_Update.c:10): policy gradient, CG, shs FVP, line search. */
+double TRPO_Update_GPU(TRPOparam param, double *Result, size_t NumThreads);
+
+/* The reference's own symbol names, so that Test_FVP_FPGA / Test_CG_FPGA (TRPOCpuCode.c:189,273) link unchanged.
+ * Compiled only into libtrpo_b200_dropin.so (they would clash with the MaxCompiler build otherwise). */
+double FVP_FPGA(TRPOparam param, double *Result, double *Input);
+double CG_FPGA(TRPOparam param, double *Result, double *b, size_t MaxIter, double ResidualTh, size_t NumThreads);
+
+/* NumParamsCalc (TRPO_Util.c:7-17) under a non-clashing name. */
+size_t trpo_num_params(const size_t *LayerSize, size_t NumLayers);
+
+/* ------------------------------------------------------------------------------------------------
+ * Persistent context API: pay file parsing / H2D staging once per rollout batch, not once per call
+ * (the reference re-reads both text files on EVERY FVP, TRPO_FVP.c:670-762).
+ * One context = one GPU = one host thread at a time.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct trpo_ctx trpo_ctx;
+
+enum { TRPO_PRECISION_FP64 = 0 };
+
+/* Kernel path selection (trpo_ctx_set_path). AUTO picks the fused DMMA kernel when the network fits it. */
+enum { TRPO_PATH_AUTO = 0, TRPO_PATH_GEMM_CHAIN = 1, TRPO_PATH_FUSED = 2 };
+
+/* Diagnostics of the last CG / update on a context. */
+typedef struct {
+    int    cg_iters;            /* FVPs executed by the last CG */
+    double cg_rdotr[34];        /* value printed as "Residual Norm" at iteration i (i <= MaxIter <= 32) */
+    double cg_xnorm[34];        /* value printed as "Soln Norm" */
+    double shs, lm, gnorm, fval;
+    int    ls_steps, ls_accepted;
+    double ls_actual[16], ls_expected[16], ls_ratio[16];
+} trpo_info;
+
+const char *trpo_last_error(void);
+
+/* device < 0: use the current CUDA device. Returns NULL on failure. */
+trpo_ctx *trpo_ctx_create(const size_t *LayerSize, const char *AcFunc, size_t NumLayers, int device, int precision);
+void      trpo_ctx_destroy(trpo_ctx *ctx);
+
+size_t trpo_ctx_num_params(const trpo_ctx *ctx);
+/* Use an external CUDA stream (cudaStream_t as void*) for all work of this context; NULL = own stream. */
+int    trpo_ctx_set_stream(trpo_ctx *ctx, void *cuda_stream);
+void  *trpo_ctx_get_stream(const trpo_ctx *ctx);
+int    trpo_ctx_set_path(trpo_ctx *ctx, int path);
+int    trpo_ctx_get_path(const trpo_ctx *ctx);      /* the path the last launch actually used */
+int    trpo_ctx_sync(trpo_ctx *ctx);
+/* Number of kernels launched by this context since creation (bench.py's gpu_launches). */
+long long trpo_ctx_launch_count(const trpo_ctx *ctx);
+
+/* Optional CUDA-event timing of the dominant kernel (the per-sample FVP sum) on the context stream.
+ * enable != 0 starts recording an event pair around every FVP-sum launch (up to 4096 pairs, then it stops recording);
+ * trpo_ctx_kernel_time_ms synchronises, returns the accumulated milliseconds, stores the number of timed launches
+ * in *launches (may be NULL) and resets the accumulator. */
+int    trpo_ctx_kernel_timing(trpo_ctx *ctx, int enable);
+double trpo_ctx_kernel_time_ms(trpo_ctx *ctx, int *launches);
+
+/* Model: theta = flat [W0,B0,...,LogStd] (TRPO_FVP.c:704-725), P doubles on the host. */
+int trpo_ctx_set_model(trpo_ctx *ctx, const double *theta);
+
+/* Rollout batch (host pointers, row-major). Std has A entries (the data file's Std columns, last row wins,
+ * TRPO_FVP.c:746-748). Mean/Action/Advantage may be NULL when only FVP/CG are used.
+ * In multi-GPU mode every rank passes ITS shard (NumSamples = local count). */
+int trpo_ctx_set_batch(trpo_ctx *ctx, size_t NumSamples, const double *Observ, const double *Std,
+                       const double *Mean, const double *Action, const double *Advantage);
+/* Same with DEVICE pointers (adopted, not copied; must stay valid until the next set_batch). */
+int trpo_ctx_set_batch_device(trpo_ctx *ctx, size_t NumSamples, const double *dObserv, const double *Std_host,
+                              const double *dMean, const double *dAction, const double *dAdvantage);
+
+/* Synchronous host-buffer calls (H2D of the P-length input, compute, D2H of the result). */
+int trpo_ctx_fvp(trpo_ctx *ctx, const double *Input, double *Result, double CG_Damping);
+int trpo_ctx_cg(trpo_ctx *ctx, const double *b, double *Result, size_t MaxIter, double ResidualTh, double CG_Damping);
+int trpo_ctx_policy_gradient(trpo_ctx *ctx, double *b_out);
+int trpo_ctx_update(trpo_ctx *ctx, double *Result, double CG_Damping);
+int trpo_ctx_get_info(const trpo_ctx *ctx, trpo_info *info);
+
+/* Asynchronous device-buffer calls: enqueue on the context stream and return (inputs/outputs are device
+ * pointers to P doubles). The CG state never leaves the device; trpo_ctx_get_info after trpo_ctx_sync. */
+int trpo_ctx_fvp_device(trpo_ctx *ctx, const double *dInput, double *dResult, double CG_Damping);
+int trpo_ctx_cg_device(trpo_ctx *ctx, const double *db, double *dResult, size_t MaxIter, double ResidualTh, double CG_Damping);
+
+/* Device scratch helpers for C callers that do not link the CUDA runtime themselves. */
+double *trpo_device_alloc(size_t n_doubles);
+void    trpo_device_free(double *p);
+int     trpo_memcpy_h2d(double *dst_dev, const double *src_host, size_t n_doubles);
+int     trpo_memcpy_d2h(double *dst_host, const double *src_dev, size_t n_doubles);
+
+/* ------------------------------------------------------------------------------------------------
+ * Multi-GPU: one process (or thread) per GPU. Samples are sharded; each FVP ends with ONE all-reduce of the
+ * P-length un-normalised sum (ncclDouble, ncclSum) before the replicated CG update.
+ * Rank 0 creates the id and ships the 128 bytes to the others by any means (bench.py: torch.distributed).
+ * ---------------------------------------------------------------------------------------------- */
+int trpo_nccl_unique_id(char id_out[128]);
+int trpo_ctx_init_comm(trpo_ctx *ctx, const char id[128], int rank, int world_size);
+/* Total sample count over all ranks (the 1/N of TRPO_FVP.c:930). Computed by init_comm+set_batch via all-reduce. */
+size_t trpo_ctx_global_samples(const trpo_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRPO_B200_H */

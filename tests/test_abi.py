@@ -1,0 +1,89 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads, exports every symbol include/trpo_b200.h declares,
+keeps the reference's TRPOparam layout, and fails loudly (no CPU fallback) without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+    src = open(os.path.join(ROOT, "include", "trpo_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\([^;{}]*\)\s*;", src)
+    return sorted(set(n for n in names if n.startswith(("trpo_", "FVP_", "CG_", "TRPO_"))))
+
+
+def test_header_declares_the_reference_entry_points():
+    names = declared_functions()
+    for must in ("FVP_GPU", "CG_GPU", "TRPO_Update_GPU", "FVP_FPGA", "CG_FPGA", "trpo_ctx_create", "trpo_ctx_fvp",
+                 "trpo_ctx_cg", "trpo_ctx_update", "trpo_ctx_init_comm"):
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    lib = C.CDLL(pkg.api.library_path())
+    dropin = C.CDLL(pkg.api.library_path(dropin=True))
+    for name in declared_functions():
+        target = dropin if name in ("FVP_FPGA", "CG_FPGA") else lib
+        assert hasattr(target, name), f"{name} declared in include/trpo_b200.h but not exported"
+    # the FPGA names must NOT leak into the plain library (they would clash with a MaxCompiler build)
+    with pytest.raises(AttributeError):
+        lib.FVP_FPGA
+
+
+def test_trpoparam_layout_matches_reference(pkg):
+    # /root/reference/src/include/TRPO.h:6-49 -- 11 fields x 8 bytes on LP64, in this order
+    P = pkg.TRPOparam
+    assert C.sizeof(P) == 88
+    names = [f[0] for f in P._fields_]
+    assert names == ["ModelFile", "BaselineFile", "ResultFile", "DataFile", "NumLayers", "AcFunc", "LayerSize",
+                     "NumSamples", "CG_Damping", "PaddedLayerSize", "NumBlocks"]
+    assert P.NumSamples.offset == 56 and P.CG_Damping.offset == 64
+
+
+def test_num_params_matches_reference_formula(pkg):
+    assert pkg.api.num_params([15, 16, 16, 3]) == 582          # ArmTest
+    assert pkg.api.num_params([17, 64, 64, 6]) == 5708
+    assert pkg.api.num_params([376, 256, 256, 17]) == 166690
+    assert pkg.api.num_params([4, 5, 2]) == pkg.synth.num_params([4, 5, 2])
+
+
+def test_missing_files_return_minus_one_like_the_reference(pkg, tmp_path, capfd):
+    # TRPO_FVP_FPGA.c:102-105: "[ERROR] Cannot open Model File [...]" then return -1
+    v = np.zeros(582)
+    out, t = pkg.FVP_GPU(str(tmp_path / "nope_model.txt"), str(tmp_path / "nope_data.txt"), [15, 16, 16, 3], "lttl", 10, 0.1, v)
+    assert t == -1.0
+    assert "[ERROR] Cannot open Model File" in capfd.readouterr().err
+    mf = tmp_path / "m.txt"
+    pkg.textio.write_model(str(mf), np.zeros(582))
+    out, t = pkg.CG_GPU(str(mf), str(tmp_path / "nope_data.txt"), [15, 16, 16, 3], "lttl", 10, 0.1, v)
+    assert t == -1.0
+    assert "[ERROR] Cannot open Data File" in capfd.readouterr().err
+
+
+def test_unsupported_activation_is_refused(pkg, capfd):
+    with pytest.raises(RuntimeError):
+        pkg.Context([4, 5, 2], "lxl")
+    assert "Unsupported" in capfd.readouterr().err
+
+
+def test_no_cpu_fallback(pkg):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        pkg.Context([15, 16, 16, 3], "lttl")
+
+
+def test_product_does_not_reference_the_oracle():
+    """The product sources must never include, link or dlopen anything under oracle/."""
+    pkg_dir = os.path.join(ROOT, "trpo-robot-control_b200")
+    for dirpath, _, files in os.walk(pkg_dir):
+        for f in files:
+            if f.endswith((".cu", ".cuh", ".c", ".h", ".py")) or f == "Makefile":
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "liboracle" not in text and "trpo_oracle" not in text and "oracle_lib" not in text, f

@@ -1,0 +1,188 @@
+"""GPU parity tests (run on the B200 box with -m gpu): the CUDA path through the C-ABI against
+ (1) the committed outputs of the compiled reference (tests/golden, FP64 tolerance 1e-10 norm-relative),
+ (2) the oracle on fresh seeded inputs,
+ (3) size-independent properties at BASELINE.json's full sizes (linearity, symmetry, CG residual, determinism)."""
+import numpy as np
+import pytest
+
+from conftest import SYNTH_NAMES, load_synth, rel_err
+
+pytestmark = pytest.mark.gpu
+
+FVP_TOL = 1e-10       # north_star: FP64 build within 1e-10 relative of the reference's double-precision CPU FVP/CG
+CG_TOL = 1e-8         # CG amplifies rounding by the conditioning of F + damping*I; measured values are ~1e-12
+ARM_LAYERS, ARM_AC = [15, 16, 16, 3], "lttl"
+
+
+def paths_for(pkg, layers, ac):
+    ps = [pkg.api.PATH_GEMM_CHAIN]
+    with pkg.Context(layers, ac) as c:
+        try:
+            c.set_path(pkg.api.PATH_FUSED)
+            ps.append(pkg.api.PATH_FUSED)
+        except RuntimeError:
+            pass
+    return ps
+
+
+@pytest.mark.parametrize("n", [3150, 2400])
+def test_fvp_armtest(pkg, armtest, n):
+    a = armtest
+    for path in paths_for(pkg, ARM_LAYERS, ARM_AC):
+        with pkg.Context(ARM_LAYERS, ARM_AC) as ctx:
+            ctx.set_path(path)
+            ctx.set_model(a["theta"])
+            ctx.set_batch(a["Observ"][:n], a["Std"])
+            z = ctx.fvp(a["fvp_in"], 0.1)
+            assert ctx.path_used() == path
+        e_max, e_l2 = rel_err(z, a[f"ref_fvpfast_{n}"])
+        assert e_max < FVP_TOL and e_l2 < FVP_TOL, (path, e_max, e_l2)
+        # the 4-pass FVP() that Test_FVP_FPGA compares against (TRPOCpuCode.c:184)
+        if n == 3150:
+            assert rel_err(z, a["ref_fvp4_3150"])[0] < FVP_TOL
+
+
+def test_cg_armtest(pkg, armtest):
+    a = armtest
+    for path in paths_for(pkg, ARM_LAYERS, ARM_AC):
+        with pkg.Context(ARM_LAYERS, ARM_AC) as ctx:
+            ctx.set_path(path)
+            ctx.set_model(a["theta"])
+            ctx.set_batch(a["Observ"], a["Std"])
+            x, info = ctx.cg(a["cg_b"], 10, 1e-10, 0.1)
+        assert info.cg_iters == 8                      # same early exit as the reference (rdotr < 1e-10 at iteration 8)
+        e_max, e_l2 = rel_err(x, a["ref_cg_3150"])
+        assert e_max < CG_TOL and e_l2 < CG_TOL, (path, e_max, e_l2)
+        assert np.allclose(np.array(info.cg_rdotr[:8]), a["cg_trace_rdotr_3150"][:8], rtol=1e-7)
+        assert np.allclose(np.array(info.cg_xnorm[:9]), a["cg_trace_xnorm_3150"][:9], rtol=1e-8)
+        # the reference's own golden (ArmTestCG.txt) at its 1e-5 level
+        assert rel_err(x, a["cg_expected"])[1] < 1e-5
+
+
+def test_update_armtest(pkg, armtest):
+    a = armtest
+    with pkg.Context(ARM_LAYERS, ARM_AC) as ctx:
+        ctx.set_model(a["theta"])
+        ctx.set_batch(a["Observ"], a["Std"], a["Mean"], a["Action"], a["Advantage"])
+        b = ctx.policy_gradient()
+        u, info = ctx.update(0.1)
+    assert info.ls_accepted == 1 and info.ls_steps == 1
+    assert abs(info.shs - 0.00294934722) < 1e-9 and abs(info.ls_ratio[0] - 0.912970423) < 1e-7
+    e_max, e_l2 = rel_err(u, a["ref_update_3150"])
+    assert e_max < CG_TOL and e_l2 < CG_TOL, (e_max, e_l2)
+
+
+@pytest.mark.parametrize("name", SYNTH_NAMES)
+def test_synthetic_cases(pkg, oracle, name):
+    s = load_synth(name)
+    L, ac = s["layers"], s["acfunc"]
+    for path in paths_for(pkg, L, ac):
+        with pkg.Context(L, ac) as ctx:
+            ctx.set_path(path)
+            ctx.set_model(s["theta"])
+            ctx.set_batch(s["Observ"], s["Std"], s["Mean"], s["Action"], s["Advantage"])
+            z = ctx.fvp(s["v"], 0.1)
+            x, info = ctx.cg(s["b"], 10, 1e-10, 0.1)
+            pg = ctx.policy_gradient()
+            u, uinfo = ctx.update(0.1)
+        assert rel_err(z, s["ref_fvpfast"])[0] < FVP_TOL, (name, path, rel_err(z, s["ref_fvpfast"]))
+        assert rel_err(z, s["ref_fvp4"])[0] < FVP_TOL
+        assert rel_err(x, s["ref_cg"])[0] < CG_TOL, (name, path, rel_err(x, s["ref_cg"]))
+        pg_ref = oracle.policy_gradient(L, ac, s["theta"], s["Observ"], s["Mean"], s["Action"], s["Advantage"])
+        assert rel_err(pg, pg_ref)[0] < FVP_TOL
+        assert rel_err(u, s["ref_update"])[0] < CG_TOL, (name, path, rel_err(u, s["ref_update"]))
+
+
+def test_file_based_dropins(pkg, armtest, tmp_path, capfd):
+    """FVP_GPU / CG_GPU / TRPO_Update_GPU with the reference's signature and text files (the Test_*_FPGA shape)."""
+    a = armtest
+    mf, df = str(tmp_path / "ArmTestModel.txt"), str(tmp_path / "ArmTestData.txt")
+    pkg.textio.write_model(mf, a["theta"])
+    pkg.textio.write_data(df, a["Mean"], a["Std"], a["Observ"], a["Action"], a["Advantage"])
+    z, t = pkg.FVP_GPU(mf, df, ARM_LAYERS, ARM_AC, 3150, 0.1, a["fvp_in"])
+    assert t >= 0 and rel_err(z, a["ref_fvpfast_3150"])[0] < FVP_TOL
+    x, t = pkg.CG_GPU(mf, df, ARM_LAYERS, ARM_AC, 3150, 0.1, a["cg_b"], 10, 1e-10, 1)
+    assert t >= 0 and rel_err(x, a["ref_cg_3150"])[0] < CG_TOL
+    out = capfd.readouterr().out
+    assert "CG Iter[0] Residual Norm=9.055952534518e-03, Soln Norm=0.000000000000e+00" in out
+    assert "CG Iter[8] Residual Norm=" in out and "CG Iter[9]" not in out
+    u, t = pkg.TRPO_Update_GPU(mf, df, ARM_LAYERS, ARM_AC, 3150, 0.1, 1)
+    assert t >= 0 and rel_err(u, a["ref_update_3150"])[0] < CG_TOL
+    out = capfd.readouterr().out
+    assert "shs: 0.002949347" in out and "a/e/r 0.009916" in out
+
+
+@pytest.mark.parametrize("n", [1, 7, 63, 64, 65, 1000, 4097])
+def test_ragged_sample_counts(pkg, oracle, n):
+    layers, ac = [17, 64, 64, 6], "lttl"
+    theta = pkg.synth.make_model(layers, 99)
+    batch = pkg.synth.make_batch(layers, ac, theta, n, 99)
+    vec = pkg.synth.make_vectors(layers, 99)
+    ref = oracle.fvp(layers, ac, theta, batch["Std"], batch["Observ"], 0.1, vec["v"])
+    for path in paths_for(pkg, layers, ac):
+        with pkg.Context(layers, ac) as ctx:
+            ctx.set_path(path)
+            ctx.set_model(theta)
+            ctx.set_batch(batch["Observ"], batch["Std"])
+            z = ctx.fvp(vec["v"], 0.1)
+        assert rel_err(z, ref)[0] < FVP_TOL, (n, path, rel_err(z, ref))
+
+
+def test_cg_termination_semantics(pkg, oracle):
+    """rdotr < ResidualTh before the first FVP -> zero iterations, x = 0; MaxIter = 0 -> x = 0 (TRPO_CG.c:59-62)."""
+    s = load_synth("net3")
+    with pkg.Context(s["layers"], s["acfunc"]) as ctx:
+        ctx.set_model(s["theta"])
+        ctx.set_batch(s["Observ"], s["Std"])
+        x, info = ctx.cg(s["b"], 10, 1e3, 0.1)
+        assert info.cg_iters == 0 and not x.any()
+        x, info = ctx.cg(s["b"], 0, 1e-10, 0.1)
+        assert info.cg_iters == 0 and not x.any()
+        x3, info = ctx.cg(s["b"], 3, 0.0, 0.1)
+        assert info.cg_iters == 3
+    ref3, nf, _, _ = oracle.cg(s["layers"], s["acfunc"], s["theta"], s["Std"], s["Observ"], 0.1, s["b"], 3, 0.0)
+    assert nf == 3 and rel_err(x3, ref3)[0] < CG_TOL
+
+
+def test_humanoid_width_against_oracle(pkg, oracle):
+    layers, ac = [376, 256, 256, 17], "lttl"
+    theta = pkg.synth.make_model(layers, 4)
+    batch = pkg.synth.make_batch(layers, ac, theta, 300, 4)
+    vec = pkg.synth.make_vectors(layers, 4)
+    ref = oracle.fvp(layers, ac, theta, batch["Std"], batch["Observ"], 0.1, vec["v"])
+    with pkg.Context(layers, ac) as ctx:
+        ctx.set_model(theta)
+        ctx.set_batch(batch["Observ"], batch["Std"])
+        z = ctx.fvp(vec["v"], 0.1)
+    assert rel_err(z, ref)[0] < FVP_TOL, rel_err(z, ref)
+
+
+def test_full_size_properties_mlp64_1m(pkg, oracle):
+    """BASELINE config 3 at full size (1M states): determinism, linearity, symmetry, CG residual, and a
+    50k-sample prefix against the oracle."""
+    layers, ac = [17, 64, 64, 6], "lttl"
+    seed = pkg.synth.SEED_BASE + 2
+    theta = pkg.synth.make_model(layers, seed)
+    N = 1_000_000
+    batch = pkg.synth.make_batch(layers, ac, theta, N, seed)
+    vec = pkg.synth.make_vectors(layers, seed)
+    rng = np.random.default_rng(5)
+    u, w = rng.standard_normal(theta.size), rng.standard_normal(theta.size)
+    with pkg.Context(layers, ac) as ctx:
+        ctx.set_model(theta)
+        ctx.set_batch(batch["Observ"], batch["Std"])
+        Fu, Fw = ctx.fvp(u, 0.0), ctx.fvp(w, 0.0)
+        assert np.array_equal(Fu, ctx.fvp(u, 0.0))                      # bitwise deterministic
+        Fc = ctx.fvp(2 * u - 3 * w, 0.0)
+        assert rel_err(Fc, 2 * Fu - 3 * Fw)[0] < 1e-11                   # linear
+        assert abs(u @ Fw - w @ Fu) < 1e-10 * abs(u @ Fw)                # symmetric
+        x, info = ctx.cg(vec["b"], 10, 0.0, 0.1)
+        assert info.cg_iters == 10
+        resid = ctx.fvp(x, 0.1) - vec["b"]
+        assert np.linalg.norm(resid) ** 2 < 1.01 * info.cg_rdotr[10] + 1e-20   # r tracked by CG == b - A x
+        # prefix vs oracle
+        n = 50_000
+        ctx.set_batch(batch["Observ"][:n], batch["Std"])
+        z = ctx.fvp(vec["v"], 0.1)
+    ref = oracle.fvp(layers, ac, theta, batch["Std"], np.ascontiguousarray(batch["Observ"][:n]), 0.1, vec["v"])
+    assert rel_err(z, ref)[0] < FVP_TOL, rel_err(z, ref)

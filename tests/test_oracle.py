@@ -1,0 +1,127 @@
+"""CPU tests: the oracle (oracle/trpo_oracle.c) against the committed golden outputs of the compiled reference,
+against the reference's own .txt goldens, and against oracle/_ref itself when it is present."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import SYNTH_NAMES, load_synth, rel_err
+from oracle_lib import Reference
+
+ARM_LAYERS, ARM_AC = [15, 16, 16, 3], "lttl"
+
+
+def test_num_params(oracle):
+    import ctypes as C
+    for layers, expect in (([15, 16, 16, 3], 582), ([17, 64, 64, 6], 5708), ([376, 256, 256, 17], 166690)):
+        arr = (C.c_size_t * len(layers))(*layers)
+        assert oracle.lib.oracle_num_params(arr, len(layers)) == expect
+
+
+@pytest.mark.parametrize("n", [3150, 2400])
+def test_fvpfast_armtest_bit_exact(oracle, armtest, n):
+    a = armtest
+    got = oracle.fvp(ARM_LAYERS, ARM_AC, a["theta"], a["Std"], a["Observ"][:n].copy(), 0.1, a["fvp_in"])
+    assert np.array_equal(got, a[f"ref_fvpfast_{n}"])
+
+
+def test_fvp4_armtest_bit_exact(oracle, armtest):
+    a = armtest
+    got = oracle.fvp(ARM_LAYERS, ARM_AC, a["theta"], a["Std"], a["Observ"], 0.1, a["fvp_in"], four_pass=True)
+    assert np.array_equal(got, a["ref_fvp4_3150"])
+    # FVP and FVPFast agree to rounding
+    assert np.abs(got - a["ref_fvpfast_3150"]).max() < 1e-14
+
+
+def test_cg_armtest_bit_exact_and_trace(oracle, armtest):
+    a = armtest
+    x, nf, rd, xn = oracle.cg(ARM_LAYERS, ARM_AC, a["theta"], a["Std"], a["Observ"], 0.1, a["cg_b"])
+    assert np.array_equal(x, a["ref_cg_3150"])
+    assert nf == 8                                         # converges at iteration 8
+    expect = [9.055952534518e-03, 3.331162390997e-03, 3.788194871309e-04, 1.337041168030e-03, 4.712672388744e-06,
+              4.777271029756e-06, 9.946297585134e-08, 8.917414723637e-10]
+    assert np.allclose(rd[:8], expect, rtol=1e-9)
+    assert rd[8] < 1e-10
+    x2400, _, _, _ = oracle.cg(ARM_LAYERS, ARM_AC, a["theta"], a["Std"], a["Observ"][:2400].copy(), 0.1, a["cg_b"])
+    assert np.array_equal(x2400, a["ref_cg_2400"])
+
+
+def test_cg_matches_reference_txt_golden(armtest):
+    """build/ArmTestCG.txt pins CG(N=3150) to rel-L2 8e-6 (the golden came from modular_rl/Theano)."""
+    a = armtest
+    _, l2 = rel_err(a["ref_cg_3150"], a["cg_expected"])
+    assert l2 < 1e-5
+    _, l2_2400 = rel_err(a["ref_cg_2400"], a["cg_expected"])
+    assert l2_2400 > 1e-2                                  # the golden belongs to N=3150, not the commented 2400
+
+
+def test_fvp_txt_golden_is_stale_except_logstd_tail(armtest):
+    """build/ArmTestFVP.txt's expected column does not belong to the shipped model/data (rel-L2 0.92);
+    only the LogStd block (2.1 * v) agrees. Recorded so nobody 'fixes' the kernels towards it."""
+    a = armtest
+    _, l2 = rel_err(a["ref_fvpfast_3150"], a["fvp_expected_stale"])
+    assert l2 > 0.5
+    assert np.abs(a["ref_fvpfast_3150"][-3:] - a["fvp_expected_stale"][-3:]).max() < 1e-7
+    assert np.allclose(a["ref_fvpfast_3150"][-3:], 2.1 * a["fvp_in"][-3:], rtol=1e-13)
+
+
+def test_update_armtest_bit_exact(oracle, armtest):
+    a = armtest
+    got, info = oracle.update(ARM_LAYERS, ARM_AC, a["theta"], a["Std"], a["Observ"], a["Mean"], a["Action"],
+                              a["Advantage"], 0.1)
+    assert np.array_equal(got, a["ref_update_3150"])
+    assert info.ls_accepted == 1 and info.ls_steps == 1
+    assert abs(info.ls_ratio[0] - 0.91297042355) < 1e-9
+    _, l2 = rel_err(got, a["updated_expected"])
+    assert l2 < 0.1                                        # ArmTestModelUpdated.txt pins it only loosely (6.5e-2)
+
+
+@pytest.mark.parametrize("name", SYNTH_NAMES)
+def test_synthetic_cases_bit_exact(oracle, name):
+    s = load_synth(name)
+    L, ac = s["layers"], s["acfunc"]
+    assert np.array_equal(oracle.fvp(L, ac, s["theta"], s["Std"], s["Observ"], 0.1, s["v"]), s["ref_fvpfast"])
+    assert np.array_equal(oracle.fvp(L, ac, s["theta"], s["Std"], s["Observ"], 0.1, s["v"], four_pass=True), s["ref_fvp4"])
+    x, _, _, _ = oracle.cg(L, ac, s["theta"], s["Std"], s["Observ"], 0.1, s["b"])
+    assert np.array_equal(x, s["ref_cg"])
+    u, _ = oracle.update(L, ac, s["theta"], s["Std"], s["Observ"], s["Mean"], s["Action"], s["Advantage"], 0.1)
+    assert np.array_equal(u, s["ref_update"])
+
+
+def test_fvp_is_linear_and_symmetric(oracle):
+    s = load_synth("net3")
+    L, ac = s["layers"], s["acfunc"]
+    rng = np.random.default_rng(0)
+    u, w = rng.standard_normal(s["theta"].size), rng.standard_normal(s["theta"].size)
+    F = lambda v: oracle.fvp(L, ac, s["theta"], s["Std"], s["Observ"], 0.0, v)
+    assert np.allclose(F(2 * u - 3 * w), 2 * F(u) - 3 * F(w), rtol=1e-11, atol=1e-12)
+    assert abs(u @ F(w) - w @ F(u)) < 1e-11 * abs(u @ F(w))
+
+
+@pytest.mark.skipif(not Reference.available() or not os.path.isdir("/root/reference/build"),
+                    reason="compiled reference / reference tree not present (GPU box)")
+def test_oracle_vs_live_reference(oracle, tmp_path):
+    """Where /root/reference exists: run the compiled reference live on a fresh random case and compare bit for bit."""
+    from __graft_entry__ import load_package
+    pkg = load_package()
+    layers, ac, N = [7, 9, 5, 3], "ltsl", 97
+    theta = pkg.synth.make_model(layers, 1234)
+    b = pkg.synth.make_batch(layers, ac, theta, N, 1234)
+    b["Mean"] = oracle.forward(layers, ac, theta, b["Observ"])
+    vec = pkg.synth.make_vectors(layers, 1234)
+    mf, df = str(tmp_path / "m.txt"), str(tmp_path / "d.txt")
+    pkg.textio.write_model(mf, theta)
+    pkg.textio.write_data(df, b["Mean"], b["Std"], b["Observ"], b["Action"], b["Advantage"])
+    ref = Reference()
+    r, _ = ref.fvp_fast(mf, df, layers, ac, N, 0.1, vec["v"])
+    assert np.array_equal(r, oracle.fvp(layers, ac, theta, b["Std"], b["Observ"], 0.1, vec["v"]))
+    r, _ = ref.cg(mf, df, layers, ac, N, 0.1, vec["b"])
+    assert np.array_equal(r, oracle.cg(layers, ac, theta, b["Std"], b["Observ"], 0.1, vec["b"])[0])
+    r, _ = ref.update(mf, df, layers, ac, N, 0.1)
+    assert np.array_equal(r, oracle.update(layers, ac, theta, b["Std"], b["Observ"], b["Mean"], b["Action"],
+                                           b["Advantage"], 0.1)[0])
+    # the loaders parse the text formats exactly like the reference
+    assert np.array_equal(oracle.load_model(mf, layers, ac), theta)
+    d = oracle.load_data(df, layers, ac, N)
+    for k in ("Mean", "Std", "Observ", "Action", "Advantage"):
+        assert np.array_equal(d[k], b[k])

@@ -1,0 +1,274 @@
+"""ctypes bindings of ``libtrpo_b200.so`` (C-ABI declared in ``include/trpo_b200.h``).
+
+Mirrors the reference's operator interface for the path:
+  FVP_FPGA / CG_FPGA  (/root/reference/src/include/TRPO.h:98,101)  ->  FVP_GPU / CG_GPU
+  TRPO_Update         (/root/reference/src/include/TRPO.h:104)      ->  TRPO_Update_GPU
+plus the persistent context (``Context``) that stages a rollout batch once.
+Fails loudly when the library is missing: there is no fallback path.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+c_double_p = C.POINTER(C.c_double)
+c_size_p = C.POINTER(C.c_size_t)
+
+PATH_AUTO, PATH_GEMM_CHAIN, PATH_FUSED = 0, 1, 2
+
+
+class TRPOparam(C.Structure):
+    """Same field order as /root/reference/src/include/TRPO.h:6-49; passed by value."""
+    _fields_ = [("ModelFile", C.c_char_p), ("BaselineFile", C.c_char_p), ("ResultFile", C.c_char_p),
+                ("DataFile", C.c_char_p), ("NumLayers", C.c_size_t), ("AcFunc", C.c_char_p),
+                ("LayerSize", c_size_p), ("NumSamples", C.c_size_t), ("CG_Damping", C.c_double),
+                ("PaddedLayerSize", c_size_p), ("NumBlocks", c_size_p)]
+
+
+class TrpoInfo(C.Structure):
+    _fields_ = [("cg_iters", C.c_int), ("cg_rdotr", C.c_double * 34), ("cg_xnorm", C.c_double * 34),
+                ("shs", C.c_double), ("lm", C.c_double), ("gnorm", C.c_double), ("fval", C.c_double),
+                ("ls_steps", C.c_int), ("ls_accepted", C.c_int),
+                ("ls_actual", C.c_double * 16), ("ls_expected", C.c_double * 16), ("ls_ratio", C.c_double * 16)]
+
+
+def library_path(dropin=False):
+    return os.path.join(PKG_DIR, "libtrpo_b200_dropin.so" if dropin else "libtrpo_b200.so")
+
+
+def build_library():
+    """Compile every CUDA/C source for sm_100a (nvcc cross-compiles without a GPU)."""
+    subprocess.run(["make", "-s", "-C", PKG_DIR, "-j8"], check=True)
+
+
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = library_path()
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} is missing: run __graft_entry__.build() (there is no CPU fallback)")
+        L = C.CDLL(path)
+        L.trpo_last_error.restype = C.c_char_p
+        L.trpo_num_params.restype = C.c_size_t
+        L.trpo_num_params.argtypes = [c_size_p, C.c_size_t]
+        L.trpo_ctx_create.restype = C.c_void_p
+        L.trpo_ctx_create.argtypes = [c_size_p, C.c_char_p, C.c_size_t, C.c_int, C.c_int]
+        L.trpo_ctx_destroy.argtypes = [C.c_void_p]
+        L.trpo_ctx_num_params.restype = C.c_size_t
+        L.trpo_ctx_num_params.argtypes = [C.c_void_p]
+        L.trpo_ctx_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+        L.trpo_ctx_get_stream.restype = C.c_void_p
+        L.trpo_ctx_get_stream.argtypes = [C.c_void_p]
+        L.trpo_ctx_set_path.argtypes = [C.c_void_p, C.c_int]
+        L.trpo_ctx_get_path.argtypes = [C.c_void_p]
+        L.trpo_ctx_sync.argtypes = [C.c_void_p]
+        L.trpo_ctx_launch_count.restype = C.c_longlong
+        L.trpo_ctx_launch_count.argtypes = [C.c_void_p]
+        L.trpo_ctx_kernel_timing.argtypes = [C.c_void_p, C.c_int]
+        L.trpo_ctx_kernel_time_ms.restype = C.c_double
+        L.trpo_ctx_kernel_time_ms.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+        L.trpo_ctx_set_model.argtypes = [C.c_void_p, c_double_p]
+        L.trpo_ctx_set_batch.argtypes = [C.c_void_p, C.c_size_t] + [c_double_p] * 5
+        L.trpo_ctx_set_batch_device.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, c_double_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.trpo_ctx_fvp.argtypes = [C.c_void_p, c_double_p, c_double_p, C.c_double]
+        L.trpo_ctx_cg.argtypes = [C.c_void_p, c_double_p, c_double_p, C.c_size_t, C.c_double, C.c_double]
+        L.trpo_ctx_policy_gradient.argtypes = [C.c_void_p, c_double_p]
+        L.trpo_ctx_update.argtypes = [C.c_void_p, c_double_p, C.c_double]
+        L.trpo_ctx_get_info.argtypes = [C.c_void_p, C.POINTER(TrpoInfo)]
+        L.trpo_ctx_fvp_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double]
+        L.trpo_ctx_cg_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_double, C.c_double]
+        L.trpo_nccl_unique_id.argtypes = [C.c_char_p]
+        L.trpo_ctx_init_comm.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int]
+        L.trpo_ctx_global_samples.restype = C.c_size_t
+        L.trpo_ctx_global_samples.argtypes = [C.c_void_p]
+        for name in ("FVP_GPU", "CG_GPU", "TRPO_Update_GPU"):
+            getattr(L, name).restype = C.c_double
+        L.FVP_GPU.argtypes = [TRPOparam, c_double_p, c_double_p]
+        L.CG_GPU.argtypes = [TRPOparam, c_double_p, c_double_p, C.c_size_t, C.c_double, C.c_size_t]
+        L.TRPO_Update_GPU.argtypes = [TRPOparam, c_double_p, C.c_size_t]
+        _LIB = L
+    return _LIB
+
+
+def last_error():
+    return lib().trpo_last_error().decode()
+
+
+def _dp(a):
+    if a is None:
+        return None
+    assert isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags["C_CONTIGUOUS"], "need contiguous float64"
+    return a.ctypes.data_as(c_double_p)
+
+
+def _check(rc):
+    if rc != 0:
+        raise RuntimeError(f"libtrpo_b200: {last_error()}")
+
+
+def num_params(layers):
+    arr = (C.c_size_t * len(layers))(*layers)
+    return lib().trpo_num_params(arr, len(layers))
+
+
+def make_param(model_file, data_file, layers, acfunc, num_samples, damping, keep):
+    ls = (C.c_size_t * len(layers))(*layers)
+    ac = C.c_char_p(acfunc.encode())
+    keep.extend([ls, ac])
+    p = TRPOparam()
+    p.ModelFile = model_file.encode()
+    p.DataFile = data_file.encode()
+    p.NumLayers = len(layers)
+    p.AcFunc = ac
+    p.LayerSize = C.cast(ls, c_size_p)
+    p.NumSamples = num_samples
+    p.CG_Damping = damping
+    return p
+
+
+def FVP_GPU(model_file, data_file, layers, acfunc, num_samples, damping, v):
+    """File-based drop-in for FVP_FPGA (/root/reference/src/TRPO_FVP_FPGA.c:13). Returns (result, seconds)."""
+    keep = []
+    p = make_param(model_file, data_file, layers, acfunc, num_samples, damping, keep)
+    out = np.zeros(num_params(layers))
+    t = lib().FVP_GPU(p, _dp(out), _dp(np.ascontiguousarray(v, dtype=np.float64)))
+    return out, t
+
+
+def CG_GPU(model_file, data_file, layers, acfunc, num_samples, damping, b, max_iter=10, residual_th=1e-10, threads=1):
+    """File-based drop-in for CG_FPGA (/root/reference/src/TRPO_CG_FPGA.c:13). Returns (result, seconds)."""
+    keep = []
+    p = make_param(model_file, data_file, layers, acfunc, num_samples, damping, keep)
+    out = np.zeros(num_params(layers))
+    t = lib().CG_GPU(p, _dp(out), _dp(np.ascontiguousarray(b, dtype=np.float64)), max_iter, residual_th, threads)
+    return out, t
+
+
+def TRPO_Update_GPU(model_file, data_file, layers, acfunc, num_samples, damping, threads=1):
+    """GPU counterpart of TRPO_Update (/root/reference/src/TRPO_Update.c:10). Returns (result, seconds)."""
+    keep = []
+    p = make_param(model_file, data_file, layers, acfunc, num_samples, damping, keep)
+    out = np.zeros(num_params(layers))
+    t = lib().TRPO_Update_GPU(p, _dp(out), threads)
+    return out, t
+
+
+class Context:
+    """Persistent device context: model + rollout batch staged once, CG state resident on the GPU."""
+
+    def __init__(self, layers, acfunc, device=-1):
+        self.layers = list(layers)
+        self.acfunc = acfunc
+        ls = (C.c_size_t * len(layers))(*layers)
+        self.h = lib().trpo_ctx_create(ls, acfunc.encode(), len(layers), device, 0)
+        if not self.h:
+            raise RuntimeError(f"libtrpo_b200: {last_error()}")
+        self.P = lib().trpo_ctx_num_params(self.h)
+        self._keep = []
+
+    def close(self):
+        if self.h:
+            lib().trpo_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_stream(self, cuda_stream_ptr):
+        _check(lib().trpo_ctx_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
+
+    def set_path(self, path):
+        _check(lib().trpo_ctx_set_path(self.h, path))
+
+    def path_used(self):
+        return lib().trpo_ctx_get_path(self.h)
+
+    def sync(self):
+        _check(lib().trpo_ctx_sync(self.h))
+
+    def launch_count(self):
+        return lib().trpo_ctx_launch_count(self.h)
+
+    def kernel_timing(self, enable=True):
+        _check(lib().trpo_ctx_kernel_timing(self.h, int(enable)))
+
+    def kernel_time_ms(self):
+        n = C.c_int(0)
+        ms = lib().trpo_ctx_kernel_time_ms(self.h, C.byref(n))
+        return ms, n.value
+
+    def set_model(self, theta):
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        assert theta.size == self.P
+        _check(lib().trpo_ctx_set_model(self.h, _dp(theta)))
+
+    def set_batch(self, observ, std, mean=None, action=None, advantage=None):
+        observ = np.ascontiguousarray(observ, dtype=np.float64)
+        std = np.ascontiguousarray(std, dtype=np.float64)
+        arrs = [None if a is None else np.ascontiguousarray(a, dtype=np.float64) for a in (mean, action, advantage)]
+        _check(lib().trpo_ctx_set_batch(self.h, observ.shape[0], _dp(observ), _dp(std), *[_dp(a) for a in arrs]))
+
+    def set_batch_device(self, num_samples, d_observ, std, d_mean=0, d_action=0, d_advantage=0):
+        std = np.ascontiguousarray(std, dtype=np.float64)
+        _check(lib().trpo_ctx_set_batch_device(self.h, num_samples, C.c_void_p(d_observ), _dp(std),
+                                               C.c_void_p(d_mean or None), C.c_void_p(d_action or None),
+                                               C.c_void_p(d_advantage or None)))
+
+    def fvp(self, v, damping):
+        v = np.ascontiguousarray(v, dtype=np.float64)
+        out = np.zeros(self.P)
+        _check(lib().trpo_ctx_fvp(self.h, _dp(v), _dp(out), damping))
+        return out
+
+    def cg(self, b, max_iter=10, residual_th=1e-10, damping=0.1):
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        out = np.zeros(self.P)
+        _check(lib().trpo_ctx_cg(self.h, _dp(b), _dp(out), max_iter, residual_th, damping))
+        return out, self.info()
+
+    def policy_gradient(self):
+        out = np.zeros(self.P)
+        _check(lib().trpo_ctx_policy_gradient(self.h, _dp(out)))
+        return out
+
+    def update(self, damping=0.1):
+        out = np.zeros(self.P)
+        _check(lib().trpo_ctx_update(self.h, _dp(out), damping))
+        return out, self.info()
+
+    def info(self):
+        info = TrpoInfo()
+        _check(lib().trpo_ctx_get_info(self.h, C.byref(info)))
+        return info
+
+    def fvp_device(self, d_in, d_out, damping):
+        _check(lib().trpo_ctx_fvp_device(self.h, C.c_void_p(d_in), C.c_void_p(d_out), damping))
+
+    def cg_device(self, d_b, d_out, max_iter=10, residual_th=1e-10, damping=0.1):
+        _check(lib().trpo_ctx_cg_device(self.h, C.c_void_p(d_b), C.c_void_p(d_out), max_iter, residual_th, damping))
+
+    def init_comm(self, unique_id, rank, world):
+        _check(lib().trpo_ctx_init_comm(self.h, unique_id, rank, world))
+
+    def global_samples(self):
+        return lib().trpo_ctx_global_samples(self.h)
+
+
+def nccl_unique_id():
+    buf = C.create_string_buffer(128)
+    _check(lib().trpo_nccl_unique_id(buf))
+    return buf.raw

@@ -1,0 +1,224 @@
+// cg_kernels.cu -- device-resident conjugate gradient (TRPO_CG.c:25-107) and the small vector kernels around it.
+//
+// One fused kernel per CG iteration does everything after the FVP sum:
+//   z = zsum/N + damping*p  (TRPO_FVP.c:928-931),  p.z,  v = r.r/p.z,  x += v p,  r -= v z,  r'.r',  mu,  p = r + mu p,
+//   |x|, trace, termination flag  (TRPO_CG.c:77-103,48-62)
+// All reductions are fixed-order (thread-strided partial -> warp shuffle tree -> shared tree), so results are
+// bitwise reproducible and identical on every rank of a multi-GPU solve.
+#include "trpo_internal.cuh"
+
+namespace {
+
+constexpr int CG_THREADS = 1024;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Block-wide fixed-order sum; result valid in every thread. red must hold 32 doubles.
+__device__ __forceinline__ double block_sum(double v, double *red) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();               // protect red from the previous use
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    double t = (threadIdx.x < nw) ? red[threadIdx.x] : 0.0;
+    if (w == 0) {
+        t = warp_sum(t);
+        if (lane == 0) red[0] = t;
+    }
+    __syncthreads();
+    return red[0];
+}
+
+// zsum[e] = sum over rows (fixed order) of partial[row][e]
+__global__ void k_reduce_partials(const double *__restrict__ partial, int rows, int P, double *__restrict__ zsum,
+                                  const int *__restrict__ done) {
+    if (done && *done) return;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= P) return;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int r = 0;
+    for (; r + 3 < rows; r += 4) {
+        s0 += partial[(size_t)r * P + e];
+        s1 += partial[(size_t)(r + 1) * P + e];
+        s2 += partial[(size_t)(r + 2) * P + e];
+        s3 += partial[(size_t)(r + 3) * P + e];
+    }
+    for (; r < rows; ++r) s0 += partial[(size_t)r * P + e];
+    zsum[e] = (s0 + s1) + (s2 + s3);
+}
+
+__global__ void k_fvp_finalise(const double *__restrict__ zsum, const double *__restrict__ v, double *__restrict__ out,
+                               int P, int logstd_off, double n_total, double damping) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= P) return;
+    // LogStd block: sum_n 2*v = 2*v*N exactly (TRPO_FVP.c:918-921)
+    const double mean = (e >= logstd_off) ? 2.0 * v[e] : zsum[e] / n_total;
+    out[e] = mean + damping * v[e];
+}
+
+__global__ void __launch_bounds__(CG_THREADS) k_cg_init(const double *__restrict__ b, double *__restrict__ x,
+                                                        double *__restrict__ r, double *__restrict__ p, int P,
+                                                        double residual_th, CgState *st) {
+    __shared__ double red[32];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        const double bi = b[i];
+        x[i] = 0.0; r[i] = bi; p[i] = bi;
+        acc += bi * bi;
+    }
+    const double rdotr = block_sum(acc, red);
+    if (threadIdx.x == 0) {
+        st->rdotr = rdotr; st->pdotz = 0.0; st->xnorm = 0.0; st->iters = 0;
+        st->trace_rdotr[0] = rdotr; st->trace_xnorm[0] = 0.0;
+        st->done = (rdotr < residual_th) ? 1 : 0;
+    }
+}
+
+__global__ void __launch_bounds__(CG_THREADS) k_cg_update(const double *__restrict__ zsum, double *__restrict__ x,
+                                                          double *__restrict__ r, double *__restrict__ p,
+                                                          double *__restrict__ z, int P, int logstd_off, double n_total,
+                                                          double damping, double residual_th, CgState *st) {
+    if (st->done) return;
+    __shared__ double red[32];
+    const double rdotr = st->rdotr;
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        const double pi = p[i];
+        const double mean = (i >= logstd_off) ? 2.0 * pi : zsum[i] / n_total;
+        const double zi = mean + damping * pi;
+        z[i] = zi;
+        acc += pi * zi;
+    }
+    const double pdotz = block_sum(acc, red);
+    const double v = rdotr / pdotz;
+    double acc_r = 0.0, acc_x = 0.0;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        const double xi = x[i] + v * p[i];
+        const double ri = r[i] - v * z[i];
+        x[i] = xi; r[i] = ri;
+        acc_r += ri * ri;
+        acc_x += xi * xi;
+    }
+    const double newrdotr = block_sum(acc_r, red);
+    const double xx = block_sum(acc_x, red);
+    const double mu = newrdotr / rdotr;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) p[i] = r[i] + mu * p[i];
+    if (threadIdx.x == 0) {
+        const int it = st->iters + 1;
+        st->iters = it;
+        st->rdotr = newrdotr; st->pdotz = pdotz; st->xnorm = sqrt(xx);
+        if (it < 34) { st->trace_rdotr[it] = newrdotr; st->trace_xnorm[it] = sqrt(xx); }
+        if (newrdotr < residual_th) st->done = 1;
+    }
+}
+
+__global__ void __launch_bounds__(CG_THREADS) k_dot(const double *__restrict__ a, const double *__restrict__ b, int n,
+                                                    double *__restrict__ out) {
+    __shared__ double red[32];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) acc += a[i] * b[i];
+    const double s = block_sum(acc, red);
+    if (threadIdx.x == 0) out[0] = s;
+}
+
+__global__ void k_axpby(double *__restrict__ out, const double *__restrict__ x, double a, const double *__restrict__ y,
+                        double b, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = a * x[i] + (y ? b * y[i] : 0.0);
+}
+
+// per-sample importance-weighted advantage (TRPO_Update.c:969-983), block partial sums in fixed order
+__global__ void __launch_bounds__(256) k_surrogate(const double *__restrict__ mean_new, const double *__restrict__ mean_old,
+                                                   const double *__restrict__ action, const double *__restrict__ adv,
+                                                   const double *__restrict__ std_old, const double *__restrict__ logstd_new,
+                                                   int A, size_t n, double *__restrict__ block_partials) {
+    __shared__ double red[32];
+    double acc = 0.0;
+    for (size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x; s < n; s += (size_t)gridDim.x * blockDim.x) {
+        double lld = 0.0;
+        for (int j = 0; j < A; ++j) {
+            const double a = action[s * A + j];
+            const double tx = (a - mean_old[s * A + j]) / std_old[j];
+            const double tn = (a - mean_new[s * A + j]) / exp(logstd_new[j]);
+            lld += tx * tx - tn * tn + log(std_old[j]) - logstd_new[j];
+        }
+        acc += exp(0.5 * lld) * adv[s];
+    }
+    const double sblk = block_sum(acc, red);
+    if (threadIdx.x == 0) block_partials[blockIdx.x] = sblk;
+}
+
+__global__ void __launch_bounds__(256) k_sum_blocks(const double *__restrict__ a, size_t n, double *__restrict__ block_partials) {
+    __shared__ double red[32];
+    double acc = 0.0;
+    for (size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x; s < n; s += (size_t)gridDim.x * blockDim.x) acc += a[s];
+    const double sblk = block_sum(acc, red);
+    if (threadIdx.x == 0) block_partials[blockIdx.x] = sblk;
+}
+
+__global__ void __launch_bounds__(CG_THREADS) k_sum_final(const double *__restrict__ a, int n, double *__restrict__ out) {
+    __shared__ double red[32];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) acc += a[i];
+    const double s = block_sum(acc, red);
+    if (threadIdx.x == 0) out[0] = s;
+}
+
+constexpr int SUM_BLOCKS = 592;   // 4 x 148 SMs
+
+}  // namespace
+
+void launch_reduce_partials(const double *d_partial, int rows, int P, double *d_zsum, const int *d_done,
+                            cudaStream_t st, long long *launches) {
+    k_reduce_partials<<<(P + 127) / 128, 128, 0, st>>>(d_partial, rows, P, d_zsum, d_done);
+    ++*launches;
+}
+
+void launch_fvp_finalise(const double *d_zsum, const double *d_v, double *d_out, int P, int logstd_off,
+                         double n_total, double damping, cudaStream_t st, long long *launches) {
+    k_fvp_finalise<<<(P + 255) / 256, 256, 0, st>>>(d_zsum, d_v, d_out, P, logstd_off, n_total, damping);
+    ++*launches;
+}
+
+void launch_cg_init(const double *d_b, double *d_x, double *d_r, double *d_p, int P, double residual_th,
+                    CgState *d_state, cudaStream_t st, long long *launches) {
+    k_cg_init<<<1, CG_THREADS, 0, st>>>(d_b, d_x, d_r, d_p, P, residual_th, d_state);
+    ++*launches;
+}
+
+void launch_cg_update(const double *d_zsum, double *d_x, double *d_r, double *d_p, double *d_z, int P, int logstd_off,
+                      double n_total, double damping, double residual_th, CgState *d_state,
+                      cudaStream_t st, long long *launches) {
+    k_cg_update<<<1, CG_THREADS, 0, st>>>(d_zsum, d_x, d_r, d_p, d_z, P, logstd_off, n_total, damping, residual_th, d_state);
+    ++*launches;
+}
+
+void launch_dot(const double *d_a, const double *d_b, int n, double *d_out, cudaStream_t st, long long *launches) {
+    k_dot<<<1, CG_THREADS, 0, st>>>(d_a, d_b, n, d_out);
+    ++*launches;
+}
+
+void launch_axpby(double *d_out, const double *d_x, double a, const double *d_y, double b, int n,
+                  cudaStream_t st, long long *launches) {
+    k_axpby<<<(n + 255) / 256, 256, 0, st>>>(d_out, d_x, a, d_y, b, n);
+    ++*launches;
+}
+
+void launch_surrogate(const double *d_mean_new, const double *d_mean_old, const double *d_action, const double *d_adv,
+                      const double *d_std_old, const double *d_logstd_new, int A, size_t nsamples,
+                      double *d_block_partials, double *d_out, cudaStream_t st, long long *launches) {
+    k_surrogate<<<SUM_BLOCKS, 256, 0, st>>>(d_mean_new, d_mean_old, d_action, d_adv, d_std_old, d_logstd_new, A, nsamples,
+                                           d_block_partials);
+    k_sum_final<<<1, CG_THREADS, 0, st>>>(d_block_partials, SUM_BLOCKS, d_out);
+    *launches += 2;
+}
+
+void launch_sum(const double *d_a, size_t n, double *d_block_partials, double *d_out, cudaStream_t st, long long *launches) {
+    k_sum_blocks<<<SUM_BLOCKS, 256, 0, st>>>(d_a, n, d_block_partials);
+    k_sum_final<<<1, CG_THREADS, 0, st>>>(d_block_partials, SUM_BLOCKS, d_out);
+    *launches += 2;
+}

@@ -1,0 +1,84 @@
+// Internal declarations shared by the CUDA translation units of libtrpo_b200.so (not part of the C-ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#define TRPO_MAX_LAYERS 16
+
+// Network description in device-friendly form. The flat parameter vector (TRPO_FVP.c:704-725) is, per weight layer i,
+// an augmented row-major matrix [(L_i + 1) x L_{i+1}] at offset w_off[i]: L_i rows of W[i] followed by the row B[i].
+struct NetDesc {
+    int K;                           // weight layers = NumLayers - 1
+    int L[TRPO_MAX_LAYERS];          // L[0..K]
+    int w_off[TRPO_MAX_LAYERS];      // offset of W[i]; B[i] is at w_off[i] + L[i]*L[i+1]
+    int logstd_off;
+    int P;
+    char ac[TRPO_MAX_LAYERS];        // ac[i] = activation producing layer i (i >= 1)
+};
+
+// Device-side CG state block (one per context).
+struct CgState {
+    double rdotr;
+    double pdotz;
+    double xnorm;
+    int    done;        // set when rdotr < ResidualTh: the remaining iterations become no-ops
+    int    iters;       // FVPs executed
+    double trace_rdotr[34];
+    double trace_xnorm[34];
+};
+
+// Scratch for the GEMM-chain path: activations of one sample chunk, row-major [chunk x L_i].
+struct ChainScratch {
+    double *Y[TRPO_MAX_LAYERS];      // Y[i] for i = 1..K (Y[0] is the observation matrix itself)
+    double *RY[2];                   // R{y} ping-pong, [chunk x maxL]
+    double *G[2];                    // R-gradient / gradient ping-pong, [chunk x maxL]
+    int chunk;                       // samples per chunk
+    int nslices;                     // split-K slices of the outer-product GEMM
+    double *partial;                 // [nslices x P] un-normalised partial sums, fixed-order reduced
+};
+
+enum ChainMode { CHAIN_FVP = 0, CHAIN_PG = 1 };
+
+// ---- gemm_chain.cu ------------------------------------------------------------------------------------------------
+// Enqueue the whole un-normalised sum  zsum[0..P) = sum_n per-sample [RGW,RGB,...] (FVP) or [GW,GB,...,GLogStd] (PG).
+// The LogStd block of zsum is written by the finalise step, not here (FVP) / by the seed kernel (PG).
+int chain_accumulate(const NetDesc &net, const ChainScratch &sc, ChainMode mode,
+                     const double *d_theta, const double *d_v, const double *d_inv_var,
+                     const double *d_obs, const double *d_mean, const double *d_action, const double *d_adv,
+                     size_t nsamples, double *d_zsum, const int *d_done, cudaStream_t st, long long *launches);
+// Forward only: writes the policy mean of every sample of [s0, s0+n) into d_out [n x A].
+int chain_forward(const NetDesc &net, const ChainScratch &sc, const double *d_theta, const double *d_obs,
+                  size_t nsamples, double *d_mean_out, cudaStream_t st, long long *launches);
+size_t chain_scratch_bytes(const NetDesc &net, int chunk, int nslices);
+
+// ---- fvp_fused.cu -------------------------------------------------------------------------------------------------
+// Fused DMMA kernel for 4-layer nets whose padded weights fit in shared memory. Returns 0 if it handled the launch,
+// 1 if the shape is not eligible.
+bool fused_eligible(const NetDesc &net);
+int  fused_partial_rows();     // number of per-CTA partial rows the fused kernel writes
+int  fused_fvp_accumulate(const NetDesc &net, const double *d_theta, const double *d_v, const double *d_inv_var,
+                          const double *d_obs, size_t nsamples, double *d_partial, double *d_zsum,
+                          const int *d_done, cudaStream_t st, long long *launches);
+
+// ---- cg_kernels.cu ------------------------------------------------------------------------------------------------
+void launch_reduce_partials(const double *d_partial, int rows, int P, double *d_zsum, const int *d_done,
+                            cudaStream_t st, long long *launches);
+// z = zsum/N + damping*v (LogStd block: 2v + damping*v), standalone FVP finalise (TRPO_FVP.c:928-931)
+void launch_fvp_finalise(const double *d_zsum, const double *d_v, double *d_out, int P, int logstd_off,
+                         double n_total, double damping, cudaStream_t st, long long *launches);
+void launch_cg_init(const double *d_b, double *d_x, double *d_r, double *d_p, int P, double residual_th,
+                    CgState *d_state, cudaStream_t st, long long *launches);
+void launch_cg_update(const double *d_zsum, double *d_x, double *d_r, double *d_p, double *d_z, int P, int logstd_off,
+                      double n_total, double damping, double residual_th, CgState *d_state,
+                      cudaStream_t st, long long *launches);
+// out[0] = sum_i a[i]*b[i] with the same fixed-order reduction (used for shs, gnorm, b.x)
+void launch_dot(const double *d_a, const double *d_b, int n, double *d_out, cudaStream_t st, long long *launches);
+void launch_axpby(double *d_out, const double *d_x, double a, const double *d_y, double b, int n,
+                  cudaStream_t st, long long *launches);
+// surrogate loss sum_n exp(lld_n) * Adv_n (TRPO_Update.c:969-983), fixed-order reduction into d_out[0]
+void launch_surrogate(const double *d_mean_new, const double *d_mean_old, const double *d_action, const double *d_adv,
+                      const double *d_std_old, const double *d_logstd_new, int A, size_t nsamples,
+                      double *d_block_partials, double *d_out, cudaStream_t st, long long *launches);
+void launch_sum(const double *d_a, size_t n, double *d_block_partials, double *d_out, cudaStream_t st, long long *launches);

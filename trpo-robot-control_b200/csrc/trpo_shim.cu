@@ -1,0 +1,531 @@
+// trpo_shim.cu -- the thin C-ABI shim between the C host code and the CUDA kernels (include/trpo_b200.h).
+// Owns device memory, the stream, the device-resident CG state and the optional NCCL communicator.
+#include <dlfcn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/trpo_b200.h"
+#include "trpo_internal.cuh"
+
+// --------------------------------------------------------------------------------------------------------------
+// errors
+static thread_local char g_err[512] = "";
+static int fail(const char *fmt, ...) {
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+    return -1;
+}
+extern "C" const char *trpo_last_error(void) { return g_err; }
+
+#define KTIME_MAX 4096
+#define CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+// --------------------------------------------------------------------------------------------------------------
+// NCCL through dlopen: the library has no link-time NCCL dependency; in a torch process this resolves to the
+// libnccl.so.2 torch already loaded, in a plain C program to the system one.
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+enum { ncclSum_ = 0 };
+enum { ncclInt64_ = 4, ncclUint64_ = 5, ncclFloat64_ = 8 };
+struct NcclApi {
+    void *handle;
+    int (*GetUniqueId)(ncclUniqueId *);
+    int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int);
+    int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t);
+    int (*CommDestroy)(ncclComm_t);
+    const char *(*GetErrorString)(int);
+};
+static NcclApi g_nccl = {};
+static int nccl_load() {
+    if (g_nccl.handle) return 0;
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return fail("cannot dlopen libnccl.so.2: %s", dlerror());
+    g_nccl.GetUniqueId = (int (*)(ncclUniqueId *))dlsym(h, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(ncclComm_t *, int, ncclUniqueId, int))dlsym(h, "ncclCommInitRank");
+    g_nccl.AllReduce = (int (*)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(h, "ncclAllReduce");
+    g_nccl.CommDestroy = (int (*)(ncclComm_t))dlsym(h, "ncclCommDestroy");
+    g_nccl.GetErrorString = (const char *(*)(int))dlsym(h, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy)
+        return fail("libnccl is missing required symbols");
+    g_nccl.handle = h;
+    return 0;
+}
+#define NC(x) do { int r_ = (x); if (r_ != 0) return fail("%s failed: %s", #x, g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "nccl error"); } while (0)
+
+// --------------------------------------------------------------------------------------------------------------
+struct trpo_ctx {
+    NetDesc net;
+    int device;
+    cudaStream_t stream;
+    bool own_stream;
+    int path_req, path_used;
+    long long launches;
+
+    double *d_theta, *d_inv_var, *d_std;
+    // batch
+    size_t n_local, n_total;
+    double *d_obs, *d_mean, *d_action, *d_adv;
+    bool own_batch;
+    size_t cap_obs, cap_mean, cap_adv;
+    // work vectors (P each)
+    double *d_in, *d_out, *d_zsum, *d_x, *d_r, *d_p, *d_z, *d_b, *d_xnew;
+    double *d_scal;            // small scalar scratch (16 doubles)
+    double *d_blockpart;       // block partial sums (1024 doubles)
+    double *d_mean_new;        // [n_local x A] line-search forward output
+    size_t cap_mean_new;
+    CgState *d_state;
+    CgState *h_state;          // pinned
+    double *h_scal;            // pinned
+    // gemm-chain scratch
+    ChainScratch sc;
+    double *sc_base;
+    size_t sc_bytes;
+    // fused path partials
+    double *d_fused_partial;
+    // optional event timing of the FVP-sum kernel(s)
+    bool ktime_on;
+    int ktime_n;
+    cudaEvent_t *ktime_ev;     // 2 * KTIME_MAX events
+    // comm
+    ncclComm_t comm;
+    int rank, world;
+    trpo_info info;
+};
+
+extern "C" size_t trpo_num_params(const size_t *LayerSize, size_t NumLayers) {
+    size_t n = 0;
+    for (size_t i = 0; i + 1 < NumLayers; ++i) n += LayerSize[i] * LayerSize[i + 1] + LayerSize[i + 1];
+    return n + LayerSize[NumLayers - 1];
+}
+
+static int ensure_chain_scratch(trpo_ctx *c) {
+    // chunk sized so one chunk's activations (~ chunk * (sumL + 4 maxL) doubles) stay within ~48 MB of the 126 MB L2
+    size_t maxL = c->net.L[0], sumL = 0;
+    for (int i = 1; i <= c->net.K; ++i) { sumL += c->net.L[i]; if ((size_t)c->net.L[i] > maxL) maxL = c->net.L[i]; }
+    size_t per_sample = 8 * (sumL + 4 * maxL);
+    size_t chunk = (48u << 20) / per_sample;
+    if (chunk > 32768) chunk = 32768;
+    if (chunk < 1024) chunk = 1024;
+    chunk = (chunk / 64) * 64;
+    if (c->n_local && chunk > ((c->n_local + 63) / 64) * 64) chunk = ((c->n_local + 63) / 64) * 64;
+    int nslices = 148;
+    if ((size_t)nslices * 16 > chunk) nslices = (int)(chunk / 16);
+    if (nslices < 1) nslices = 1;
+    size_t bytes = chain_scratch_bytes(c->net, (int)chunk, nslices);
+    if (c->sc_base && bytes <= c->sc_bytes && c->sc.chunk == (int)chunk && c->sc.nslices == nslices) return 0;
+    if (c->sc_base) cudaFree(c->sc_base);
+    c->sc_base = nullptr;
+    CU(cudaMalloc(&c->sc_base, bytes));
+    CU(cudaMemsetAsync(c->sc_base, 0, bytes, c->stream));
+    c->sc_bytes = bytes;
+    double *p = c->sc_base;
+    for (int i = 1; i <= c->net.K; ++i) { c->sc.Y[i] = p; p += chunk * c->net.L[i]; }
+    for (int j = 0; j < 2; ++j) { c->sc.RY[j] = p; p += chunk * maxL; }
+    for (int j = 0; j < 2; ++j) { c->sc.G[j] = p; p += chunk * maxL; }
+    c->sc.partial = p;
+    c->sc.chunk = (int)chunk;
+    c->sc.nslices = nslices;
+    return 0;
+}
+
+extern "C" trpo_ctx *trpo_ctx_create(const size_t *LayerSize, const char *AcFunc, size_t NumLayers, int device, int precision) {
+    if (!LayerSize || !AcFunc || NumLayers < 2 || NumLayers > TRPO_MAX_LAYERS) { fail("bad network description"); return nullptr; }
+    if (precision != TRPO_PRECISION_FP64) { fail("only TRPO_PRECISION_FP64 is built"); return nullptr; }
+    for (size_t i = 1; i < NumLayers; ++i) {
+        const char a = AcFunc[i];
+        if (a != 'l' && a != 't' && a != 'o' && a != 's') {
+            // the reference prints this and carries on with stale values (TRPO_FVP.c:831-833); we refuse instead
+            fprintf(stderr, "[ERROR] AC Function for Layer[%zu] is %c. Unsupported.\n", i, a);
+            fail("unsupported activation '%c' for layer %zu", a, i);
+            return nullptr;
+        }
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        fail("no CUDA device available: this library has no CPU fallback");
+        return nullptr;
+    }
+    if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
+    if (cudaSetDevice(device) != cudaSuccess) { fail("cudaSetDevice(%d) failed", device); return nullptr; }
+    trpo_ctx *c = (trpo_ctx *)calloc(1, sizeof(trpo_ctx));
+    c->device = device;
+    c->net.K = (int)NumLayers - 1;
+    int pos = 0;
+    for (size_t i = 0; i < NumLayers; ++i) { c->net.L[i] = (int)LayerSize[i]; c->net.ac[i] = i ? AcFunc[i] : 'l'; }
+    for (int i = 0; i < c->net.K; ++i) { c->net.w_off[i] = pos; pos += c->net.L[i] * c->net.L[i + 1] + c->net.L[i + 1]; }
+    c->net.logstd_off = pos;
+    c->net.P = pos + c->net.L[c->net.K];
+    c->world = 1;
+    const size_t P = c->net.P, A = c->net.L[c->net.K];
+    bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
+    c->own_stream = true;
+    double **vecs[] = {&c->d_theta, &c->d_in, &c->d_out, &c->d_zsum, &c->d_x, &c->d_r, &c->d_p, &c->d_z, &c->d_b, &c->d_xnew};
+    for (auto v : vecs) ok = ok && cudaMalloc(v, P * sizeof(double)) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->d_inv_var, A * sizeof(double)) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->d_std, A * sizeof(double)) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->d_scal, 16 * sizeof(double)) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->d_blockpart, 1024 * sizeof(double)) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->d_state, sizeof(CgState)) == cudaSuccess;
+    ok = ok && cudaMallocHost(&c->h_state, sizeof(CgState)) == cudaSuccess;
+    ok = ok && cudaMallocHost(&c->h_scal, 16 * sizeof(double)) == cudaSuccess;
+    if (ok && fused_eligible(c->net))
+        ok = cudaMalloc(&c->d_fused_partial, (size_t)fused_partial_rows() * P * sizeof(double)) == cudaSuccess;
+    if (ok) ok = cudaMemset(c->d_state, 0, sizeof(CgState)) == cudaSuccess;
+    if (!ok) { fail("device allocation failed: %s", cudaGetErrorString(cudaGetLastError())); trpo_ctx_destroy(c); return nullptr; }
+    return c;
+}
+
+static void free_batch(trpo_ctx *c) {
+    if (c->own_batch) { cudaFree(c->d_obs); cudaFree(c->d_mean); cudaFree(c->d_action); cudaFree(c->d_adv); }
+    c->d_obs = c->d_mean = c->d_action = c->d_adv = nullptr;
+    c->cap_obs = c->cap_mean = c->cap_adv = 0;
+    c->own_batch = false;
+}
+
+extern "C" void trpo_ctx_destroy(trpo_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    free_batch(c);
+    double *vecs[] = {c->d_theta, c->d_in, c->d_out, c->d_zsum, c->d_x, c->d_r, c->d_p, c->d_z, c->d_b, c->d_xnew,
+                      c->d_inv_var, c->d_std, c->d_scal, c->d_blockpart, c->d_mean_new, c->sc_base, c->d_fused_partial};
+    for (double *v : vecs) if (v) cudaFree(v);
+    if (c->d_state) cudaFree(c->d_state);
+    if (c->h_state) cudaFreeHost(c->h_state);
+    if (c->h_scal) cudaFreeHost(c->h_scal);
+    if (c->ktime_ev) { for (int i = 0; i < 2 * KTIME_MAX; ++i) if (c->ktime_ev[i]) cudaEventDestroy(c->ktime_ev[i]); free(c->ktime_ev); }
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    free(c);
+}
+
+extern "C" size_t trpo_ctx_num_params(const trpo_ctx *c) { return c ? (size_t)c->net.P : 0; }
+extern "C" int trpo_ctx_set_stream(trpo_ctx *c, void *s) {
+    if (!c) return fail("null context");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    if (s) { c->stream = (cudaStream_t)s; c->own_stream = false; }
+    else { CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+    return 0;
+}
+extern "C" void *trpo_ctx_get_stream(const trpo_ctx *c) { return c ? (void *)c->stream : nullptr; }
+extern "C" int trpo_ctx_set_path(trpo_ctx *c, int path) {
+    if (!c) return fail("null context");
+    if (path == TRPO_PATH_FUSED && !fused_eligible(c->net)) return fail("network shape is not eligible for the fused kernel");
+    c->path_req = path;
+    return 0;
+}
+extern "C" int trpo_ctx_get_path(const trpo_ctx *c) { return c ? c->path_used : 0; }
+extern "C" int trpo_ctx_sync(trpo_ctx *c) {
+    if (!c) return fail("null context");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+extern "C" long long trpo_ctx_launch_count(const trpo_ctx *c) { return c ? c->launches : 0; }
+
+extern "C" int trpo_ctx_set_model(trpo_ctx *c, const double *theta) {
+    if (!c || !theta) return fail("null argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(c->d_theta, theta, c->net.P * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+static int set_std(trpo_ctx *c, const double *Std) {
+    const int A = c->net.L[c->net.K];
+    double iv[TRPO_MAX_LAYERS * 64];
+    if (A > (int)(sizeof(iv) / sizeof(iv[0]))) return fail("action dimension too large");
+    for (int j = 0; j < A; ++j) iv[j] = 1.0 / (Std[j] * Std[j]);
+    CU(cudaMemcpyAsync(c->d_std, Std, A * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_inv_var, iv, A * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+static int update_global_samples(trpo_ctx *c) {
+    c->n_total = c->n_local;
+    if (c->comm) {
+        unsigned long long *d = (unsigned long long *)c->d_scal;
+        unsigned long long v = c->n_local;
+        CU(cudaMemcpyAsync(d, &v, sizeof(v), cudaMemcpyHostToDevice, c->stream));
+        NC(g_nccl.AllReduce(d, d, 1, ncclUint64_, ncclSum_, c->comm, c->stream));
+        CU(cudaMemcpyAsync(&v, d, sizeof(v), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        c->n_total = (size_t)v;
+    }
+    return 0;
+}
+
+extern "C" int trpo_ctx_set_batch(trpo_ctx *c, size_t N, const double *Observ, const double *Std,
+                                  const double *Mean, const double *Action, const double *Advantage) {
+    if (!c || !Observ || !Std || N == 0) return fail("bad batch arguments");
+    CU(cudaSetDevice(c->device));
+    const size_t O = c->net.L[0], A = c->net.L[c->net.K];
+    if (!c->own_batch) free_batch(c);
+    c->own_batch = true;
+    if (N * O > c->cap_obs) { cudaFree(c->d_obs); c->d_obs = nullptr; CU(cudaMalloc(&c->d_obs, N * O * sizeof(double))); c->cap_obs = N * O; }
+    CU(cudaMemcpyAsync(c->d_obs, Observ, N * O * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if (Mean && Action && Advantage) {
+        if (N * A > c->cap_mean) {
+            cudaFree(c->d_mean); cudaFree(c->d_action); c->d_mean = c->d_action = nullptr;
+            CU(cudaMalloc(&c->d_mean, N * A * sizeof(double)));
+            CU(cudaMalloc(&c->d_action, N * A * sizeof(double)));
+            c->cap_mean = N * A;
+        }
+        if (N > c->cap_adv) { cudaFree(c->d_adv); c->d_adv = nullptr; CU(cudaMalloc(&c->d_adv, N * sizeof(double))); c->cap_adv = N; }
+        CU(cudaMemcpyAsync(c->d_mean, Mean, N * A * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(c->d_action, Action, N * A * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(c->d_adv, Advantage, N * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    }
+    c->n_local = N;
+    if (set_std(c, Std)) return -1;
+    return update_global_samples(c);
+}
+
+extern "C" int trpo_ctx_set_batch_device(trpo_ctx *c, size_t N, const double *dObserv, const double *Std_host,
+                                         const double *dMean, const double *dAction, const double *dAdvantage) {
+    if (!c || !dObserv || !Std_host || N == 0) return fail("bad batch arguments");
+    CU(cudaSetDevice(c->device));
+    free_batch(c);
+    c->own_batch = false;
+    c->d_obs = (double *)dObserv; c->d_mean = (double *)dMean; c->d_action = (double *)dAction; c->d_adv = (double *)dAdvantage;
+    c->n_local = N;
+    if (set_std(c, Std_host)) return -1;
+    return update_global_samples(c);
+}
+
+// --------------------------------------------------------------------------------------------------------------
+extern "C" int trpo_ctx_kernel_timing(trpo_ctx *c, int enable) {
+    if (!c) return fail("null context");
+    CU(cudaSetDevice(c->device));
+    if (enable && !c->ktime_ev) {
+        c->ktime_ev = (cudaEvent_t *)calloc(2 * KTIME_MAX, sizeof(cudaEvent_t));
+        for (int i = 0; i < 2 * KTIME_MAX; ++i) CU(cudaEventCreate(&c->ktime_ev[i]));
+    }
+    c->ktime_on = enable != 0;
+    c->ktime_n = 0;
+    return 0;
+}
+extern "C" double trpo_ctx_kernel_time_ms(trpo_ctx *c, int *launches) {
+    if (!c || !c->ktime_ev) { if (launches) *launches = 0; return 0.0; }
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    double total = 0.0;
+    for (int i = 0; i < c->ktime_n; ++i) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, c->ktime_ev[2 * i], c->ktime_ev[2 * i + 1]) == cudaSuccess) total += ms;
+    }
+    if (launches) *launches = c->ktime_n;
+    c->ktime_n = 0;
+    return total;
+}
+
+// un-normalised FVP sum of the local shard into d_zsum, then the cross-GPU sum
+static int fvp_sum(trpo_ctx *c, const double *d_v, const int *d_done) {
+    if (!c->d_obs || c->n_local == 0) return fail("no batch staged: call trpo_ctx_set_batch first");
+    int path = c->path_req;
+    if (path == TRPO_PATH_AUTO) path = fused_eligible(c->net) ? TRPO_PATH_FUSED : TRPO_PATH_GEMM_CHAIN;
+    c->path_used = path;
+    const bool timed = c->ktime_on && c->ktime_n < KTIME_MAX;
+    if (timed) cudaEventRecord(c->ktime_ev[2 * c->ktime_n], c->stream);
+    if (path == TRPO_PATH_FUSED) {
+        if (fused_fvp_accumulate(c->net, c->d_theta, d_v, c->d_inv_var, c->d_obs, c->n_local, c->d_fused_partial,
+                                 c->d_zsum, d_done, c->stream, &c->launches))
+            return fail("fused FVP launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    } else {
+        if (ensure_chain_scratch(c)) return -1;
+        if (chain_accumulate(c->net, c->sc, CHAIN_FVP, c->d_theta, d_v, c->d_inv_var, c->d_obs, nullptr, nullptr, nullptr,
+                             c->n_local, c->d_zsum, d_done, c->stream, &c->launches))
+            return fail("gemm-chain FVP launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    if (timed) { cudaEventRecord(c->ktime_ev[2 * c->ktime_n + 1], c->stream); ++c->ktime_n; }
+    if (c->comm) NC(g_nccl.AllReduce(c->d_zsum, c->d_zsum, c->net.P, ncclFloat64_, ncclSum_, c->comm, c->stream));
+    return 0;
+}
+
+extern "C" int trpo_ctx_fvp_device(trpo_ctx *c, const double *dInput, double *dResult, double damping) {
+    if (!c || !dInput || !dResult) return fail("null argument");
+    CU(cudaSetDevice(c->device));
+    if (fvp_sum(c, dInput, nullptr)) return -1;
+    launch_fvp_finalise(c->d_zsum, dInput, dResult, c->net.P, c->net.logstd_off, (double)c->n_total, damping, c->stream, &c->launches);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int trpo_ctx_cg_device(trpo_ctx *c, const double *db, double *dResult, size_t MaxIter, double ResidualTh, double damping) {
+    if (!c || !db || !dResult) return fail("null argument");
+    if (MaxIter > 32) return fail("MaxIter > 32 not supported by the device trace buffer");
+    CU(cudaSetDevice(c->device));
+    launch_cg_init(db, c->d_x, c->d_r, c->d_p, c->net.P, ResidualTh, c->d_state, c->stream, &c->launches);
+    for (size_t it = 0; it < MaxIter; ++it) {
+        if (fvp_sum(c, c->d_p, &c->d_state->done)) return -1;
+        launch_cg_update(c->d_zsum, c->d_x, c->d_r, c->d_p, c->d_z, c->net.P, c->net.logstd_off, (double)c->n_total, damping,
+                         ResidualTh, c->d_state, c->stream, &c->launches);
+    }
+    CU(cudaMemcpyAsync(dResult, c->d_x, c->net.P * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaGetLastError());
+    return 0;
+}
+
+static int fetch_cg_info(trpo_ctx *c) {
+    CU(cudaMemcpyAsync(c->h_state, c->d_state, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->info.cg_iters = c->h_state->iters;
+    memcpy(c->info.cg_rdotr, c->h_state->trace_rdotr, sizeof(c->info.cg_rdotr));
+    memcpy(c->info.cg_xnorm, c->h_state->trace_xnorm, sizeof(c->info.cg_xnorm));
+    return 0;
+}
+
+extern "C" int trpo_ctx_fvp(trpo_ctx *c, const double *Input, double *Result, double damping) {
+    if (!c || !Input || !Result) return fail("null argument");
+    CU(cudaSetDevice(c->device));
+    const size_t bytes = c->net.P * sizeof(double);
+    CU(cudaMemcpyAsync(c->d_in, Input, bytes, cudaMemcpyHostToDevice, c->stream));
+    if (trpo_ctx_fvp_device(c, c->d_in, c->d_out, damping)) return -1;
+    CU(cudaMemcpyAsync(Result, c->d_out, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int trpo_ctx_cg(trpo_ctx *c, const double *b, double *Result, size_t MaxIter, double ResidualTh, double damping) {
+    if (!c || !b || !Result) return fail("null argument");
+    CU(cudaSetDevice(c->device));
+    const size_t bytes = c->net.P * sizeof(double);
+    CU(cudaMemcpyAsync(c->d_b, b, bytes, cudaMemcpyHostToDevice, c->stream));
+    if (trpo_ctx_cg_device(c, c->d_b, c->d_out, MaxIter, ResidualTh, damping)) return -1;
+    CU(cudaMemcpyAsync(Result, c->d_out, bytes, cudaMemcpyDeviceToHost, c->stream));
+    return fetch_cg_info(c);
+}
+
+extern "C" int trpo_ctx_get_info(const trpo_ctx *c, trpo_info *info) {
+    if (!c || !info) return fail("null argument");
+    *info = c->info;
+    return 0;
+}
+
+// policy gradient b = (1/N) sum_n grad (TRPO_Update.c:254-378) into c->d_b
+static int policy_gradient_device(trpo_ctx *c) {
+    if (!c->d_obs || !c->d_mean || !c->d_action || !c->d_adv) return fail("policy gradient needs Mean/Action/Advantage in the batch");
+    if (ensure_chain_scratch(c)) return -1;
+    if (chain_accumulate(c->net, c->sc, CHAIN_PG, c->d_theta, nullptr, nullptr, c->d_obs, c->d_mean, c->d_action, c->d_adv,
+                         c->n_local, c->d_zsum, nullptr, c->stream, &c->launches))
+        return fail("policy-gradient launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (c->comm) NC(g_nccl.AllReduce(c->d_zsum, c->d_zsum, c->net.P, ncclFloat64_, ncclSum_, c->comm, c->stream));
+    // b = zsum / N: same kernel as the FVP finalise with no damping and no LogStd special case
+    launch_fvp_finalise(c->d_zsum, c->d_zsum, c->d_b, c->net.P, c->net.P, (double)c->n_total, 0.0, c->stream, &c->launches);
+    return 0;
+}
+
+extern "C" int trpo_ctx_policy_gradient(trpo_ctx *c, double *b_out) {
+    if (!c || !b_out) return fail("null argument");
+    CU(cudaSetDevice(c->device));
+    if (policy_gradient_device(c)) return -1;
+    CU(cudaMemcpyAsync(b_out, c->d_b, c->net.P * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+__global__ void k_linesearch_point(double *__restrict__ out, const double *__restrict__ theta, const double *__restrict__ x,
+                                   double lm, double stepfrac, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = theta[i] + stepfrac * (x[i] / lm);     // fullstep = x / lm (TRPO_Update.c:836-838,899-902)
+}
+
+static int allreduce_scalars(trpo_ctx *c, double *d, int n) {
+    if (c->comm) NC(g_nccl.AllReduce(d, d, n, ncclFloat64_, ncclSum_, c->comm, c->stream));
+    return 0;
+}
+
+extern "C" int trpo_ctx_update(trpo_ctx *c, double *Result, double damping) {
+    if (!c || !Result) return fail("null argument");
+    CU(cudaSetDevice(c->device));
+    // constants of TRPO_Update.c:29-33
+    const double ResidualTh = 1e-10, MaxKL = 0.01, AcceptRatio = 0.1;
+    const size_t MaxIter = 10, MaxBackTracks = 10;
+    const int P = c->net.P, A = c->net.L[c->net.K];
+    memset(&c->info, 0, sizeof(c->info));
+    if (policy_gradient_device(c)) return -1;
+    if (trpo_ctx_cg_device(c, c->d_b, c->d_out, MaxIter, ResidualTh, damping)) return -1;   // d_x = stepdir
+    if (trpo_ctx_fvp_device(c, c->d_x, c->d_z, damping)) return -1;                          // z = F x + damping x
+    launch_dot(c->d_z, c->d_x, P, c->d_scal + 0, c->stream, &c->launches);                   // 2*shs
+    launch_dot(c->d_b, c->d_b, P, c->d_scal + 1, c->stream, &c->launches);                   // gnorm^2
+    launch_dot(c->d_b, c->d_x, P, c->d_scal + 2, c->stream, &c->launches);                   // -g . stepdir
+    launch_sum(c->d_adv, c->n_local, c->d_blockpart, c->d_scal + 3, c->stream, &c->launches);
+    if (allreduce_scalars(c, c->d_scal + 3, 1)) return -1;
+    CU(cudaMemcpyAsync(c->h_scal, c->d_scal, 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (fetch_cg_info(c)) return -1;
+    const double shs = 0.5 * c->h_scal[0];
+    const double lm = sqrt(shs / MaxKL);
+    const double gnorm = sqrt(c->h_scal[1]);
+    const double rate = c->h_scal[2] / lm;
+    const double fval = -c->h_scal[3] / (double)c->n_total;
+    c->info.shs = shs; c->info.lm = lm; c->info.gnorm = gnorm; c->info.fval = fval;
+    if (c->n_local * A > c->cap_mean_new) {
+        if (c->d_mean_new) cudaFree(c->d_mean_new);
+        c->d_mean_new = nullptr;
+        CU(cudaMalloc(&c->d_mean_new, c->n_local * A * sizeof(double)));
+        c->cap_mean_new = c->n_local * A;
+    }
+    // fall-back result = step direction, the reference's quirk (TRPO_Update.c:852)
+    const double *d_result = c->d_x;
+    for (size_t t = 0; t < MaxBackTracks; ++t) {
+        const double stepfrac = pow(0.5, (double)t);
+        k_linesearch_point<<<(P + 255) / 256, 256, 0, c->stream>>>(c->d_xnew, c->d_theta, c->d_x, lm, stepfrac, P);
+        ++c->launches;
+        if (chain_forward(c->net, c->sc, c->d_xnew, c->d_obs, c->n_local, c->d_mean_new, c->stream, &c->launches))
+            return fail("line-search forward launch failed");
+        launch_surrogate(c->d_mean_new, c->d_mean, c->d_action, c->d_adv, c->d_std, c->d_xnew + c->net.logstd_off, A,
+                         c->n_local, c->d_blockpart, c->d_scal + 4, c->stream, &c->launches);
+        if (allreduce_scalars(c, c->d_scal + 4, 1)) return -1;
+        CU(cudaMemcpyAsync(c->h_scal + 4, c->d_scal + 4, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        const double newfval = -c->h_scal[4] / (double)c->n_total;
+        const double actual = fval - newfval;
+        const double expected = rate * stepfrac;
+        const double ratio = actual / expected;
+        c->info.ls_actual[t] = actual; c->info.ls_expected[t] = expected; c->info.ls_ratio[t] = ratio;
+        c->info.ls_steps = (int)t + 1;
+        if (ratio > AcceptRatio && actual > 0) { c->info.ls_accepted = 1; d_result = c->d_xnew; break; }
+    }
+    CU(cudaMemcpyAsync(Result, d_result, P * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// --------------------------------------------------------------------------------------------------------------
+extern "C" double *trpo_device_alloc(size_t n) {
+    double *p = nullptr;
+    if (cudaMalloc(&p, n * sizeof(double)) != cudaSuccess) { fail("cudaMalloc failed"); return nullptr; }
+    return p;
+}
+extern "C" void trpo_device_free(double *p) { if (p) cudaFree(p); }
+extern "C" int trpo_memcpy_h2d(double *dst, const double *src, size_t n) { CU(cudaMemcpy(dst, src, n * sizeof(double), cudaMemcpyHostToDevice)); return 0; }
+extern "C" int trpo_memcpy_d2h(double *dst, const double *src, size_t n) { CU(cudaMemcpy(dst, src, n * sizeof(double), cudaMemcpyDeviceToHost)); return 0; }
+
+extern "C" int trpo_nccl_unique_id(char id_out[128]) {
+    if (nccl_load()) return -1;
+    ncclUniqueId id;
+    NC(g_nccl.GetUniqueId(&id));
+    memcpy(id_out, id.internal, 128);
+    return 0;
+}
+
+extern "C" int trpo_ctx_init_comm(trpo_ctx *c, const char id[128], int rank, int world) {
+    if (!c || !id) return fail("null argument");
+    if (world <= 1) { c->rank = 0; c->world = 1; return 0; }
+    if (nccl_load()) return -1;
+    CU(cudaSetDevice(c->device));
+    ncclUniqueId uid;
+    memcpy(uid.internal, id, 128);
+    NC(g_nccl.CommInitRank(&c->comm, world, uid, rank));
+    c->rank = rank; c->world = world;
+    if (c->n_local) return update_global_samples(c);
+    return 0;
+}
+
+extern "C" size_t trpo_ctx_global_samples(const trpo_ctx *c) { return c ? c->n_total : 0; }
