@@ -1,6 +1,439 @@
-// fvp_fused.cu -- placeholder until the fused DMMA kernel lands: nothing is eligible, the GEMM-chain path runs.
+// fvp_fused.cu -- fused per-sample Fisher-vector-product kernel for 4-layer policies whose weights fit in shared memory.
+//
+// Computes the un-normalised sum over samples of the reference's FVPFast loop (TRPO_FVP.c:771-924) on the FP64 tensor
+// pipe (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4; tcgen05 has no f64 kind).  One persistent CTA per SM, NW warps, tiles of
+// S = 8*NW samples:
+//   phase A (per warp, 8 samples, no block sync): combined forward + R-forward (:783-836), R-gradient seed (:852-854)
+//            and R-backward (:857-900) chained through REGISTERS: the m8n8 accumulator layout of one layer is used
+//            directly as the A fragment of the next by permuting the contraction index, which only changes which
+//            weight rows a B fragment holds -- and the weights sit in shared memory in exactly that fragment order.
+//            W1/W2 are stored once, in an XOR-swizzled 8x8-block layout that serves both the forward (W) and the
+//            backward (W^T) fragment reads without bank conflicts.
+//   phase B (block-wide): the parameter-gradient outer products [Y_{i-1},1]^T * RG_i (:890-921), contraction over the
+//            S samples of the tile; each warp owns a fixed set of 8x8 output tiles whose accumulators stay in registers
+//            for the whole kernel.  Activations are exchanged through shared memory [sample][neuron] (+4 padding:
+//            conflict-free transposed fragment reads).
+// At the end every CTA writes its P-length partial row; rows are summed in fixed order by k_reduce_partials, so the
+// result is bitwise deterministic.
 #include "trpo_internal.cuh"
-bool fused_eligible(const NetDesc &) { return false; }
-int fused_partial_rows() { return 0; }
-int fused_fvp_accumulate(const NetDesc &, const double *, const double *, const double *, const double *, size_t,
-                         double *, double *, const int *, cudaStream_t, long long *) { return 1; }
+
+namespace {
+
+__device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+        : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+
+// y = f(x) and d = f'(x) written through y (TRPO_FVP.c:806-834,869-882). ACT == 0: runtime switch on `a`.
+template <char ACT>
+__device__ __forceinline__ void act_fwd(char a, double x, double &y, double &d) {
+    const char k = ACT ? ACT : a;
+    if (k == 't') { y = tanh(x); d = 1.0 - y * y; }
+    else if (k == 's') { y = 1.0 / (1.0 + exp(-x)); d = y * (1.0 - y); }
+    else if (k == 'o') { y = 0.1 * x; d = 0.1; }
+    else { y = x; d = 1.0; }
+}
+template <char ACT>
+__device__ __forceinline__ double act_deriv_y(char a, double y) {
+    const char k = ACT ? ACT : a;
+    if (k == 't') return 1.0 - y * y;
+    if (k == 's') return y * (1.0 - y);
+    if (k == 'o') return 0.1;
+    return 1.0;
+}
+
+__host__ __device__ constexpr int pad_rs(int k) {   // smallest row stride >= k with stride % 16 in {4, 12}
+    int r = k;
+    while ((r % 16) != 4 && (r % 16) != 12) ++r;
+    return r;
+}
+__host__ __device__ constexpr int cmax(int a, int b) { return a > b ? a : b; }
+
+// position of element (rr, cc) inside a swizzled 8x8 block
+__host__ __device__ __forceinline__ int swz(int rr, int cc) {
+    const int a = rr >> 1, rp = rr & 1, cq = cc >> 1, cp = cc & 1;
+    return (a & 1) + 2 * (cq & 1) + 4 * ((a >> 1) ^ rp) + 8 * (cp ^ (cq >> 1)) + 16 * rp + 32 * (cq >> 1);
+}
+
+template <int K0_, int H1_, int H2_, int AP_, int NW_>
+struct Cfg {
+    static constexpr int K0 = K0_, H1 = H1_, H2 = H2_, AP = AP_, NW = NW_;
+    static constexpr int S = 8 * NW, NTHREADS = 32 * NW;
+    static constexpr int Q0 = K0 / 4, MT0 = (K0 + 7) / 8;
+    static constexpr int NT1 = H1 / 8, NT2 = H2 / 8, NT3 = AP / 8;
+    static constexpr int RS0 = pad_rs(K0), RS1 = H1 + 4, RS2 = H2 + 4, RS3 = AP + 4, RSB = cmax(RS1, RS2);
+    // shared memory carve-up (in doubles)
+    static constexpr int oW0 = 0, oVW0 = oW0 + K0 * H1, oW1 = oVW0 + K0 * H1, oVW1 = oW1 + H1 * H2,
+                         oW2 = oVW1 + H1 * H2, oVW2 = oW2 + H2 * AP, oB0 = oVW2 + H2 * AP, oVB0 = oB0 + H1,
+                         oB1 = oVB0 + H1, oVB1 = oB1 + H2, oVB2 = oVB1 + H2, oIV = oVB2 + AP,
+                         oY0 = oIV + AP, oA = oY0 + S * RS0 + 8, oC = oA + S * RS1, oB = oC + S * RS2,
+                         oD = oB + S * RSB, TOTAL = oD + S * RS3;
+    static constexpr size_t SMEM_BYTES = sizeof(double) * TOTAL;
+    static_assert(K0 % 4 == 0 && H1 % 8 == 0 && H2 % 8 == 0 && AP % 8 == 0, "padded sizes");
+    static_assert(NT1 <= NW && NT2 <= NW && NT3 <= NW, "one output tile row per warp");
+};
+
+struct FusedArgs {
+    const double *theta, *v, *inv_var, *obs;
+    double *partial;
+    const int *done;
+    long long nsamples;
+    int L0, L1, L2, L3;
+    int w_off0, w_off1, w_off2;
+    int P;
+    char act1, act2, act3;
+};
+
+template <typename C, char ACT1, char ACT2>
+__global__ void __launch_bounds__(C::NTHREADS, 1) k_fvp_fused(const FusedArgs p) {
+    if (p.done && *p.done) return;
+    extern __shared__ __align__(16) double sm[];
+    constexpr int K0 = C::K0, H1 = C::H1, H2 = C::H2, AP = C::AP, NW = C::NW, S = C::S, NT = C::NTHREADS;
+    constexpr int Q0 = C::Q0, MT0 = C::MT0, NT1 = C::NT1, NT2 = C::NT2, NT3 = C::NT3;
+    constexpr int RS0 = C::RS0, RS1 = C::RS1, RS2 = C::RS2, RS3 = C::RS3, RSB = C::RSB;
+    double *W0f = sm + C::oW0, *VW0f = sm + C::oVW0, *W1s = sm + C::oW1, *VW1s = sm + C::oVW1;
+    double *W2s = sm + C::oW2, *VW2s = sm + C::oVW2, *B0s = sm + C::oB0, *VB0s = sm + C::oVB0;
+    double *B1s = sm + C::oB1, *VB1s = sm + C::oVB1, *VB2s = sm + C::oVB2, *IVs = sm + C::oIV;
+    double *Y0s = sm + C::oY0, *BufA = sm + C::oA, *BufC = sm + C::oC, *BufB = sm + C::oB, *BufD = sm + C::oD;
+
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
+    const int L0 = p.L0, L1 = p.L1, L2 = p.L2, L3 = p.L3;
+
+    // ---------------- prologue: weights and direction into shared memory, in fragment order ----------------
+    for (int idx = tid; idx < K0 * H1; idx += NT) {
+        const int k = idx / H1, n = idx % H1;
+        const bool in = k < L0 && n < L1;
+        const int dst = ((k >> 2) * NT1 + (n >> 3)) * 32 + (n & 7) * 4 + (k & 3);
+        W0f[dst]  = in ? p.theta[p.w_off0 + k * L1 + n] : 0.0;
+        VW0f[dst] = in ? p.v[p.w_off0 + k * L1 + n] : 0.0;
+    }
+    for (int idx = tid; idx < H1 * H2; idx += NT) {
+        const int j = idx / H2, n = idx % H2;
+        const bool in = j < L1 && n < L2;
+        const int dst = ((j >> 3) * NT2 + (n >> 3)) * 64 + swz(j & 7, n & 7);
+        W1s[dst]  = in ? p.theta[p.w_off1 + j * L2 + n] : 0.0;
+        VW1s[dst] = in ? p.v[p.w_off1 + j * L2 + n] : 0.0;
+    }
+    for (int idx = tid; idx < H2 * AP; idx += NT) {
+        const int j = idx / AP, n = idx % AP;
+        const bool in = j < L2 && n < L3;
+        const int dst = ((j >> 3) * NT3 + (n >> 3)) * 64 + swz(j & 7, n & 7);
+        W2s[dst]  = in ? p.theta[p.w_off2 + j * L3 + n] : 0.0;
+        VW2s[dst] = in ? p.v[p.w_off2 + j * L3 + n] : 0.0;
+    }
+    for (int n = tid; n < H1; n += NT) {
+        B0s[n]  = n < L1 ? p.theta[p.w_off0 + L0 * L1 + n] : 0.0;
+        VB0s[n] = n < L1 ? p.v[p.w_off0 + L0 * L1 + n] : 0.0;
+    }
+    for (int n = tid; n < H2; n += NT) {
+        B1s[n]  = n < L2 ? p.theta[p.w_off1 + L1 * L2 + n] : 0.0;
+        VB1s[n] = n < L2 ? p.v[p.w_off1 + L1 * L2 + n] : 0.0;
+    }
+    for (int n = tid; n < AP; n += NT) {
+        VB2s[n] = n < L3 ? p.v[p.w_off2 + L2 * L3 + n] : 0.0;
+        IVs[n]  = n < L3 ? p.inv_var[n] : 0.0;
+    }
+    for (int i = tid; i < 8; i += NT) Y0s[S * RS0 + i] = 0.0;
+
+    // per-lane offsets into a swizzled block: forward fragment (row 2t+r, col g), transposed fragment (row g, col 2t+r)
+    int sf[2], sb[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) { sf[r] = swz(2 * t + r, g); sb[r] = swz(g, 2 * t + r); }
+    const double d3 = (p.act3 == 'o') ? 0.1 : 1.0;      // last layer is linear or 0.1x on this path
+    const double ones = (g == 0) ? 1.0 : 0.0;            // A fragment whose row 0 is all ones: column sums (bias gradients)
+
+    // ---------------- persistent parameter-gradient accumulators (C-fragment layout) ----------------
+    double acc0[MT0][2], accb0[2];      // warp w < NT1: [Y0;1]^T * G1, output columns 8w..8w+7
+    double acc1[NT2][2], accb1[2];      // warp w < NT1: rows 8w..8w+7 of Y1^T * G2; warp w < NT2: bias tile w
+    double acc2[NT3][2], accb2[NT3][2]; // warp w < NT2: rows 8w..8w+7 of Y2^T * G3; last warp: bias
+#pragma unroll
+    for (int i = 0; i < MT0; ++i) acc0[i][0] = acc0[i][1] = 0.0;
+#pragma unroll
+    for (int i = 0; i < NT2; ++i) acc1[i][0] = acc1[i][1] = 0.0;
+#pragma unroll
+    for (int i = 0; i < NT3; ++i) acc2[i][0] = acc2[i][1] = accb2[i][0] = accb2[i][1] = 0.0;
+    accb0[0] = accb0[1] = accb1[0] = accb1[1] = 0.0;
+
+    const long long ntiles = (p.nsamples + S - 1) / S;
+    const int rowA = 8 * w + g;                          // this lane's sample row inside the tile (phase A)
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long s0 = tile * S;
+        // ---- stage the observation tile [S][K0] (zero padded) ----
+        for (int idx = tid; idx < S * K0; idx += NT) {
+            const int row = idx / K0, col = idx % K0;
+            const long long gs = s0 + row;
+            Y0s[row * RS0 + col] = (gs < p.nsamples && col < L0) ? p.obs[gs * L0 + col] : 0.0;
+        }
+        __syncthreads();
+
+        // ======================= phase A: this warp's 8 samples =======================
+        double y1[NT1][2], ry1[NT1][2];
+        {   // layer 0: x1 = [y0,1]*[W0;B0], Rx1 = [y0,1]*[VW0;VB0]   (Ry0 = 0)
+#pragma unroll
+            for (int c = 0; c < NT1; ++c)
+#pragma unroll
+                for (int r = 0; r < 2; ++r) { y1[c][r] = B0s[8 * c + 2 * t + r]; ry1[c][r] = VB0s[8 * c + 2 * t + r]; }
+#pragma unroll
+            for (int q = 0; q < Q0; ++q) {
+                const double a = Y0s[rowA * RS0 + 4 * q + t];
+#pragma unroll
+                for (int c = 0; c < NT1; ++c) {
+                    dmma(y1[c], a, W0f[(q * NT1 + c) * 32 + lane]);
+                    dmma(ry1[c], a, VW0f[(q * NT1 + c) * 32 + lane]);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < NT1; ++c) {
+                double d;
+#pragma unroll
+                for (int r = 0; r < 2; ++r) { act_fwd<ACT1>(p.act1, y1[c][r], y1[c][r], d); ry1[c][r] *= d; }
+                *reinterpret_cast<double2 *>(&BufA[rowA * RS1 + 8 * c + 2 * t]) = make_double2(y1[c][0], y1[c][1]);
+            }
+        }
+        double rx3[NT3][2];
+#pragma unroll
+        for (int c = 0; c < NT3; ++c)
+#pragma unroll
+            for (int r = 0; r < 2; ++r) rx3[c][r] = VB2s[8 * c + 2 * t + r];
+        // layer 1 in column groups of <= 4 output tiles (keeps the live register set small); each finished group is
+        // consumed immediately by layer 2 (only Rx3 is needed: y3 does not enter the FVP when the last layer is linear)
+        constexpr int GRP = NT2 < 4 ? NT2 : 4;
+#pragma unroll
+        for (int c0 = 0; c0 < NT2; c0 += GRP) {
+            double x2[GRP][2], rx2[GRP][2];
+#pragma unroll
+            for (int cc = 0; cc < GRP; ++cc)
+#pragma unroll
+                for (int r = 0; r < 2; ++r) { x2[cc][r] = B1s[8 * (c0 + cc) + 2 * t + r]; rx2[cc][r] = VB1s[8 * (c0 + cc) + 2 * t + r]; }
+#pragma unroll
+            for (int b = 0; b < NT1; ++b)
+#pragma unroll
+                for (int r = 0; r < 2; ++r)
+#pragma unroll
+                    for (int cc = 0; cc < GRP; ++cc) {
+                        const double bw = W1s[(b * NT2 + c0 + cc) * 64 + sf[r]];
+                        const double bv = VW1s[(b * NT2 + c0 + cc) * 64 + sf[r]];
+                        dmma(x2[cc], y1[b][r], bw);
+                        dmma(rx2[cc], ry1[b][r], bw);
+                        dmma(rx2[cc], y1[b][r], bv);
+                    }
+#pragma unroll
+            for (int cc = 0; cc < GRP; ++cc) {
+                double d;
+#pragma unroll
+                for (int r = 0; r < 2; ++r) { act_fwd<ACT2>(p.act2, x2[cc][r], x2[cc][r], d); rx2[cc][r] *= d; }
+                *reinterpret_cast<double2 *>(&BufC[rowA * RS2 + 8 * (c0 + cc) + 2 * t]) = make_double2(x2[cc][0], x2[cc][1]);
+                // layer 2 contribution of this k-block: Rx3 += Ry2*W2 + y2*VW2
+#pragma unroll
+                for (int r = 0; r < 2; ++r)
+#pragma unroll
+                    for (int c = 0; c < NT3; ++c) {
+                        dmma(rx3[c], rx2[cc][r], W2s[((c0 + cc) * NT3 + c) * 64 + sf[r]]);
+                        dmma(rx3[c], x2[cc][r], VW2s[((c0 + cc) * NT3 + c) * 64 + sf[r]]);
+                    }
+            }
+        }
+        // R-gradient seed: RG3 = Ry3 / sigma^2 (times the constant f' of the last layer, twice: Ry3 = f' Rx3, RG3 *= f')
+        const bool valid = (s0 + rowA) < p.nsamples;     // rows past the end of the batch contribute nothing
+        double g3[NT3][2];
+#pragma unroll
+        for (int c = 0; c < NT3; ++c) {
+#pragma unroll
+            for (int r = 0; r < 2; ++r) g3[c][r] = valid ? rx3[c][r] * d3 * IVs[8 * c + 2 * t + r] * d3 : 0.0;
+            *reinterpret_cast<double2 *>(&BufD[rowA * RS3 + 8 * c + 2 * t]) = make_double2(g3[c][0], g3[c][1]);
+        }
+        // backward through layer 2: RG2 = (RG3 * W2^T) .* f'(y2)
+        double g2[NT2][2];
+#pragma unroll
+        for (int b = 0; b < NT2; ++b) g2[b][0] = g2[b][1] = 0.0;
+#pragma unroll
+        for (int c = 0; c < NT3; ++c)
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+                for (int b = 0; b < NT2; ++b) dmma(g2[b], g3[c][r], W2s[(b * NT3 + c) * 64 + sb[r]]);
+#pragma unroll
+        for (int b = 0; b < NT2; ++b) {
+            const double2 y = *reinterpret_cast<const double2 *>(&BufC[rowA * RS2 + 8 * b + 2 * t]);
+            g2[b][0] *= act_deriv_y<ACT2>(p.act2, y.x);
+            g2[b][1] *= act_deriv_y<ACT2>(p.act2, y.y);
+            *reinterpret_cast<double2 *>(&BufB[rowA * RSB + 8 * b + 2 * t]) = make_double2(g2[b][0], g2[b][1]);
+        }
+        // backward through layer 1: RG1 = (RG2 * W1^T) .* f'(y1); stays in registers until BufB is free again
+        double g1[NT1][2];
+#pragma unroll
+        for (int b = 0; b < NT1; ++b) g1[b][0] = g1[b][1] = 0.0;
+#pragma unroll
+        for (int c = 0; c < NT2; ++c)
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+                for (int b = 0; b < NT1; ++b) dmma(g1[b], g2[c][r], W1s[(b * NT2 + c) * 64 + sb[r]]);
+#pragma unroll
+        for (int b = 0; b < NT1; ++b) {
+            const double2 y = *reinterpret_cast<const double2 *>(&BufA[rowA * RS1 + 8 * b + 2 * t]);
+            g1[b][0] *= act_deriv_y<ACT1>(p.act1, y.x);
+            g1[b][1] *= act_deriv_y<ACT1>(p.act1, y.y);
+        }
+        __syncthreads();
+
+        // ======================= phase B1: W1 / B1 and W2 / B2 gradients over the whole tile =======================
+        if (w < NT1 || w < NT2 || w == NW - 1) {
+#pragma unroll 4
+            for (int h = 0; h < S / 4; ++h) {
+                const int srow = 4 * h + t;
+                if (w < NT1) {            // rows 8w.. of Y1^T * G2
+                    const double a = BufA[srow * RS1 + 8 * w + g];
+#pragma unroll
+                    for (int j = 0; j < NT2; ++j) dmma(acc1[j], a, BufB[srow * RSB + 8 * j + g]);
+                }
+                if (w < NT2) {            // bias gradient tile w of layer 1, rows 8w.. of Y2^T * G3
+                    dmma(accb1, ones, BufB[srow * RSB + 8 * w + g]);
+                    const double a2 = BufC[srow * RS2 + 8 * w + g];
+#pragma unroll
+                    for (int c = 0; c < NT3; ++c) dmma(acc2[c], a2, BufD[srow * RS3 + 8 * c + g]);
+                }
+                if (w == NW - 1) {
+#pragma unroll
+                    for (int c = 0; c < NT3; ++c) dmma(accb2[c], ones, BufD[srow * RS3 + 8 * c + g]);
+                }
+            }
+        }
+        __syncthreads();
+        // RG1 takes over BufB
+#pragma unroll
+        for (int b = 0; b < NT1; ++b)
+            *reinterpret_cast<double2 *>(&BufB[rowA * RSB + 8 * b + 2 * t]) = make_double2(g1[b][0], g1[b][1]);
+        __syncthreads();
+        // ======================= phase B2: W0 / B0 gradients =======================
+        if (w < NT1) {
+#pragma unroll 4
+            for (int h = 0; h < S / 4; ++h) {
+                const int srow = 4 * h + t;
+                const double bg = BufB[srow * RSB + 8 * w + g];
+#pragma unroll
+                for (int m = 0; m < MT0; ++m) dmma(acc0[m], Y0s[srow * RS0 + 8 * m + g], bg);
+                dmma(accb0, ones, bg);
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---------------- epilogue: this CTA's partial row (only real, un-padded entries) ----------------
+    double *out = p.partial + (size_t)blockIdx.x * p.P;
+    if (w < NT1) {
+#pragma unroll
+        for (int m = 0; m < MT0; ++m)
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int row = 8 * m + g, col = 8 * w + 2 * t + r;
+                if (row < L0 && col < L1) out[p.w_off0 + row * L1 + col] = acc0[m][r];
+            }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int col = 8 * w + 2 * t + r;
+            if (g == 0 && col < L1) out[p.w_off0 + L0 * L1 + col] = accb0[r];
+        }
+#pragma unroll
+        for (int j = 0; j < NT2; ++j)
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int row = 8 * w + g, col = 8 * j + 2 * t + r;
+                if (row < L1 && col < L2) out[p.w_off1 + row * L2 + col] = acc1[j][r];
+            }
+    }
+    if (w < NT2) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int col = 8 * w + 2 * t + r;
+            if (g == 0 && col < L2) out[p.w_off1 + L1 * L2 + col] = accb1[r];
+        }
+#pragma unroll
+        for (int c = 0; c < NT3; ++c)
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int row = 8 * w + g, col = 8 * c + 2 * t + r;
+                if (row < L2 && col < L3) out[p.w_off2 + row * L3 + col] = acc2[c][r];
+            }
+    }
+    if (w == NW - 1) {
+#pragma unroll
+        for (int c = 0; c < NT3; ++c)
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int col = 8 * c + 2 * t + r;
+                if (g == 0 && col < L3) out[p.w_off2 + L2 * L3 + col] = accb2[c][r];
+            }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int FUSED_MAX_ROWS = 148;
+
+using CfgArm  = Cfg<16, 16, 16, 8, 8>;     // armDOF_0: 15-16-16-3
+using CfgP64  = Cfg<4, 64, 64, 8, 8>;      // InvertedPendulum-size: 4-64-64-1
+using CfgM64  = Cfg<20, 64, 64, 8, 8>;     // 17-64-64-6 (and anything with L0 <= 20, hidden <= 64, A <= 8)
+
+enum FusedShape { SHAPE_NONE = 0, SHAPE_ARM, SHAPE_P64, SHAPE_M64 };
+
+FusedShape pick_shape(const NetDesc &net) {
+    if (net.K != 3) return SHAPE_NONE;
+    if (net.ac[3] != 'l' && net.ac[3] != 'o') return SHAPE_NONE;
+    const int L0 = net.L[0], L1 = net.L[1], L2 = net.L[2], L3 = net.L[3];
+    if (L3 > 8) return SHAPE_NONE;
+    if (L0 <= 16 && L1 <= 16 && L2 <= 16) return SHAPE_ARM;
+    if (L0 <= 4 && L1 <= 64 && L2 <= 64) return SHAPE_P64;
+    if (L0 <= 20 && L1 <= 64 && L2 <= 64) return SHAPE_M64;
+    return SHAPE_NONE;
+}
+
+template <typename C, char A1, char A2>
+int launch_cfg(const FusedArgs &a, int grid, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(k_fvp_fused<C, A1, A2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES) != cudaSuccess)
+            return -1;
+        configured = true;
+    }
+    k_fvp_fused<C, A1, A2><<<grid, C::NTHREADS, C::SMEM_BYTES, st>>>(a);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+template <typename C>
+int launch_shape(const FusedArgs &a, cudaStream_t st, int *rows) {
+    const long long ntiles = (a.nsamples + C::S - 1) / C::S;
+    const int grid = (int)(ntiles < FUSED_MAX_ROWS ? ntiles : FUSED_MAX_ROWS);
+    *rows = grid;
+    if (a.act1 == 't' && a.act2 == 't') return launch_cfg<C, 't', 't'>(a, grid, st);
+    return launch_cfg<C, 0, 0>(a, grid, st);
+}
+
+}  // namespace
+
+bool fused_eligible(const NetDesc &net) { return pick_shape(net) != SHAPE_NONE; }
+int fused_partial_rows() { return FUSED_MAX_ROWS; }
+
+int fused_fvp_accumulate(const NetDesc &net, const double *d_theta, const double *d_v, const double *d_inv_var,
+                         const double *d_obs, size_t nsamples, double *d_partial, double *d_zsum,
+                         const int *d_done, cudaStream_t st, long long *launches) {
+    const FusedShape shape = pick_shape(net);
+    if (shape == SHAPE_NONE) return 1;
+    FusedArgs a;
+    a.theta = d_theta; a.v = d_v; a.inv_var = d_inv_var; a.obs = d_obs; a.partial = d_partial; a.done = d_done;
+    a.nsamples = (long long)nsamples;
+    a.L0 = net.L[0]; a.L1 = net.L[1]; a.L2 = net.L[2]; a.L3 = net.L[3];
+    a.w_off0 = net.w_off[0]; a.w_off1 = net.w_off[1]; a.w_off2 = net.w_off[2];
+    a.P = net.P;
+    a.act1 = net.ac[1]; a.act2 = net.ac[2]; a.act3 = net.ac[3];
+    int rows = 0, rc = -1;
+    switch (shape) {
+        case SHAPE_ARM: rc = launch_shape<CfgArm>(a, st, &rows); break;
+        case SHAPE_P64: rc = launch_shape<CfgP64>(a, st, &rows); break;
+        case SHAPE_M64: rc = launch_shape<CfgM64>(a, st, &rows); break;
+        default: return 1;
+    }
+    if (rc) return -1;
+    ++*launches;
+    launch_reduce_partials(d_partial, rows, net.P, d_zsum, d_done, st, launches);
+    return 0;
+}
