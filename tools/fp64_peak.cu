@@ -211,6 +211,21 @@ int main(int argc, char **argv) {
         ms = time_ms([&] { k_tanh<<<grid, 256>>>(out, iters / 16, 0.7); }, reps);
         printf("bps=%d tanh(f64)   : %8.3f ms  %7.2f Gtanh/s\n", bps, ms, thr * 4 * (iters / 16) / ms / 1e6);
     }
+    // DMMA / DFMA dependent-issue latency: one warp per SM sub-partition (128 threads per SM), CH independent chains
+    {
+        const int grid = sms;
+        float ms;
+        ms = time_ms([&] { k_dmma884<1><<<grid, 128>>>(out, iters, 1.0000001, 1e-9); }, reps);
+        printf("latency dmma884 1 chain : %8.3f ms  => %.1f cycles per dependent DMMA at 1.965 GHz\n", ms, ms * 1e-3 * 1.965e9 / iters);
+        ms = time_ms([&] { k_dmma884<2><<<grid, 128>>>(out, iters, 1.0000001, 1e-9); }, reps);
+        printf("latency dmma884 2 chains: %8.3f ms  => %.1f cycles per DMMA issue\n", ms, ms * 1e-3 * 1.965e9 / iters / 2);
+        ms = time_ms([&] { k_dmma884<4><<<grid, 128>>>(out, iters, 1.0000001, 1e-9); }, reps);
+        printf("latency dmma884 4 chains: %8.3f ms  => %.1f cycles per DMMA issue\n", ms, ms * 1e-3 * 1.965e9 / iters / 4);
+        ms = time_ms([&] { k_dmma884<8><<<grid, 128>>>(out, iters, 1.0000001, 1e-9); }, reps);
+        printf("latency dmma884 8 chains: %8.3f ms  => %.1f cycles per DMMA issue\n", ms, ms * 1e-3 * 1.965e9 / iters / 8);
+        ms = time_ms([&] { k_dfma<1><<<grid, 128>>>(out, iters, 1.0000001, 1e-9); }, reps);
+        printf("latency dfma 1 chain    : %8.3f ms  => %.1f cycles per dependent DFMA\n", ms, ms * 1e-3 * 1.965e9 / iters);
+    }
     CK(cudaFree(out));
     return 0;
 }

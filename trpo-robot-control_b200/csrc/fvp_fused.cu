@@ -24,6 +24,13 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
         : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
 
+// 8-byte async global->shared copy (LDGSTS); src_bytes == 0 zero-fills the destination
+__device__ __forceinline__ void cp_async8(double *dst_smem, const double *src, int src_bytes) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" :: "r"(d), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
 // y = f(x) and d = f'(x) written through y (TRPO_FVP.c:806-834,869-882). ACT == 0: runtime switch on `a`.
 template <char ACT>
 __device__ __forceinline__ void act_fwd(char a, double x, double &y, double &d) {
@@ -40,6 +47,86 @@ __device__ __forceinline__ double act_deriv_y(char a, double y) {
     if (k == 's') return y * (1.0 - y);
     if (k == 'o') return 0.1;
     return 1.0;
+}
+
+// Branch-free FP64 tanh for N values in lock step: tanh(x) = sign(x) * (1 - 2 / (exp(2|x|) + 1)).
+// The library tanh() has data-dependent branches, so the unrolled per-element calls cannot be interleaved and every
+// call runs as one ~30-deep dependent DFMA chain (11.6 cycles each): with 2 warps per scheduler that was a third of
+// the kernel's time. Here every stage is applied to all N values before the next one, so the FP64 pipe sees N
+// independent chains. exp(2a) = 2^n * e^{2h}, h = a - n*ln2/2 (|h| <= 0.174), degree-12 Taylor polynomial in h
+// (truncation 1.7e-16), 2^n applied through the exponent bits; 1/(E+1) from MUFU.RCP64H + two Newton steps.
+// Max absolute error 2.6e-16 over [-25, 25] (tests/test_host_logic.py holds the same algorithm in numpy).
+template <int N>
+__device__ __forceinline__ void tanh_vec(double (&x)[N], double (&d)[N]) {
+    constexpr double MAGIC = 6755399441055744.0;            // 1.5 * 2^52: rounds to nearest integer in the low word
+    constexpr double L2E2 = 2.8853900817779268;             // 2 / ln 2
+    constexpr double LN2H_HI = 0.3465735901845619, LN2H_LO = 9.541074646352939e-11;   // ln2/2 = HI + LO, HI has 21 trailing zero bits
+    constexpr double C[13] = {1.0, 2.0, 2.0, 1.3333333333333333, 0.6666666666666666, 0.26666666666666666,
+                              0.08888888888888889, 0.025396825396825397, 0.006349206349206349, 0.0014109347442680777,
+                              0.0002821869488536155, 5.130671797338464e-05, 8.551119662230774e-06};   // 2^k / k!
+    double a[N], h[N], q[N];
+    int ni[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) a[i] = fmin(fabs(x[i]), 20.0);       // tanh(20) == 1 in double
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const double tt = fma(a[i], L2E2, MAGIC);
+        ni[i] = __double2loint(tt);
+        const double nf = tt - MAGIC;
+        h[i] = fma(nf, -LN2H_HI, a[i]);
+        h[i] = fma(nf, -LN2H_LO, h[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) q[i] = fma(C[12], h[i], C[11]);
+#pragma unroll
+    for (int k = 10; k >= 0; --k)
+#pragma unroll
+        for (int i = 0; i < N; ++i) q[i] = fma(q[i], h[i], C[k]);
+    double s[N], y[N], e[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const double E = __hiloint2double(__double2hiint(q[i]) + (ni[i] << 20), __double2loint(q[i]));
+        s[i] = E + 1.0;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y[i]) : "d"(s[i]));
+    }
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) e[i] = fma(-s[i], y[i], 1.0);
+#pragma unroll
+        for (int i = 0; i < N; ++i) y[i] = fma(y[i], e[i], y[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const double r = copysign(fma(-2.0, y[i], 1.0), x[i]);
+        x[i] = r;
+        d[i] = fma(-r, r, 1.0);
+    }
+}
+
+// Activation of CNT accumulator tiles starting at tile C0: x <- f(x), rx <- rx * f'(x)
+template <char ACT, int C0, int CNT, int NTILES>
+__device__ __forceinline__ void activate_tiles(char a, double (&x)[NTILES][2], double (&rx)[NTILES][2]) {
+    if constexpr (ACT == 't') {
+        double xv[2 * CNT], dv[2 * CNT];
+#pragma unroll
+        for (int c = 0; c < CNT; ++c) { xv[2 * c] = x[C0 + c][0]; xv[2 * c + 1] = x[C0 + c][1]; }
+        tanh_vec<2 * CNT>(xv, dv);
+#pragma unroll
+        for (int c = 0; c < CNT; ++c) {
+            x[C0 + c][0] = xv[2 * c]; x[C0 + c][1] = xv[2 * c + 1];
+            rx[C0 + c][0] *= dv[2 * c]; rx[C0 + c][1] *= dv[2 * c + 1];
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < CNT; ++c)
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                double d;
+                act_fwd<ACT>(a, x[C0 + c][r], x[C0 + c][r], d);
+                rx[C0 + c][r] *= d;
+            }
+    }
 }
 
 __host__ __device__ constexpr int pad_rs(int k) {   // smallest row stride >= k with stride % 16 in {4, 12}
@@ -66,7 +153,7 @@ struct Cfg {
     static constexpr int oW0 = 0, oVW0 = oW0 + K0 * H1, oW1 = oVW0 + K0 * H1, oVW1 = oW1 + H1 * H2,
                          oW2 = oVW1 + H1 * H2, oVW2 = oW2 + H2 * AP, oB0 = oVW2 + H2 * AP, oVB0 = oB0 + H1,
                          oB1 = oVB0 + H1, oVB1 = oB1 + H2, oVB2 = oVB1 + H2, oIV = oVB2 + AP,
-                         oY0 = oIV + AP, oA = oY0 + S * RS0 + 8, oC = oA + S * RS1, oB = oC + S * RS2,
+                         oY0 = oIV + AP, Y0SZ = S * RS0 + 8, oA = oY0 + 2 * Y0SZ, oC = oA + S * RS1, oB = oC + S * RS2,
                          oD = oB + S * RSB, TOTAL = oD + S * RS3;
     static constexpr size_t SMEM_BYTES = sizeof(double) * TOTAL;
     static_assert(K0 % 4 == 0 && H1 % 8 == 0 && H2 % 8 == 0 && AP % 8 == 0, "padded sizes");
@@ -133,7 +220,19 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_fvp_fused(const FusedArgs p)
         VB2s[n] = n < L3 ? p.v[p.w_off2 + L2 * L3 + n] : 0.0;
         IVs[n]  = n < L3 ? p.inv_var[n] : 0.0;
     }
-    for (int i = tid; i < 8; i += NT) Y0s[S * RS0 + i] = 0.0;
+    for (int i = tid; i < 2 * C::Y0SZ; i += NT) Y0s[i] = 0.0;
+    __syncthreads();
+    // observation tile [S][K0] (zero padded / zero past the end of the batch), staged asynchronously one tile ahead
+    auto stage_obs = [&](long long tile_idx, int buf) {
+        double *dst = Y0s + buf * C::Y0SZ;
+        const long long s0n = tile_idx * S;
+        for (int idx = tid; idx < S * K0; idx += NT) {
+            const int row = idx / K0, col = idx % K0;
+            const long long gs = s0n + row;
+            const bool in = gs < p.nsamples && col < L0;
+            cp_async8(&dst[row * RS0 + col], in ? &p.obs[gs * L0 + col] : p.obs, in ? 8 : 0);
+        }
+    };
 
     // per-lane offsets into a swizzled block: forward fragment (row 2t+r, col g), transposed fragment (row g, col 2t+r)
     int sf[2], sb[2];
@@ -156,15 +255,14 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_fvp_fused(const FusedArgs p)
 
     const long long ntiles = (p.nsamples + S - 1) / S;
     const int rowA = 8 * w + g;                          // this lane's sample row inside the tile (phase A)
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    if ((long long)blockIdx.x < ntiles) stage_obs(blockIdx.x, 0);
+    cp_async_wait_all();
+    __syncthreads();
+    int buf = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1) {
         const long long s0 = tile * S;
-        // ---- stage the observation tile [S][K0] (zero padded) ----
-        for (int idx = tid; idx < S * K0; idx += NT) {
-            const int row = idx / K0, col = idx % K0;
-            const long long gs = s0 + row;
-            Y0s[row * RS0 + col] = (gs < p.nsamples && col < L0) ? p.obs[gs * L0 + col] : 0.0;
-        }
-        __syncthreads();
+        const double *Y0c = Y0s + buf * C::Y0SZ;
+        if (tile + gridDim.x < ntiles) stage_obs(tile + gridDim.x, buf ^ 1);     // lands during this tile's math
 
         // ======================= phase A: this warp's 8 samples =======================
         double y1[NT1][2], ry1[NT1][2];
@@ -175,29 +273,37 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_fvp_fused(const FusedArgs p)
                 for (int r = 0; r < 2; ++r) { y1[c][r] = B0s[8 * c + 2 * t + r]; ry1[c][r] = VB0s[8 * c + 2 * t + r]; }
 #pragma unroll
             for (int q = 0; q < Q0; ++q) {
-                const double a = Y0s[rowA * RS0 + 4 * q + t];
+                const double a = Y0c[rowA * RS0 + 4 * q + t];
 #pragma unroll
                 for (int c = 0; c < NT1; ++c) {
                     dmma(y1[c], a, W0f[(q * NT1 + c) * 32 + lane]);
                     dmma(ry1[c], a, VW0f[(q * NT1 + c) * 32 + lane]);
                 }
             }
+            constexpr int ACH = NT1 < 4 ? NT1 : 4;       // activation chunk: 8 values in flight per thread
+            static_assert(NT1 % ACH == 0, "layer-1 width must split into equal activation chunks");
+            if constexpr (NT1 >= 1 * ACH) activate_tiles<ACT1, 0 * ACH, ACH>(p.act1, y1, ry1);
+            if constexpr (NT1 >= 2 * ACH) activate_tiles<ACT1, 1 * ACH, ACH>(p.act1, y1, ry1);
+            if constexpr (NT1 >= 3 * ACH) activate_tiles<ACT1, 2 * ACH, ACH>(p.act1, y1, ry1);
+            if constexpr (NT1 >= 4 * ACH) activate_tiles<ACT1, 3 * ACH, ACH>(p.act1, y1, ry1);
+            static_assert(NT1 <= 4 * ACH, "add activation chunks");
 #pragma unroll
-            for (int c = 0; c < NT1; ++c) {
-                double d;
-#pragma unroll
-                for (int r = 0; r < 2; ++r) { act_fwd<ACT1>(p.act1, y1[c][r], y1[c][r], d); ry1[c][r] *= d; }
+            for (int c = 0; c < NT1; ++c)
                 *reinterpret_cast<double2 *>(&BufA[rowA * RS1 + 8 * c + 2 * t]) = make_double2(y1[c][0], y1[c][1]);
-            }
         }
-        double rx3[NT3][2];
-#pragma unroll
-        for (int c = 0; c < NT3; ++c)
-#pragma unroll
-            for (int r = 0; r < 2; ++r) rx3[c][r] = VB2s[8 * c + 2 * t + r];
         // layer 1 in column groups of <= 4 output tiles (keeps the live register set small); each finished group is
-        // consumed immediately by layer 2 (only Rx3 is needed: y3 does not enter the FVP when the last layer is linear)
+        // consumed immediately by layer 2 (only Rx3 is needed: y3 does not enter the FVP when the last layer is linear).
+        // DMMAs that hit the same accumulator are issued GRP instructions apart: warps issue in order, so a
+        // back-to-back dependent pair would stall the warp for the full DMMA latency.
         constexpr int GRP = NT2 < 4 ? NT2 : 4;
+        static_assert(NT2 % GRP == 0, "layer-2 width must split into equal column groups");
+        double rx3p[GRP][NT3][2];            // GRP independent partial sums of Rx3
+#pragma unroll
+        for (int cc = 0; cc < GRP; ++cc)
+#pragma unroll
+            for (int c = 0; c < NT3; ++c)
+#pragma unroll
+                for (int r = 0; r < 2; ++r) rx3p[cc][c][r] = (cc == 0) ? VB2s[8 * c + 2 * t + r] : 0.0;
 #pragma unroll
         for (int c0 = 0; c0 < NT2; c0 += GRP) {
             double x2[GRP][2], rx2[GRP][2];
@@ -208,31 +314,45 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_fvp_fused(const FusedArgs p)
 #pragma unroll
             for (int b = 0; b < NT1; ++b)
 #pragma unroll
-                for (int r = 0; r < 2; ++r)
+                for (int r = 0; r < 2; ++r) {
+                    double bw[GRP], bv[GRP];
 #pragma unroll
                     for (int cc = 0; cc < GRP; ++cc) {
-                        const double bw = W1s[(b * NT2 + c0 + cc) * 64 + sf[r]];
-                        const double bv = VW1s[(b * NT2 + c0 + cc) * 64 + sf[r]];
-                        dmma(x2[cc], y1[b][r], bw);
-                        dmma(rx2[cc], ry1[b][r], bw);
-                        dmma(rx2[cc], y1[b][r], bv);
+                        bw[cc] = W1s[(b * NT2 + c0 + cc) * 64 + sf[r]];
+                        bv[cc] = VW1s[(b * NT2 + c0 + cc) * 64 + sf[r]];
                     }
 #pragma unroll
-            for (int cc = 0; cc < GRP; ++cc) {
-                double d;
+                    for (int cc = 0; cc < GRP; ++cc) dmma(x2[cc], y1[b][r], bw[cc]);
 #pragma unroll
-                for (int r = 0; r < 2; ++r) { act_fwd<ACT2>(p.act2, x2[cc][r], x2[cc][r], d); rx2[cc][r] *= d; }
+                    for (int cc = 0; cc < GRP; ++cc) dmma(rx2[cc], ry1[b][r], bw[cc]);
+#pragma unroll
+                    for (int cc = 0; cc < GRP; ++cc) dmma(rx2[cc], y1[b][r], bv[cc]);
+                }
+            activate_tiles<ACT2, 0, GRP>(p.act2, x2, rx2);
+#pragma unroll
+            for (int cc = 0; cc < GRP; ++cc)
                 *reinterpret_cast<double2 *>(&BufC[rowA * RS2 + 8 * (c0 + cc) + 2 * t]) = make_double2(x2[cc][0], x2[cc][1]);
-                // layer 2 contribution of this k-block: Rx3 += Ry2*W2 + y2*VW2
+            // layer 2 contribution of these k-blocks: Rx3 += Ry2*W2 + y2*VW2
 #pragma unroll
-                for (int r = 0; r < 2; ++r)
+            for (int r = 0; r < 2; ++r)
 #pragma unroll
-                    for (int c = 0; c < NT3; ++c) {
-                        dmma(rx3[c], rx2[cc][r], W2s[((c0 + cc) * NT3 + c) * 64 + sf[r]]);
-                        dmma(rx3[c], x2[cc][r], VW2s[((c0 + cc) * NT3 + c) * 64 + sf[r]]);
-                    }
-            }
+                for (int c = 0; c < NT3; ++c) {
+#pragma unroll
+                    for (int cc = 0; cc < GRP; ++cc) dmma(rx3p[cc][c], rx2[cc][r], W2s[((c0 + cc) * NT3 + c) * 64 + sf[r]]);
+#pragma unroll
+                    for (int cc = 0; cc < GRP; ++cc) dmma(rx3p[cc][c], x2[cc][r], VW2s[((c0 + cc) * NT3 + c) * 64 + sf[r]]);
+                }
         }
+        double rx3[NT3][2];
+#pragma unroll
+        for (int c = 0; c < NT3; ++c)
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                double sum = rx3p[0][c][r];
+#pragma unroll
+                for (int cc = 1; cc < GRP; ++cc) sum += rx3p[cc][c][r];
+                rx3[c][r] = sum;
+            }
         // R-gradient seed: RG3 = Ry3 / sigma^2 (times the constant f' of the last layer, twice: Ry3 = f' Rx3, RG3 *= f')
         const bool valid = (s0 + rowA) < p.nsamples;     // rows past the end of the batch contribute nothing
         double g3[NT3][2];
@@ -312,10 +432,11 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_fvp_fused(const FusedArgs p)
                 const int srow = 4 * h + t;
                 const double bg = BufB[srow * RSB + 8 * w + g];
 #pragma unroll
-                for (int m = 0; m < MT0; ++m) dmma(acc0[m], Y0s[srow * RS0 + 8 * m + g], bg);
+                for (int m = 0; m < MT0; ++m) dmma(acc0[m], Y0c[srow * RS0 + 8 * m + g], bg);
                 dmma(accb0, ones, bg);
             }
         }
+        cp_async_wait_all();
         __syncthreads();
     }
 
