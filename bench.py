@@ -34,6 +34,8 @@ DAMPING = 0.1
 # measured on this pool's B200 with tools/fp64_peak.cu (profiles/fp64_peak_r01.txt): DMMA.8x8x4 and DFMA share one
 # FP64 pipe, 37.1 TFLOP/s = 148 SMs x 64 FMA/clk x 2 x 1.96 GHz. MEASURED_PEAKS.json has no FP64 entry.
 FP64_PEAK_TFLOPS = 37.1
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_fvp_fused launch, ncu --set full (profiles/r01_summary.md)
+NCU_TRAFFIC_BYTES = {("mlp64", 1_000_000, "fused_dmma"): 136_153_600 + 4_317_696}
 WORKLOAD_INDEX = {"arm": 1, "mlp64": 2, "pendulum64": 2, "humanoid64": 2, "humanoid256": 3}
 
 
@@ -192,6 +194,13 @@ def run_gpu_arm(args, pkg):
             uid.copy_(torch.frombuffer(bytearray(pkg.api.nccl_unique_id()), dtype=torch.uint8))
         dist.broadcast(uid, 0)
         ctx.init_comm(bytes(uid.cpu().numpy().tobytes()), rank, world)
+        if args.comm == "p2p":
+            # peer-memory all-reduce fused into our kernels: exchange the CUDA IPC handles of the comm buffers
+            mine = torch.frombuffer(bytearray(ctx.p2p_export()), dtype=torch.uint8).to(dev)
+            allh = [torch.zeros(64, dtype=torch.uint8, device=dev) for _ in range(world)]
+            dist.all_gather(allh, mine)
+            ctx.p2p_attach(b"".join(bytes(h.cpu().numpy().tobytes()) for h in allh))
+            dist.barrier()
     ctx.set_model(theta)
     ctx.set_batch(obs_pin.numpy(), batch["Std"])
     assert ctx.global_samples() == n_total
@@ -277,6 +286,7 @@ def run_gpu_arm(args, pkg):
     path_used = {1: "gemm_chain", 2: "fused_dmma"}.get(ctx.path_used(), "?")
     x_dev = d_x.cpu().numpy()
     assert np.isfinite(x_dev).all() and np.isfinite(x_pin.numpy()).all()
+    assert ctx.comm_error() == 0, "a peer-memory wait timed out"
 
     if rank == 0:
         fl = flops_min_per_sample(layers)
@@ -289,13 +299,15 @@ def run_gpu_arm(args, pkg):
             "config": {"workload": f"{args.workload}: {'-'.join(map(str, layers))} policy, {n_total} synthetic states, "
                                    f"{CG_ITERS}-iteration CG (ResidualTh=0), damping {DAMPING}",
                        "kernel_path": path_used, "l2": "flushed between steps (256 MiB write); 1M-state shard is 136 MB > L2",
-                       "parallelism": f"samples sharded over {world} GPU(s), 1 all-reduce of P={P} doubles per FVP"},
+                       "parallelism": f"samples sharded over {world} GPU(s), 1 all-reduce of P={P} doubles per FVP"
+                                      + (f" ({args.comm})" if world > 1 else "")},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
-                         "frac": (achieved / FP64_PEAK_TFLOPS) if achieved else None, "traffic": None,
+                         "frac": (achieved / FP64_PEAK_TFLOPS) if achieved else None,
+                         "traffic": NCU_TRAFFIC_BYTES.get((args.workload, n_local, path_used)),
                          "kernel": path_used, "kernel_avg_ms": k_avg_ms, "kernel_launches_timed": k_n,
                          "flops_per_sample": fl,
                          "peak_source": "measured FP64 DMMA/DFMA pipe, profiles/fp64_peak_r01.txt (MEASURED_PEAKS.json has no FP64 entry)"},
@@ -324,6 +336,8 @@ def main():
     ap.add_argument("--states", type=int, default=0, help="override the number of synthetic states")
     ap.add_argument("--path", default="", choices=["", "chain", "fused"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"],
+                    help="multi-GPU FVP-sum all-reduce: fused NVLink peer-memory kernels (default) or ncclAllReduce")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     from __graft_entry__ import load_package

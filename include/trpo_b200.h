@@ -151,6 +151,17 @@ int     trpo_memcpy_d2h(double *dst_host, const double *src_dev, size_t n_double
  * ---------------------------------------------------------------------------------------------- */
 int trpo_nccl_unique_id(char id_out[128]);
 int trpo_ctx_init_comm(trpo_ctx *ctx, const char id[128], int rank, int world_size);
+/* Peer-memory (NVLink / NVSwitch) all-reduce for the FVP sums, replacing the ncclAllReduce: the send side is fused into
+ * the kernel that reduces the per-CTA partial rows (each rank pushes its sum into every peer's memory), the receive side
+ * into the CG-update / FVP-finalise kernel (waits on local flags, sums the ranks in fixed order). One PROCESS per GPU:
+ * every rank exports its communication buffer as a 64-byte CUDA IPC handle (after trpo_ctx_init_comm), the application
+ * all-gathers the handles (rank order) and attaches them. A barrier across ranks must separate attach from first use. */
+int trpo_ctx_p2p_export(trpo_ctx *ctx, char handle_out[64]);
+int trpo_ctx_p2p_attach(trpo_ctx *ctx, const char *handles /* world_size x 64 bytes */);
+enum { TRPO_COMM_NCCL = 0, TRPO_COMM_P2P = 1 };
+int trpo_ctx_set_comm_mode(trpo_ctx *ctx, int mode);       /* P2P becomes the default once attached */
+int trpo_ctx_comm_error(trpo_ctx *ctx);                    /* non-zero if a peer wait timed out (synchronises) */
+
 /* Total sample count over all ranks (the 1/N of TRPO_FVP.c:930). Computed by init_comm+set_batch via all-reduce. */
 size_t trpo_ctx_global_samples(const trpo_ctx *ctx);
 

@@ -1,0 +1,89 @@
+"""Multi-GPU parity (needs >= 2 GPUs: `gpurun --gpus 2 -- python -m pytest tests/test_gpu_multi.py -m gpu`):
+samples sharded over 2 ranks, FVP sums all-reduced by ncclAllReduce and by the fused peer-memory kernels; both must
+reproduce the single-batch reference result and leave bitwise identical CG state on every rank."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out_dir, name):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from __graft_entry__ import load_package
+    from bench import shard_bounds
+    from conftest import load_synth
+    pkg = load_package()
+    s = load_synth(name)
+    L, ac = s["layers"], s["acfunc"]
+    N = s["Observ"].shape[0]
+    lo, hi = shard_bounds(N, world, rank)
+    ctx = pkg.Context(L, ac, device=rank)
+    uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        uid.copy_(torch.frombuffer(bytearray(pkg.api.nccl_unique_id()), dtype=torch.uint8))
+    dist.broadcast(uid, 0)
+    ctx.init_comm(bytes(uid.cpu().numpy().tobytes()), rank, world)
+    ctx.set_model(s["theta"])
+    ctx.set_batch(s["Observ"][lo:hi], s["Std"], s["Mean"][lo:hi], s["Action"][lo:hi], s["Advantage"][lo:hi])
+    assert ctx.global_samples() == N
+    out = {}
+    out["fvp_nccl"] = ctx.fvp(s["v"], 0.1)
+    out["cg_nccl"], info = ctx.cg(s["b"], 10, 1e-10, 0.1)
+    out["iters_nccl"] = np.array(info.cg_iters)
+    out["upd_nccl"], _ = ctx.update(0.1)
+    mine = torch.frombuffer(bytearray(ctx.p2p_export()), dtype=torch.uint8).to(dev)
+    allh = [torch.zeros(64, dtype=torch.uint8, device=dev) for _ in range(world)]
+    dist.all_gather(allh, mine)
+    ctx.p2p_attach(b"".join(bytes(h.cpu().numpy().tobytes()) for h in allh))
+    dist.barrier()
+    out["fvp_p2p"] = ctx.fvp(s["v"], 0.1)
+    out["cg_p2p"], info = ctx.cg(s["b"], 10, 1e-10, 0.1)
+    out["iters_p2p"] = np.array(info.cg_iters)
+    out["fvp_p2p_again"] = ctx.fvp(s["v"], 0.1)
+    out["upd_p2p"], _ = ctx.update(0.1)
+    out["comm_error"] = np.array(ctx.comm_error())
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), **out)
+    dist.barrier()
+    ctx.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("name", ["arm_sigma", "mlp64", "acts5"])
+def test_two_gpu_sharded_solve(tmp_path, name):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    from conftest import load_synth, rel_err
+    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path), name), nprocs=2, join=True)
+    r0, r1 = (dict(np.load(tmp_path / f"rank{r}.npz")) for r in range(2))
+    s = load_synth(name)
+    for k in r0:
+        assert np.array_equal(r0[k], r1[k]), f"{k} differs between ranks"
+    assert r0["comm_error"] == 0
+    for tag in ("nccl", "p2p"):
+        assert rel_err(r0[f"fvp_{tag}"], s["ref_fvpfast"])[0] < 1e-10
+        assert rel_err(r0[f"cg_{tag}"], s["ref_cg"])[0] < 1e-8
+        assert rel_err(r0[f"upd_{tag}"], s["ref_update"])[0] < 1e-8
+    assert np.array_equal(r0["fvp_p2p"], r0["fvp_p2p_again"])
+    assert np.array_equal(r0["fvp_p2p"], r0["fvp_nccl"])       # 2 ranks: a+b in either order is the same double

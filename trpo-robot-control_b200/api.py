@@ -17,6 +17,7 @@ c_double_p = C.POINTER(C.c_double)
 c_size_p = C.POINTER(C.c_size_t)
 
 PATH_AUTO, PATH_GEMM_CHAIN, PATH_FUSED = 0, 1, 2
+COMM_NCCL, COMM_P2P = 0, 1
 
 
 class TRPOparam(C.Structure):
@@ -84,6 +85,10 @@ def lib():
         L.trpo_ctx_cg_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_double, C.c_double]
         L.trpo_nccl_unique_id.argtypes = [C.c_char_p]
         L.trpo_ctx_init_comm.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int]
+        L.trpo_ctx_p2p_export.argtypes = [C.c_void_p, C.c_char_p]
+        L.trpo_ctx_p2p_attach.argtypes = [C.c_void_p, C.c_char_p]
+        L.trpo_ctx_set_comm_mode.argtypes = [C.c_void_p, C.c_int]
+        L.trpo_ctx_comm_error.argtypes = [C.c_void_p]
         L.trpo_ctx_global_samples.restype = C.c_size_t
         L.trpo_ctx_global_samples.argtypes = [C.c_void_p]
         for name in ("FVP_GPU", "CG_GPU", "TRPO_Update_GPU"):
@@ -263,6 +268,20 @@ class Context:
 
     def init_comm(self, unique_id, rank, world):
         _check(lib().trpo_ctx_init_comm(self.h, unique_id, rank, world))
+
+    def p2p_export(self):
+        buf = C.create_string_buffer(64)
+        _check(lib().trpo_ctx_p2p_export(self.h, buf))
+        return buf.raw
+
+    def p2p_attach(self, handles):
+        _check(lib().trpo_ctx_p2p_attach(self.h, handles))
+
+    def set_comm_mode(self, mode):
+        _check(lib().trpo_ctx_set_comm_mode(self.h, mode))
+
+    def comm_error(self):
+        return lib().trpo_ctx_comm_error(self.h)
 
     def global_samples(self):
         return lib().trpo_ctx_global_samples(self.h)

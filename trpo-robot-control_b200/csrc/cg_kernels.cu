@@ -33,12 +33,7 @@ __device__ __forceinline__ double block_sum(double v, double *red) {
     return red[0];
 }
 
-// zsum[e] = sum over rows (fixed order) of partial[row][e]
-__global__ void k_reduce_partials(const double *__restrict__ partial, int rows, int P, double *__restrict__ zsum,
-                                  const int *__restrict__ done) {
-    if (done && *done) return;
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= P) return;
+__device__ __forceinline__ double row_sum(const double *__restrict__ partial, int rows, int P, int e) {
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
     int r = 0;
     for (; r + 3 < rows; r += 4) {
@@ -48,8 +43,84 @@ __global__ void k_reduce_partials(const double *__restrict__ partial, int rows, 
         s3 += partial[(size_t)(r + 3) * P + e];
     }
     for (; r < rows; ++r) s0 += partial[(size_t)r * P + e];
-    zsum[e] = (s0 + s1) + (s2 + s3);
+    return (s0 + s1) + (s2 + s3);
 }
+
+// zsum[e] = sum over rows (fixed order) of partial[row][e]
+__global__ void k_reduce_partials(const double *__restrict__ partial, int rows, int P, double *__restrict__ zsum,
+                                  const int *__restrict__ done) {
+    if (done && *done) return;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= P) return;
+    zsum[e] = row_sum(partial, rows, P, e);
+}
+
+// ---- peer-memory all-reduce, send side: fused into the partial-row reduction --------------------------------
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Every thread pushes its element of this rank's sum into slot [parity][rank] of EVERY rank (NVLink stores for the
+// peers); the last block to finish publishes the sequence number into every rank's flag [parity][rank].
+__global__ void k_reduce_partials_push(const double *__restrict__ partial, int rows, double *__restrict__ zsum,
+                                       const int *__restrict__ done, const P2PComm c) {
+    if (done && *done) return;
+    const int P = c.P;
+    const unsigned long long seq = *c.seq_dev + 1;
+    const size_t slot = ((size_t)(seq & 1) * c.world + c.rank) * P;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < P) {
+        const double v = row_sum(partial, rows, P, e);
+        zsum[e] = v;
+        for (int r = 0; r < c.world; ++r) c.slots[r][slot + e] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(c.block_counter, 1u);
+        if (prev == gridDim.x - 1) {
+            *c.block_counter = 0;
+            __threadfence_system();
+            for (int r = 0; r < c.world; ++r) st_release_sys(&c.flags[r][(seq & 1) * c.world + c.rank], seq);
+        }
+    }
+}
+
+// Receive side: wait until every rank's contribution number `seq` has landed in OUR memory. Called by one block's
+// threads r < world; a bounded spin (about 4 s) records an error instead of hanging the GPU.
+__device__ __forceinline__ void p2p_wait(const P2PComm &c, unsigned long long seq) {
+    if ((int)threadIdx.x < c.world) {
+        const unsigned long long *f = &c.flags[c.rank][(seq & 1) * c.world + threadIdx.x];
+        const long long t0 = clock64();
+        while (ld_acquire_sys(f) < seq) {
+            if (clock64() - t0 > 8000000000LL) { *c.error = 1; break; }
+        }
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ double p2p_sum(const P2PComm &c, unsigned long long seq, int e) {
+    const double *base = c.slots[c.rank] + (size_t)(seq & 1) * c.world * c.P;
+    double s = base[e];
+    for (int r = 1; r < c.world; ++r) s += base[(size_t)r * c.P + e];     // fixed rank order: identical on all ranks
+    return s;
+}
+
+// all-reduce receive + finalise for a stand-alone FVP (every block waits on the local flags itself)
+__global__ void k_fvp_finalise_p2p(const double *__restrict__ v, double *__restrict__ out, int logstd_off,
+                                   double n_total, double damping, const P2PComm c) {
+    const unsigned long long seq = *c.seq_dev + 1;
+    p2p_wait(c, seq);
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= c.P) return;
+    const double mean = (e >= logstd_off) ? 2.0 * v[e] : p2p_sum(c, seq, e) / n_total;
+    out[e] = mean + damping * v[e];
+}
+__global__ void k_seq_bump(unsigned long long *seq_dev) { *seq_dev += 1; }
 
 __global__ void k_fvp_finalise(const double *__restrict__ zsum, const double *__restrict__ v, double *__restrict__ out,
                                int P, int logstd_off, double n_total, double damping) {
@@ -78,17 +149,22 @@ __global__ void __launch_bounds__(CG_THREADS) k_cg_init(const double *__restrict
     }
 }
 
+// P2P: the cross-GPU sum is formed here, from the slots the peers pushed into this GPU's memory (all-reduce receive
+// fused into the CG update); otherwise zsum already holds the (NCCL- or single-GPU) sum.
+template <bool P2P>
 __global__ void __launch_bounds__(CG_THREADS) k_cg_update(const double *__restrict__ zsum, double *__restrict__ x,
                                                           double *__restrict__ r, double *__restrict__ p,
                                                           double *__restrict__ z, int P, int logstd_off, double n_total,
-                                                          double damping, double residual_th, CgState *st) {
+                                                          double damping, double residual_th, CgState *st, const P2PComm c) {
     if (st->done) return;
     __shared__ double red[32];
+    unsigned long long seq = 0;
+    if (P2P) { seq = *c.seq_dev + 1; p2p_wait(c, seq); }
     const double rdotr = st->rdotr;
     double acc = 0.0;
     for (int i = threadIdx.x; i < P; i += blockDim.x) {
         const double pi = p[i];
-        const double mean = (i >= logstd_off) ? 2.0 * pi : zsum[i] / n_total;
+        const double mean = (i >= logstd_off) ? 2.0 * pi : (P2P ? p2p_sum(c, seq, i) : zsum[i]) / n_total;
         const double zi = mean + damping * pi;
         z[i] = zi;
         acc += pi * zi;
@@ -113,6 +189,7 @@ __global__ void __launch_bounds__(CG_THREADS) k_cg_update(const double *__restri
         st->rdotr = newrdotr; st->pdotz = pdotz; st->xnorm = sqrt(xx);
         if (it < 34) { st->trace_rdotr[it] = newrdotr; st->trace_xnorm[it] = sqrt(xx); }
         if (newrdotr < residual_th) st->done = 1;
+        if (P2P) *c.seq_dev = seq;
     }
 }
 
@@ -173,13 +250,20 @@ constexpr int SUM_BLOCKS = 592;   // 4 x 148 SMs
 }  // namespace
 
 void launch_reduce_partials(const double *d_partial, int rows, int P, double *d_zsum, const int *d_done,
-                            cudaStream_t st, long long *launches) {
-    k_reduce_partials<<<(P + 127) / 128, 128, 0, st>>>(d_partial, rows, P, d_zsum, d_done);
+                            const P2PComm *p2p, cudaStream_t st, long long *launches) {
+    if (p2p && p2p->world > 1) k_reduce_partials_push<<<(P + 127) / 128, 128, 0, st>>>(d_partial, rows, d_zsum, d_done, *p2p);
+    else k_reduce_partials<<<(P + 127) / 128, 128, 0, st>>>(d_partial, rows, P, d_zsum, d_done);
     ++*launches;
 }
 
 void launch_fvp_finalise(const double *d_zsum, const double *d_v, double *d_out, int P, int logstd_off,
-                         double n_total, double damping, cudaStream_t st, long long *launches) {
+                         double n_total, double damping, const P2PComm *p2p, cudaStream_t st, long long *launches) {
+    if (p2p && p2p->world > 1) {
+        k_fvp_finalise_p2p<<<(P + 255) / 256, 256, 0, st>>>(d_v, d_out, logstd_off, n_total, damping, *p2p);
+        k_seq_bump<<<1, 1, 0, st>>>(p2p->seq_dev);
+        *launches += 2;
+        return;
+    }
     k_fvp_finalise<<<(P + 255) / 256, 256, 0, st>>>(d_zsum, d_v, d_out, P, logstd_off, n_total, damping);
     ++*launches;
 }
@@ -191,9 +275,12 @@ void launch_cg_init(const double *d_b, double *d_x, double *d_r, double *d_p, in
 }
 
 void launch_cg_update(const double *d_zsum, double *d_x, double *d_r, double *d_p, double *d_z, int P, int logstd_off,
-                      double n_total, double damping, double residual_th, CgState *d_state,
+                      double n_total, double damping, double residual_th, CgState *d_state, const P2PComm *p2p,
                       cudaStream_t st, long long *launches) {
-    k_cg_update<<<1, CG_THREADS, 0, st>>>(d_zsum, d_x, d_r, d_p, d_z, P, logstd_off, n_total, damping, residual_th, d_state);
+    if (p2p && p2p->world > 1)
+        k_cg_update<true><<<1, CG_THREADS, 0, st>>>(d_zsum, d_x, d_r, d_p, d_z, P, logstd_off, n_total, damping, residual_th, d_state, *p2p);
+    else
+        k_cg_update<false><<<1, CG_THREADS, 0, st>>>(d_zsum, d_x, d_r, d_p, d_z, P, logstd_off, n_total, damping, residual_th, d_state, P2PComm{});
     ++*launches;
 }
 

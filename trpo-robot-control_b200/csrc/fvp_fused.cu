@@ -322,11 +322,11 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_fvp_fused(const FusedArgs p)
                         bv[cc] = VW1s[(b * NT2 + c0 + cc) * 64 + sf[r]];
                     }
 #pragma unroll
-                    for (int cc = 0; cc < GRP; ++cc) dmma(x2[cc], y1[b][r], bw[cc]);
-#pragma unroll
-                    for (int cc = 0; cc < GRP; ++cc) dmma(rx2[cc], ry1[b][r], bw[cc]);
-#pragma unroll
-                    for (int cc = 0; cc < GRP; ++cc) dmma(rx2[cc], y1[b][r], bv[cc]);
+                    for (int cc = 0; cc < GRP; ++cc) {
+                        dmma(rx2[cc], ry1[b][r], bw[cc]);
+                        dmma(x2[cc], y1[b][r], bw[cc]);
+                        dmma(rx2[cc], y1[b][r], bv[cc]);
+                    }
                 }
             activate_tiles<ACT2, 0, GRP>(p.act2, x2, rx2);
 #pragma unroll
@@ -536,7 +536,7 @@ int fused_partial_rows() { return FUSED_MAX_ROWS; }
 
 int fused_fvp_accumulate(const NetDesc &net, const double *d_theta, const double *d_v, const double *d_inv_var,
                          const double *d_obs, size_t nsamples, double *d_partial, double *d_zsum,
-                         const int *d_done, cudaStream_t st, long long *launches) {
+                         const int *d_done, const P2PComm *p2p, cudaStream_t st, long long *launches) {
     const FusedShape shape = pick_shape(net);
     if (shape == SHAPE_NONE) return 1;
     FusedArgs a;
@@ -555,6 +555,6 @@ int fused_fvp_accumulate(const NetDesc &net, const double *d_theta, const double
     }
     if (rc) return -1;
     ++*launches;
-    launch_reduce_partials(d_partial, rows, net.P, d_zsum, d_done, st, launches);
+    launch_reduce_partials(d_partial, rows, net.P, d_zsum, d_done, p2p, st, launches);
     return 0;
 }

@@ -271,7 +271,8 @@ size_t chain_scratch_bytes(const NetDesc &net, int chunk, int nslices) {
 int chain_accumulate(const NetDesc &net, const ChainScratch &sc, ChainMode mode,
                      const double *d_theta, const double *d_v, const double *d_inv_var,
                      const double *d_obs, const double *d_mean, const double *d_action, const double *d_adv,
-                     size_t nsamples, double *d_zsum, const int *d_done, cudaStream_t st, long long *launches) {
+                     size_t nsamples, double *d_zsum, const int *d_done, const P2PComm *p2p, cudaStream_t st,
+                     long long *launches) {
     const int K = net.K, A = net.L[K];
     const bool fvp = (mode == CHAIN_FVP);
     int chunk_idx = 0;
@@ -326,7 +327,7 @@ int chain_accumulate(const NetDesc &net, const ChainScratch &sc, ChainMode mode,
             }
         }
     }
-    launch_reduce_partials(sc.partial, sc.nslices, net.P, d_zsum, d_done, st, launches);
+    launch_reduce_partials(sc.partial, sc.nslices, net.P, d_zsum, d_done, p2p, st, launches);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 

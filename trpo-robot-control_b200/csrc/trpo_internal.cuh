@@ -41,13 +41,30 @@ struct ChainScratch {
 
 enum ChainMode { CHAIN_FVP = 0, CHAIN_PG = 1 };
 
+// Peer-memory all-reduce state (one process per GPU, buffers exchanged as CUDA IPC handles). Every rank owns
+//   slots[2][world][P] doubles  and  flags[2][world] sequence numbers;
+// rank s PUSHES its un-normalised FVP sum into slots[parity][s] of every rank over NVLink and then publishes the
+// sequence number into flags[parity][s]; the consumer (CG update / FVP finalise) waits on its LOCAL flags and sums the
+// world slots in rank order, so every rank forms bitwise the same sum. world == 0 means "not in use".
+#define TRPO_MAX_RANKS 8
+struct P2PComm {
+    int world, rank;
+    double *slots[TRPO_MAX_RANKS];               // slots[r]: base of rank r's slot area (peer-mapped; own for r == rank)
+    unsigned long long *flags[TRPO_MAX_RANKS];   // flags[r]: base of rank r's flag area
+    unsigned long long *seq_dev;                 // completed all-reduces (local, advanced by the consumer)
+    unsigned int *block_counter;                 // last-block detection of the push kernel (local)
+    int *error;                                  // set when a wait timed out (local)
+    int P;
+};
+
 // ---- gemm_chain.cu ------------------------------------------------------------------------------------------------
 // Enqueue the whole un-normalised sum  zsum[0..P) = sum_n per-sample [RGW,RGB,...] (FVP) or [GW,GB,...,GLogStd] (PG).
 // The LogStd block of zsum is written by the finalise step, not here (FVP) / by the seed kernel (PG).
 int chain_accumulate(const NetDesc &net, const ChainScratch &sc, ChainMode mode,
                      const double *d_theta, const double *d_v, const double *d_inv_var,
                      const double *d_obs, const double *d_mean, const double *d_action, const double *d_adv,
-                     size_t nsamples, double *d_zsum, const int *d_done, cudaStream_t st, long long *launches);
+                     size_t nsamples, double *d_zsum, const int *d_done, const P2PComm *p2p, cudaStream_t st,
+                     long long *launches);
 // Forward only: writes the policy mean of every sample of [s0, s0+n) into d_out [n x A].
 int chain_forward(const NetDesc &net, const ChainScratch &sc, const double *d_theta, const double *d_obs,
                   size_t nsamples, double *d_mean_out, cudaStream_t st, long long *launches);
@@ -60,18 +77,19 @@ bool fused_eligible(const NetDesc &net);
 int  fused_partial_rows();     // number of per-CTA partial rows the fused kernel writes
 int  fused_fvp_accumulate(const NetDesc &net, const double *d_theta, const double *d_v, const double *d_inv_var,
                           const double *d_obs, size_t nsamples, double *d_partial, double *d_zsum,
-                          const int *d_done, cudaStream_t st, long long *launches);
+                          const int *d_done, const P2PComm *p2p, cudaStream_t st, long long *launches);
 
 // ---- cg_kernels.cu ------------------------------------------------------------------------------------------------
+// p2p != NULL: the fixed-order row sum is pushed straight into every rank's slot (fused reduce + all-reduce send)
 void launch_reduce_partials(const double *d_partial, int rows, int P, double *d_zsum, const int *d_done,
-                            cudaStream_t st, long long *launches);
+                            const P2PComm *p2p, cudaStream_t st, long long *launches);
 // z = zsum/N + damping*v (LogStd block: 2v + damping*v), standalone FVP finalise (TRPO_FVP.c:928-931)
 void launch_fvp_finalise(const double *d_zsum, const double *d_v, double *d_out, int P, int logstd_off,
-                         double n_total, double damping, cudaStream_t st, long long *launches);
+                         double n_total, double damping, const P2PComm *p2p, cudaStream_t st, long long *launches);
 void launch_cg_init(const double *d_b, double *d_x, double *d_r, double *d_p, int P, double residual_th,
                     CgState *d_state, cudaStream_t st, long long *launches);
 void launch_cg_update(const double *d_zsum, double *d_x, double *d_r, double *d_p, double *d_z, int P, int logstd_off,
-                      double n_total, double damping, double residual_th, CgState *d_state,
+                      double n_total, double damping, double residual_th, CgState *d_state, const P2PComm *p2p,
                       cudaStream_t st, long long *launches);
 // out[0] = sum_i a[i]*b[i] with the same fixed-order reduction (used for shs, gnorm, b.x)
 void launch_dot(const double *d_a, const double *d_b, int n, double *d_out, cudaStream_t st, long long *launches);

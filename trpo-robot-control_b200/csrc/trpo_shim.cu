@@ -92,6 +92,11 @@ struct trpo_ctx {
     // comm
     ncclComm_t comm;
     int rank, world;
+    // peer-memory all-reduce
+    P2PComm p2p;               // world == 0 until attached
+    bool p2p_on;
+    char *p2p_buf;             // own communication buffer (header + slots)
+    void *p2p_peer[TRPO_MAX_RANKS];
     trpo_info info;
 };
 
@@ -190,6 +195,8 @@ extern "C" void trpo_ctx_destroy(trpo_ctx *c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    for (int r = 0; r < TRPO_MAX_RANKS; ++r) if (c->p2p_peer[r]) cudaIpcCloseMemHandle(c->p2p_peer[r]);
+    if (c->p2p_buf) cudaFree(c->p2p_buf);
     free_batch(c);
     double *vecs[] = {c->d_theta, c->d_in, c->d_out, c->d_zsum, c->d_x, c->d_r, c->d_p, c->d_z, c->d_b, c->d_xnew,
                       c->d_inv_var, c->d_std, c->d_scal, c->d_blockpart, c->d_mean_new, c->sc_base, c->d_fused_partial};
@@ -300,6 +307,8 @@ extern "C" int trpo_ctx_set_batch_device(trpo_ctx *c, size_t N, const double *dO
 }
 
 // --------------------------------------------------------------------------------------------------------------
+static inline const P2PComm *active_p2p(const trpo_ctx *c) { return (c->p2p_on && c->p2p.world > 1) ? &c->p2p : nullptr; }
+
 extern "C" int trpo_ctx_kernel_timing(trpo_ctx *c, int enable) {
     if (!c) return fail("null context");
     CU(cudaSetDevice(c->device));
@@ -335,16 +344,16 @@ static int fvp_sum(trpo_ctx *c, const double *d_v, const int *d_done) {
     if (timed) cudaEventRecord(c->ktime_ev[2 * c->ktime_n], c->stream);
     if (path == TRPO_PATH_FUSED) {
         if (fused_fvp_accumulate(c->net, c->d_theta, d_v, c->d_inv_var, c->d_obs, c->n_local, c->d_fused_partial,
-                                 c->d_zsum, d_done, c->stream, &c->launches))
+                                 c->d_zsum, d_done, active_p2p(c), c->stream, &c->launches))
             return fail("fused FVP launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     } else {
         if (ensure_chain_scratch(c)) return -1;
         if (chain_accumulate(c->net, c->sc, CHAIN_FVP, c->d_theta, d_v, c->d_inv_var, c->d_obs, nullptr, nullptr, nullptr,
-                             c->n_local, c->d_zsum, d_done, c->stream, &c->launches))
+                             c->n_local, c->d_zsum, d_done, active_p2p(c), c->stream, &c->launches))
             return fail("gemm-chain FVP launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
     if (timed) { cudaEventRecord(c->ktime_ev[2 * c->ktime_n + 1], c->stream); ++c->ktime_n; }
-    if (c->comm) NC(g_nccl.AllReduce(c->d_zsum, c->d_zsum, c->net.P, ncclFloat64_, ncclSum_, c->comm, c->stream));
+    if (c->comm && !active_p2p(c)) NC(g_nccl.AllReduce(c->d_zsum, c->d_zsum, c->net.P, ncclFloat64_, ncclSum_, c->comm, c->stream));
     return 0;
 }
 
@@ -352,7 +361,7 @@ extern "C" int trpo_ctx_fvp_device(trpo_ctx *c, const double *dInput, double *dR
     if (!c || !dInput || !dResult) return fail("null argument");
     CU(cudaSetDevice(c->device));
     if (fvp_sum(c, dInput, nullptr)) return -1;
-    launch_fvp_finalise(c->d_zsum, dInput, dResult, c->net.P, c->net.logstd_off, (double)c->n_total, damping, c->stream, &c->launches);
+    launch_fvp_finalise(c->d_zsum, dInput, dResult, c->net.P, c->net.logstd_off, (double)c->n_total, damping, active_p2p(c), c->stream, &c->launches);
     CU(cudaGetLastError());
     return 0;
 }
@@ -365,7 +374,7 @@ extern "C" int trpo_ctx_cg_device(trpo_ctx *c, const double *db, double *dResult
     for (size_t it = 0; it < MaxIter; ++it) {
         if (fvp_sum(c, c->d_p, &c->d_state->done)) return -1;
         launch_cg_update(c->d_zsum, c->d_x, c->d_r, c->d_p, c->d_z, c->net.P, c->net.logstd_off, (double)c->n_total, damping,
-                         ResidualTh, c->d_state, c->stream, &c->launches);
+                         ResidualTh, c->d_state, active_p2p(c), c->stream, &c->launches);
     }
     CU(cudaMemcpyAsync(dResult, c->d_x, c->net.P * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
     CU(cudaGetLastError());
@@ -413,11 +422,11 @@ static int policy_gradient_device(trpo_ctx *c) {
     if (!c->d_obs || !c->d_mean || !c->d_action || !c->d_adv) return fail("policy gradient needs Mean/Action/Advantage in the batch");
     if (ensure_chain_scratch(c)) return -1;
     if (chain_accumulate(c->net, c->sc, CHAIN_PG, c->d_theta, nullptr, nullptr, c->d_obs, c->d_mean, c->d_action, c->d_adv,
-                         c->n_local, c->d_zsum, nullptr, c->stream, &c->launches))
+                         c->n_local, c->d_zsum, nullptr, nullptr, c->stream, &c->launches))
         return fail("policy-gradient launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     if (c->comm) NC(g_nccl.AllReduce(c->d_zsum, c->d_zsum, c->net.P, ncclFloat64_, ncclSum_, c->comm, c->stream));
     // b = zsum / N: same kernel as the FVP finalise with no damping and no LogStd special case
-    launch_fvp_finalise(c->d_zsum, c->d_zsum, c->d_b, c->net.P, c->net.P, (double)c->n_total, 0.0, c->stream, &c->launches);
+    launch_fvp_finalise(c->d_zsum, c->d_zsum, c->d_b, c->net.P, c->net.P, (double)c->n_total, 0.0, nullptr, c->stream, &c->launches);
     return 0;
 }
 
@@ -526,6 +535,72 @@ extern "C" int trpo_ctx_init_comm(trpo_ctx *c, const char id[128], int rank, int
     c->rank = rank; c->world = world;
     if (c->n_local) return update_global_samples(c);
     return 0;
+}
+
+// ---- peer-memory all-reduce plumbing ------------------------------------------------------------------------
+// buffer layout: [0,256) flags[2][8] u64 | 256: seq_dev u64 | 264: block_counter u32 | 268: error i32 | 1024: slots[2][world][P]
+#define P2P_HDR 1024
+extern "C" int trpo_ctx_p2p_export(trpo_ctx *c, char handle_out[64]) {
+    if (!c || !handle_out) return fail("null argument");
+    if (c->world < 2) return fail("trpo_ctx_init_comm with world_size >= 2 first");
+    if (c->world > TRPO_MAX_RANKS) return fail("peer-memory all-reduce supports at most %d ranks", TRPO_MAX_RANKS);
+    CU(cudaSetDevice(c->device));
+    if (!c->p2p_buf) {
+        const size_t bytes = P2P_HDR + sizeof(double) * 2 * (size_t)c->world * c->net.P;
+        CU(cudaMalloc(&c->p2p_buf, bytes));
+        CU(cudaMemset(c->p2p_buf, 0, bytes));
+        CU(cudaDeviceSynchronize());
+    }
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, c->p2p_buf));
+    static_assert(sizeof(h) == 64, "CUDA IPC handle size");
+    memcpy(handle_out, &h, 64);
+    return 0;
+}
+
+extern "C" int trpo_ctx_p2p_attach(trpo_ctx *c, const char *handles) {
+    if (!c || !handles) return fail("null argument");
+    if (!c->p2p_buf) return fail("call trpo_ctx_p2p_export first");
+    CU(cudaSetDevice(c->device));
+    memset(&c->p2p, 0, sizeof(c->p2p));
+    for (int r = 0; r < c->world; ++r) {
+        char *base;
+        if (r == c->rank) base = c->p2p_buf;
+        else {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, handles + 64 * r, 64);
+            void *ptr = nullptr;
+            CU(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+            c->p2p_peer[r] = ptr;
+            base = (char *)ptr;
+        }
+        c->p2p.flags[r] = (unsigned long long *)base;
+        c->p2p.slots[r] = (double *)(base + P2P_HDR);
+    }
+    c->p2p.seq_dev = (unsigned long long *)(c->p2p_buf + 256);
+    c->p2p.block_counter = (unsigned int *)(c->p2p_buf + 264);
+    c->p2p.error = (int *)(c->p2p_buf + 268);
+    c->p2p.world = c->world;
+    c->p2p.rank = c->rank;
+    c->p2p.P = c->net.P;
+    c->p2p_on = true;
+    return 0;
+}
+
+extern "C" int trpo_ctx_set_comm_mode(trpo_ctx *c, int mode) {
+    if (!c) return fail("null context");
+    if (mode == TRPO_COMM_P2P && c->p2p.world < 2) return fail("peer buffers are not attached");
+    c->p2p_on = (mode == TRPO_COMM_P2P);
+    return 0;
+}
+
+extern "C" int trpo_ctx_comm_error(trpo_ctx *c) {
+    if (!c || !c->p2p_buf) return 0;
+    int e = 0;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    cudaMemcpy(&e, c->p2p_buf + 268, sizeof(int), cudaMemcpyDeviceToHost);
+    return e;
 }
 
 extern "C" size_t trpo_ctx_global_samples(const trpo_ctx *c) { return c ? c->n_total : 0; }
