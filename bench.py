@@ -336,7 +336,7 @@ def main():
     ap.add_argument("--states", type=int, default=0, help="override the number of synthetic states")
     ap.add_argument("--path", default="", choices=["", "chain", "fused"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"],
+    ap.add_argument("--comm", default="nccl", choices=["p2p", "nccl"],
                     help="multi-GPU FVP-sum all-reduce: fused NVLink peer-memory kernels (default) or ncclAllReduce")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

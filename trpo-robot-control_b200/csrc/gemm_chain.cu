@@ -7,12 +7,21 @@
 //   outer    (per layer i)   [RGW_{i-1};RGB_{i-1}] += [Y_{i-1},1]^T * G_i   (split-K over sample slices)            (:890-921)
 // The flat parameter layout already stores [W_i;B_i] as one (L_i+1) x L_{i+1} row-major matrix, so the bias is the
 // "ones" row of the augmented operand and no packing is needed.
+//
+// All three are one tiled GEMM on the FP64 tensor pipe (DMMA.8x8x4): CTA tile 128 x 64, k-step 16, 8 warps of 32 x 32
+// (4 x 4 MMA tiles), operands staged by 8-byte cp.async (zero-filled at the ragged edges, so odd sizes such as 15, 17,
+// 376 need no padding in HBM) into a double-buffered shared tile whose row strides (20 / 68 doubles) make every
+// fragment read bank-conflict-free. The forward kernel carries two accumulator sets (x and R{x}) and issues the three
+// products of the R-op per fragment pair; tanh runs branch-free on 8 values in lock step (dmma_common.cuh).
 // Determinism: every output element has exactly one owner thread per (slice); slices are summed in fixed order.
 #include "trpo_internal.cuh"
+#include "dmma_common.cuh"
 
 namespace {
 
-constexpr int BM = 64, BN = 64, BK = 16, TM = 4, TN = 4, NT = 256;
+constexpr int BM = 128, BN = 64, BK = 16, NT = 256;
+constexpr int RSA = 20, RSB = 68;                       // shared row strides: % 16 == 4 -> conflict-free fragment reads
+constexpr int A_TILE = BM * RSA, B_TILE = BK * RSB;     // doubles per operand tile
 
 __device__ __forceinline__ double act_apply(char a, double x) {
     switch (a) {
@@ -31,215 +40,257 @@ __device__ __forceinline__ double act_deriv(char a, double y) {   // f'(x) expre
     }
 }
 
-// A-tile loader for row-major activations X[rows x ld]: As[k][m] = X[(m0+m)*ld + k0+k]; k == ld -> ones_val.
-__device__ __forceinline__ void load_act_tile(double (*As)[BM], const double *X, int rows, int ld, int m0, int k0,
-                                              double ones_val, int tid) {
-    const int m = tid >> 2, ks = (tid & 3) * 4;
-    const int gm = m0 + m;
+// ---- tile loaders (all 256 threads; 8-byte cp.async, src-size 0 = zero fill) --------------------------------------
+// A tile from row-major activations X[rows x ld]: As[m][k] = X[(m0+m)*ld + k0+k]; column k == ld is the augmented
+// "ones" column (value ones_val) when aug is set.
+__device__ __forceinline__ void load_a_rowmajor(double *As, const double *X, int rows, int ld, int m0, int k0,
+                                                bool aug, double ones_val, int tid) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const int gk = k0 + ks + q;
-        double v = 0.0;
-        if (gm < rows) {
-            if (gk < ld) v = X ? X[(size_t)gm * ld + gk] : 0.0;
-            else if (gk == ld) v = ones_val;
-        }
-        As[ks + q][m] = v;
+    for (int it = 0; it < BM * BK / NT; ++it) {
+        const int idx = tid + it * NT, m = idx >> 4, k = idx & 15;
+        const int gm = m0 + m, gk = k0 + k;
+        const bool in = X != nullptr && gm < rows && gk < ld;
+        if (aug && gk == ld && gm < rows) As[m * RSA + k] = ones_val;
+        else cp_async8(&As[m * RSA + k], in ? &X[(size_t)gm * ld + gk] : X, in ? 8 : 0);
+    }
+}
+// A tile for the outer product: As[m][k] = Yprev[(s0+k)*M0 + m0+m] for m < M0, 1.0 for m == M0 (bias-gradient row)
+__device__ __forceinline__ void load_a_transposed(double *As, const double *Y, int s_end, int M0, int m0, int s0, int tid) {
+#pragma unroll
+    for (int it = 0; it < BM * BK / NT; ++it) {
+        const int idx = tid + it * NT, k = idx >> 7, m = idx & 127;
+        const int gm = m0 + m, gs = s0 + k;
+        const bool in = Y != nullptr && gm < M0 && gs < s_end;
+        if (gm == M0 && gs < s_end) As[m * RSA + k] = 1.0;
+        else cp_async8(&As[m * RSA + k], in ? &Y[(size_t)gs * M0 + gm] : Y, in ? 8 : 0);
+    }
+}
+// B tile from a row-major matrix M[kdim x N]: Bs[k][n] = M[(k0+k)*N + n0+n]
+__device__ __forceinline__ void load_b_rowmajor(double *Bs, const double *M, int kdim, int N, int k0, int n0, int tid) {
+#pragma unroll
+    for (int it = 0; it < BK * BN / NT; ++it) {
+        const int idx = tid + it * NT, k = idx >> 6, n = idx & 63;
+        const int gk = k0 + k, gn = n0 + n;
+        const bool in = gk < kdim && gn < N;
+        cp_async8(&Bs[k * RSB + n], in ? &M[(size_t)gk * N + gn] : M, in ? 8 : 0);
+    }
+}
+// B tile from W[N x Kd] row-major used transposed: Bs[k][n] = W[(n0+n)*Kd + k0+k]
+__device__ __forceinline__ void load_b_transposed(double *Bs, const double *W, int Kd, int N, int k0, int n0, int tid) {
+#pragma unroll
+    for (int it = 0; it < BK * BN / NT; ++it) {
+        const int idx = tid + it * NT, n = idx >> 4, k = idx & 15;
+        const int gk = k0 + k, gn = n0 + n;
+        const bool in = gk < Kd && gn < N;
+        cp_async8(&Bs[k * RSB + n], in ? &W[(size_t)gn * Kd + gk] : W, in ? 8 : 0);
     }
 }
 
-// B-tile loader for a row-major matrix M[kdim x N]: Bs[k][n] = M[(k0+k)*N + n0+n]
-__device__ __forceinline__ void load_rowmajor_tile(double (*Bs)[BN], const double *M, int kdim, int N, int k0, int n0, int tid) {
-    const int k = tid >> 4, ns = (tid & 15) * 4;
-    const int gk = k0 + k;
+// one k-step (16) of a warp's 32 x 32 sub-tile: acc += A*B [, racc += RA*B + A*VB]
+template <bool DUAL, bool HAS_RA>
+__device__ __forceinline__ void mma_stage(double (&acc)[4][4][2], double (&racc)[4][4][2], const double *As,
+                                          const double *RAs, const double *Bs, const double *VBs, int wm, int wn, int g, int t) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const int gn = n0 + ns + q;
-        Bs[k][ns + q] = (gk < kdim && gn < N) ? M[(size_t)gk * N + gn] : 0.0;
+    for (int q = 0; q < BK / 4; ++q) {
+        double a[4], ra[4], b[4], vb[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            a[i] = As[(32 * wm + 8 * i + g) * RSA + 4 * q + t];
+            if (DUAL && HAS_RA) ra[i] = RAs[(32 * wm + 8 * i + g) * RSA + 4 * q + t];
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            b[j] = Bs[(4 * q + t) * RSB + 32 * wn + 8 * j + g];
+            if (DUAL) vb[j] = VBs[(4 * q + t) * RSB + 32 * wn + 8 * j + g];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (DUAL && HAS_RA) dmma(racc[i][j], ra[i], b[j]);
+                dmma(acc[i][j], a[i], b[j]);
+                if (DUAL) dmma(racc[i][j], a[i], vb[j]);
+            }
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// forward: DUAL = also propagate R{} (FVP); otherwise ordinary forward only (policy gradient / line search).
-template <bool DUAL>
-__global__ void __launch_bounds__(NT) k_chain_fwd(const double *__restrict__ Yin, const double *__restrict__ RYin,
-                                                  const double *__restrict__ W, const double *__restrict__ VW,
-                                                  int rows, int Kd, int N, char act,
-                                                  double *__restrict__ Yout, double *__restrict__ RYout,
-                                                  double *__restrict__ Gout, const double *__restrict__ inv_var,
-                                                  const int *__restrict__ done) {
+// forward: DUAL = also propagate R{} (FVP); HAS_RA = the incoming R{y} is non-zero (false for layer 0).
+template <bool DUAL, bool HAS_RA>
+__global__ void __launch_bounds__(NT, 1) k_chain_fwd(const double *__restrict__ Yin, const double *__restrict__ RYin,
+                                                     const double *__restrict__ W, const double *__restrict__ VW,
+                                                     int rows, int Kd, int N, char act,
+                                                     double *__restrict__ Yout, double *__restrict__ RYout,
+                                                     double *__restrict__ Gout, const double *__restrict__ inv_var,
+                                                     const int *__restrict__ done) {
     if (done && *done) return;
-    __shared__ __align__(16) double As[BK][BM], Bs[BK][BN];
-    __shared__ __align__(16) double RAs[DUAL ? BK : 1][BM], VBs[DUAL ? BK : 1][BN];
-    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    extern __shared__ __align__(16) double smem[];
+    constexpr int STAGE = A_TILE * (DUAL && HAS_RA ? 2 : 1) + B_TILE * (DUAL ? 2 : 1);
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3, wm = w >> 1, wn = w & 1;
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
-    double ax[TM][TN] = {}, arx[TM][TN] = {};
-    for (int k0 = 0; k0 < Kd + 1; k0 += BK) {
-        load_act_tile(As, Yin, rows, Kd, m0, k0, 1.0, tid);
-        load_rowmajor_tile(Bs, W, Kd + 1, N, k0, n0, tid);
+    double acc[4][4][2] = {}, racc[4][4][2] = {};
+    const int nk = (Kd + 1 + BK - 1) / BK;              // augmented contraction length Kd + 1 (bias row)
+    auto stage_ptrs = [&](int st, double *&As, double *&RAs, double *&Bs, double *&VBs) {
+        double *p = smem + st * STAGE;
+        As = p; p += A_TILE;
+        RAs = p; if (DUAL && HAS_RA) p += A_TILE;
+        Bs = p; p += B_TILE;
+        VBs = p;
+    };
+    auto load = [&](int st, int k0) {
+        double *As, *RAs, *Bs, *VBs;
+        stage_ptrs(st, As, RAs, Bs, VBs);
+        load_a_rowmajor(As, Yin, rows, Kd, m0, k0, true, 1.0, tid);
+        load_b_rowmajor(Bs, W, Kd + 1, N, k0, n0, tid);
         if (DUAL) {
-            load_act_tile(RAs, RYin, rows, Kd, m0, k0, 0.0, tid);
-            load_rowmajor_tile(VBs, VW, Kd + 1, N, k0, n0, tid);
+            if (HAS_RA) load_a_rowmajor(RAs, RYin, rows, Kd, m0, k0, false, 0.0, tid);
+            load_b_rowmajor(VBs, VW, Kd + 1, N, k0, n0, tid);
         }
+        cp_async_commit();
+    };
+    load(0, 0);
+    for (int it = 0; it < nk; ++it) {
+        if (it + 1 < nk) { load((it + 1) & 1, (it + 1) * BK); cp_async_wait_group<1>(); }
+        else cp_async_wait_group<0>();
         __syncthreads();
-#pragma unroll
-        for (int kk = 0; kk < BK; ++kk) {
-            double a[TM], b[TN], ra[TM], vb[TN];
-#pragma unroll
-            for (int i = 0; i < TM; ++i) a[i] = As[kk][ty * TM + i];
-#pragma unroll
-            for (int j = 0; j < TN; ++j) b[j] = Bs[kk][tx * TN + j];
-            if (DUAL) {
-#pragma unroll
-                for (int i = 0; i < TM; ++i) ra[i] = RAs[kk][ty * TM + i];
-#pragma unroll
-                for (int j = 0; j < TN; ++j) vb[j] = VBs[kk][tx * TN + j];
-            }
-#pragma unroll
-            for (int i = 0; i < TM; ++i)
-#pragma unroll
-                for (int j = 0; j < TN; ++j) {
-                    ax[i][j] = fma(a[i], b[j], ax[i][j]);
-                    if (DUAL) {
-                        arx[i][j] = fma(ra[i], b[j], arx[i][j]);
-                        arx[i][j] = fma(a[i], vb[j], arx[i][j]);
-                    }
-                }
-        }
+        double *As, *RAs, *Bs, *VBs;
+        stage_ptrs(it & 1, As, RAs, Bs, VBs);
+        mma_stage<DUAL, HAS_RA>(acc, racc, As, RAs, Bs, VBs, wm, wn, g, t);
         __syncthreads();
     }
+    // epilogue: activation, R{y} = R{x} f'(x), last layer: R-gradient seed RG_K = Ry_K / sigma^2 * f' (TRPO_FVP.c:852-882)
 #pragma unroll
-    for (int i = 0; i < TM; ++i) {
-        const int gm = m0 + ty * TM + i;
+    for (int i = 0; i < 4; ++i) {
+        const int gm = m0 + 32 * wm + 8 * i + g;
+        double xv[8], dv[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { xv[2 * j] = acc[i][j][0]; xv[2 * j + 1] = acc[i][j][1]; }
+        if (act == 't') tanh_vec<8>(xv, dv);
+        else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { xv[e] = act_apply(act, xv[e]); dv[e] = act_deriv(act, xv[e]); }
+        }
         if (gm >= rows) continue;
 #pragma unroll
-        for (int j = 0; j < TN; ++j) {
-            const int gn = n0 + tx * TN + j;
-            if (gn >= N) continue;
-            const double y = act_apply(act, ax[i][j]);
-            const double d = act_deriv(act, y);
-            if (Yout) Yout[(size_t)gm * N + gn] = y;
-            if (DUAL) {
-                const double ry = arx[i][j] * d;
-                if (RYout) RYout[(size_t)gm * N + gn] = ry;
-                // last layer: R-gradient seed RG_K = Ry_K / sigma^2 (TRPO_FVP.c:852-854), already times f'(y_K) (:869-882)
-                if (Gout) Gout[(size_t)gm * N + gn] = ry * inv_var[gn] * d;
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int gn = n0 + 32 * wn + 8 * j + 2 * t + r;
+                if (gn >= N) continue;
+                const double y = xv[2 * j + r], d = dv[2 * j + r];
+                if (Yout) Yout[(size_t)gm * N + gn] = y;
+                if (DUAL) {
+                    const double ry = racc[i][j][r] * d;
+                    if (RYout) RYout[(size_t)gm * N + gn] = ry;
+                    if (Gout) Gout[(size_t)gm * N + gn] = ry * inv_var[gn] * d;
+                }
             }
-        }
     }
 }
 
 // backward: Gout[s][n] = f'(Yprev[s][n]) * sum_k Gin[s][k] * W[n][k]       (W is [N x Kd] row-major)
-__global__ void __launch_bounds__(NT) k_chain_bwd(const double *__restrict__ Gin, const double *__restrict__ W,
-                                                  const double *__restrict__ Yprev, int rows, int Kd, int N, char act_prev,
-                                                  double *__restrict__ Gout, const int *__restrict__ done) {
+__global__ void __launch_bounds__(NT, 1) k_chain_bwd(const double *__restrict__ Gin, const double *__restrict__ W,
+                                                     const double *__restrict__ Yprev, int rows, int Kd, int N, char act_prev,
+                                                     double *__restrict__ Gout, const int *__restrict__ done) {
     if (done && *done) return;
-    __shared__ __align__(16) double As[BK][BM], Bs[BK][BN];
-    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    extern __shared__ __align__(16) double smem[];
+    constexpr int STAGE = A_TILE + B_TILE;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3, wm = w >> 1, wn = w & 1;
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
-    double acc[TM][TN] = {};
-    for (int k0 = 0; k0 < Kd; k0 += BK) {
-        load_act_tile(As, Gin, rows, Kd, m0, k0, 0.0, tid);
-        {   // Bs[k][n] = W[(n0+n)*Kd + k0+k]: walk k contiguously, store transposed
-            const int n = tid >> 2, ks = (tid & 3) * 4, gn = n0 + n;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int gk = k0 + ks + q;
-                Bs[ks + q][n] = (gn < N && gk < Kd) ? W[(size_t)gn * Kd + gk] : 0.0;
-            }
-        }
+    double acc[4][4][2] = {}, dummy[4][4][2];
+    const int nk = (Kd + BK - 1) / BK;
+    auto load = [&](int st, int k0) {
+        double *As = smem + st * STAGE, *Bs = As + A_TILE;
+        load_a_rowmajor(As, Gin, rows, Kd, m0, k0, false, 0.0, tid);
+        load_b_transposed(Bs, W, Kd, N, k0, n0, tid);
+        cp_async_commit();
+    };
+    load(0, 0);
+    for (int it = 0; it < nk; ++it) {
+        if (it + 1 < nk) { load((it + 1) & 1, (it + 1) * BK); cp_async_wait_group<1>(); }
+        else cp_async_wait_group<0>();
         __syncthreads();
-#pragma unroll
-        for (int kk = 0; kk < BK; ++kk) {
-            double a[TM], b[TN];
-#pragma unroll
-            for (int i = 0; i < TM; ++i) a[i] = As[kk][ty * TM + i];
-#pragma unroll
-            for (int j = 0; j < TN; ++j) b[j] = Bs[kk][tx * TN + j];
-#pragma unroll
-            for (int i = 0; i < TM; ++i)
-#pragma unroll
-                for (int j = 0; j < TN; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
-        }
+        const double *As = smem + (it & 1) * STAGE, *Bs = As + A_TILE;
+        mma_stage<false, false>(acc, dummy, As, nullptr, Bs, nullptr, wm, wn, g, t);
         __syncthreads();
     }
 #pragma unroll
-    for (int i = 0; i < TM; ++i) {
-        const int gm = m0 + ty * TM + i;
+    for (int i = 0; i < 4; ++i) {
+        const int gm = m0 + 32 * wm + 8 * i + g;
         if (gm >= rows) continue;
 #pragma unroll
-        for (int j = 0; j < TN; ++j) {
-            const int gn = n0 + tx * TN + j;
-            if (gn >= N) continue;
-            const double d = act_deriv(act_prev, Yprev[(size_t)gm * N + gn]);
-            Gout[(size_t)gm * N + gn] = acc[i][j] * d;
-        }
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int gn = n0 + 32 * wn + 8 * j + 2 * t + r;
+                if (gn >= N) continue;
+                Gout[(size_t)gm * N + gn] = acc[i][j][r] * act_deriv(act_prev, Yprev[(size_t)gm * N + gn]);
+            }
     }
 }
 
 // outer: out[slice][m*N + n] (+)= sum_{s in slice} [Yprev,1][s][m] * G[s][n],  m in [0, M0]  (row M0 = bias gradient)
-__global__ void __launch_bounds__(NT) k_chain_outer(const double *__restrict__ Yprev, const double *__restrict__ G,
-                                                    int rows, int M0, int N, int per_slice, int tiles_n,
-                                                    double *__restrict__ partial, int P, int out_off, int accumulate,
-                                                    const int *__restrict__ done) {
+__global__ void __launch_bounds__(NT, 1) k_chain_outer(const double *__restrict__ Yprev, const double *__restrict__ G,
+                                                       int rows, int M0, int N, int per_slice, int tiles_n,
+                                                       double *__restrict__ partial, int P, int out_off, int accumulate,
+                                                       const int *__restrict__ done) {
     if (done && *done) return;
-    __shared__ __align__(16) double As[BK][BM], Bs[BK][BN];
-    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    extern __shared__ __align__(16) double smem[];
+    constexpr int STAGE = A_TILE + B_TILE;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3, wm = w >> 1, wn = w & 1;
     const int m0 = (blockIdx.x / tiles_n) * BM, n0 = (blockIdx.x % tiles_n) * BN;
     const int slice = blockIdx.y;
     const int s0 = slice * per_slice;
     const int s1 = min(rows, s0 + per_slice);
-    double acc[TM][TN] = {};
-    for (int k0 = s0; k0 < s1; k0 += BK) {
-        {   // As[k][m] = Yprev[(k0+k)*M0 + m0+m], ones at m == M0
-            const int k = tid >> 4, ms = (tid & 15) * 4, gs = k0 + k;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int gmm = m0 + ms + q;
-                double v = 0.0;
-                if (gs < s1) {
-                    if (gmm < M0) v = Yprev[(size_t)gs * M0 + gmm];
-                    else if (gmm == M0) v = 1.0;
-                }
-                As[k][ms + q] = v;
-            }
-        }
-        {
-            const int k = tid >> 4, ns = (tid & 15) * 4, gs = k0 + k;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int gn = n0 + ns + q;
-                Bs[k][ns + q] = (gs < s1 && gn < N) ? G[(size_t)gs * N + gn] : 0.0;
-            }
-        }
+    double acc[4][4][2] = {}, dummy[4][4][2];
+    const int nk = s1 > s0 ? (s1 - s0 + BK - 1) / BK : 0;
+    auto load = [&](int st, int ks) {
+        double *As = smem + st * STAGE, *Bs = As + A_TILE;
+        load_a_transposed(As, Yprev, s1, M0, m0, ks, tid);
+        load_b_rowmajor(Bs, G + (size_t)ks * N, s1 - ks, N, 0, n0, tid);
+        cp_async_commit();
+    };
+    if (nk) load(0, s0);
+    for (int it = 0; it < nk; ++it) {
+        if (it + 1 < nk) { load((it + 1) & 1, s0 + (it + 1) * BK); cp_async_wait_group<1>(); }
+        else cp_async_wait_group<0>();
         __syncthreads();
-#pragma unroll
-        for (int kk = 0; kk < BK; ++kk) {
-            double a[TM], b[TN];
-#pragma unroll
-            for (int i = 0; i < TM; ++i) a[i] = As[kk][ty * TM + i];
-#pragma unroll
-            for (int j = 0; j < TN; ++j) b[j] = Bs[kk][tx * TN + j];
-#pragma unroll
-            for (int i = 0; i < TM; ++i)
-#pragma unroll
-                for (int j = 0; j < TN; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
-        }
+        const double *As = smem + (it & 1) * STAGE, *Bs = As + A_TILE;
+        mma_stage<false, false>(acc, dummy, As, nullptr, Bs, nullptr, wm, wn, g, t);
         __syncthreads();
     }
     double *out = partial + (size_t)slice * P + out_off;
 #pragma unroll
-    for (int i = 0; i < TM; ++i) {
-        const int gm = m0 + ty * TM + i;
+    for (int i = 0; i < 4; ++i) {
+        const int gm = m0 + 32 * wm + 8 * i + g;
         if (gm > M0) continue;
 #pragma unroll
-        for (int j = 0; j < TN; ++j) {
-            const int gn = n0 + tx * TN + j;
-            if (gn >= N) continue;
-            const size_t o = (size_t)gm * N + gn;
-            out[o] = accumulate ? out[o] + acc[i][j] : acc[i][j];
-        }
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int gn = n0 + 32 * wn + 8 * j + 2 * t + r;
+                if (gn >= N) continue;
+                const size_t o = (size_t)gm * N + gn;
+                out[o] = accumulate ? out[o] + acc[i][j][r] : acc[i][j][r];
+            }
     }
+}
+
+constexpr size_t SMEM_FWD_DUAL = sizeof(double) * 2 * (2 * A_TILE + 2 * B_TILE);
+constexpr size_t SMEM_FWD_L0   = sizeof(double) * 2 * (A_TILE + 2 * B_TILE);
+constexpr size_t SMEM_SINGLE   = sizeof(double) * 2 * (A_TILE + B_TILE);
+
+bool configure_kernels() {
+    static bool ok = false;
+    if (ok) return true;
+    bool r = true;
+    r = r && cudaFuncSetAttribute(k_chain_fwd<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_FWD_DUAL) == cudaSuccess;
+    r = r && cudaFuncSetAttribute(k_chain_fwd<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_FWD_L0) == cudaSuccess;
+    r = r && cudaFuncSetAttribute(k_chain_fwd<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_SINGLE) == cudaSuccess;
+    r = r && cudaFuncSetAttribute(k_chain_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_SINGLE) == cudaSuccess;
+    r = r && cudaFuncSetAttribute(k_chain_outer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_SINGLE) == cudaSuccess;
+    ok = r;
+    return r;
 }
 
 // policy-gradient seed (TRPO_Update.c:297-301) followed by f'(y_K) (:310-324): G[s][j] and GL[s][j]
@@ -259,6 +310,15 @@ __global__ void k_pg_seed(const double *__restrict__ mean, const double *__restr
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
+// split-K slices of one outer-product GEMM: about two CTAs per SM in total, never more than the partial rows available.
+// Wide layers get few slices (each CTA then amortises its 128 x 64 partial-tile read-modify-write over many samples);
+// rows of the partial buffer a layer does not use stay zero from the allocation-time memset.
+inline int layer_slices(int tiles, int max_slices) {
+    int ns = cdiv(296, tiles);
+    if (ns > max_slices) ns = max_slices;
+    return ns < 1 ? 1 : ns;
+}
+
 }  // namespace
 
 size_t chain_scratch_bytes(const NetDesc &net, int chunk, int nslices) {
@@ -275,11 +335,11 @@ int chain_accumulate(const NetDesc &net, const ChainScratch &sc, ChainMode mode,
                      long long *launches) {
     const int K = net.K, A = net.L[K];
     const bool fvp = (mode == CHAIN_FVP);
+    if (!configure_kernels()) return -1;
     int chunk_idx = 0;
     for (size_t c0 = 0; c0 < nsamples; c0 += sc.chunk, ++chunk_idx) {
         const int rows = (int)((nsamples - c0 < (size_t)sc.chunk) ? nsamples - c0 : sc.chunk);
         const int accumulate = chunk_idx > 0;
-        const int per_slice = cdiv(cdiv(rows, sc.nslices), BK) * BK;
         // ---- forward ----
         for (int i = 0; i < K; ++i) {
             const double *Yin = (i == 0) ? d_obs + c0 * net.L[0] : sc.Y[i];
@@ -288,12 +348,18 @@ int chain_accumulate(const NetDesc &net, const ChainScratch &sc, ChainMode mode,
             if (fvp) {
                 const double *RYin = (i == 0) ? nullptr : sc.RY[i & 1];
                 const bool needY = !last || net.ac[K] == 't' || net.ac[K] == 's';
-                k_chain_fwd<true><<<grid, NT, 0, st>>>(Yin, RYin, d_theta + net.w_off[i], d_v + net.w_off[i], rows,
+                if (i == 0)
+                    k_chain_fwd<true, false><<<grid, NT, SMEM_FWD_L0, st>>>(Yin, nullptr, d_theta + net.w_off[i], d_v + net.w_off[i], rows,
+                                                      net.L[i], net.L[i + 1], net.ac[i + 1],
+                                                      needY ? sc.Y[i + 1] : nullptr, last ? nullptr : sc.RY[(i + 1) & 1],
+                                                      last ? sc.G[K & 1] : nullptr, d_inv_var, d_done);
+                else
+                    k_chain_fwd<true, true><<<grid, NT, SMEM_FWD_DUAL, st>>>(Yin, RYin, d_theta + net.w_off[i], d_v + net.w_off[i], rows,
                                                       net.L[i], net.L[i + 1], net.ac[i + 1],
                                                       needY ? sc.Y[i + 1] : nullptr, last ? nullptr : sc.RY[(i + 1) & 1],
                                                       last ? sc.G[K & 1] : nullptr, d_inv_var, d_done);
             } else {
-                k_chain_fwd<false><<<grid, NT, 0, st>>>(Yin, nullptr, d_theta + net.w_off[i], nullptr, rows,
+                k_chain_fwd<false, false><<<grid, NT, SMEM_SINGLE, st>>>(Yin, nullptr, d_theta + net.w_off[i], nullptr, rows,
                                                        net.L[i], net.L[i + 1], net.ac[i + 1], sc.Y[i + 1], nullptr,
                                                        nullptr, nullptr, d_done);
             }
@@ -305,9 +371,10 @@ int chain_accumulate(const NetDesc &net, const ChainScratch &sc, ChainMode mode,
             k_pg_seed<<<cdiv(n, 256), 256, 0, st>>>(d_mean + c0 * A, d_action + c0 * A, d_adv + c0, d_theta + net.logstd_off,
                                                     sc.Y[K], net.ac[K], rows, A, sc.G[K & 1], sc.RY[0]);
             ++*launches;
-            dim3 g1(cdiv(1, BM) * cdiv(A, BN), sc.nslices);
-            k_chain_outer<<<g1, NT, 0, st>>>(nullptr, sc.RY[0], rows, 0, A, per_slice, cdiv(A, BN), sc.partial, net.P,
-                                             net.logstd_off, accumulate, d_done);
+            const int tl = cdiv(1, BM) * cdiv(A, BN), nsl = layer_slices(tl, sc.nslices);
+            dim3 g1(tl, nsl);
+            k_chain_outer<<<g1, NT, SMEM_SINGLE, st>>>(nullptr, sc.RY[0], rows, 0, A, cdiv(cdiv(rows, nsl), BK) * BK, cdiv(A, BN),
+                                             sc.partial, net.P, net.logstd_off, accumulate, d_done);
             ++*launches;
         }
         // ---- backward + outer products ----
@@ -315,13 +382,14 @@ int chain_accumulate(const NetDesc &net, const ChainScratch &sc, ChainMode mode,
             const double *Yprev = (i == 1) ? d_obs + c0 * net.L[0] : sc.Y[i - 1];
             const int M0 = net.L[i - 1], N = net.L[i];
             const int tiles_m = cdiv(M0 + 1, BM), tiles_n = cdiv(N, BN);
-            dim3 go(tiles_m * tiles_n, sc.nslices);
-            k_chain_outer<<<go, NT, 0, st>>>(Yprev, sc.G[i & 1], rows, M0, N, per_slice, tiles_n, sc.partial, net.P,
-                                             net.w_off[i - 1], accumulate, d_done);
+            const int ns = layer_slices(tiles_m * tiles_n, sc.nslices);
+            dim3 go(tiles_m * tiles_n, ns);
+            k_chain_outer<<<go, NT, SMEM_SINGLE, st>>>(Yprev, sc.G[i & 1], rows, M0, N, cdiv(cdiv(rows, ns), BK) * BK, tiles_n,
+                                             sc.partial, net.P, net.w_off[i - 1], accumulate, d_done);
             ++*launches;
             if (i > 1) {
                 dim3 gb(cdiv(rows, BM), cdiv(M0, BN));
-                k_chain_bwd<<<gb, NT, 0, st>>>(sc.G[i & 1], d_theta + net.w_off[i - 1], sc.Y[i - 1], rows, N, M0,
+                k_chain_bwd<<<gb, NT, SMEM_SINGLE, st>>>(sc.G[i & 1], d_theta + net.w_off[i - 1], sc.Y[i - 1], rows, N, M0,
                                                net.ac[i - 1], sc.G[(i - 1) & 1], d_done);
                 ++*launches;
             }
@@ -334,13 +402,14 @@ int chain_accumulate(const NetDesc &net, const ChainScratch &sc, ChainMode mode,
 int chain_forward(const NetDesc &net, const ChainScratch &sc, const double *d_theta, const double *d_obs,
                   size_t nsamples, double *d_mean_out, cudaStream_t st, long long *launches) {
     const int K = net.K, A = net.L[K];
+    if (!configure_kernels()) return -1;
     for (size_t c0 = 0; c0 < nsamples; c0 += sc.chunk) {
         const int rows = (int)((nsamples - c0 < (size_t)sc.chunk) ? nsamples - c0 : sc.chunk);
         for (int i = 0; i < K; ++i) {
             const double *Yin = (i == 0) ? d_obs + c0 * net.L[0] : sc.Y[i];
             double *Yout = (i == K - 1) ? d_mean_out + c0 * A : sc.Y[i + 1];
             dim3 grid(cdiv(rows, BM), cdiv(net.L[i + 1], BN));
-            k_chain_fwd<false><<<grid, NT, 0, st>>>(Yin, nullptr, d_theta + net.w_off[i], nullptr, rows, net.L[i],
+            k_chain_fwd<false, false><<<grid, NT, SMEM_SINGLE, st>>>(Yin, nullptr, d_theta + net.w_off[i], nullptr, rows, net.L[i],
                                                    net.L[i + 1], net.ac[i + 1], Yout, nullptr, nullptr, nullptr, nullptr);
             ++*launches;
         }

@@ -107,15 +107,15 @@ extern "C" size_t trpo_num_params(const size_t *LayerSize, size_t NumLayers) {
 }
 
 static int ensure_chain_scratch(trpo_ctx *c) {
-    // chunk sized so one chunk's activations (~ chunk * (sumL + 4 maxL) doubles) stay within ~48 MB of the 126 MB L2
+    // chunk sized so one chunk's activations (~ chunk * (sumL + 4 maxL) doubles) stay within ~96 MB of the 126 MB L2
     size_t maxL = c->net.L[0], sumL = 0;
     for (int i = 1; i <= c->net.K; ++i) { sumL += c->net.L[i]; if ((size_t)c->net.L[i] > maxL) maxL = c->net.L[i]; }
     size_t per_sample = 8 * (sumL + 4 * maxL);
-    size_t chunk = (48u << 20) / per_sample;
+    size_t chunk = (96u << 20) / per_sample;
     if (chunk > 32768) chunk = 32768;
     if (chunk < 1024) chunk = 1024;
-    chunk = (chunk / 64) * 64;
-    if (c->n_local && chunk > ((c->n_local + 63) / 64) * 64) chunk = ((c->n_local + 63) / 64) * 64;
+    chunk = (chunk / 128) * 128;
+    if (c->n_local && chunk > ((c->n_local + 127) / 128) * 128) chunk = ((c->n_local + 127) / 128) * 128;
     int nslices = 148;
     if ((size_t)nslices * 16 > chunk) nslices = (int)(chunk / 16);
     if (nslices < 1) nslices = 1;
