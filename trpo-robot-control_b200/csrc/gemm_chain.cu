@@ -314,7 +314,7 @@ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 // Wide layers get few slices (each CTA then amortises its 128 x 64 partial-tile read-modify-write over many samples);
 // rows of the partial buffer a layer does not use stay zero from the allocation-time memset.
 inline int layer_slices(int tiles, int max_slices) {
-    int ns = cdiv(296, tiles);
+    int ns = 296 / tiles;                                // floor: whole waves of 148 CTAs
     if (ns > max_slices) ns = max_slices;
     return ns < 1 ? 1 : ns;
 }

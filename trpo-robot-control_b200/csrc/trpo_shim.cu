@@ -107,14 +107,23 @@ extern "C" size_t trpo_num_params(const size_t *LayerSize, size_t NumLayers) {
 }
 
 static int ensure_chain_scratch(trpo_ctx *c) {
-    // chunk sized so one chunk's activations (~ chunk * (sumL + 4 maxL) doubles) stay within ~96 MB of the 126 MB L2
+    // chunk: several whole waves of CTAs per kernel so the fixed per-launch cost (first-tile latency, epilogue, tail) is
+    // amortised; up to 512 MB of scratch. Wide layers are compute bound even from HBM (>= 100 flop/B), so the chunk does not
+    // have to stay L2 resident.
     size_t maxL = c->net.L[0], sumL = 0;
     for (int i = 1; i <= c->net.K; ++i) { sumL += c->net.L[i]; if ((size_t)c->net.L[i] > maxL) maxL = c->net.L[i]; }
     size_t per_sample = 8 * (sumL + 4 * maxL);
-    size_t chunk = (96u << 20) / per_sample;
-    if (chunk > 32768) chunk = 32768;
-    if (chunk < 1024) chunk = 1024;
-    chunk = (chunk / 128) * 128;
+    // rows per chunk = 128 * m with m * (n-tiles of the widest layer) a multiple of the 148 SMs: whole waves of CTAs
+    size_t maxH = 1;
+    for (int i = 1; i <= c->net.K; ++i) if ((size_t)c->net.L[i] > maxH) maxH = c->net.L[i];
+    const size_t tiles_n = (maxH + 63) / 64;
+    size_t gcd = 148, b = tiles_n;
+    while (b) { size_t r = gcd % b; gcd = b; b = r; }
+    const size_t unit = 128 * (148 / gcd);
+    size_t chunk = ((512u << 20) / per_sample / unit) * unit;
+    if (chunk < unit) chunk = unit;
+    if (chunk > 8 * unit) chunk = 8 * unit;
+    if (chunk > 131072) chunk = (131072 / unit) * unit;
     if (c->n_local && chunk > ((c->n_local + 127) / 128) * 128) chunk = ((c->n_local + 127) / 128) * 128;
     int nslices = 148;
     if ((size_t)nslices * 16 > chunk) nslices = (int)(chunk / 16);
