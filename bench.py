@@ -173,146 +173,158 @@ def run_gpu_arm(args, pkg):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    layers, ac, n_total, theta, batch, vec = make_workload(pkg, args.workload, args.states)
-    lo, hi = shard_bounds(n_total, world, rank)
-    n_local = hi - lo
-    P = len(theta)
-
-    # pinned host staging buffers (the e2e leg copies from these every step)
-    obs_pin = torch.from_numpy(np.ascontiguousarray(batch["Observ"][lo:hi])).pin_memory()
-    b_pin = torch.from_numpy(vec["b"].copy()).pin_memory()
-    x_pin = torch.zeros(P, dtype=torch.float64).pin_memory()
-
-    stream = torch.cuda.Stream(device=dev)
-    ctx = pkg.Context(layers, ac, device=local_rank)
-    ctx.set_stream(stream.cuda_stream)
-    if args.path:
-        ctx.set_path({"chain": pkg.api.PATH_GEMM_CHAIN, "fused": pkg.api.PATH_FUSED}[args.path])
-    if world > 1:
-        uid = torch.zeros(128, dtype=torch.uint8, device=dev)
-        if rank == 0:
-            uid.copy_(torch.frombuffer(bytearray(pkg.api.nccl_unique_id()), dtype=torch.uint8))
-        dist.broadcast(uid, 0)
-        ctx.init_comm(bytes(uid.cpu().numpy().tobytes()), rank, world)
-        if args.comm == "p2p":
-            # peer-memory all-reduce fused into our kernels: exchange the CUDA IPC handles of the comm buffers
-            mine = torch.frombuffer(bytearray(ctx.p2p_export()), dtype=torch.uint8).to(dev)
-            allh = [torch.zeros(64, dtype=torch.uint8, device=dev) for _ in range(world)]
-            dist.all_gather(allh, mine)
-            ctx.p2p_attach(b"".join(bytes(h.cpu().numpy().tobytes()) for h in allh))
-            dist.barrier()
-    ctx.set_model(theta)
-    ctx.set_batch(obs_pin.numpy(), batch["Std"])
-    assert ctx.global_samples() == n_total
-
-    d_b = torch.from_numpy(vec["b"]).to(dev)
-    d_x = torch.zeros(P, dtype=torch.float64, device=dev)
-    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed_loop(step_fn, steps, warmup, count_launches=False):
+    def measure(workload, states, steps, warmup, with_clocks):
+        """One workload: resident leg (value), end-to-end leg (e2e) and the FVP-kernel roofline. Returns a dict."""
+        layers, ac, n_total, theta, batch, vec = make_workload(pkg, workload, states)
+        lo, hi = shard_bounds(n_total, world, rank)
+        n_local = hi - lo
+        P = len(theta)
+        # pinned host staging buffers (the e2e leg copies from these every step)
+        obs_pin = torch.from_numpy(np.ascontiguousarray(batch["Observ"][lo:hi])).pin_memory()
+        b_pin = torch.from_numpy(vec["b"].copy()).pin_memory()
+        x_pin = torch.zeros(P, dtype=torch.float64).pin_memory()
+        stream = torch.cuda.Stream(device=dev)
+        ctx = pkg.Context(layers, ac, device=local_rank)
+        ctx.set_stream(stream.cuda_stream)
+        if args.path:
+            ctx.set_path({"chain": pkg.api.PATH_GEMM_CHAIN, "fused": pkg.api.PATH_FUSED}[args.path])
+        if world > 1:
+            uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+            if rank == 0:
+                uid.copy_(torch.frombuffer(bytearray(pkg.api.nccl_unique_id()), dtype=torch.uint8))
+            dist.broadcast(uid, 0)
+            ctx.init_comm(bytes(uid.cpu().numpy().tobytes()), rank, world)
+            if args.comm == "p2p":
+                # peer-memory all-reduce fused into our kernels: exchange the CUDA IPC handles of the comm buffers
+                mine = torch.frombuffer(bytearray(ctx.p2p_export()), dtype=torch.uint8).to(dev)
+                allh = [torch.zeros(64, dtype=torch.uint8, device=dev) for _ in range(world)]
+                dist.all_gather(allh, mine)
+                ctx.p2p_attach(b"".join(bytes(h.cpu().numpy().tobytes()) for h in allh))
+                dist.barrier()
+        ctx.set_model(theta)
+        ctx.set_batch(obs_pin.numpy(), batch["Std"])
+        assert ctx.global_samples() == n_total
+        d_b = torch.from_numpy(vec["b"]).to(dev)
+        d_x = torch.zeros(P, dtype=torch.float64, device=dev)
+
+        def timed_loop(step_fn, nsteps, nwarm):
+            with torch.cuda.stream(stream):
+                for _ in range(nwarm):
+                    flush_buf.zero_()
+                    step_fn()
+                barrier()
+                evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nsteps)]
+                l0 = ctx.launch_count()
+                t_wall = time.perf_counter()
+                for e0, e1 in evs:
+                    flush_buf.zero_()              # L2 flush between timed steps (outside the event pair)
+                    e0.record(stream)
+                    step_fn()
+                    e1.record(stream)
+                barrier()
+                t_wall = time.perf_counter() - t_wall
+                l1 = ctx.launch_count()
+            ms = sum(e0.elapsed_time(e1) for e0, e1 in evs)
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item()) / nsteps, (l1 - l0), t_wall
+
+        # ---- leg 1: device-resident (value) ---------------------------------------------------------------------
+        def step_resident():
+            ctx.cg_device(d_b.data_ptr(), d_x.data_ptr(), CG_ITERS, 0.0, DAMPING)
+
+        ctx.kernel_timing(True)
         with torch.cuda.stream(stream):
             for _ in range(warmup):
-                flush_buf.zero_()
-                step_fn()
-            barrier()
-            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-            l0 = ctx.launch_count()
-            t_wall = time.perf_counter()
-            for e0, e1 in evs:
-                flush_buf.zero_()              # L2 flush between timed steps (outside the event pair)
-                e0.record(stream)
-                step_fn()
-                e1.record(stream)
-            barrier()
-            t_wall = time.perf_counter() - t_wall
-            l1 = ctx.launch_count()
-        ms = sum(e0.elapsed_time(e1) for e0, e1 in evs)
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()) / steps, (l1 - l0), t_wall
+                step_resident()
+            torch.cuda.synchronize()
+        ctx.kernel_time_ms()
+        sampler = ClockSampler(local_rank)
+        if with_clocks:
+            sampler.start()
+        ms_step, launches, _ = timed_loop(step_resident, steps, 0)
+        clocks = sampler.stop() if with_clocks else None
+        k_ms, k_n = ctx.kernel_time_ms()
+        ctx.kernel_timing(False)
 
-    # ---- leg 1: device-resident (value) -------------------------------------------------------------------------
-    def step_resident():
-        ctx.cg_device(d_b.data_ptr(), d_x.data_ptr(), CG_ITERS, 0.0, DAMPING)
-
-    sampler = ClockSampler(local_rank)
-    ctx.kernel_timing(True)
-    ctx.kernel_time_ms()
-    # warm-up first, then start sampling clocks for the timed region only
-    with torch.cuda.stream(stream):
-        for _ in range(args.warmup):
-            step_resident()
-        torch.cuda.synchronize()
-    ctx.kernel_time_ms()
-    sampler.start()
-    ms_step, launches, _ = timed_loop(step_resident, args.steps, 0)
-    clocks = sampler.stop()
-    k_ms, k_n = ctx.kernel_time_ms()
-    ctx.kernel_timing(False)
-    value = CG_ITERS * n_total / (ms_step * 1e-3)
-
-    # ---- leg 2: end to end through the host-buffer C-ABI (e2e) ---------------------------------------------------
-    def step_e2e():
-        ctx.set_batch(obs_pin.numpy(), batch["Std"])                                  # H2D of the rollout batch
-        x, _ = ctx_cg_host()
-
-    def ctx_cg_host():
+        # ---- leg 2: end to end through the host-buffer C-ABI (e2e) -----------------------------------------------
         import ctypes as C
         L = pkg.api.lib()
-        rc = L.trpo_ctx_cg(ctx.h, C.cast(b_pin.data_ptr(), pkg.api.c_double_p), C.cast(x_pin.data_ptr(), pkg.api.c_double_p),
-                           CG_ITERS, 0.0, DAMPING)
-        if rc:
-            raise RuntimeError(pkg.api.last_error())
-        return x_pin, None
 
-    ms_e2e, _, wall_e2e = timed_loop(step_e2e, args.steps, max(1, args.warmup // 2))
-    # the host-buffer calls synchronise internally, so wall clock per step is the honest end-to-end figure
-    e2e_ms = max(ms_e2e, wall_e2e * 1e3 / args.steps)
-    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t.item())
-    e2e_value = CG_ITERS * n_total / (e2e_ms * 1e-3)
-    A = layers[-1]
-    h2d = n_local * layers[0] * 8 + 2 * A * 8 + P * 8
-    d2h = P * 8 + 576
+        def step_e2e():
+            ctx.set_batch(obs_pin.numpy(), batch["Std"])                                  # H2D of the rollout batch
+            rc = L.trpo_ctx_cg(ctx.h, C.cast(b_pin.data_ptr(), pkg.api.c_double_p),
+                               C.cast(x_pin.data_ptr(), pkg.api.c_double_p), CG_ITERS, 0.0, DAMPING)
+            if rc:
+                raise RuntimeError(pkg.api.last_error())
 
-    path_used = {1: "gemm_chain", 2: "fused_dmma"}.get(ctx.path_used(), "?")
-    x_dev = d_x.cpu().numpy()
-    assert np.isfinite(x_dev).all() and np.isfinite(x_pin.numpy()).all()
-    assert ctx.comm_error() == 0, "a peer-memory wait timed out"
-
-    if rank == 0:
+        ms_e2e, _, wall_e2e = timed_loop(step_e2e, steps, max(1, warmup // 2))
+        # the host-buffer calls synchronise internally, so wall clock per step is the honest end-to-end figure
+        e2e_ms = max(ms_e2e, wall_e2e * 1e3 / steps)
+        t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+        A = layers[-1]
+        path_used = {1: "gemm_chain", 2: "fused_dmma"}.get(ctx.path_used(), "?")
+        assert np.isfinite(d_x.cpu().numpy()).all() and np.isfinite(x_pin.numpy()).all()
+        assert ctx.comm_error() == 0, "a peer-memory wait timed out"
+        ctx.close()
         fl = flops_min_per_sample(layers)
         k_avg_ms = k_ms / max(k_n, 1)
         achieved = fl * n_local / (k_avg_ms * 1e-3) / 1e12 if k_n else None
-        line = {
-            "metric": "fvp_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "cg_solve_ms": ms_step,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {'-'.join(map(str, layers))} policy, {n_total} synthetic states, "
-                                   f"{CG_ITERS}-iteration CG (ResidualTh=0), damping {DAMPING}",
-                       "kernel_path": path_used, "l2": "flushed between steps (256 MiB write); 1M-state shard is 136 MB > L2",
-                       "parallelism": f"samples sharded over {world} GPU(s), 1 all-reduce of P={P} doubles per FVP"
-                                      + (f" ({args.comm})" if world > 1 else "")},
-            "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": int(launches),
+        return {
+            "layers": layers, "n_total": n_total, "P": P, "ms_step": ms_step, "launches": int(launches), "clocks": clocks,
+            "value": CG_ITERS * n_total / (ms_step * 1e-3), "e2e_ms": e2e_ms,
+            "e2e_value": CG_ITERS * n_total / (e2e_ms * 1e-3),
+            "h2d": n_local * layers[0] * 8 + 2 * A * 8 + P * 8, "d2h": P * 8 + 576, "path": path_used,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
                          "frac": (achieved / FP64_PEAK_TFLOPS) if achieved else None,
-                         "traffic": NCU_TRAFFIC_BYTES.get((args.workload, n_local, path_used)),
+                         "traffic": NCU_TRAFFIC_BYTES.get((workload, n_local, path_used)),
                          "kernel": path_used, "kernel_avg_ms": k_avg_ms, "kernel_launches_timed": k_n,
                          "flops_per_sample": fl,
                          "peak_source": "measured FP64 DMMA/DFMA pipe, profiles/fp64_peak_r01.txt (MEASURED_PEAKS.json has no FP64 entry)"},
+            "theta": theta, "batch": batch, "vec": vec, "ac": ac,
         }
+
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+    m = measure(args.workload, args.states, args.steps, args.warmup, True)
+    also = {}
+    if args.workload == "mlp64" and not args.states and not args.no_secondary:
+        # BASELINE configs[1] (armDOF_0 policy, 50 k states) measured in the same run, reported beside the headline
+        a = measure("arm", 0, args.steps, args.warmup, False)
+        also["arm_50k"] = {"workload": "arm: 15-16-16-3 policy, 50000 synthetic states, 10-iteration CG",
+                           "value": a["value"], "unit": "samples/s", "cg_solve_ms": a["ms_step"],
+                           "e2e_value": a["e2e_value"], "e2e_ms_per_step": a["e2e_ms"], "kernel_path": a["path"],
+                           "roofline_frac": a["roofline"]["frac"], "kernel_avg_ms": a["roofline"]["kernel_avg_ms"]}
+
+    if rank == 0:
+        layers, n_total, P = m["layers"], m["n_total"], m["P"]
+        line = {
+            "metric": "fvp_samples_per_sec", "value": m["value"], "unit": "samples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": m["ms_step"], "cg_solve_ms": m["ms_step"],
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {'-'.join(map(str, layers))} policy, {n_total} synthetic states, "
+                                   f"{CG_ITERS}-iteration CG (ResidualTh=0), damping {DAMPING}",
+                       "kernel_path": m["path"], "l2": "flushed between steps (256 MiB write); the 1M-state batch (136 MB) exceeds L2",
+                       "parallelism": f"samples sharded over {world} GPU(s), 1 all-reduce of P={P} doubles per FVP"
+                                      + (f" ({args.comm})" if world > 1 else "")},
+            "clocks": m["clocks"],
+            "e2e": {"value": m["e2e_value"], "unit": "samples/s", "ms_per_step": m["e2e_ms"],
+                    "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": m["d2h"]},
+            "gpu_launches": m["launches"],
+            "roofline": m["roofline"],
+        }
+        if also:
+            line["also"] = also
         if world == 1 and not args.no_cpu_baseline:
+            theta, batch, vec, ac = m["theta"], m["batch"], m["vec"], m["ac"]
             flops_ref = 10 * sum(layers[i] * layers[i + 1] for i in range(len(layers) - 1))
             n_sample = int(min(n_total, max(512, 12.0 / (CG_ITERS * flops_ref * 1.3e-9))))
             with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as tmp:
@@ -321,7 +333,6 @@ def run_gpu_arm(args, pkg):
                                     "sample": f"one {CG_ITERS}-iteration CG() of the unmodified reference on the first {n_sample} "
                                               f"states ({t_step:.1f} s), NumThreads=1 of {os.cpu_count()} host cores"}
         print(json.dumps(line), flush=True)
-    ctx.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -336,16 +347,24 @@ def main():
     ap.add_argument("--states", type=int, default=0, help="override the number of synthetic states")
     ap.add_argument("--path", default="", choices=["", "chain", "fused"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the arm-50k secondary measurement")
     ap.add_argument("--comm", default="nccl", choices=["p2p", "nccl"],
                     help="multi-GPU FVP-sum all-reduce: fused NVLink peer-memory kernels (default) or ncclAllReduce")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     from __graft_entry__ import load_package
     pkg = load_package()
+    # Only the JSON line may reach stdout: NCCL / the reference's printf write to fd 1, so point fd 1 at stderr for the
+    # run and print the result through a private copy of the real stdout.
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
     if args.impl == "reference":
         run_reference_arm(args, pkg)
     else:
         run_gpu_arm(args, pkg)
+    real_stdout.flush()
 
 
 if __name__ == "__main__":

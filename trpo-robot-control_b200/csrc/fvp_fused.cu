@@ -76,9 +76,9 @@ __host__ __device__ __forceinline__ int swz(int rr, int cc) {
     return (a & 1) + 2 * (cq & 1) + 4 * ((a >> 1) ^ rp) + 8 * (cp ^ (cq >> 1)) + 16 * rp + 32 * (cq >> 1);
 }
 
-template <int K0_, int H1_, int H2_, int AP_, int NW_>
+template <int K0_, int H1_, int H2_, int AP_, int NW_, int CTAS_PER_SM_ = 1>
 struct Cfg {
-    static constexpr int K0 = K0_, H1 = H1_, H2 = H2_, AP = AP_, NW = NW_;
+    static constexpr int K0 = K0_, H1 = H1_, H2 = H2_, AP = AP_, NW = NW_, CTAS_PER_SM = CTAS_PER_SM_;
     static constexpr int S = 8 * NW, NTHREADS = 32 * NW;
     static constexpr int Q0 = K0 / 4, MT0 = (K0 + 7) / 8;
     static constexpr int NT1 = H1 / 8, NT2 = H2 / 8, NT3 = AP / 8;
@@ -106,7 +106,7 @@ struct FusedArgs {
 };
 
 template <typename C, char ACT1, char ACT2>
-__global__ void __launch_bounds__(C::NTHREADS, 1) k_fvp_fused(const FusedArgs p) {
+__global__ void __launch_bounds__(C::NTHREADS, C::CTAS_PER_SM) k_fvp_fused(const FusedArgs p) {
     if (p.done && *p.done) return;
     extern __shared__ __align__(16) double sm[];
     constexpr int K0 = C::K0, H1 = C::H1, H2 = C::H2, AP = C::AP, NW = C::NW, S = C::S, NT = C::NTHREADS;
@@ -423,9 +423,12 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_fvp_fused(const FusedArgs p)
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int FUSED_MAX_ROWS = 148;
+constexpr int FUSED_SMS = 148;
+constexpr int FUSED_MAX_ROWS = 4 * FUSED_SMS;
 
-using CfgArm  = Cfg<16, 16, 16, 8, 8>;     // armDOF_0: 15-16-16-3
+// armDOF_0 (15-16-16-3): the weights are 9 KB, so small CTAs (4 warps, 32-sample tiles), four per SM, hide each
+// other's barrier and load latencies; the 64-wide nets need the whole SM's shared memory for one CTA.
+using CfgArm  = Cfg<16, 16, 16, 8, 4, 4>;
 using CfgP64  = Cfg<4, 64, 64, 8, 8>;      // InvertedPendulum-size: 4-64-64-1
 using CfgM64  = Cfg<20, 64, 64, 8, 8>;     // 17-64-64-6 (and anything with L0 <= 20, hidden <= 64, A <= 8)
 
@@ -457,7 +460,8 @@ int launch_cfg(const FusedArgs &a, int grid, cudaStream_t st) {
 template <typename C>
 int launch_shape(const FusedArgs &a, cudaStream_t st, int *rows) {
     const long long ntiles = (a.nsamples + C::S - 1) / C::S;
-    const int grid = (int)(ntiles < FUSED_MAX_ROWS ? ntiles : FUSED_MAX_ROWS);
+    const int max_grid = FUSED_SMS * C::CTAS_PER_SM;
+    const int grid = (int)(ntiles < max_grid ? ntiles : max_grid);
     *rows = grid;
     if (a.act1 == 't' && a.act2 == 't') return launch_cfg<C, 't', 't'>(a, grid, st);
     return launch_cfg<C, 0, 0>(a, grid, st);
