@@ -33,26 +33,41 @@ __device__ __forceinline__ double block_sum(double v, double *red) {
     return red[0];
 }
 
-__device__ __forceinline__ double row_sum(const double *__restrict__ partial, int rows, int P, int e) {
+// Fixed-order column sums of the partial rows. A block owns 32 columns; its 8 warps each sum every 8th row (4 independent
+// accumulators, coalesced 256-byte row segments), then the 8 row-group sums are added in a fixed order. With few columns
+// (P = 582 for the arm policy) one thread per column walking all rows serially was latency bound (80 us for 592 rows).
+constexpr int RED_COLS = 32, RED_GROUPS = 8;
+__device__ __forceinline__ double column_sum(const double *__restrict__ partial, int rows, int P, int e, bool valid,
+                                             double (*sh)[RED_COLS]) {
+    const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    int r = 0;
-    for (; r + 3 < rows; r += 4) {
-        s0 += partial[(size_t)r * P + e];
-        s1 += partial[(size_t)(r + 1) * P + e];
-        s2 += partial[(size_t)(r + 2) * P + e];
-        s3 += partial[(size_t)(r + 3) * P + e];
+    if (valid) {
+        int r = ry;
+        for (; r + 3 * RED_GROUPS < rows; r += 4 * RED_GROUPS) {
+            s0 += partial[(size_t)r * P + e];
+            s1 += partial[(size_t)(r + RED_GROUPS) * P + e];
+            s2 += partial[(size_t)(r + 2 * RED_GROUPS) * P + e];
+            s3 += partial[(size_t)(r + 3 * RED_GROUPS) * P + e];
+        }
+        for (; r < rows; r += RED_GROUPS) s0 += partial[(size_t)r * P + e];
     }
-    for (; r < rows; ++r) s0 += partial[(size_t)r * P + e];
-    return (s0 + s1) + (s2 + s3);
+    sh[ry][cx] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    double t = sh[0][cx];
+#pragma unroll
+    for (int k = 1; k < RED_GROUPS; ++k) t += sh[k][cx];
+    return t;                                            // meaningful in every thread of the column (all row groups)
 }
 
 // zsum[e] = sum over rows (fixed order) of partial[row][e]
-__global__ void k_reduce_partials(const double *__restrict__ partial, int rows, int P, double *__restrict__ zsum,
-                                  const int *__restrict__ done) {
+__global__ void __launch_bounds__(RED_COLS * RED_GROUPS) k_reduce_partials(const double *__restrict__ partial, int rows, int P,
+                                                                           double *__restrict__ zsum,
+                                                                           const int *__restrict__ done) {
     if (done && *done) return;
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= P) return;
-    zsum[e] = row_sum(partial, rows, P, e);
+    __shared__ double sh[RED_GROUPS][RED_COLS];
+    const int e = blockIdx.x * RED_COLS + (threadIdx.x & 31);
+    const double v = column_sum(partial, rows, P, e, e < P, sh);
+    if (e < P && (threadIdx.x >> 5) == 0) zsum[e] = v;
 }
 
 // ---- peer-memory all-reduce, send side: fused into the partial-row reduction --------------------------------
@@ -67,17 +82,19 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 
 // Every thread pushes its element of this rank's sum into slot [parity][rank] of EVERY rank (NVLink stores for the
 // peers); the last block to finish publishes the sequence number into every rank's flag [parity][rank].
-__global__ void k_reduce_partials_push(const double *__restrict__ partial, int rows, double *__restrict__ zsum,
-                                       const int *__restrict__ done, const P2PComm c) {
+__global__ void __launch_bounds__(RED_COLS * RED_GROUPS) k_reduce_partials_push(const double *__restrict__ partial, int rows,
+                                                                                double *__restrict__ zsum,
+                                                                                const int *__restrict__ done, const P2PComm c) {
     if (done && *done) return;
+    __shared__ double sh[RED_GROUPS][RED_COLS];
     const int P = c.P;
     const unsigned long long seq = *c.seq_dev + 1;
     const size_t slot = ((size_t)(seq & 1) * c.world + c.rank) * P;
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    const int e = blockIdx.x * RED_COLS + (threadIdx.x & 31), grp = threadIdx.x >> 5;
+    const double v = column_sum(partial, rows, P, e, e < P, sh);
     if (e < P) {
-        const double v = row_sum(partial, rows, P, e);
-        zsum[e] = v;
-        for (int r = 0; r < c.world; ++r) c.slots[r][slot + e] = v;
+        if (grp == 0) zsum[e] = v;
+        for (int r = grp; r < c.world; r += RED_GROUPS) c.slots[r][slot + e] = v;     // warp `grp` serves ranks grp, grp+8, ..
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -253,8 +270,9 @@ constexpr int SUM_BLOCKS = 592;   // 4 x 148 SMs
 
 void launch_reduce_partials(const double *d_partial, int rows, int P, double *d_zsum, const int *d_done,
                             const P2PComm *p2p, cudaStream_t st, long long *launches) {
-    if (p2p && p2p->world > 1) k_reduce_partials_push<<<(P + 127) / 128, 128, 0, st>>>(d_partial, rows, d_zsum, d_done, *p2p);
-    else k_reduce_partials<<<(P + 127) / 128, 128, 0, st>>>(d_partial, rows, P, d_zsum, d_done);
+    const int grid = (P + RED_COLS - 1) / RED_COLS, block = RED_COLS * RED_GROUPS;
+    if (p2p && p2p->world > 1) k_reduce_partials_push<<<grid, block, 0, st>>>(d_partial, rows, d_zsum, d_done, *p2p);
+    else k_reduce_partials<<<grid, block, 0, st>>>(d_partial, rows, P, d_zsum, d_done);
     ++*launches;
 }
 

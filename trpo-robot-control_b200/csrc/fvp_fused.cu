@@ -15,6 +15,8 @@
 //            conflict-free transposed fragment reads).
 // At the end every CTA writes its P-length partial row; rows are summed in fixed order by k_reduce_partials, so the
 // result is bitwise deterministic.
+#include <stdlib.h>
+
 #include "trpo_internal.cuh"
 #include "dmma_common.cuh"
 
@@ -426,9 +428,11 @@ __global__ void __launch_bounds__(C::NTHREADS, C::CTAS_PER_SM) k_fvp_fused(const
 constexpr int FUSED_SMS = 148;
 constexpr int FUSED_MAX_ROWS = 4 * FUSED_SMS;
 
-// armDOF_0 (15-16-16-3): the weights are 9 KB, so small CTAs (4 warps, 32-sample tiles), four per SM, hide each
-// other's barrier and load latencies; the 64-wide nets need the whole SM's shared memory for one CTA.
-using CfgArm  = Cfg<16, 16, 16, 8, 4, 4>;
+// armDOF_0 (15-16-16-3). Measured at 50 k states (profiles/r01_summary.md): one 8-warp CTA per SM gives a 30.7 us kernel +
+// a 148-row partial reduction; four 4-warp CTAs per SM give 26.0 us but 592 partial rows, and lose end to end
+// (0.57 vs 0.51 ms per 10-iteration solve). The small-CTA variant stays selectable with TRPO_FUSED_ARM_VARIANT=4.
+using CfgArm  = Cfg<16, 16, 16, 8, 8, 1>;
+using CfgArm4 = Cfg<16, 16, 16, 8, 4, 4>;
 using CfgP64  = Cfg<4, 64, 64, 8, 8>;      // InvertedPendulum-size: 4-64-64-1
 using CfgM64  = Cfg<20, 64, 64, 8, 8>;     // 17-64-64-6 (and anything with L0 <= 20, hidden <= 64, A <= 8)
 
@@ -486,7 +490,11 @@ int fused_fvp_accumulate(const NetDesc &net, const double *d_theta, const double
     a.act1 = net.ac[1]; a.act2 = net.ac[2]; a.act3 = net.ac[3];
     int rows = 0, rc = -1;
     switch (shape) {
-        case SHAPE_ARM: rc = launch_shape<CfgArm>(a, st, &rows); break;
+        case SHAPE_ARM: {
+            static const bool v4 = getenv("TRPO_FUSED_ARM_VARIANT") && atoi(getenv("TRPO_FUSED_ARM_VARIANT")) == 4;
+            rc = v4 ? launch_shape<CfgArm4>(a, st, &rows) : launch_shape<CfgArm>(a, st, &rows);
+            break;
+        }
         case SHAPE_P64: rc = launch_shape<CfgP64>(a, st, &rows); break;
         case SHAPE_M64: rc = launch_shape<CfgM64>(a, st, &rows); break;
         default: return 1;
