@@ -117,7 +117,9 @@ double trpo_ctx_kernel_time_ms(trpo_ctx *ctx, int *launches);
 /* Model: theta = flat [W0,B0,...,LogStd] (TRPO_FVP.c:704-725), P doubles on the host. */
 int trpo_ctx_set_model(trpo_ctx *ctx, const double *theta);
 
-/* Rollout batch (host pointers, row-major). Std has A entries (the data file's Std columns, last row wins,
+/* Rollout batch (host pointers, row-major). When Observ is PINNED host memory and the batch is large, the copy is issued
+ * asynchronously in chunks and the first fused FVP after this call overlaps it (the kernel polls a chunk counter the
+ * copy engine advances); the caller must keep Observ unchanged until the next synchronising call returns. Std has A entries (the data file's Std columns, last row wins,
  * TRPO_FVP.c:746-748). Mean/Action/Advantage may be NULL when only FVP/CG are used.
  * In multi-GPU mode every rank passes ITS shard (NumSamples = local count). */
 int trpo_ctx_set_batch(trpo_ctx *ctx, size_t NumSamples, const double *Observ, const double *Std,
@@ -160,7 +162,7 @@ int trpo_ctx_p2p_export(trpo_ctx *ctx, char handle_out[64]);
 int trpo_ctx_p2p_attach(trpo_ctx *ctx, const char *handles /* world_size x 64 bytes */);
 enum { TRPO_COMM_NCCL = 0, TRPO_COMM_P2P = 1 };
 int trpo_ctx_set_comm_mode(trpo_ctx *ctx, int mode);       /* P2P becomes the default once attached */
-int trpo_ctx_comm_error(trpo_ctx *ctx);                    /* non-zero if a peer wait timed out (synchronises) */
+int trpo_ctx_comm_error(trpo_ctx *ctx);                    /* non-zero if a peer / staging wait timed out (synchronises) */
 
 /* Total sample count over all ranks (the 1/N of TRPO_FVP.c:930). Computed by init_comm+set_batch via all-reduce. */
 size_t trpo_ctx_global_samples(const trpo_ctx *ctx);

@@ -180,6 +180,18 @@ def test_full_size_properties_mlp64_1m(pkg, oracle):
         assert info.cg_iters == 10
         resid = ctx.fvp(x, 0.1) - vec["b"]
         assert np.linalg.norm(resid) ** 2 < 1.01 * info.cg_rdotr[10] + 1e-20   # r tracked by CG == b - A x
+        # streamed staging: pinned source, the first FVP overlaps the chunked H2D copy -- bitwise the same result
+        import torch
+        pinned = torch.from_numpy(batch["Observ"]).pin_memory()
+        for _ in range(2):
+            ctx.set_batch(pinned.numpy(), batch["Std"])
+            assert np.array_equal(Fu, ctx.fvp(u, 0.0))
+            assert np.array_equal(Fw, ctx.fvp(w, 0.0))
+        x2, _ = ctx.cg(vec["b"], 10, 0.0, 0.1)
+        ctx.set_batch(pinned.numpy(), batch["Std"])
+        x3, _ = ctx.cg(vec["b"], 10, 0.0, 0.1)
+        assert np.array_equal(x, x2) and np.array_equal(x, x3)
+        assert pkg.api.lib().trpo_ctx_comm_error(ctx.h) == 0
         # prefix vs oracle
         n = 50_000
         ctx.set_batch(batch["Observ"][:n], batch["Std"])

@@ -105,7 +105,28 @@ struct FusedArgs {
     int w_off0, w_off1, w_off2;
     int P;
     char act1, act2, act3;
+    // streamed staging: the observation rows arrive by DMA in chunks of chunk_samples while this kernel already runs;
+    // *ready counts the chunks that have landed (written by the copy engine after each chunk). NULL = all resident.
+    const int *ready;
+    long long chunk_samples;
+    int *error;
 };
+
+__device__ __forceinline__ int ld_volatile_i32(const int *p) {
+    int v;
+    asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// Block until the chunk holding sample `last_sample` has been copied in (bounded spin: ~4 s, then flag an error).
+__device__ __forceinline__ void wait_samples(const FusedArgs &p, long long last_sample) {
+    if (p.ready == nullptr) return;
+    const int need = (int)(last_sample / p.chunk_samples) + 1;
+    if (ld_volatile_i32(p.ready) >= need) return;
+    const long long t0 = clock64();
+    while (ld_volatile_i32(p.ready) < need) {
+        if (clock64() - t0 > 8000000000LL) { *p.error = 2; break; }
+    }
+}
 
 template <typename C, char ACT1, char ACT2>
 __global__ void __launch_bounds__(C::NTHREADS, C::CTAS_PER_SM) k_fvp_fused(const FusedArgs p) {
@@ -162,6 +183,7 @@ __global__ void __launch_bounds__(C::NTHREADS, C::CTAS_PER_SM) k_fvp_fused(const
     auto stage_obs = [&](long long tile_idx, int buf) {
         double *dst = Y0s + buf * C::Y0SZ;
         const long long s0n = tile_idx * S;
+        wait_samples(p, (s0n + S < p.nsamples ? s0n + S : p.nsamples) - 1);
         for (int idx = tid; idx < S * K0; idx += NT) {
             const int row = idx / K0, col = idx % K0;
             const long long gs = s0n + row;
@@ -478,7 +500,8 @@ int fused_partial_rows() { return FUSED_MAX_ROWS; }
 
 int fused_fvp_accumulate(const NetDesc &net, const double *d_theta, const double *d_v, const double *d_inv_var,
                          const double *d_obs, size_t nsamples, double *d_partial, double *d_zsum,
-                         const int *d_done, const P2PComm *p2p, cudaStream_t st, long long *launches) {
+                         const int *d_done, const P2PComm *p2p, const int *stream_ready, size_t stream_chunk,
+                         int *stream_error, cudaStream_t st, long long *launches) {
     const FusedShape shape = pick_shape(net);
     if (shape == SHAPE_NONE) return 1;
     FusedArgs a;
@@ -488,6 +511,7 @@ int fused_fvp_accumulate(const NetDesc &net, const double *d_theta, const double
     a.w_off0 = net.w_off[0]; a.w_off1 = net.w_off[1]; a.w_off2 = net.w_off[2];
     a.P = net.P;
     a.act1 = net.ac[1]; a.act2 = net.ac[2]; a.act3 = net.ac[3];
+    a.ready = stream_ready; a.chunk_samples = (long long)(stream_chunk ? stream_chunk : 1); a.error = stream_error;
     int rows = 0, rc = -1;
     switch (shape) {
         case SHAPE_ARM: {

@@ -77,7 +77,8 @@ bool fused_eligible(const NetDesc &net);
 int  fused_partial_rows();     // number of per-CTA partial rows the fused kernel writes
 int  fused_fvp_accumulate(const NetDesc &net, const double *d_theta, const double *d_v, const double *d_inv_var,
                           const double *d_obs, size_t nsamples, double *d_partial, double *d_zsum,
-                          const int *d_done, const P2PComm *p2p, cudaStream_t st, long long *launches);
+                          const int *d_done, const P2PComm *p2p, const int *stream_ready, size_t stream_chunk,
+                          int *stream_error, cudaStream_t st, long long *launches);
 
 // ---- cg_kernels.cu ------------------------------------------------------------------------------------------------
 // p2p != NULL: the fixed-order row sum is pushed straight into every rank's slot (fused reduce + all-reduce send)

@@ -20,6 +20,7 @@ static int fail(const char *fmt, ...) {
 extern "C" const char *trpo_last_error(void) { return g_err; }
 
 #define KTIME_MAX 4096
+#define STAGE_CHUNKS 8
 #define CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
 
 // --------------------------------------------------------------------------------------------------------------
@@ -92,6 +93,15 @@ struct trpo_ctx {
     // comm
     ncclComm_t comm;
     int rank, world;
+    // streamed staging of the observation matrix (pinned host source, fused path): the first FVP after set_batch
+    // overlaps the host-to-device copy, the kernel polling d_ready for the chunks it needs
+    cudaStream_t copy_stream;
+    cudaEvent_t ev_compute, ev_copy;
+    int *d_ready;              // [0]: chunks landed, [1]: error flag
+    int *h_ready_vals;         // pinned 0..STAGE_CHUNKS
+    bool copy_inflight;        // an asynchronous batch copy has been issued and not yet joined into c->stream
+    bool stream_first_fvp;     // the next fused FVP may start before the copy has finished
+    size_t stage_chunk;        // samples per staged chunk
     // peer-memory all-reduce
     P2PComm p2p;               // world == 0 until attached
     bool p2p_on;
@@ -185,6 +195,13 @@ extern "C" trpo_ctx *trpo_ctx_create(const size_t *LayerSize, const char *AcFunc
     ok = ok && cudaMalloc(&c->d_state, sizeof(CgState)) == cudaSuccess;
     ok = ok && cudaMallocHost(&c->h_state, sizeof(CgState)) == cudaSuccess;
     ok = ok && cudaMallocHost(&c->h_scal, 16 * sizeof(double)) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&c->ev_compute, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->d_ready, 2 * sizeof(int)) == cudaSuccess;
+    ok = ok && cudaMemset(c->d_ready, 0, 2 * sizeof(int)) == cudaSuccess;
+    ok = ok && cudaMallocHost(&c->h_ready_vals, (STAGE_CHUNKS + 1) * sizeof(int)) == cudaSuccess;
+    if (ok) for (int i = 0; i <= STAGE_CHUNKS; ++i) c->h_ready_vals[i] = i;
     if (ok && fused_eligible(c->net))
         ok = cudaMalloc(&c->d_fused_partial, (size_t)fused_partial_rows() * P * sizeof(double)) == cudaSuccess;
     if (ok) ok = cudaMemset(c->d_state, 0, sizeof(CgState)) == cudaSuccess;
@@ -213,6 +230,11 @@ extern "C" void trpo_ctx_destroy(trpo_ctx *c) {
     if (c->d_state) cudaFree(c->d_state);
     if (c->h_state) cudaFreeHost(c->h_state);
     if (c->h_scal) cudaFreeHost(c->h_scal);
+    if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+    if (c->ev_compute) cudaEventDestroy(c->ev_compute);
+    if (c->ev_copy) cudaEventDestroy(c->ev_copy);
+    if (c->d_ready) cudaFree(c->d_ready);
+    if (c->h_ready_vals) cudaFreeHost(c->h_ready_vals);
     if (c->ktime_ev) { for (int i = 0; i < 2 * KTIME_MAX; ++i) if (c->ktime_ev[i]) cudaEventDestroy(c->ktime_ev[i]); free(c->ktime_ev); }
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     free(c);
@@ -285,7 +307,32 @@ extern "C" int trpo_ctx_set_batch(trpo_ctx *c, size_t N, const double *Observ, c
     if (!c->own_batch) free_batch(c);
     c->own_batch = true;
     if (N * O > c->cap_obs) { cudaFree(c->d_obs); c->d_obs = nullptr; CU(cudaMalloc(&c->d_obs, N * O * sizeof(double))); c->cap_obs = N * O; }
-    CU(cudaMemcpyAsync(c->d_obs, Observ, N * O * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    // join any copy still in flight, then decide how to stage the observations
+    if (c->copy_inflight) { CU(cudaStreamWaitEvent(c->stream, c->ev_copy, 0)); c->copy_inflight = false; }
+    c->stream_first_fvp = false;
+    cudaPointerAttributes attr;
+    const bool pinned = cudaPointerGetAttributes(&attr, Observ) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (pinned && N >= 65536 && fused_eligible(c->net) && c->path_req != TRPO_PATH_GEMM_CHAIN) {
+        // pinned source: DMA in STAGE_CHUNKS pieces on the copy stream, bumping the device-side chunk counter after each
+        // piece; the compute stream is not made to wait (the fused kernel polls the counter, see wait_samples)
+        c->stage_chunk = ((N + STAGE_CHUNKS - 1) / STAGE_CHUNKS + 63) / 64 * 64;
+        CU(cudaEventRecord(c->ev_compute, c->stream));
+        CU(cudaStreamWaitEvent(c->copy_stream, c->ev_compute, 0));          // do not overwrite rows still being read
+        CU(cudaMemcpyAsync(c->d_ready, &c->h_ready_vals[0], sizeof(int), cudaMemcpyHostToDevice, c->copy_stream));
+        int landed = 0;
+        for (size_t s0 = 0; s0 < N; s0 += c->stage_chunk) {
+            const size_t n = (N - s0 < c->stage_chunk) ? N - s0 : c->stage_chunk;
+            CU(cudaMemcpyAsync(c->d_obs + s0 * O, Observ + s0 * O, n * O * sizeof(double), cudaMemcpyHostToDevice, c->copy_stream));
+            ++landed;
+            CU(cudaMemcpyAsync(c->d_ready, &c->h_ready_vals[landed], sizeof(int), cudaMemcpyHostToDevice, c->copy_stream));
+        }
+        CU(cudaEventRecord(c->ev_copy, c->copy_stream));
+        c->copy_inflight = true;
+        c->stream_first_fvp = true;
+    } else {
+        CU(cudaMemcpyAsync(c->d_obs, Observ, N * O * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    }
     if (Mean && Action && Advantage) {
         if (N * A > c->cap_mean) {
             cudaFree(c->d_mean); cudaFree(c->d_action); c->d_mean = c->d_action = nullptr;
@@ -307,6 +354,8 @@ extern "C" int trpo_ctx_set_batch_device(trpo_ctx *c, size_t N, const double *dO
                                          const double *dMean, const double *dAction, const double *dAdvantage) {
     if (!c || !dObserv || !Std_host || N == 0) return fail("bad batch arguments");
     CU(cudaSetDevice(c->device));
+    if (c->copy_inflight) { CU(cudaStreamWaitEvent(c->stream, c->ev_copy, 0)); c->copy_inflight = false; }
+    c->stream_first_fvp = false;
     free_batch(c);
     c->own_batch = false;
     c->d_obs = (double *)dObserv; c->d_mean = (double *)dMean; c->d_action = (double *)dAction; c->d_adv = (double *)dAdvantage;
@@ -352,10 +401,19 @@ static int fvp_sum(trpo_ctx *c, const double *d_v, const int *d_done) {
     const bool timed = c->ktime_on && c->ktime_n < KTIME_MAX;
     if (timed) cudaEventRecord(c->ktime_ev[2 * c->ktime_n], c->stream);
     if (path == TRPO_PATH_FUSED) {
+        const bool streaming = c->stream_first_fvp && c->copy_inflight;
         if (fused_fvp_accumulate(c->net, c->d_theta, d_v, c->d_inv_var, c->d_obs, c->n_local, c->d_fused_partial,
-                                 c->d_zsum, d_done, active_p2p(c), c->stream, &c->launches))
+                                 c->d_zsum, d_done, active_p2p(c), streaming ? c->d_ready : nullptr, c->stage_chunk,
+                                 c->d_ready + 1, c->stream, &c->launches))
             return fail("fused FVP launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        if (c->copy_inflight) {      // everything enqueued after this FVP sees a fully resident batch
+            CU(cudaStreamWaitEvent(c->stream, c->ev_copy, 0));
+            c->copy_inflight = false;
+        }
+        c->stream_first_fvp = false;
     } else {
+        if (c->copy_inflight) { CU(cudaStreamWaitEvent(c->stream, c->ev_copy, 0)); c->copy_inflight = false; }
+        c->stream_first_fvp = false;
         if (ensure_chain_scratch(c)) return -1;
         if (chain_accumulate(c->net, c->sc, CHAIN_FVP, c->d_theta, d_v, c->d_inv_var, c->d_obs, nullptr, nullptr, nullptr,
                              c->n_local, c->d_zsum, d_done, active_p2p(c), c->stream, &c->launches))
@@ -429,6 +487,8 @@ extern "C" int trpo_ctx_get_info(const trpo_ctx *c, trpo_info *info) {
 // policy gradient b = (1/N) sum_n grad (TRPO_Update.c:254-378) into c->d_b
 static int policy_gradient_device(trpo_ctx *c) {
     if (!c->d_obs || !c->d_mean || !c->d_action || !c->d_adv) return fail("policy gradient needs Mean/Action/Advantage in the batch");
+    if (c->copy_inflight) { CU(cudaStreamWaitEvent(c->stream, c->ev_copy, 0)); c->copy_inflight = false; }
+    c->stream_first_fvp = false;
     if (ensure_chain_scratch(c)) return -1;
     if (chain_accumulate(c->net, c->sc, CHAIN_PG, c->d_theta, nullptr, nullptr, c->d_obs, c->d_mean, c->d_action, c->d_adv,
                          c->n_local, c->d_zsum, nullptr, nullptr, c->stream, &c->launches))
@@ -604,12 +664,13 @@ extern "C" int trpo_ctx_set_comm_mode(trpo_ctx *c, int mode) {
 }
 
 extern "C" int trpo_ctx_comm_error(trpo_ctx *c) {
-    if (!c || !c->p2p_buf) return 0;
-    int e = 0;
+    if (!c) return 0;
+    int e = 0, e2 = 0;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    cudaMemcpy(&e, c->p2p_buf + 268, sizeof(int), cudaMemcpyDeviceToHost);
-    return e;
+    if (c->p2p_buf) cudaMemcpy(&e, c->p2p_buf + 268, sizeof(int), cudaMemcpyDeviceToHost);
+    if (c->d_ready) cudaMemcpy(&e2, c->d_ready + 1, sizeof(int), cudaMemcpyDeviceToHost);   // streamed-staging wait timed out
+    return e | e2;
 }
 
 extern "C" size_t trpo_ctx_global_samples(const trpo_ctx *c) { return c ? c->n_total : 0; }
