@@ -19,9 +19,13 @@
 
 namespace {
 
-constexpr int BM = 128, BN = 64, BK = 16, NT = 256;
-constexpr int RSA = 20, RSB = 68;                       // shared row strides: % 16 == 4 -> conflict-free fragment reads
-constexpr int A_TILE = BM * RSA, B_TILE = BK * RSB;     // doubles per operand tile
+constexpr int BM = 128, BN = 64, NT = 256;
+constexpr int BK_DUAL = 16, BK_SINGLE = 32;             // k-step: the dual (forward R-op) kernel holds 4 operand tiles per stage
+constexpr int RSB = 68;                                 // shared row strides: % 16 == 4 -> conflict-free fragment reads
+template <int BK> struct Tile {
+    static constexpr int RSA = BK + 4;                  // 20 / 36
+    static constexpr int A = BM * RSA, B = BK * RSB;    // doubles per operand tile
+};
 
 __device__ __forceinline__ double act_apply(char a, double x) {
     switch (a) {
@@ -43,11 +47,13 @@ __device__ __forceinline__ double act_deriv(char a, double y) {   // f'(x) expre
 // ---- tile loaders (all 256 threads; 8-byte cp.async, src-size 0 = zero fill) --------------------------------------
 // A tile from row-major activations X[rows x ld]: As[m][k] = X[(m0+m)*ld + k0+k]; column k == ld is the augmented
 // "ones" column (value ones_val) when aug is set.
+template <int BK>
 __device__ __forceinline__ void load_a_rowmajor(double *As, const double *X, int rows, int ld, int m0, int k0,
                                                 bool aug, double ones_val, int tid) {
 #pragma unroll
     for (int it = 0; it < BM * BK / NT; ++it) {
-        const int idx = tid + it * NT, m = idx >> 4, k = idx & 15;
+        constexpr int RSA = Tile<BK>::RSA;
+        const int idx = tid + it * NT, m = idx / BK, k = idx % BK;
         const int gm = m0 + m, gk = k0 + k;
         const bool in = X != nullptr && gm < rows && gk < ld;
         if (aug && gk == ld && gm < rows) As[m * RSA + k] = ones_val;
@@ -55,9 +61,11 @@ __device__ __forceinline__ void load_a_rowmajor(double *As, const double *X, int
     }
 }
 // A tile for the outer product: As[m][k] = Yprev[(s0+k)*M0 + m0+m] for m < M0, 1.0 for m == M0 (bias-gradient row)
+template <int BK>
 __device__ __forceinline__ void load_a_transposed(double *As, const double *Y, int s_end, int M0, int m0, int s0, int tid) {
 #pragma unroll
     for (int it = 0; it < BM * BK / NT; ++it) {
+        constexpr int RSA = Tile<BK>::RSA;
         const int idx = tid + it * NT, k = idx >> 7, m = idx & 127;
         const int gm = m0 + m, gs = s0 + k;
         const bool in = Y != nullptr && gm < M0 && gs < s_end;
@@ -66,6 +74,7 @@ __device__ __forceinline__ void load_a_transposed(double *As, const double *Y, i
     }
 }
 // B tile from a row-major matrix M[kdim x N]: Bs[k][n] = M[(k0+k)*N + n0+n]
+template <int BK>
 __device__ __forceinline__ void load_b_rowmajor(double *Bs, const double *M, int kdim, int N, int k0, int n0, int tid) {
 #pragma unroll
     for (int it = 0; it < BK * BN / NT; ++it) {
@@ -76,10 +85,11 @@ __device__ __forceinline__ void load_b_rowmajor(double *Bs, const double *M, int
     }
 }
 // B tile from W[N x Kd] row-major used transposed: Bs[k][n] = W[(n0+n)*Kd + k0+k]
+template <int BK>
 __device__ __forceinline__ void load_b_transposed(double *Bs, const double *W, int Kd, int N, int k0, int n0, int tid) {
 #pragma unroll
     for (int it = 0; it < BK * BN / NT; ++it) {
-        const int idx = tid + it * NT, n = idx >> 4, k = idx & 15;
+        const int idx = tid + it * NT, n = idx / BK, k = idx % BK;
         const int gk = k0 + k, gn = n0 + n;
         const bool in = gk < Kd && gn < N;
         cp_async8(&Bs[k * RSB + n], in ? &W[(size_t)gn * Kd + gk] : W, in ? 8 : 0);
@@ -87,9 +97,10 @@ __device__ __forceinline__ void load_b_transposed(double *Bs, const double *W, i
 }
 
 // one k-step (16) of a warp's 32 x 32 sub-tile: acc += A*B [, racc += RA*B + A*VB]
-template <bool DUAL, bool HAS_RA>
+template <bool DUAL, bool HAS_RA, int BK>
 __device__ __forceinline__ void mma_stage(double (&acc)[4][4][2], double (&racc)[4][4][2], const double *As,
                                           const double *RAs, const double *Bs, const double *VBs, int wm, int wn, int g, int t) {
+    constexpr int RSA = Tile<BK>::RSA;
 #pragma unroll
     for (int q = 0; q < BK / 4; ++q) {
         double a[4], ra[4], b[4], vb[4];
@@ -125,6 +136,8 @@ __global__ void __launch_bounds__(NT, 1) k_chain_fwd(const double *__restrict__ 
                                                      const int *__restrict__ done) {
     if (done && *done) return;
     extern __shared__ __align__(16) double smem[];
+    constexpr int BK = DUAL ? BK_DUAL : BK_SINGLE;
+    constexpr int A_TILE = Tile<BK>::A, B_TILE = Tile<BK>::B;
     constexpr int STAGE = A_TILE * (DUAL && HAS_RA ? 2 : 1) + B_TILE * (DUAL ? 2 : 1);
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3, wm = w >> 1, wn = w & 1;
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
@@ -140,11 +153,11 @@ __global__ void __launch_bounds__(NT, 1) k_chain_fwd(const double *__restrict__ 
     auto load = [&](int st, int k0) {
         double *As, *RAs, *Bs, *VBs;
         stage_ptrs(st, As, RAs, Bs, VBs);
-        load_a_rowmajor(As, Yin, rows, Kd, m0, k0, true, 1.0, tid);
-        load_b_rowmajor(Bs, W, Kd + 1, N, k0, n0, tid);
+        load_a_rowmajor<BK>(As, Yin, rows, Kd, m0, k0, true, 1.0, tid);
+        load_b_rowmajor<BK>(Bs, W, Kd + 1, N, k0, n0, tid);
         if (DUAL) {
-            if (HAS_RA) load_a_rowmajor(RAs, RYin, rows, Kd, m0, k0, false, 0.0, tid);
-            load_b_rowmajor(VBs, VW, Kd + 1, N, k0, n0, tid);
+            if (HAS_RA) load_a_rowmajor<BK>(RAs, RYin, rows, Kd, m0, k0, false, 0.0, tid);
+            load_b_rowmajor<BK>(VBs, VW, Kd + 1, N, k0, n0, tid);
         }
         cp_async_commit();
     };
@@ -155,7 +168,7 @@ __global__ void __launch_bounds__(NT, 1) k_chain_fwd(const double *__restrict__ 
         __syncthreads();
         double *As, *RAs, *Bs, *VBs;
         stage_ptrs(it & 1, As, RAs, Bs, VBs);
-        mma_stage<DUAL, HAS_RA>(acc, racc, As, RAs, Bs, VBs, wm, wn, g, t);
+        mma_stage<DUAL, HAS_RA, BK>(acc, racc, As, RAs, Bs, VBs, wm, wn, g, t);
         __syncthreads();
     }
     // epilogue: activation, R{y} = R{x} f'(x), last layer: R-gradient seed RG_K = Ry_K / sigma^2 * f' (TRPO_FVP.c:852-882)
@@ -194,6 +207,7 @@ __global__ void __launch_bounds__(NT, 1) k_chain_bwd(const double *__restrict__ 
                                                      double *__restrict__ Gout, const int *__restrict__ done) {
     if (done && *done) return;
     extern __shared__ __align__(16) double smem[];
+    constexpr int BK = BK_SINGLE, A_TILE = Tile<BK>::A, B_TILE = Tile<BK>::B;
     constexpr int STAGE = A_TILE + B_TILE;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3, wm = w >> 1, wn = w & 1;
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
@@ -201,8 +215,8 @@ __global__ void __launch_bounds__(NT, 1) k_chain_bwd(const double *__restrict__ 
     const int nk = (Kd + BK - 1) / BK;
     auto load = [&](int st, int k0) {
         double *As = smem + st * STAGE, *Bs = As + A_TILE;
-        load_a_rowmajor(As, Gin, rows, Kd, m0, k0, false, 0.0, tid);
-        load_b_transposed(Bs, W, Kd, N, k0, n0, tid);
+        load_a_rowmajor<BK>(As, Gin, rows, Kd, m0, k0, false, 0.0, tid);
+        load_b_transposed<BK>(Bs, W, Kd, N, k0, n0, tid);
         cp_async_commit();
     };
     load(0, 0);
@@ -211,7 +225,7 @@ __global__ void __launch_bounds__(NT, 1) k_chain_bwd(const double *__restrict__ 
         else cp_async_wait_group<0>();
         __syncthreads();
         const double *As = smem + (it & 1) * STAGE, *Bs = As + A_TILE;
-        mma_stage<false, false>(acc, dummy, As, nullptr, Bs, nullptr, wm, wn, g, t);
+        mma_stage<false, false, BK>(acc, dummy, As, nullptr, Bs, nullptr, wm, wn, g, t);
         __syncthreads();
     }
 #pragma unroll
@@ -236,6 +250,7 @@ __global__ void __launch_bounds__(NT, 1) k_chain_outer(const double *__restrict_
                                                        const int *__restrict__ done) {
     if (done && *done) return;
     extern __shared__ __align__(16) double smem[];
+    constexpr int BK = BK_SINGLE, A_TILE = Tile<BK>::A, B_TILE = Tile<BK>::B;
     constexpr int STAGE = A_TILE + B_TILE;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3, wm = w >> 1, wn = w & 1;
     const int m0 = (blockIdx.x / tiles_n) * BM, n0 = (blockIdx.x % tiles_n) * BN;
@@ -246,8 +261,8 @@ __global__ void __launch_bounds__(NT, 1) k_chain_outer(const double *__restrict_
     const int nk = s1 > s0 ? (s1 - s0 + BK - 1) / BK : 0;
     auto load = [&](int st, int ks) {
         double *As = smem + st * STAGE, *Bs = As + A_TILE;
-        load_a_transposed(As, Yprev, s1, M0, m0, ks, tid);
-        load_b_rowmajor(Bs, G + (size_t)ks * N, s1 - ks, N, 0, n0, tid);
+        load_a_transposed<BK>(As, Yprev, s1, M0, m0, ks, tid);
+        load_b_rowmajor<BK>(Bs, G + (size_t)ks * N, s1 - ks, N, 0, n0, tid);
         cp_async_commit();
     };
     if (nk) load(0, s0);
@@ -256,7 +271,7 @@ __global__ void __launch_bounds__(NT, 1) k_chain_outer(const double *__restrict_
         else cp_async_wait_group<0>();
         __syncthreads();
         const double *As = smem + (it & 1) * STAGE, *Bs = As + A_TILE;
-        mma_stage<false, false>(acc, dummy, As, nullptr, Bs, nullptr, wm, wn, g, t);
+        mma_stage<false, false, BK>(acc, dummy, As, nullptr, Bs, nullptr, wm, wn, g, t);
         __syncthreads();
     }
     double *out = partial + (size_t)slice * P + out_off;
@@ -276,9 +291,9 @@ __global__ void __launch_bounds__(NT, 1) k_chain_outer(const double *__restrict_
     }
 }
 
-constexpr size_t SMEM_FWD_DUAL = sizeof(double) * 2 * (2 * A_TILE + 2 * B_TILE);
-constexpr size_t SMEM_FWD_L0   = sizeof(double) * 2 * (A_TILE + 2 * B_TILE);
-constexpr size_t SMEM_SINGLE   = sizeof(double) * 2 * (A_TILE + B_TILE);
+constexpr size_t SMEM_FWD_DUAL = sizeof(double) * 2 * (2 * Tile<BK_DUAL>::A + 2 * Tile<BK_DUAL>::B);
+constexpr size_t SMEM_FWD_L0   = sizeof(double) * 2 * (Tile<BK_DUAL>::A + 2 * Tile<BK_DUAL>::B);
+constexpr size_t SMEM_SINGLE   = sizeof(double) * 2 * (Tile<BK_SINGLE>::A + Tile<BK_SINGLE>::B);
 
 bool configure_kernels() {
     static bool ok = false;
@@ -373,7 +388,7 @@ int chain_accumulate(const NetDesc &net, const ChainScratch &sc, ChainMode mode,
             ++*launches;
             const int tl = cdiv(1, BM) * cdiv(A, BN), nsl = layer_slices(tl, sc.nslices);
             dim3 g1(tl, nsl);
-            k_chain_outer<<<g1, NT, SMEM_SINGLE, st>>>(nullptr, sc.RY[0], rows, 0, A, cdiv(cdiv(rows, nsl), BK) * BK, cdiv(A, BN),
+            k_chain_outer<<<g1, NT, SMEM_SINGLE, st>>>(nullptr, sc.RY[0], rows, 0, A, cdiv(cdiv(rows, nsl), BK_SINGLE) * BK_SINGLE, cdiv(A, BN),
                                              sc.partial, net.P, net.logstd_off, accumulate, d_done);
             ++*launches;
         }
@@ -384,7 +399,7 @@ int chain_accumulate(const NetDesc &net, const ChainScratch &sc, ChainMode mode,
             const int tiles_m = cdiv(M0 + 1, BM), tiles_n = cdiv(N, BN);
             const int ns = layer_slices(tiles_m * tiles_n, sc.nslices);
             dim3 go(tiles_m * tiles_n, ns);
-            k_chain_outer<<<go, NT, SMEM_SINGLE, st>>>(Yprev, sc.G[i & 1], rows, M0, N, cdiv(cdiv(rows, ns), BK) * BK, tiles_n,
+            k_chain_outer<<<go, NT, SMEM_SINGLE, st>>>(Yprev, sc.G[i & 1], rows, M0, N, cdiv(cdiv(rows, ns), BK_SINGLE) * BK_SINGLE, tiles_n,
                                              sc.partial, net.P, net.w_off[i - 1], accumulate, d_done);
             ++*launches;
             if (i > 1) {
