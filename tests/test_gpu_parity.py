@@ -198,3 +198,60 @@ def test_full_size_properties_mlp64_1m(pkg, oracle):
         z = ctx.fvp(vec["v"], 0.1)
     ref = oracle.fvp(layers, ac, theta, batch["Std"], np.ascontiguousarray(batch["Observ"][:n]), 0.1, vec["v"])
     assert rel_err(z, ref)[0] < FVP_TOL, rel_err(z, ref)
+
+
+def test_c_harness_binary(pkg, armtest, tmp_path):
+    """The plain-C driver (host/trpo_test_main.c, the shape of the reference's Test_CG / Test_FVP_FPGA harness,
+    TRPOCpuCode.c:76-223) linked against libtrpo_b200.so: no Python between the caller and the C-ABI."""
+    import os
+    import re
+    import subprocess
+    a = armtest
+    exe = os.path.join(os.path.dirname(pkg.api.library_path()), "trpo_test_gpu")
+    assert os.path.exists(exe), "run __graft_entry__.build()"
+    mf, df = str(tmp_path / "ArmTestModel.txt"), str(tmp_path / "ArmTestData.txt")
+    pkg.textio.write_model(mf, a["theta"])
+    pkg.textio.write_data(df, a["Mean"], a["Std"], a["Observ"], a["Action"], a["Advantage"])
+    # vectors file in the ArmTestCG.txt format: "input expected" with the compiled reference's result as expectation
+    cgf = str(tmp_path / "cg.txt")
+    with open(cgf, "w") as f:
+        for b, e in zip(a["cg_b"], a["ref_cg_3150"]):
+            f.write(f"{b!r} {e!r}\n")
+    out = subprocess.run([exe, "cg", mf, df, "3150", cgf], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    assert "CG Iter[8] Residual Norm=" in out.stdout
+    m = re.search(r"max\|d\|/max\|ref\| = ([0-9.e+-]+), rel-L2 = ([0-9.e+-]+)", out.stdout)
+    assert m and float(m.group(1)) < CG_TOL and float(m.group(2)) < CG_TOL, out.stdout[-400:]
+    fvf = str(tmp_path / "fvp.txt")
+    with open(fvf, "w") as f:
+        for b, e in zip(a["fvp_in"], a["ref_fvpfast_3150"]):
+            f.write(f"{b!r} {e!r}\n")
+    out = subprocess.run([exe, "fvp", mf, df, "3150", fvf], capture_output=True, text=True, timeout=300)
+    m = re.search(r"max\|d\|/max\|ref\| = ([0-9.e+-]+), rel-L2 = ([0-9.e+-]+)", out.stdout)
+    assert out.returncode == 0 and m and float(m.group(1)) < FVP_TOL, out.stdout[-400:]
+    # a missing model file: the reference's error text and a non-zero exit
+    out = subprocess.run([exe, "fvp", str(tmp_path / "none.txt"), df, "3150", fvf], capture_output=True, text=True, timeout=60)
+    assert out.returncode != 0 and "[ERROR] Cannot open Model File" in out.stderr
+
+
+def test_reference_symbol_names_in_dropin_library(pkg, armtest, tmp_path):
+    """FVP_FPGA / CG_FPGA (TRPO.h:98,101) resolved from libtrpo_b200_dropin.so and called with TRPOparam by value."""
+    import ctypes as C
+    a = armtest
+    mf, df = str(tmp_path / "m.txt"), str(tmp_path / "d.txt")
+    pkg.textio.write_model(mf, a["theta"])
+    pkg.textio.write_data(df, a["Mean"], a["Std"], a["Observ"], a["Action"], a["Advantage"])
+    lib = C.CDLL(pkg.api.library_path(dropin=True))
+    lib.FVP_FPGA.restype = C.c_double
+    lib.FVP_FPGA.argtypes = [pkg.TRPOparam, pkg.api.c_double_p, pkg.api.c_double_p]
+    lib.CG_FPGA.restype = C.c_double
+    lib.CG_FPGA.argtypes = [pkg.TRPOparam, pkg.api.c_double_p, pkg.api.c_double_p, C.c_size_t, C.c_double, C.c_size_t]
+    keep = []
+    p = pkg.api.make_param(mf, df, ARM_LAYERS, ARM_AC, 3150, 0.1, keep)
+    out = np.zeros(582)
+    v = np.ascontiguousarray(a["fvp_in"])
+    t = lib.FVP_FPGA(p, out.ctypes.data_as(pkg.api.c_double_p), v.ctypes.data_as(pkg.api.c_double_p))
+    assert t >= 0 and rel_err(out, a["ref_fvpfast_3150"])[0] < FVP_TOL
+    b = np.ascontiguousarray(a["cg_b"])
+    t = lib.CG_FPGA(p, out.ctypes.data_as(pkg.api.c_double_p), b.ctypes.data_as(pkg.api.c_double_p), 10, 1e-10, 4)
+    assert t >= 0 and rel_err(out, a["ref_cg_3150"])[0] < CG_TOL
