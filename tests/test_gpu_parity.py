@@ -216,7 +216,7 @@ def test_c_harness_binary(pkg, armtest, tmp_path):
     cgf = str(tmp_path / "cg.txt")
     with open(cgf, "w") as f:
         for b, e in zip(a["cg_b"], a["ref_cg_3150"]):
-            f.write(f"{b!r} {e!r}\n")
+            f.write(f"{float(b)!r} {float(e)!r}\n")
     out = subprocess.run([exe, "cg", mf, df, "3150", cgf], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr
     assert "CG Iter[8] Residual Norm=" in out.stdout
@@ -225,7 +225,7 @@ def test_c_harness_binary(pkg, armtest, tmp_path):
     fvf = str(tmp_path / "fvp.txt")
     with open(fvf, "w") as f:
         for b, e in zip(a["fvp_in"], a["ref_fvpfast_3150"]):
-            f.write(f"{b!r} {e!r}\n")
+            f.write(f"{float(b)!r} {float(e)!r}\n")
     out = subprocess.run([exe, "fvp", mf, df, "3150", fvf], capture_output=True, text=True, timeout=300)
     m = re.search(r"max\|d\|/max\|ref\| = ([0-9.e+-]+), rel-L2 = ([0-9.e+-]+)", out.stdout)
     assert out.returncode == 0 and m and float(m.group(1)) < FVP_TOL, out.stdout[-400:]
