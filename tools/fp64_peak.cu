@@ -146,6 +146,28 @@ __global__ void __launch_bounds__(256) k_ffma(float *out, int iters, float a, fl
     if (s == 12345.678f) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// legacy warp-level TF32 / BF16 tensor MMA (candidate for a 3xTF32 FP32 mode)
+template <int CHAINS>
+__global__ void __launch_bounds__(256) k_mma_tf32(float *out, int iters, float a, float b) {
+    float c[CHAINS][4];
+    unsigned af[4], bf[2];
+    for (int i = 0; i < 4; ++i) af[i] = __float_as_uint(a + i);
+    for (int i = 0; i < 2; ++i) bf[i] = __float_as_uint(b + i);
+#pragma unroll
+    for (int i = 0; i < CHAINS; ++i) { c[i][0] = threadIdx.x + i; c[i][1] = i; c[i][2] = 1; c[i][3] = 2; }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < CHAINS; ++i)
+            asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                         : "+f"(c[i][0]), "+f"(c[i][1]), "+f"(c[i][2]), "+f"(c[i][3])
+                         : "r"(af[0]), "r"(af[1]), "r"(af[2]), "r"(af[3]), "r"(bf[0]), "r"(bf[1]));
+    }
+    float s = 0;
+#pragma unroll
+    for (int i = 0; i < CHAINS; ++i) s += c[i][0] + c[i][1] + c[i][2] + c[i][3];
+    if (s == 12345.678f) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 // tanh cost on the FP64 pipe
 __global__ void __launch_bounds__(256) k_tanh(double *out, int iters, double a) {
     double x[4] = {a + threadIdx.x * 1e-3, a * 0.5, -a, a * 0.25};
@@ -210,6 +232,12 @@ int main(int argc, char **argv) {
         printf("bps=%d ffma16      : %8.3f ms  %7.2f TFLOP/s\n", bps, ms, thr * 16 * iters * 2 / ms / 1e9);
         ms = time_ms([&] { k_tanh<<<grid, 256>>>(out, iters / 16, 0.7); }, reps);
         printf("bps=%d tanh(f64)   : %8.3f ms  %7.2f Gtanh/s\n", bps, ms, thr * 4 * (iters / 16) / ms / 1e6);
+    }
+    for (int bps = 1; bps <= 4; bps *= 2) {
+        const int grid = sms * bps;
+        const double thr = (double)grid * 256;
+        float ms = time_ms([&] { k_mma_tf32<8><<<grid, 256>>>((float *)out, iters, 1.0000001f, 1e-9f); }, reps);
+        printf("bps=%d mma.sync m16n8k8 tf32 x8: %8.3f ms  %7.2f TFLOP/s\n", bps, ms, thr / 32 * 8 * iters * (2.0 * 16 * 8 * 8) / ms / 1e9);
     }
     // DMMA / DFMA dependent-issue latency: one warp per SM sub-partition (128 threads per SM), CH independent chains
     {
