@@ -189,7 +189,7 @@ def run_gpu_arm(args, pkg):
         b_pin = torch.from_numpy(vec["b"].copy()).pin_memory()
         x_pin = torch.zeros(P, dtype=torch.float64).pin_memory()
         stream = torch.cuda.Stream(device=dev)
-        ctx = pkg.Context(layers, ac, device=local_rank)
+        ctx = pkg.Context(layers, ac, device=local_rank, precision=1 if args.precision == "fp32" else 0)
         ctx.set_stream(stream.cuda_stream)
         if args.path:
             ctx.set_path({"chain": pkg.api.PATH_GEMM_CHAIN, "fused": pkg.api.PATH_FUSED}[args.path])
@@ -309,7 +309,9 @@ def run_gpu_arm(args, pkg):
         line = {
             "metric": "fvp_samples_per_sec", "value": m["value"], "unit": "samples/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": m["ms_step"], "cg_solve_ms": m["ms_step"],
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64" if args.precision == "fp64" else "f32 (3xTF32 products, f32 slice sums, f64 reduction + CG)",
+            "data": "synthetic",
             "config": {"workload": f"{args.workload}: {'-'.join(map(str, layers))} policy, {n_total} synthetic states, "
                                    f"{CG_ITERS}-iteration CG (ResidualTh=0), damping {DAMPING}",
                        "kernel_path": m["path"], "l2": "flushed between steps (256 MiB write); the 1M-state batch (136 MB) exceeds L2",
@@ -346,6 +348,8 @@ def main():
     ap.add_argument("--workload", default="mlp64")
     ap.add_argument("--states", type=int, default=0, help="override the number of synthetic states")
     ap.add_argument("--path", default="", choices=["", "chain", "fused"])
+    ap.add_argument("--precision", default="fp64", choices=["fp64", "fp32"],
+                    help="fp32 = the optional 3xTF32 mode of the FVP (stated tolerance 1e-4); the headline is fp64")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the arm-50k secondary measurement")
     ap.add_argument("--comm", default="nccl", choices=["p2p", "nccl"],

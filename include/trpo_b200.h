@@ -76,7 +76,10 @@ size_t trpo_num_params(const size_t *LayerSize, size_t NumLayers);
  * ---------------------------------------------------------------------------------------------- */
 typedef struct trpo_ctx trpo_ctx;
 
-enum { TRPO_PRECISION_FP64 = 0 };
+/* FP64: the reference's arithmetic (parity <= 1e-10). FP32: optional mode for the FVP inside CG -- FP32 storage, 3xTF32
+ * tensor-core products, FP32 per-slice sums, FP64 reduction and CG; stated tolerance 1e-4 relative (norm-wise) on the FVP.
+ * The policy gradient and the line search of trpo_ctx_update stay FP64 in either mode. */
+enum { TRPO_PRECISION_FP64 = 0, TRPO_PRECISION_FP32 = 1 };
 
 /* Kernel path selection (trpo_ctx_set_path). AUTO picks the fused DMMA kernel when the network fits it. */
 enum { TRPO_PATH_AUTO = 0, TRPO_PATH_GEMM_CHAIN = 1, TRPO_PATH_FUSED = 2 };

@@ -255,3 +255,38 @@ def test_reference_symbol_names_in_dropin_library(pkg, armtest, tmp_path):
     b = np.ascontiguousarray(a["cg_b"])
     t = lib.CG_FPGA(p, out.ctypes.data_as(pkg.api.c_double_p), b.ctypes.data_as(pkg.api.c_double_p), 10, 1e-10, 4)
     assert t >= 0 and rel_err(out, a["ref_cg_3150"])[0] < CG_TOL
+
+
+FP32_TOL = 1e-4       # stated tolerance of the optional FP32 mode (north_star: "~1e-4")
+
+
+@pytest.mark.parametrize("name", ["mlp64", "arm_sigma", "acts5", "odd_tanh_out"])
+def test_fp32_mode_within_stated_tolerance(pkg, name):
+    """Optional FP32 mode (3xTF32 tensor-core products, FP32 slice sums, FP64 reduction + CG) against the compiled
+    reference's FP64 results: norm-relative error below the stated 1e-4."""
+    s = load_synth(name)
+    L, ac = s["layers"], s["acfunc"]
+    with pkg.Context(L, ac, precision=pkg.api.PRECISION_FP32) as ctx:
+        ctx.set_model(s["theta"])
+        ctx.set_batch(s["Observ"], s["Std"], s["Mean"], s["Action"], s["Advantage"])
+        z = ctx.fvp(s["v"], 0.1)
+        x, info = ctx.cg(s["b"], 10, 1e-10, 0.1)
+    e = rel_err(z, s["ref_fvpfast"])
+    assert e[0] < FP32_TOL and e[1] < FP32_TOL, (name, e)
+    assert e[1] > 1e-12                       # it really is the FP32 path
+    e = rel_err(x, s["ref_cg"])
+    assert e[1] < 5e-3, (name, e)             # CG amplifies the FVP error by the conditioning of F + damping*I
+
+
+def test_fp32_mode_humanoid_width(pkg, oracle):
+    layers, ac = [376, 256, 256, 17], "lttl"
+    theta = pkg.synth.make_model(layers, 4)
+    batch = pkg.synth.make_batch(layers, ac, theta, 300, 4)
+    vec = pkg.synth.make_vectors(layers, 4)
+    ref = oracle.fvp(layers, ac, theta, batch["Std"], batch["Observ"], 0.1, vec["v"])
+    with pkg.Context(layers, ac, precision=pkg.api.PRECISION_FP32) as ctx:
+        ctx.set_model(theta)
+        ctx.set_batch(batch["Observ"], batch["Std"])
+        z = ctx.fvp(vec["v"], 0.1)
+    e = rel_err(z, ref)
+    assert e[0] < FP32_TOL and e[1] < FP32_TOL, e

@@ -18,6 +18,7 @@ c_size_p = C.POINTER(C.c_size_t)
 
 PATH_AUTO, PATH_GEMM_CHAIN, PATH_FUSED = 0, 1, 2
 COMM_NCCL, COMM_P2P = 0, 1
+PRECISION_FP64, PRECISION_FP32 = 0, 1
 
 
 class TRPOparam(C.Structure):
@@ -166,11 +167,11 @@ def TRPO_Update_GPU(model_file, data_file, layers, acfunc, num_samples, damping,
 class Context:
     """Persistent device context: model + rollout batch staged once, CG state resident on the GPU."""
 
-    def __init__(self, layers, acfunc, device=-1):
+    def __init__(self, layers, acfunc, device=-1, precision=0):
         self.layers = list(layers)
         self.acfunc = acfunc
         ls = (C.c_size_t * len(layers))(*layers)
-        self.h = lib().trpo_ctx_create(ls, acfunc.encode(), len(layers), device, 0)
+        self.h = lib().trpo_ctx_create(ls, acfunc.encode(), len(layers), device, precision)
         if not self.h:
             raise RuntimeError(f"libtrpo_b200: {last_error()}")
         self.P = lib().trpo_ctx_num_params(self.h)

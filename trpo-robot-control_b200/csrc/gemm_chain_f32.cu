@@ -1,0 +1,390 @@
+// gemm_chain_f32.cu -- optional FP32 mode of the Fisher-vector product (stated tolerance ~1e-4 relative).
+//
+// Same GEMM chain as gemm_chain.cu (forward R-op dual GEMM, backward GEMM, split-K outer product), but activations,
+// weights and observations are FP32 and the products run on the tensor cores as 3xTF32: each FP32 operand is split
+// into a TF32 head and a TF32 tail (x = hi + lo) and a product is issued as lo*hi + hi*lo + hi*hi with FP32 accumulation,
+// which keeps ~FP32 accuracy (a single TF32 product would lose 13 mantissa bits and miss the 1e-4 target).
+// Measured on this box (profiles/tf32_peak_r01.txt): mma.sync.m16n8k8.tf32 (SASS HMMA.1688.F32.TF32) 278 TFLOP/s, i.e.
+// 93 TFLOP/s effective for 3xTF32 against 37.1 for the FP64 tensor pipe and 71.7 for plain FFMA.
+// CTA tile 128 x 64, k-step 32, 8 warps of 32 x 32 (2 x 4 MMA tiles of 16 x 8), 4-byte cp.async with zero fill, shared
+// row strides 36 / 72 floats (conflict-free fragment reads). Per-slice partial sums are FP32; the fixed-order slice
+// reduction and everything downstream (CG) are FP64.
+#include "trpo_internal.cuh"
+
+namespace {
+
+constexpr int BM = 128, BN = 64, BK = 32, NT = 256;
+constexpr int RSA = BK + 4, RSB = BN + 8;               // 36: g*4+t distinct banks; 72: t*8+g distinct banks
+constexpr int A_TILE = BM * RSA, B_TILE = BK * RSB;     // floats per operand tile
+
+__device__ __forceinline__ void cp_async4(float *dst_smem, const float *src, int src_bytes) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" :: "r"(d), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(N) : "memory"); }
+
+__device__ __forceinline__ void split_tf32(float x, unsigned &hi, unsigned &lo) {
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+    const float rest = x - __uint_as_float(hi);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(rest));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
+    asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+// c += a*b with 3xTF32 error compensation (small terms first)
+__device__ __forceinline__ void mma3(float (&c)[4], const unsigned (&ahi)[4], const unsigned (&alo)[4],
+                                     const unsigned (&bhi)[2], const unsigned (&blo)[2]) {
+    mma_tf32(c, alo, bhi);
+    mma_tf32(c, ahi, blo);
+    mma_tf32(c, ahi, bhi);
+}
+
+__device__ __forceinline__ float act_apply(char a, float x) {
+    switch (a) {
+        case 't': return tanhf(x);
+        case 'o': return 0.1f * x;
+        case 's': return 1.0f / (1.0f + expf(-x));
+        default:  return x;
+    }
+}
+__device__ __forceinline__ float act_deriv(char a, float y) {
+    switch (a) {
+        case 't': return 1.0f - y * y;
+        case 'o': return 0.1f;
+        case 's': return y * (1.0f - y);
+        default:  return 1.0f;
+    }
+}
+
+__device__ __forceinline__ void load_a_rowmajor(float *As, const float *X, int rows, int ld, int m0, int k0,
+                                                bool aug, float ones_val, int tid) {
+#pragma unroll
+    for (int it = 0; it < BM * BK / NT; ++it) {
+        const int idx = tid + it * NT, m = idx / BK, k = idx % BK;
+        const int gm = m0 + m, gk = k0 + k;
+        const bool in = X != nullptr && gm < rows && gk < ld;
+        if (aug && gk == ld && gm < rows) As[m * RSA + k] = ones_val;
+        else cp_async4(&As[m * RSA + k], in ? &X[(size_t)gm * ld + gk] : X, in ? 4 : 0);
+    }
+}
+__device__ __forceinline__ void load_a_transposed(float *As, const float *Y, int s_end, int M0, int m0, int s0, int tid) {
+#pragma unroll
+    for (int it = 0; it < BM * BK / NT; ++it) {
+        const int idx = tid + it * NT, k = idx >> 7, m = idx & 127;
+        const int gm = m0 + m, gs = s0 + k;
+        const bool in = Y != nullptr && gm < M0 && gs < s_end;
+        if (gm == M0 && gs < s_end) As[m * RSA + k] = 1.0f;
+        else cp_async4(&As[m * RSA + k], in ? &Y[(size_t)gs * M0 + gm] : Y, in ? 4 : 0);
+    }
+}
+__device__ __forceinline__ void load_b_rowmajor(float *Bs, const float *M, int kdim, int N, int k0, int n0, int tid) {
+#pragma unroll
+    for (int it = 0; it < BK * BN / NT; ++it) {
+        const int idx = tid + it * NT, k = idx >> 6, n = idx & 63;
+        const int gk = k0 + k, gn = n0 + n;
+        const bool in = gk < kdim && gn < N;
+        cp_async4(&Bs[k * RSB + n], in ? &M[(size_t)gk * N + gn] : M, in ? 4 : 0);
+    }
+}
+__device__ __forceinline__ void load_b_transposed(float *Bs, const float *W, int Kd, int N, int k0, int n0, int tid) {
+#pragma unroll
+    for (int it = 0; it < BK * BN / NT; ++it) {
+        const int idx = tid + it * NT, n = idx / BK, k = idx % BK;
+        const int gk = k0 + k, gn = n0 + n;
+        const bool in = gk < Kd && gn < N;
+        cp_async4(&Bs[k * RSB + n], in ? &W[(size_t)gn * Kd + gk] : W, in ? 4 : 0);
+    }
+}
+
+// one k-step (32) of a warp's 32 x 32 sub-tile. Fragment layout of m16n8k8 (lane = 4g + t):
+//   A: (g, t) (g+8, t) (g, t+4) (g+8, t+4)    B: (t, g) (t+4, g)    C: (g, 2t) (g, 2t+1) (g+8, 2t) (g+8, 2t+1)
+template <bool DUAL, bool HAS_RA>
+__device__ __forceinline__ void mma_stage(float (&acc)[2][4][4], float (&racc)[2][4][4], const float *As, const float *RAs,
+                                          const float *Bs, const float *VBs, int wm, int wn, int g, int t) {
+#pragma unroll
+    for (int q = 0; q < BK / 8; ++q) {
+        unsigned ahi[2][4], alo[2][4], rhi[2][4], rlo[2][4], bhi[4][2], blo[4][2], vhi[4][2], vlo[4][2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int row = 32 * wm + 16 * i + g + 8 * (e & 1), col = 8 * q + t + 4 * (e >> 1);
+                split_tf32(As[row * RSA + col], ahi[i][e], alo[i][e]);
+                if (DUAL && HAS_RA) split_tf32(RAs[row * RSA + col], rhi[i][e], rlo[i][e]);
+            }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int row = 8 * q + t + 4 * e, col = 32 * wn + 8 * j + g;
+                split_tf32(Bs[row * RSB + col], bhi[j][e], blo[j][e]);
+                if (DUAL) split_tf32(VBs[row * RSB + col], vhi[j][e], vlo[j][e]);
+            }
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                mma3(acc[i][j], ahi[i], alo[i], bhi[j], blo[j]);
+                if (DUAL) {
+                    if (HAS_RA) mma3(racc[i][j], rhi[i], rlo[i], bhi[j], blo[j]);
+                    mma3(racc[i][j], ahi[i], alo[i], vhi[j], vlo[j]);
+                }
+            }
+    }
+}
+
+template <bool DUAL, bool HAS_RA>
+__global__ void __launch_bounds__(NT, 1) k_fwd(const float *__restrict__ Yin, const float *__restrict__ RYin,
+                                               const float *__restrict__ W, const float *__restrict__ VW,
+                                               int rows, int Kd, int N, char act,
+                                               float *__restrict__ Yout, float *__restrict__ RYout,
+                                               float *__restrict__ Gout, const float *__restrict__ inv_var,
+                                               const int *__restrict__ done) {
+    if (done && *done) return;
+    extern __shared__ __align__(16) float smem_f[];
+    constexpr int STAGE = A_TILE * (DUAL && HAS_RA ? 2 : 1) + B_TILE * (DUAL ? 2 : 1);
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3, wm = w >> 1, wn = w & 1;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    float acc[2][4][4] = {}, racc[2][4][4] = {};
+    const int nk = (Kd + 1 + BK - 1) / BK;
+    auto stage_ptrs = [&](int st, float *&As, float *&RAs, float *&Bs, float *&VBs) {
+        float *p = smem_f + st * STAGE;
+        As = p; p += A_TILE;
+        RAs = p; if (DUAL && HAS_RA) p += A_TILE;
+        Bs = p; p += B_TILE;
+        VBs = p;
+    };
+    auto load = [&](int st, int k0) {
+        float *As, *RAs, *Bs, *VBs;
+        stage_ptrs(st, As, RAs, Bs, VBs);
+        load_a_rowmajor(As, Yin, rows, Kd, m0, k0, true, 1.0f, tid);
+        load_b_rowmajor(Bs, W, Kd + 1, N, k0, n0, tid);
+        if (DUAL) {
+            if (HAS_RA) load_a_rowmajor(RAs, RYin, rows, Kd, m0, k0, false, 0.0f, tid);
+            load_b_rowmajor(VBs, VW, Kd + 1, N, k0, n0, tid);
+        }
+        cp_commit();
+    };
+    load(0, 0);
+    for (int it = 0; it < nk; ++it) {
+        if (it + 1 < nk) { load((it + 1) & 1, (it + 1) * BK); cp_wait<1>(); }
+        else cp_wait<0>();
+        __syncthreads();
+        float *As, *RAs, *Bs, *VBs;
+        stage_ptrs(it & 1, As, RAs, Bs, VBs);
+        mma_stage<DUAL, HAS_RA>(acc, racc, As, RAs, Bs, VBs, wm, wn, g, t);
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int gm = m0 + 32 * wm + 16 * i + g + 8 * (e >> 1), gn = n0 + 32 * wn + 8 * j + 2 * t + (e & 1);
+                if (gm >= rows || gn >= N) continue;
+                const float y = act_apply(act, acc[i][j][e]);
+                const float d = act_deriv(act, y);
+                if (Yout) Yout[(size_t)gm * N + gn] = y;
+                if (DUAL) {
+                    const float ry = racc[i][j][e] * d;
+                    if (RYout) RYout[(size_t)gm * N + gn] = ry;
+                    if (Gout) Gout[(size_t)gm * N + gn] = ry * inv_var[gn] * d;
+                }
+            }
+}
+
+__global__ void __launch_bounds__(NT, 1) k_bwd(const float *__restrict__ Gin, const float *__restrict__ W,
+                                               const float *__restrict__ Yprev, int rows, int Kd, int N, char act_prev,
+                                               float *__restrict__ Gout, const int *__restrict__ done) {
+    if (done && *done) return;
+    extern __shared__ __align__(16) float smem_f[];
+    constexpr int STAGE = A_TILE + B_TILE;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3, wm = w >> 1, wn = w & 1;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    float acc[2][4][4] = {}, dummy[2][4][4];
+    const int nk = (Kd + BK - 1) / BK;
+    auto load = [&](int st, int k0) {
+        float *As = smem_f + st * STAGE, *Bs = As + A_TILE;
+        load_a_rowmajor(As, Gin, rows, Kd, m0, k0, false, 0.0f, tid);
+        load_b_transposed(Bs, W, Kd, N, k0, n0, tid);
+        cp_commit();
+    };
+    load(0, 0);
+    for (int it = 0; it < nk; ++it) {
+        if (it + 1 < nk) { load((it + 1) & 1, (it + 1) * BK); cp_wait<1>(); }
+        else cp_wait<0>();
+        __syncthreads();
+        const float *As = smem_f + (it & 1) * STAGE, *Bs = As + A_TILE;
+        mma_stage<false, false>(acc, dummy, As, nullptr, Bs, nullptr, wm, wn, g, t);
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int gm = m0 + 32 * wm + 16 * i + g + 8 * (e >> 1), gn = n0 + 32 * wn + 8 * j + 2 * t + (e & 1);
+                if (gm >= rows || gn >= N) continue;
+                Gout[(size_t)gm * N + gn] = acc[i][j][e] * act_deriv(act_prev, Yprev[(size_t)gm * N + gn]);
+            }
+}
+
+__global__ void __launch_bounds__(NT, 1) k_outer(const float *__restrict__ Yprev, const float *__restrict__ G,
+                                                 int rows, int M0, int N, int per_slice, int tiles_n,
+                                                 float *__restrict__ partial, int P, int out_off, int accumulate,
+                                                 const int *__restrict__ done) {
+    if (done && *done) return;
+    extern __shared__ __align__(16) float smem_f[];
+    constexpr int STAGE = A_TILE + B_TILE;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3, wm = w >> 1, wn = w & 1;
+    const int m0 = (blockIdx.x / tiles_n) * BM, n0 = (blockIdx.x % tiles_n) * BN;
+    const int slice = blockIdx.y;
+    const int s0 = slice * per_slice;
+    const int s1 = min(rows, s0 + per_slice);
+    float acc[2][4][4] = {}, dummy[2][4][4];
+    const int nk = s1 > s0 ? (s1 - s0 + BK - 1) / BK : 0;
+    auto load = [&](int st, int ks) {
+        float *As = smem_f + st * STAGE, *Bs = As + A_TILE;
+        load_a_transposed(As, Yprev, s1, M0, m0, ks, tid);
+        load_b_rowmajor(Bs, G + (size_t)ks * N, s1 - ks, N, 0, n0, tid);
+        cp_commit();
+    };
+    if (nk) load(0, s0);
+    for (int it = 0; it < nk; ++it) {
+        if (it + 1 < nk) { load((it + 1) & 1, s0 + (it + 1) * BK); cp_wait<1>(); }
+        else cp_wait<0>();
+        __syncthreads();
+        const float *As = smem_f + (it & 1) * STAGE, *Bs = As + A_TILE;
+        mma_stage<false, false>(acc, dummy, As, nullptr, Bs, nullptr, wm, wn, g, t);
+        __syncthreads();
+    }
+    float *out = partial + (size_t)slice * P + out_off;
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int gm = m0 + 32 * wm + 16 * i + g + 8 * (e >> 1), gn = n0 + 32 * wn + 8 * j + 2 * t + (e & 1);
+                if (gm > M0 || gn >= N) continue;
+                const size_t o = (size_t)gm * N + gn;
+                out[o] = accumulate ? out[o] + acc[i][j][e] : acc[i][j][e];
+            }
+}
+
+__global__ void k_to_float(const double *__restrict__ src, float *__restrict__ dst, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = (float)src[i];
+}
+
+// zsum[e] (FP64) = fixed-order sum over slices of the FP32 partial rows
+__global__ void __launch_bounds__(256) k_reduce_f32(const float *__restrict__ partial, int rows, int P,
+                                                    double *__restrict__ zsum, const int *__restrict__ done) {
+    if (done && *done) return;
+    __shared__ double sh[8][32];
+    const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5, e = blockIdx.x * 32 + cx;
+    double s = 0.0;
+    if (e < P)
+        for (int r = ry; r < rows; r += 8) s += (double)partial[(size_t)r * P + e];
+    sh[ry][cx] = s;
+    __syncthreads();
+    if (ry == 0 && e < P) {
+        double t = sh[0][cx];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) t += sh[k][cx];
+        zsum[e] = t;
+    }
+}
+
+constexpr size_t SMEM_DUAL = sizeof(float) * 2 * (2 * A_TILE + 2 * B_TILE);
+constexpr size_t SMEM_L0 = sizeof(float) * 2 * (A_TILE + 2 * B_TILE);
+constexpr size_t SMEM_SINGLE = sizeof(float) * 2 * (A_TILE + B_TILE);
+
+bool configure() {
+    static bool ok = false;
+    if (ok) return true;
+    bool r = true;
+    r = r && cudaFuncSetAttribute(k_fwd<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_DUAL) == cudaSuccess;
+    r = r && cudaFuncSetAttribute(k_fwd<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_L0) == cudaSuccess;
+    r = r && cudaFuncSetAttribute(k_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_SINGLE) == cudaSuccess;
+    r = r && cudaFuncSetAttribute(k_outer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_SINGLE) == cudaSuccess;
+    ok = r;
+    return r;
+}
+
+inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+inline int layer_slices(int tiles, int max_slices) {
+    int ns = 296 / tiles;
+    if (ns > max_slices) ns = max_slices;
+    return ns < 1 ? 1 : ns;
+}
+
+}  // namespace
+
+size_t chain_f32_scratch_floats(const NetDesc &net, int chunk, int nslices) {
+    size_t maxL = net.L[0], sumL = 0;
+    for (int i = 1; i <= net.K; ++i) { sumL += net.L[i]; if ((size_t)net.L[i] > maxL) maxL = net.L[i]; }
+    return (size_t)chunk * (sumL + 4 * maxL) + (size_t)nslices * net.P + 2 * (size_t)net.P + 64;
+}
+
+void chain_f32_convert(const double *d_src, float *d_dst, size_t n, cudaStream_t st, long long *launches) {
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
+    k_to_float<<<blocks, 256, 0, st>>>(d_src, d_dst, n);
+    ++*launches;
+}
+
+// FP32 counterpart of chain_accumulate(CHAIN_FVP): zsum (FP64) = sum_n per-sample [RGW, RGB, ...]
+int chain_f32_accumulate(const NetDesc &net, const ChainScratchF32 &sc, const float *f_theta, const float *f_v,
+                         const float *f_inv_var, const float *f_obs, size_t nsamples, double *d_zsum,
+                         const int *d_done, const P2PComm *p2p, cudaStream_t st, long long *launches) {
+    if (!configure()) return -1;
+    const int K = net.K;
+    int chunk_idx = 0;
+    for (size_t c0 = 0; c0 < nsamples; c0 += sc.chunk, ++chunk_idx) {
+        const int rows = (int)((nsamples - c0 < (size_t)sc.chunk) ? nsamples - c0 : sc.chunk);
+        const int accumulate = chunk_idx > 0;
+        for (int i = 0; i < K; ++i) {
+            const float *Yin = (i == 0) ? f_obs + c0 * net.L[0] : sc.Y[i];
+            const bool last = (i == K - 1);
+            const bool needY = !last || net.ac[K] == 't' || net.ac[K] == 's';
+            dim3 grid(cdiv(rows, BM), cdiv(net.L[i + 1], BN));
+            if (i == 0)
+                k_fwd<true, false><<<grid, NT, SMEM_L0, st>>>(Yin, nullptr, f_theta + net.w_off[i], f_v + net.w_off[i], rows,
+                        net.L[i], net.L[i + 1], net.ac[i + 1], needY ? sc.Y[i + 1] : nullptr,
+                        last ? nullptr : sc.RY[(i + 1) & 1], last ? sc.G[K & 1] : nullptr, f_inv_var, d_done);
+            else
+                k_fwd<true, true><<<grid, NT, SMEM_DUAL, st>>>(Yin, sc.RY[i & 1], f_theta + net.w_off[i], f_v + net.w_off[i], rows,
+                        net.L[i], net.L[i + 1], net.ac[i + 1], needY ? sc.Y[i + 1] : nullptr,
+                        last ? nullptr : sc.RY[(i + 1) & 1], last ? sc.G[K & 1] : nullptr, f_inv_var, d_done);
+            ++*launches;
+        }
+        for (int i = K; i >= 1; --i) {
+            const float *Yprev = (i == 1) ? f_obs + c0 * net.L[0] : sc.Y[i - 1];
+            const int M0 = net.L[i - 1], N = net.L[i];
+            const int tiles_m = cdiv(M0 + 1, BM), tiles_n = cdiv(N, BN);
+            const int ns = layer_slices(tiles_m * tiles_n, sc.nslices);
+            dim3 go(tiles_m * tiles_n, ns);
+            k_outer<<<go, NT, SMEM_SINGLE, st>>>(Yprev, sc.G[i & 1], rows, M0, N, cdiv(cdiv(rows, ns), BK) * BK, tiles_n,
+                                                sc.partial, net.P, net.w_off[i - 1], accumulate, d_done);
+            ++*launches;
+            if (i > 1) {
+                dim3 gb(cdiv(rows, BM), cdiv(M0, BN));
+                k_bwd<<<gb, NT, SMEM_SINGLE, st>>>(sc.G[i & 1], f_theta + net.w_off[i - 1], sc.Y[i - 1], rows, N, M0,
+                                                  net.ac[i - 1], sc.G[(i - 1) & 1], d_done);
+                ++*launches;
+            }
+        }
+    }
+    k_reduce_f32<<<(net.P + 31) / 32, 256, 0, st>>>(sc.partial, sc.nslices, net.P, d_zsum, d_done);
+    ++*launches;
+    (void)p2p;
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}

@@ -70,6 +70,20 @@ int chain_forward(const NetDesc &net, const ChainScratch &sc, const double *d_th
                   size_t nsamples, double *d_mean_out, cudaStream_t st, long long *launches);
 size_t chain_scratch_bytes(const NetDesc &net, int chunk, int nslices);
 
+// ---- gemm_chain_f32.cu (optional FP32 mode) ------------------------------------------------------------------------
+struct ChainScratchF32 {
+    float *Y[TRPO_MAX_LAYERS];
+    float *RY[2];
+    float *G[2];
+    int chunk, nslices;
+    float *partial;                  // [nslices x P] FP32 partial sums
+};
+size_t chain_f32_scratch_floats(const NetDesc &net, int chunk, int nslices);
+void chain_f32_convert(const double *d_src, float *d_dst, size_t n, cudaStream_t st, long long *launches);
+int chain_f32_accumulate(const NetDesc &net, const ChainScratchF32 &sc, const float *f_theta, const float *f_v,
+                         const float *f_inv_var, const float *f_obs, size_t nsamples, double *d_zsum,
+                         const int *d_done, const P2PComm *p2p, cudaStream_t st, long long *launches);
+
 // ---- fvp_fused.cu -------------------------------------------------------------------------------------------------
 // Fused DMMA kernel for 4-layer nets whose padded weights fit in shared memory. Returns 0 if it handled the launch,
 // 1 if the shape is not eligible.

@@ -86,6 +86,13 @@ struct trpo_ctx {
     size_t sc_bytes;
     // fused path partials
     double *d_fused_partial;
+    // optional FP32 mode (FVP inside CG): FP32 copies of the model, direction and observations + FP32 scratch
+    int precision;
+    float *f_theta, *f_v, *f_inv_var, *f_obs;
+    size_t cap_fobs;
+    ChainScratchF32 scf;
+    float *scf_base;
+    size_t scf_floats;
     // optional event timing of the FVP-sum kernel(s)
     bool ktime_on;
     int ktime_n;
@@ -157,7 +164,7 @@ static int ensure_chain_scratch(trpo_ctx *c) {
 
 extern "C" trpo_ctx *trpo_ctx_create(const size_t *LayerSize, const char *AcFunc, size_t NumLayers, int device, int precision) {
     if (!LayerSize || !AcFunc || NumLayers < 2 || NumLayers > TRPO_MAX_LAYERS) { fail("bad network description"); return nullptr; }
-    if (precision != TRPO_PRECISION_FP64) { fail("only TRPO_PRECISION_FP64 is built"); return nullptr; }
+    if (precision != TRPO_PRECISION_FP64 && precision != TRPO_PRECISION_FP32) { fail("unknown precision %d", precision); return nullptr; }
     for (size_t i = 1; i < NumLayers; ++i) {
         const char a = AcFunc[i];
         if (a != 'l' && a != 't' && a != 'o' && a != 's') {
@@ -183,6 +190,8 @@ extern "C" trpo_ctx *trpo_ctx_create(const size_t *LayerSize, const char *AcFunc
     c->net.logstd_off = pos;
     c->net.P = pos + c->net.L[c->net.K];
     c->world = 1;
+    c->precision = precision;
+    if (precision == TRPO_PRECISION_FP32) c->path_req = TRPO_PATH_GEMM_CHAIN;      // the FP32 mode is a GEMM-chain mode
     const size_t P = c->net.P, A = c->net.L[c->net.K];
     bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
     c->own_stream = true;
@@ -204,6 +213,10 @@ extern "C" trpo_ctx *trpo_ctx_create(const size_t *LayerSize, const char *AcFunc
     if (ok) for (int i = 0; i <= STAGE_CHUNKS; ++i) c->h_ready_vals[i] = i;
     if (ok && fused_eligible(c->net))
         ok = cudaMalloc(&c->d_fused_partial, (size_t)fused_partial_rows() * P * sizeof(double)) == cudaSuccess;
+    if (ok && precision == TRPO_PRECISION_FP32) {
+        ok = cudaMalloc(&c->f_theta, P * sizeof(float)) == cudaSuccess && cudaMalloc(&c->f_v, P * sizeof(float)) == cudaSuccess &&
+             cudaMalloc(&c->f_inv_var, A * sizeof(float)) == cudaSuccess;
+    }
     if (ok) ok = cudaMemset(c->d_state, 0, sizeof(CgState)) == cudaSuccess;
     if (!ok) { fail("device allocation failed: %s", cudaGetErrorString(cudaGetLastError())); trpo_ctx_destroy(c); return nullptr; }
     return c;
@@ -227,6 +240,8 @@ extern "C" void trpo_ctx_destroy(trpo_ctx *c) {
     double *vecs[] = {c->d_theta, c->d_in, c->d_out, c->d_zsum, c->d_x, c->d_r, c->d_p, c->d_z, c->d_b, c->d_xnew,
                       c->d_inv_var, c->d_std, c->d_scal, c->d_blockpart, c->d_mean_new, c->sc_base, c->d_fused_partial};
     for (double *v : vecs) if (v) cudaFree(v);
+    float *fvecs[] = {c->f_theta, c->f_v, c->f_inv_var, c->f_obs, c->scf_base};
+    for (float *v : fvecs) if (v) cudaFree(v);
     if (c->d_state) cudaFree(c->d_state);
     if (c->h_state) cudaFreeHost(c->h_state);
     if (c->h_scal) cudaFreeHost(c->h_scal);
@@ -253,6 +268,8 @@ extern "C" int trpo_ctx_set_stream(trpo_ctx *c, void *s) {
 extern "C" void *trpo_ctx_get_stream(const trpo_ctx *c) { return c ? (void *)c->stream : nullptr; }
 extern "C" int trpo_ctx_set_path(trpo_ctx *c, int path) {
     if (!c) return fail("null context");
+    if (c->precision == TRPO_PRECISION_FP32 && path == TRPO_PATH_FUSED) return fail("the FP32 mode has no fused kernel");
+    if (c->precision == TRPO_PRECISION_FP32) path = TRPO_PATH_GEMM_CHAIN;
     if (path == TRPO_PATH_FUSED && !fused_eligible(c->net)) return fail("network shape is not eligible for the fused kernel");
     c->path_req = path;
     return 0;
@@ -270,6 +287,7 @@ extern "C" int trpo_ctx_set_model(trpo_ctx *c, const double *theta) {
     if (!c || !theta) return fail("null argument");
     CU(cudaSetDevice(c->device));
     CU(cudaMemcpyAsync(c->d_theta, theta, c->net.P * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if (c->precision == TRPO_PRECISION_FP32) chain_f32_convert(c->d_theta, c->f_theta, c->net.P, c->stream, &c->launches);
     CU(cudaStreamSynchronize(c->stream));
     return 0;
 }
@@ -281,6 +299,18 @@ static int set_std(trpo_ctx *c, const double *Std) {
     for (int j = 0; j < A; ++j) iv[j] = 1.0 / (Std[j] * Std[j]);
     CU(cudaMemcpyAsync(c->d_std, Std, A * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(c->d_inv_var, iv, A * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if (c->precision == TRPO_PRECISION_FP32) {
+        chain_f32_convert(c->d_inv_var, c->f_inv_var, A, c->stream, &c->launches);
+        // FP32 copy of the observations (they are already on the stream: set_std runs after the batch copy / adoption)
+        const size_t n = c->n_local * (size_t)c->net.L[0];
+        if (n > c->cap_fobs) {
+            if (c->f_obs) cudaFree(c->f_obs);
+            c->f_obs = nullptr;
+            CU(cudaMalloc(&c->f_obs, n * sizeof(float)));
+            c->cap_fobs = n;
+        }
+        chain_f32_convert(c->d_obs, c->f_obs, n, c->stream, &c->launches);
+    }
     CU(cudaStreamSynchronize(c->stream));
     return 0;
 }
@@ -365,7 +395,9 @@ extern "C" int trpo_ctx_set_batch_device(trpo_ctx *c, size_t N, const double *dO
 }
 
 // --------------------------------------------------------------------------------------------------------------
-static inline const P2PComm *active_p2p(const trpo_ctx *c) { return (c->p2p_on && c->p2p.world > 1) ? &c->p2p : nullptr; }
+static inline const P2PComm *active_p2p(const trpo_ctx *c) {
+    return (c->p2p_on && c->p2p.world > 1 && c->precision == TRPO_PRECISION_FP64) ? &c->p2p : nullptr;
+}
 
 extern "C" int trpo_ctx_kernel_timing(trpo_ctx *c, int enable) {
     if (!c) return fail("null context");
@@ -393,8 +425,59 @@ extern "C" double trpo_ctx_kernel_time_ms(trpo_ctx *c, int *launches) {
 }
 
 // un-normalised FVP sum of the local shard into d_zsum, then the cross-GPU sum
+static int ensure_f32_scratch(trpo_ctx *c) {
+    size_t maxL = c->net.L[0], sumL = 0, maxH = 1;
+    for (int i = 1; i <= c->net.K; ++i) {
+        sumL += c->net.L[i];
+        if ((size_t)c->net.L[i] > maxL) maxL = c->net.L[i];
+        if ((size_t)c->net.L[i] > maxH) maxH = c->net.L[i];
+    }
+    const size_t per_sample = 4 * (sumL + 4 * maxL);
+    const size_t tiles_n = (maxH + 63) / 64;
+    size_t gcd = 148, b = tiles_n;
+    while (b) { size_t r = gcd % b; gcd = b; b = r; }
+    const size_t unit = 128 * (148 / gcd);
+    size_t chunk = ((512u << 20) / per_sample / unit) * unit;
+    if (chunk < unit) chunk = unit;
+    if (chunk > 8 * unit) chunk = 8 * unit;
+    if (chunk > 131072) chunk = (131072 / unit) * unit;
+    if (c->n_local && chunk > ((c->n_local + 127) / 128) * 128) chunk = ((c->n_local + 127) / 128) * 128;
+    int nslices = 148;
+    if ((size_t)nslices * 32 > chunk) nslices = (int)(chunk / 32);
+    if (nslices < 1) nslices = 1;
+    const size_t floats = chain_f32_scratch_floats(c->net, (int)chunk, nslices);
+    if (c->scf_base && floats <= c->scf_floats && c->scf.chunk == (int)chunk && c->scf.nslices == nslices) return 0;
+    if (c->scf_base) cudaFree(c->scf_base);
+    c->scf_base = nullptr;
+    CU(cudaMalloc(&c->scf_base, floats * sizeof(float)));
+    CU(cudaMemsetAsync(c->scf_base, 0, floats * sizeof(float), c->stream));
+    c->scf_floats = floats;
+    float *p = c->scf_base;
+    for (int i = 1; i <= c->net.K; ++i) { c->scf.Y[i] = p; p += chunk * c->net.L[i]; }
+    for (int j = 0; j < 2; ++j) { c->scf.RY[j] = p; p += chunk * maxL; }
+    for (int j = 0; j < 2; ++j) { c->scf.G[j] = p; p += chunk * maxL; }
+    c->scf.partial = p;
+    c->scf.chunk = (int)chunk;
+    c->scf.nslices = nslices;
+    return 0;
+}
+
 static int fvp_sum(trpo_ctx *c, const double *d_v, const int *d_done) {
     if (!c->d_obs || c->n_local == 0) return fail("no batch staged: call trpo_ctx_set_batch first");
+    if (c->precision == TRPO_PRECISION_FP32) {
+        c->path_used = TRPO_PATH_GEMM_CHAIN;
+        if (c->copy_inflight) { CU(cudaStreamWaitEvent(c->stream, c->ev_copy, 0)); c->copy_inflight = false; }
+        if (ensure_f32_scratch(c)) return -1;
+        const bool timed32 = c->ktime_on && c->ktime_n < KTIME_MAX;
+        if (timed32) cudaEventRecord(c->ktime_ev[2 * c->ktime_n], c->stream);
+        chain_f32_convert(d_v, c->f_v, c->net.P, c->stream, &c->launches);
+        if (chain_f32_accumulate(c->net, c->scf, c->f_theta, c->f_v, c->f_inv_var, c->f_obs, c->n_local, c->d_zsum, d_done,
+                                 nullptr, c->stream, &c->launches))
+            return fail("FP32 gemm-chain FVP launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        if (timed32) { cudaEventRecord(c->ktime_ev[2 * c->ktime_n + 1], c->stream); ++c->ktime_n; }
+        if (c->comm) NC(g_nccl.AllReduce(c->d_zsum, c->d_zsum, c->net.P, ncclFloat64_, ncclSum_, c->comm, c->stream));
+        return 0;
+    }
     int path = c->path_req;
     if (path == TRPO_PATH_AUTO) path = fused_eligible(c->net) ? TRPO_PATH_FUSED : TRPO_PATH_GEMM_CHAIN;
     c->path_used = path;
