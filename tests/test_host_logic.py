@@ -45,20 +45,20 @@ def test_shard_bounds_cover_all_samples(pkg):
 
 
 def test_branch_free_tanh_algorithm_accuracy():
-    """The fused kernel's tanh (csrc/fvp_fused.cu: tanh_vec) restated in numpy: |error| < 4e-16 against libm."""
-    MAGIC, L2E2 = 6755399441055744.0, 2.8853900817779268
-    HI, LO = 0.3465735901845619, 9.541074646352939e-11
-    C = [1.0, 2.0, 2.0, 1.3333333333333333, 0.6666666666666666, 0.26666666666666666, 0.08888888888888889,
-         0.025396825396825397, 0.006349206349206349, 0.0014109347442680777, 0.0002821869488536155,
-         5.130671797338464e-05, 8.551119662230774e-06]
+    """The kernels' tanh (csrc/dmma_common.cuh: tanh_vec) restated in numpy: |error| < 4e-16 against libm."""
+    MAGIC, INV = 6755399441055744.0, 92.33248261689366
+    HI, LO = 0.010830424667801708, 2.8447437476627285e-11
+    tab = np.exp2(np.arange(64) / 64.0)
     x = np.concatenate([np.linspace(-25, 25, 100001), np.logspace(-14, 1.3, 5000), -np.logspace(-14, 1.3, 5000)])
-    a = np.minimum(np.abs(x), 20.0)
-    nf = (a * L2E2 + MAGIC) - MAGIC
-    h = (a - nf * HI) - nf * LO
-    q = np.full_like(a, C[12])
-    for k in range(11, -1, -1):
-        q = q * h + C[k]
-    s = np.ldexp(q, nf.astype(int)) + 1.0
+    z = 2 * np.minimum(np.abs(x), 20.0)
+    kf = (z * INV + MAGIC) - MAGIC
+    k = kf.astype(np.int64)
+    r = (z - kf * HI) - kf * LO
+    assert np.abs(r).max() < 0.0055
+    q = np.full_like(z, 1.0 / 120.0)
+    for c in (1.0 / 24.0, 1.0 / 6.0, 0.5, 1.0, 1.0):
+        q = q * r + c
+    s = np.ldexp(q * tab[k & 63], (k >> 6).astype(int)) + 1.0
     y = (1.0 / s).astype(np.float32).astype(np.float64)          # stands in for MUFU.RCP64H (>= 20 good bits)
     for _ in range(2):
         y = y + y * (1.0 - s * y)

@@ -42,12 +42,12 @@ __device__ __forceinline__ double act_deriv_y(char a, double y) {
 
 // Activation of CNT accumulator tiles starting at tile C0: x <- f(x), rx <- rx * f'(x)
 template <char ACT, int C0, int CNT, int NTILES>
-__device__ __forceinline__ void activate_tiles(char a, double (&x)[NTILES][2], double (&rx)[NTILES][2]) {
+__device__ __forceinline__ void activate_tiles(char a, double (&x)[NTILES][2], double (&rx)[NTILES][2], const double *tab) {
     if constexpr (ACT == 't') {
         double xv[2 * CNT], dv[2 * CNT];
 #pragma unroll
         for (int c = 0; c < CNT; ++c) { xv[2 * c] = x[C0 + c][0]; xv[2 * c + 1] = x[C0 + c][1]; }
-        tanh_vec<2 * CNT>(xv, dv);
+        tanh_vec<2 * CNT>(xv, dv, tab);
 #pragma unroll
         for (int c = 0; c < CNT; ++c) {
             x[C0 + c][0] = xv[2 * c]; x[C0 + c][1] = xv[2 * c + 1];
@@ -90,7 +90,7 @@ struct Cfg {
                          oW2 = oVW1 + H1 * H2, oVW2 = oW2 + H2 * AP, oB0 = oVW2 + H2 * AP, oVB0 = oB0 + H1,
                          oB1 = oVB0 + H1, oVB1 = oB1 + H2, oVB2 = oVB1 + H2, oIV = oVB2 + AP,
                          oY0 = oIV + AP, Y0SZ = S * RS0 + 8, oA = oY0 + 2 * Y0SZ, oC = oA + S * RS1, oB = oC + S * RS2,
-                         oD = oB + S * RSB, TOTAL = oD + S * RS3;
+                         oD = oB + S * RSB, oTab = oD + S * RS3, TOTAL = oTab + 64;
     static constexpr size_t SMEM_BYTES = sizeof(double) * TOTAL;
     static_assert(K0 % 4 == 0 && H1 % 8 == 0 && H2 % 8 == 0 && AP % 8 == 0, "padded sizes");
     static_assert(NT1 <= NW && NT2 <= NW && NT3 <= NW, "one output tile row per warp");
@@ -139,14 +139,20 @@ __global__ void __launch_bounds__(C::NTHREADS, C::CTAS_PER_SM) k_fvp_fused(const
     double *W2s = sm + C::oW2, *VW2s = sm + C::oVW2, *B0s = sm + C::oB0, *VB0s = sm + C::oVB0;
     double *B1s = sm + C::oB1, *VB1s = sm + C::oVB1, *VB2s = sm + C::oVB2, *IVs = sm + C::oIV;
     double *Y0s = sm + C::oY0, *BufA = sm + C::oA, *BufC = sm + C::oC, *BufB = sm + C::oB, *BufD = sm + C::oD;
+    double *Tab = sm + C::oTab;
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
     const int L0 = p.L0, L1 = p.L1, L2 = p.L2, L3 = p.L3;
 
     // ---------------- prologue: weights and direction into shared memory, in fragment order ----------------
+    // A padded input column (K0 > L0) carries the layer-0 bias for free: the observation tile holds 1.0 in column L0 and
+    // row L0 of the staged weights is the bias row -- which is simply the next row of the flat [W0;B0] matrix. The bias
+    // then needs neither an accumulator init nor its own gradient tile (row L0 of Y0^T * RG1 is the bias gradient).
+    const bool free_col = L0 < K0;
+    const int rows0 = L0 + (free_col ? 1 : 0);
     for (int idx = tid; idx < K0 * H1; idx += NT) {
         const int k = idx / H1, n = idx % H1;
-        const bool in = k < L0 && n < L1;
+        const bool in = k < rows0 && n < L1;
         const int dst = ((k >> 2) * NT1 + (n >> 3)) * 32 + (n & 7) * 4 + (k & 3);
         W0f[dst]  = in ? p.theta[p.w_off0 + k * L1 + n] : 0.0;
         VW0f[dst] = in ? p.v[p.w_off0 + k * L1 + n] : 0.0;
@@ -177,6 +183,7 @@ __global__ void __launch_bounds__(C::NTHREADS, C::CTAS_PER_SM) k_fvp_fused(const
         VB2s[n] = n < L3 ? p.v[p.w_off2 + L2 * L3 + n] : 0.0;
         IVs[n]  = n < L3 ? p.inv_var[n] : 0.0;
     }
+    load_exp2_table(Tab);
     for (int i = tid; i < 2 * C::Y0SZ; i += NT) Y0s[i] = 0.0;
     __syncthreads();
     // observation tile [S][K0] (zero padded / zero past the end of the batch), staged asynchronously one tile ahead
@@ -188,7 +195,8 @@ __global__ void __launch_bounds__(C::NTHREADS, C::CTAS_PER_SM) k_fvp_fused(const
             const int row = idx / K0, col = idx % K0;
             const long long gs = s0n + row;
             const bool in = gs < p.nsamples && col < L0;
-            cp_async8(&dst[row * RS0 + col], in ? &p.obs[gs * L0 + col] : p.obs, in ? 8 : 0);
+            if (free_col && col == L0) dst[row * RS0 + col] = (gs < p.nsamples) ? 1.0 : 0.0;
+            else cp_async8(&dst[row * RS0 + col], in ? &p.obs[gs * L0 + col] : p.obs, in ? 8 : 0);
         }
     };
 
@@ -228,7 +236,10 @@ __global__ void __launch_bounds__(C::NTHREADS, C::CTAS_PER_SM) k_fvp_fused(const
 #pragma unroll
             for (int c = 0; c < NT1; ++c)
 #pragma unroll
-                for (int r = 0; r < 2; ++r) { y1[c][r] = B0s[8 * c + 2 * t + r]; ry1[c][r] = VB0s[8 * c + 2 * t + r]; }
+                for (int r = 0; r < 2; ++r) {
+                    y1[c][r] = free_col ? 0.0 : B0s[8 * c + 2 * t + r];
+                    ry1[c][r] = free_col ? 0.0 : VB0s[8 * c + 2 * t + r];
+                }
 #pragma unroll
             for (int q = 0; q < Q0; ++q) {
                 const double a = Y0c[rowA * RS0 + 4 * q + t];
@@ -240,10 +251,10 @@ __global__ void __launch_bounds__(C::NTHREADS, C::CTAS_PER_SM) k_fvp_fused(const
             }
             constexpr int ACH = NT1 < 4 ? NT1 : 4;       // activation chunk: 8 values in flight per thread
             static_assert(NT1 % ACH == 0, "layer-1 width must split into equal activation chunks");
-            if constexpr (NT1 >= 1 * ACH) activate_tiles<ACT1, 0 * ACH, ACH>(p.act1, y1, ry1);
-            if constexpr (NT1 >= 2 * ACH) activate_tiles<ACT1, 1 * ACH, ACH>(p.act1, y1, ry1);
-            if constexpr (NT1 >= 3 * ACH) activate_tiles<ACT1, 2 * ACH, ACH>(p.act1, y1, ry1);
-            if constexpr (NT1 >= 4 * ACH) activate_tiles<ACT1, 3 * ACH, ACH>(p.act1, y1, ry1);
+            if constexpr (NT1 >= 1 * ACH) activate_tiles<ACT1, 0 * ACH, ACH>(p.act1, y1, ry1, Tab);
+            if constexpr (NT1 >= 2 * ACH) activate_tiles<ACT1, 1 * ACH, ACH>(p.act1, y1, ry1, Tab);
+            if constexpr (NT1 >= 3 * ACH) activate_tiles<ACT1, 2 * ACH, ACH>(p.act1, y1, ry1, Tab);
+            if constexpr (NT1 >= 4 * ACH) activate_tiles<ACT1, 3 * ACH, ACH>(p.act1, y1, ry1, Tab);
             static_assert(NT1 <= 4 * ACH, "add activation chunks");
 #pragma unroll
             for (int c = 0; c < NT1; ++c)
@@ -286,7 +297,7 @@ __global__ void __launch_bounds__(C::NTHREADS, C::CTAS_PER_SM) k_fvp_fused(const
                         dmma(rx2[cc], y1[b][r], bv[cc]);
                     }
                 }
-            activate_tiles<ACT2, 0, GRP>(p.act2, x2, rx2);
+            activate_tiles<ACT2, 0, GRP>(p.act2, x2, rx2, Tab);
 #pragma unroll
             for (int cc = 0; cc < GRP; ++cc)
                 *reinterpret_cast<double2 *>(&BufC[rowA * RS2 + 8 * (c0 + cc) + 2 * t]) = make_double2(x2[cc][0], x2[cc][1]);
@@ -391,7 +402,7 @@ __global__ void __launch_bounds__(C::NTHREADS, C::CTAS_PER_SM) k_fvp_fused(const
                 const double bg = BufB[srow * RSB + 8 * w + g];
 #pragma unroll
                 for (int m = 0; m < MT0; ++m) dmma(acc0[m], Y0c[srow * RS0 + 8 * m + g], bg);
-                dmma(accb0, ones, bg);
+                if (!free_col) dmma(accb0, ones, bg);
             }
         }
         cp_async_wait_all();
@@ -406,12 +417,12 @@ __global__ void __launch_bounds__(C::NTHREADS, C::CTAS_PER_SM) k_fvp_fused(const
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
                 const int row = 8 * m + g, col = 8 * w + 2 * t + r;
-                if (row < L0 && col < L1) out[p.w_off0 + row * L1 + col] = acc0[m][r];
+                if (row < rows0 && col < L1) out[p.w_off0 + row * L1 + col] = acc0[m][r];
             }
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
             const int col = 8 * w + 2 * t + r;
-            if (g == 0 && col < L1) out[p.w_off0 + L0 * L1 + col] = accb0[r];
+            if (!free_col && g == 0 && col < L1) out[p.w_off0 + L0 * L1 + col] = accb0[r];
         }
 #pragma unroll
         for (int j = 0; j < NT2; ++j)

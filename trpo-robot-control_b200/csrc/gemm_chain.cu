@@ -142,6 +142,8 @@ __global__ void __launch_bounds__(NT, 1) k_chain_fwd(const double *__restrict__ 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3, wm = w >> 1, wn = w & 1;
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
     double acc[4][4][2] = {}, racc[4][4][2] = {};
+    __shared__ double exp2_tab[64];
+    load_exp2_table(exp2_tab);                          // visible after the first barrier of the k loop
     const int nk = (Kd + 1 + BK - 1) / BK;              // augmented contraction length Kd + 1 (bias row)
     auto stage_ptrs = [&](int st, double *&As, double *&RAs, double *&Bs, double *&VBs) {
         double *p = smem + st * STAGE;
@@ -178,7 +180,7 @@ __global__ void __launch_bounds__(NT, 1) k_chain_fwd(const double *__restrict__ 
         double xv[8], dv[8];
 #pragma unroll
         for (int j = 0; j < 4; ++j) { xv[2 * j] = acc[i][j][0]; xv[2 * j + 1] = acc[i][j][1]; }
-        if (act == 't') tanh_vec<8>(xv, dv);
+        if (act == 't') tanh_vec<8>(xv, dv, exp2_tab);
         else {
 #pragma unroll
             for (int e = 0; e < 8; ++e) { xv[e] = act_apply(act, xv[e]); dv[e] = act_deriv(act, xv[e]); }
