@@ -108,6 +108,55 @@ __global__ void __launch_bounds__(256) k_dmma16816(double *out, int iters, doubl
     if (s == 12345.678) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// DMMA stream with distinct A/B operand registers per instruction (the microbenchmark above reuses one a and one b)
+template <int ACCS>
+__global__ void __launch_bounds__(256) k_dmma_varied(double *out, int iters, double a0, double b0) {
+    double c0[ACCS], c1[ACCS], a[8], b[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a[i] = a0 + i * 1e-3 + threadIdx.x * 1e-6; b[i] = b0 + i * 1e-4; }
+#pragma unroll
+    for (int i = 0; i < ACCS; ++i) { c0[i] = threadIdx.x + i; c1[i] = i; }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int i = 0; i < ACCS; ++i) dmma884(c0[i], c1[i], a[(i + u) & 7], b[(i * 3 + u) & 7]);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < ACCS; ++i) s += c0[i] + c1[i];
+    if (s == 12345.678) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// DMMA stream fed from shared memory like the fused kernel's layer 1: per k-step 2 fragment loads (LDS.64), 3 DMMAs
+template <int ACCS>
+__global__ void __launch_bounds__(256) k_dmma_lds(double *out, int iters, double a0) {
+    __shared__ double w[2][8 * ACCS * 32];
+    for (int i = threadIdx.x; i < 2 * 8 * ACCS * 32; i += blockDim.x) (&w[0][0])[i] = 1.0 + 1e-9 * i;
+    __syncthreads();
+    double x0[ACCS], x1[ACCS], r0[ACCS], r1[ACCS];
+#pragma unroll
+    for (int i = 0; i < ACCS; ++i) { x0[i] = threadIdx.x + i; x1[i] = i; r0[i] = 1; r1[i] = 2; }
+    const int lane = threadIdx.x & 31;
+    double ay = a0, ar = a0 * 0.5;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll 1
+        for (int k = 0; k < 16; ++k) {
+#pragma unroll
+            for (int i = 0; i < ACCS; ++i) {
+                const double bw = w[0][((k & 7) * ACCS + i) * 32 + lane], bv = w[1][((k & 7) * ACCS + i) * 32 + lane];
+                dmma884(r0[i], r1[i], ar, bw);
+                dmma884(x0[i], x1[i], ay, bw);
+                dmma884(r0[i], r1[i], ay, bv);
+            }
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < ACCS; ++i) s += x0[i] + x1[i] + r0[i] + r1[i];
+    if (s == 12345.678) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 // mix: DM dmma884 per DF dfma in the same warp (are the pipes shared?)
 template <int DM, int DF>
 __global__ void __launch_bounds__(256) k_mix(double *out, int iters, double a, double b) {
@@ -232,6 +281,18 @@ int main(int argc, char **argv) {
         printf("bps=%d ffma16      : %8.3f ms  %7.2f TFLOP/s\n", bps, ms, thr * 16 * iters * 2 / ms / 1e9);
         ms = time_ms([&] { k_tanh<<<grid, 256>>>(out, iters / 16, 0.7); }, reps);
         printf("bps=%d tanh(f64)   : %8.3f ms  %7.2f Gtanh/s\n", bps, ms, thr * 4 * (iters / 16) / ms / 1e6);
+    }
+    {
+        const int grid = sms;
+        const double thr = (double)grid * 256;
+        float ms = time_ms([&] { k_dmma_varied<16><<<grid, 256>>>(out, iters / 4, 1.0000001, 1e-9); }, reps);
+        printf("dmma884 16 accs, varied a/b regs, 8 warps/SM: %8.3f ms  %7.2f TFLOP/s\n", ms, thr / 32 * 16 * 4 * (iters / 4) * 512.0 / ms / 1e9);
+        ms = time_ms([&] { k_dmma_varied<8><<<grid, 256>>>(out, iters / 4, 1.0000001, 1e-9); }, reps);
+        printf("dmma884  8 accs, varied a/b regs, 8 warps/SM: %8.3f ms  %7.2f TFLOP/s\n", ms, thr / 32 * 8 * 4 * (iters / 4) * 512.0 / ms / 1e9);
+        ms = time_ms([&] { k_dmma_lds<8><<<grid, 256>>>(out, iters / 64, 1.0000001); }, reps);
+        printf("dmma884 LDS-fed (2 LDS.64 per 3 DMMA, 16 accs), 8 warps/SM: %8.3f ms  %7.2f TFLOP/s\n", ms, thr / 32 * 8 * 3 * 16 * (iters / 64) * 512.0 / ms / 1e9);
+        ms = time_ms([&] { k_dmma_lds<4><<<grid, 256>>>(out, iters / 64, 1.0000001); }, reps);
+        printf("dmma884 LDS-fed (2 LDS.64 per 3 DMMA,  8 accs), 8 warps/SM: %8.3f ms  %7.2f TFLOP/s\n", ms, thr / 32 * 4 * 3 * 16 * (iters / 64) * 512.0 / ms / 1e9);
     }
     for (int bps = 1; bps <= 4; bps *= 2) {
         const int grid = sms * bps;
