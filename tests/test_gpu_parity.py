@@ -290,3 +290,30 @@ def test_fp32_mode_humanoid_width(pkg, oracle):
         z = ctx.fvp(vec["v"], 0.1)
     e = rel_err(z, ref)
     assert e[0] < FP32_TOL and e[1] < FP32_TOL, e
+
+
+@pytest.mark.parametrize("layers,ac", [([5, 3], "ll"), ([9, 4], "lt"), ([6, 7, 8, 9, 10, 3], "ltstol"),
+                                       ([20, 64, 64, 8], "lttl"), ([3, 130, 70, 2], "ltsl")])
+def test_unusual_depths_and_widths(pkg, oracle, layers, ac):
+    """NumLayers 2 and 6, widths that straddle the tile sizes, shapes at the fused kernel's eligibility limits."""
+    seed = 1000 + sum(layers)
+    theta = pkg.synth.make_model(layers, seed)
+    batch = pkg.synth.make_batch(layers, ac, theta, 777, seed)
+    batch["Mean"] = oracle.forward(layers, ac, theta, batch["Observ"])
+    vec = pkg.synth.make_vectors(layers, seed)
+    z_ref = oracle.fvp(layers, ac, theta, batch["Std"], batch["Observ"], 0.1, vec["v"])
+    x_ref, nf, _, _ = oracle.cg(layers, ac, theta, batch["Std"], batch["Observ"], 0.1, vec["b"])
+    u_ref, uinfo = oracle.update(layers, ac, theta, batch["Std"], batch["Observ"], batch["Mean"], batch["Action"],
+                                 batch["Advantage"], 0.1)
+    for path in paths_for(pkg, layers, ac):
+        with pkg.Context(layers, ac) as ctx:
+            ctx.set_path(path)
+            ctx.set_model(theta)
+            ctx.set_batch(batch["Observ"], batch["Std"], batch["Mean"], batch["Action"], batch["Advantage"])
+            z = ctx.fvp(vec["v"], 0.1)
+            x, info = ctx.cg(vec["b"], 10, 1e-10, 0.1)
+            u, ginfo = ctx.update(0.1)
+        assert rel_err(z, z_ref)[0] < FVP_TOL, (layers, path, rel_err(z, z_ref))
+        assert info.cg_iters == nf and rel_err(x, x_ref)[0] < CG_TOL, (layers, path, rel_err(x, x_ref))
+        assert ginfo.ls_steps == uinfo.ls_steps and ginfo.ls_accepted == uinfo.ls_accepted
+        assert rel_err(u, u_ref)[0] < CG_TOL, (layers, path, rel_err(u, u_ref))
