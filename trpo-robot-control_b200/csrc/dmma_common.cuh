@@ -13,6 +13,11 @@ __device__ __forceinline__ void cp_async8(double *dst_smem, const double *src, i
     const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" :: "r"(d), "l"(src), "r"(src_bytes) : "memory");
 }
+// 16-byte variant (both addresses 16-byte aligned); src_bytes in {0, 8, 16}: the remainder is zero-filled
+__device__ __forceinline__ void cp_async16(double *dst_smem, const double *src, int src_bytes) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" :: "r"(d), "l"(src), "r"(src_bytes) : "memory");
+}
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }

@@ -14,6 +14,8 @@
 // fragment read bank-conflict-free. The forward kernel carries two accumulator sets (x and R{x}) and issues the three
 // products of the R-op per fragment pair; tanh runs branch-free on 8 values in lock step (dmma_common.cuh).
 // Determinism: every output element has exactly one owner thread per (slice); slices are summed in fixed order.
+#include <stdint.h>
+
 #include "trpo_internal.cuh"
 #include "dmma_common.cuh"
 
@@ -47,13 +49,28 @@ __device__ __forceinline__ double act_deriv(char a, double y) {   // f'(x) expre
 // ---- tile loaders (all 256 threads; 8-byte cp.async, src-size 0 = zero fill) --------------------------------------
 // A tile from row-major activations X[rows x ld]: As[m][k] = X[(m0+m)*ld + k0+k]; column k == ld is the augmented
 // "ones" column (value ones_val) when aug is set.
-template <int BK>
+template <int BK, int NTH>
 __device__ __forceinline__ void load_a_rowmajor(double *As, const double *X, int rows, int ld, int m0, int k0,
                                                 bool aug, double ones_val, int tid) {
+    constexpr int RSA = Tile<BK>::RSA;
+    if (X != nullptr && (ld & 1) == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0) {
+        // even leading dimension: 16-byte copies (half the LDGSTS instructions); k0 and RSA are even
 #pragma unroll
-    for (int it = 0; it < BM * BK / NT; ++it) {
-        constexpr int RSA = Tile<BK>::RSA;
-        const int idx = tid + it * NT, m = idx / BK, k = idx % BK;
+        for (int it = 0; it < BM * BK / 2 / NTH; ++it) {
+            const int idx = tid + it * NTH, m = idx / (BK / 2), k = (idx % (BK / 2)) * 2;
+            const int gm = m0 + m, gk = k0 + k;
+            double *dst = &As[m * RSA + k];
+            if (aug && gk == ld && gm < rows) { dst[0] = ones_val; dst[1] = 0.0; }
+            else {
+                const bool in = gm < rows && gk < ld;      // ld even: gk < ld implies gk + 1 < ld
+                cp_async16(dst, in ? &X[(size_t)gm * ld + gk] : X, in ? 16 : 0);
+            }
+        }
+        return;
+    }
+#pragma unroll
+    for (int it = 0; it < BM * BK / NTH; ++it) {
+        const int idx = tid + it * NTH, m = idx / BK, k = idx % BK;
         const int gm = m0 + m, gk = k0 + k;
         const bool in = X != nullptr && gm < rows && gk < ld;
         if (aug && gk == ld && gm < rows) As[m * RSA + k] = ones_val;
@@ -63,10 +80,13 @@ __device__ __forceinline__ void load_a_rowmajor(double *As, const double *X, int
 // A tile for the outer product: As[m][k] = Yprev[(s0+k)*M0 + m0+m] for m < M0, 1.0 for m == M0 (bias-gradient row)
 template <int BK>
 __device__ __forceinline__ void load_a_transposed(double *As, const double *Y, int s_end, int M0, int m0, int s0, int tid) {
+    // A warp copies an 8 (m) x 4 (k) patch per step: 64-byte global segments along m, and shared addresses
+    // m*RSA + k that fall on 16 distinct banks per half warp (lanes along m only would be an 8-way conflict: RSA % 16 == 4).
+    constexpr int RSA = Tile<BK>::RSA;
+    const int lane = tid & 31, w = tid >> 5, mm = lane & 7, kk = lane >> 3;
 #pragma unroll
     for (int it = 0; it < BM * BK / NT; ++it) {
-        constexpr int RSA = Tile<BK>::RSA;
-        const int idx = tid + it * NT, k = idx >> 7, m = idx & 127;
+        const int blk = it * 8 + w, m = (blk & 15) * 8 + mm, k = (blk >> 4) * 4 + kk;
         const int gm = m0 + m, gs = s0 + k;
         const bool in = Y != nullptr && gm < M0 && gs < s_end;
         if (gm == M0 && gs < s_end) As[m * RSA + k] = 1.0;
@@ -74,11 +94,21 @@ __device__ __forceinline__ void load_a_transposed(double *As, const double *Y, i
     }
 }
 // B tile from a row-major matrix M[kdim x N]: Bs[k][n] = M[(k0+k)*N + n0+n]
-template <int BK>
+template <int BK, int NTH>
 __device__ __forceinline__ void load_b_rowmajor(double *Bs, const double *M, int kdim, int N, int k0, int n0, int tid) {
+    if ((N & 1) == 0 && (reinterpret_cast<uintptr_t>(M) & 15) == 0) {
 #pragma unroll
-    for (int it = 0; it < BK * BN / NT; ++it) {
-        const int idx = tid + it * NT, k = idx >> 6, n = idx & 63;
+        for (int it = 0; it < BK * BN / 2 / NTH; ++it) {
+            const int idx = tid + it * NTH, k = idx >> 5, n = (idx & 31) * 2;
+            const int gk = k0 + k, gn = n0 + n;
+            const bool in = gk < kdim && gn < N;
+            cp_async16(&Bs[k * RSB + n], in ? &M[(size_t)gk * N + gn] : M, in ? 16 : 0);
+        }
+        return;
+    }
+#pragma unroll
+    for (int it = 0; it < BK * BN / NTH; ++it) {
+        const int idx = tid + it * NTH, k = idx >> 6, n = idx & 63;
         const int gk = k0 + k, gn = n0 + n;
         const bool in = gk < kdim && gn < N;
         cp_async8(&Bs[k * RSB + n], in ? &M[(size_t)gk * N + gn] : M, in ? 8 : 0);
@@ -87,9 +117,13 @@ __device__ __forceinline__ void load_b_rowmajor(double *Bs, const double *M, int
 // B tile from W[N x Kd] row-major used transposed: Bs[k][n] = W[(n0+n)*Kd + k0+k]
 template <int BK>
 __device__ __forceinline__ void load_b_transposed(double *Bs, const double *W, int Kd, int N, int k0, int n0, int tid) {
+    // 8 (k) x 4 (n) patch per warp and step: 64-byte global segments along k, shared addresses k*RSB + n at most 2-way
+    // conflicting (lanes along k only: 8-way, RSB % 16 == 4)
+    const int lane = tid & 31, w = tid >> 5, kk = lane & 7, nn = lane >> 3;
+    constexpr int KB = BK / 8;                              // k-patches per tile row
 #pragma unroll
     for (int it = 0; it < BK * BN / NT; ++it) {
-        const int idx = tid + it * NT, n = idx / BK, k = idx % BK;
+        const int blk = it * 8 + w, k = (blk % KB) * 8 + kk, n = (blk / KB) * 4 + nn;
         const int gk = k0 + k, gn = n0 + n;
         const bool in = gk < Kd && gn < N;
         cp_async8(&Bs[k * RSB + n], in ? &W[(size_t)gn * Kd + gk] : W, in ? 8 : 0);
@@ -97,27 +131,27 @@ __device__ __forceinline__ void load_b_transposed(double *Bs, const double *W, i
 }
 
 // one k-step (16) of a warp's 32 x 32 sub-tile: acc += A*B [, racc += RA*B + A*VB]
-template <bool DUAL, bool HAS_RA, int BK>
-__device__ __forceinline__ void mma_stage(double (&acc)[4][4][2], double (&racc)[4][4][2], const double *As,
+template <bool DUAL, bool HAS_RA, int BK, int NJ>
+__device__ __forceinline__ void mma_stage(double (&acc)[4][NJ][2], double (&racc)[4][NJ][2], const double *As,
                                           const double *RAs, const double *Bs, const double *VBs, int wm, int wn, int g, int t) {
     constexpr int RSA = Tile<BK>::RSA;
 #pragma unroll
     for (int q = 0; q < BK / 4; ++q) {
-        double a[4], ra[4], b[4], vb[4];
+        double a[4], ra[4], b[NJ], vb[NJ];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             a[i] = As[(32 * wm + 8 * i + g) * RSA + 4 * q + t];
             if (DUAL && HAS_RA) ra[i] = RAs[(32 * wm + 8 * i + g) * RSA + 4 * q + t];
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            b[j] = Bs[(4 * q + t) * RSB + 32 * wn + 8 * j + g];
-            if (DUAL) vb[j] = VBs[(4 * q + t) * RSB + 32 * wn + 8 * j + g];
+        for (int j = 0; j < NJ; ++j) {
+            b[j] = Bs[(4 * q + t) * RSB + 8 * NJ * wn + 8 * j + g];
+            if (DUAL) vb[j] = VBs[(4 * q + t) * RSB + 8 * NJ * wn + 8 * j + g];
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < NJ; ++j) {
                 if (DUAL && HAS_RA) dmma(racc[i][j], ra[i], b[j]);
                 dmma(acc[i][j], a[i], b[j]);
                 if (DUAL) dmma(racc[i][j], a[i], vb[j]);
@@ -127,8 +161,10 @@ __device__ __forceinline__ void mma_stage(double (&acc)[4][4][2], double (&racc)
 
 // ---------------------------------------------------------------------------------------------------------------
 // forward: DUAL = also propagate R{} (FVP); HAS_RA = the incoming R{y} is non-zero (false for layer 0).
+// The dual (R-op) kernel carries two accumulator sets; to keep 16 warps per SM it runs 512 threads with 32 x 16 warp tiles
+// (64 accumulator registers per thread) instead of 256 threads with 32 x 32 tiles (128 registers, 8 warps per SM).
 template <bool DUAL, bool HAS_RA>
-__global__ void __launch_bounds__(NT, 1) k_chain_fwd(const double *__restrict__ Yin, const double *__restrict__ RYin,
+__global__ void __launch_bounds__(DUAL ? 512 : NT, 1) k_chain_fwd(const double *__restrict__ Yin, const double *__restrict__ RYin,
                                                      const double *__restrict__ W, const double *__restrict__ VW,
                                                      int rows, int Kd, int N, char act,
                                                      double *__restrict__ Yout, double *__restrict__ RYout,
@@ -137,11 +173,12 @@ __global__ void __launch_bounds__(NT, 1) k_chain_fwd(const double *__restrict__ 
     if (done && *done) return;
     extern __shared__ __align__(16) double smem[];
     constexpr int BK = DUAL ? BK_DUAL : BK_SINGLE;
+    constexpr int NTH = DUAL ? 512 : NT, WN = NTH / 128, NJ = BN / 8 / WN;     // warps along n, n-tiles per warp
     constexpr int A_TILE = Tile<BK>::A, B_TILE = Tile<BK>::B;
     constexpr int STAGE = A_TILE * (DUAL && HAS_RA ? 2 : 1) + B_TILE * (DUAL ? 2 : 1);
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3, wm = w >> 1, wn = w & 1;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3, wm = w / WN, wn = w % WN;
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
-    double acc[4][4][2] = {}, racc[4][4][2] = {};
+    double acc[4][NJ][2] = {}, racc[4][NJ][2] = {};
     __shared__ double exp2_tab[64];
     load_exp2_table(exp2_tab);                          // visible after the first barrier of the k loop
     const int nk = (Kd + 1 + BK - 1) / BK;              // augmented contraction length Kd + 1 (bias row)
@@ -155,11 +192,11 @@ __global__ void __launch_bounds__(NT, 1) k_chain_fwd(const double *__restrict__ 
     auto load = [&](int st, int k0) {
         double *As, *RAs, *Bs, *VBs;
         stage_ptrs(st, As, RAs, Bs, VBs);
-        load_a_rowmajor<BK>(As, Yin, rows, Kd, m0, k0, true, 1.0, tid);
-        load_b_rowmajor<BK>(Bs, W, Kd + 1, N, k0, n0, tid);
+        load_a_rowmajor<BK, NTH>(As, Yin, rows, Kd, m0, k0, true, 1.0, tid);
+        load_b_rowmajor<BK, NTH>(Bs, W, Kd + 1, N, k0, n0, tid);
         if (DUAL) {
-            if (HAS_RA) load_a_rowmajor<BK>(RAs, RYin, rows, Kd, m0, k0, false, 0.0, tid);
-            load_b_rowmajor<BK>(VBs, VW, Kd + 1, N, k0, n0, tid);
+            if (HAS_RA) load_a_rowmajor<BK, NTH>(RAs, RYin, rows, Kd, m0, k0, false, 0.0, tid);
+            load_b_rowmajor<BK, NTH>(VBs, VW, Kd + 1, N, k0, n0, tid);
         }
         cp_async_commit();
     };
@@ -170,41 +207,48 @@ __global__ void __launch_bounds__(NT, 1) k_chain_fwd(const double *__restrict__ 
         __syncthreads();
         double *As, *RAs, *Bs, *VBs;
         stage_ptrs(it & 1, As, RAs, Bs, VBs);
-        mma_stage<DUAL, HAS_RA, BK>(acc, racc, As, RAs, Bs, VBs, wm, wn, g, t);
+        mma_stage<DUAL, HAS_RA, BK, NJ>(acc, racc, As, RAs, Bs, VBs, wm, wn, g, t);
         __syncthreads();
     }
     // epilogue: activation, R{y} = R{x} f'(x), last layer: R-gradient seed RG_K = Ry_K / sigma^2 * f' (TRPO_FVP.c:852-882)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int gm = m0 + 32 * wm + 8 * i + g;
+    for (int i0 = 0; i0 < 4; i0 += 8 / (2 * NJ)) {
+        // 8 values per lock-step tanh: (8 / (2 NJ)) row blocks x NJ tiles x 2 columns
+        constexpr int RB = 8 / (2 * NJ);
         double xv[8], dv[8];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { xv[2 * j] = acc[i][j][0]; xv[2 * j + 1] = acc[i][j][1]; }
+        for (int ii = 0; ii < RB; ++ii)
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) { xv[(ii * NJ + j) * 2] = acc[i0 + ii][j][0]; xv[(ii * NJ + j) * 2 + 1] = acc[i0 + ii][j][1]; }
         if (act == 't') tanh_vec<8>(xv, dv, exp2_tab);
         else {
 #pragma unroll
             for (int e = 0; e < 8; ++e) { xv[e] = act_apply(act, xv[e]); dv[e] = act_deriv(act, xv[e]); }
         }
-        if (gm >= rows) continue;
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int ii = 0; ii < RB; ++ii) {
+            const int i = i0 + ii, gm = m0 + 32 * wm + 8 * i + g;
+            if (gm >= rows) continue;
 #pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                const int gn = n0 + 32 * wn + 8 * j + 2 * t + r;
-                if (gn >= N) continue;
-                const double y = xv[2 * j + r], d = dv[2 * j + r];
-                if (Yout) Yout[(size_t)gm * N + gn] = y;
-                if (DUAL) {
-                    const double ry = racc[i][j][r] * d;
-                    if (RYout) RYout[(size_t)gm * N + gn] = ry;
-                    if (Gout) Gout[(size_t)gm * N + gn] = ry * inv_var[gn] * d;
+            for (int j = 0; j < NJ; ++j)
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    const int gn = n0 + 8 * NJ * wn + 8 * j + 2 * t + r;
+                    if (gn >= N) continue;
+                    const double y = xv[(ii * NJ + j) * 2 + r], d = dv[(ii * NJ + j) * 2 + r];
+                    if (Yout) Yout[(size_t)gm * N + gn] = y;
+                    if (DUAL) {
+                        const double ry = racc[i][j][r] * d;
+                        if (RYout) RYout[(size_t)gm * N + gn] = ry;
+                        if (Gout) Gout[(size_t)gm * N + gn] = ry * inv_var[gn] * d;
+                    }
                 }
-            }
+        }
     }
 }
 
 // backward: Gout[s][n] = f'(Yprev[s][n]) * sum_k Gin[s][k] * W[n][k]       (W is [N x Kd] row-major)
-__global__ void __launch_bounds__(NT, 1) k_chain_bwd(const double *__restrict__ Gin, const double *__restrict__ W,
+__global__ void __launch_bounds__(NT, 2) k_chain_bwd(const double *__restrict__ Gin, const double *__restrict__ W,
                                                      const double *__restrict__ Yprev, int rows, int Kd, int N, char act_prev,
                                                      double *__restrict__ Gout, const int *__restrict__ done) {
     if (done && *done) return;
@@ -217,7 +261,7 @@ __global__ void __launch_bounds__(NT, 1) k_chain_bwd(const double *__restrict__ 
     const int nk = (Kd + BK - 1) / BK;
     auto load = [&](int st, int k0) {
         double *As = smem + st * STAGE, *Bs = As + A_TILE;
-        load_a_rowmajor<BK>(As, Gin, rows, Kd, m0, k0, false, 0.0, tid);
+        load_a_rowmajor<BK, NT>(As, Gin, rows, Kd, m0, k0, false, 0.0, tid);
         load_b_transposed<BK>(Bs, W, Kd, N, k0, n0, tid);
         cp_async_commit();
     };
@@ -227,7 +271,7 @@ __global__ void __launch_bounds__(NT, 1) k_chain_bwd(const double *__restrict__ 
         else cp_async_wait_group<0>();
         __syncthreads();
         const double *As = smem + (it & 1) * STAGE, *Bs = As + A_TILE;
-        mma_stage<false, false, BK>(acc, dummy, As, nullptr, Bs, nullptr, wm, wn, g, t);
+        mma_stage<false, false, BK, 4>(acc, dummy, As, nullptr, Bs, nullptr, wm, wn, g, t);
         __syncthreads();
     }
 #pragma unroll
@@ -246,7 +290,7 @@ __global__ void __launch_bounds__(NT, 1) k_chain_bwd(const double *__restrict__ 
 }
 
 // outer: out[slice][m*N + n] (+)= sum_{s in slice} [Yprev,1][s][m] * G[s][n],  m in [0, M0]  (row M0 = bias gradient)
-__global__ void __launch_bounds__(NT, 1) k_chain_outer(const double *__restrict__ Yprev, const double *__restrict__ G,
+__global__ void __launch_bounds__(NT, 2) k_chain_outer(const double *__restrict__ Yprev, const double *__restrict__ G,
                                                        int rows, int M0, int N, int per_slice, int tiles_n,
                                                        double *__restrict__ partial, int P, int out_off, int accumulate,
                                                        const int *__restrict__ done) {
@@ -264,7 +308,7 @@ __global__ void __launch_bounds__(NT, 1) k_chain_outer(const double *__restrict_
     auto load = [&](int st, int ks) {
         double *As = smem + st * STAGE, *Bs = As + A_TILE;
         load_a_transposed<BK>(As, Yprev, s1, M0, m0, ks, tid);
-        load_b_rowmajor<BK>(Bs, G + (size_t)ks * N, s1 - ks, N, 0, n0, tid);
+        load_b_rowmajor<BK, NT>(Bs, G + (size_t)ks * N, s1 - ks, N, 0, n0, tid);
         cp_async_commit();
     };
     if (nk) load(0, s0);
@@ -273,7 +317,7 @@ __global__ void __launch_bounds__(NT, 1) k_chain_outer(const double *__restrict_
         else cp_async_wait_group<0>();
         __syncthreads();
         const double *As = smem + (it & 1) * STAGE, *Bs = As + A_TILE;
-        mma_stage<false, false, BK>(acc, dummy, As, nullptr, Bs, nullptr, wm, wn, g, t);
+        mma_stage<false, false, BK, 4>(acc, dummy, As, nullptr, Bs, nullptr, wm, wn, g, t);
         __syncthreads();
     }
     double *out = partial + (size_t)slice * P + out_off;
@@ -366,12 +410,12 @@ int chain_accumulate(const NetDesc &net, const ChainScratch &sc, ChainMode mode,
                 const double *RYin = (i == 0) ? nullptr : sc.RY[i & 1];
                 const bool needY = !last || net.ac[K] == 't' || net.ac[K] == 's';
                 if (i == 0)
-                    k_chain_fwd<true, false><<<grid, NT, SMEM_FWD_L0, st>>>(Yin, nullptr, d_theta + net.w_off[i], d_v + net.w_off[i], rows,
+                    k_chain_fwd<true, false><<<grid, 512, SMEM_FWD_L0, st>>>(Yin, nullptr, d_theta + net.w_off[i], d_v + net.w_off[i], rows,
                                                       net.L[i], net.L[i + 1], net.ac[i + 1],
                                                       needY ? sc.Y[i + 1] : nullptr, last ? nullptr : sc.RY[(i + 1) & 1],
                                                       last ? sc.G[K & 1] : nullptr, d_inv_var, d_done);
                 else
-                    k_chain_fwd<true, true><<<grid, NT, SMEM_FWD_DUAL, st>>>(Yin, RYin, d_theta + net.w_off[i], d_v + net.w_off[i], rows,
+                    k_chain_fwd<true, true><<<grid, 512, SMEM_FWD_DUAL, st>>>(Yin, RYin, d_theta + net.w_off[i], d_v + net.w_off[i], rows,
                                                       net.L[i], net.L[i + 1], net.ac[i + 1],
                                                       needY ? sc.Y[i + 1] : nullptr, last ? nullptr : sc.RY[(i + 1) & 1],
                                                       last ? sc.G[K & 1] : nullptr, d_inv_var, d_done);
