@@ -35,7 +35,7 @@ DAMPING = 0.1
 # FP64 pipe, 37.1 TFLOP/s = 148 SMs x 64 FMA/clk x 2 x 1.96 GHz. MEASURED_PEAKS.json has no FP64 entry.
 FP64_PEAK_TFLOPS = 37.1
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_fvp_fused launch, ncu --set full (profiles/r01_summary.md)
-NCU_TRAFFIC_BYTES = {("mlp64", 1_000_000, "fused_dmma"): 136_153_600 + 4_317_696}
+NCU_TRAFFIC_BYTES = {("mlp64", 1_000_000, "fused_dmma"): 136_495_872 + 4_343_808}
 WORKLOAD_INDEX = {"arm": 1, "mlp64": 2, "pendulum64": 2, "humanoid64": 2, "humanoid256": 3}
 
 
