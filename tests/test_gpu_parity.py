@@ -321,3 +321,26 @@ def test_unusual_depths_and_widths(pkg, oracle, layers, ac):
         assert info.cg_iters == nf and rel_err(x, x_ref)[0] < cg_tol, (layers, path, rel_err(x, x_ref))
         assert ginfo.ls_steps == uinfo.ls_steps and ginfo.ls_accepted == uinfo.ls_accepted
         assert rel_err(u, u_ref)[0] < cg_tol, (layers, path, rel_err(u, u_ref))
+
+
+def test_repeated_solves_replay_a_cuda_graph_bitwise(pkg, armtest):
+    """The 2nd identical solve is captured into a CUDA graph and the following ones replay it: every repetition must
+    return bitwise the same x and the same trace as the first (directly launched) one; a different b falls back."""
+    a = armtest
+    with pkg.Context(ARM_LAYERS, ARM_AC) as ctx:
+        ctx.set_model(a["theta"])
+        ctx.set_batch(a["Observ"], a["Std"])
+        xs, iters = [], []
+        for _ in range(5):
+            x, info = ctx.cg(a["cg_b"], 10, 1e-10, 0.1)
+            xs.append(x); iters.append(info.cg_iters)
+        x_other, _ = ctx.cg(2.0 * a["cg_b"], 10, 1e-10, 0.1)
+        x_back, _ = ctx.cg(a["cg_b"], 10, 1e-10, 0.1)
+        # a new model must be picked up by the replayed graph (same device pointers, new contents)
+        ctx.set_model(1.01 * a["theta"])
+        x_new_model, _ = ctx.cg(a["cg_b"], 10, 1e-10, 0.1)
+    assert all(np.array_equal(xs[0], x) for x in xs[1:]) and iters == [8] * 5
+    assert np.array_equal(xs[0], x_back)
+    assert rel_err(xs[0], a["ref_cg_3150"])[0] < CG_TOL
+    assert rel_err(x_other, 2.0 * a["ref_cg_3150"])[0] < 1e-6       # linear system: x scales with b (different early exit point)
+    assert not np.array_equal(x_new_model, xs[0])

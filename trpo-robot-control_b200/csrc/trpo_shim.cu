@@ -109,6 +109,11 @@ struct trpo_ctx {
     bool copy_inflight;        // an asynchronous batch copy has been issued and not yet joined into c->stream
     bool stream_first_fvp;     // the next fused FVP may start before the copy has finished
     size_t stage_chunk;        // samples per staged chunk
+    // CUDA graph of a whole CG solve (single GPU, fused path): captured on the second identical call, replayed afterwards
+    struct CgKey { const double *db; double *dres; size_t iters; double th, damping; const double *obs; size_t n; cudaStream_t st; int path; } cg_key;
+    int cg_key_seen;
+    cudaGraphExec_t cg_exec;
+    long long cg_graph_launches;
     // peer-memory all-reduce
     P2PComm p2p;               // world == 0 until attached
     bool p2p_on;
@@ -250,6 +255,7 @@ extern "C" void trpo_ctx_destroy(trpo_ctx *c) {
     if (c->ev_copy) cudaEventDestroy(c->ev_copy);
     if (c->d_ready) cudaFree(c->d_ready);
     if (c->h_ready_vals) cudaFreeHost(c->h_ready_vals);
+    if (c->cg_exec) cudaGraphExecDestroy(c->cg_exec);
     if (c->ktime_ev) { for (int i = 0; i < 2 * KTIME_MAX; ++i) if (c->ktime_ev[i]) cudaEventDestroy(c->ktime_ev[i]); free(c->ktime_ev); }
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     free(c);
@@ -516,10 +522,7 @@ extern "C" int trpo_ctx_fvp_device(trpo_ctx *c, const double *dInput, double *dR
     return 0;
 }
 
-extern "C" int trpo_ctx_cg_device(trpo_ctx *c, const double *db, double *dResult, size_t MaxIter, double ResidualTh, double damping) {
-    if (!c || !db || !dResult) return fail("null argument");
-    if (MaxIter > 32) return fail("MaxIter > 32 not supported by the device trace buffer");
-    CU(cudaSetDevice(c->device));
+static int cg_enqueue(trpo_ctx *c, const double *db, double *dResult, size_t MaxIter, double ResidualTh, double damping) {
     launch_cg_init(db, c->d_x, c->d_r, c->d_p, c->net.P, ResidualTh, c->d_state, c->stream, &c->launches);
     for (size_t it = 0; it < MaxIter; ++it) {
         if (fvp_sum(c, c->d_p, &c->d_state->done)) return -1;
@@ -527,6 +530,55 @@ extern "C" int trpo_ctx_cg_device(trpo_ctx *c, const double *db, double *dResult
                          ResidualTh, c->d_state, active_p2p(c), c->stream, &c->launches);
     }
     CU(cudaMemcpyAsync(dResult, c->d_x, c->net.P * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    return 0;
+}
+
+extern "C" int trpo_ctx_cg_device(trpo_ctx *c, const double *db, double *dResult, size_t MaxIter, double ResidualTh, double damping) {
+    if (!c || !db || !dResult) return fail("null argument");
+    if (MaxIter > 32) return fail("MaxIter > 32 not supported by the device trace buffer");
+    CU(cudaSetDevice(c->device));
+    // A solve is 3 launches per iteration; for small batches (armDOF_0 x 50 k states: a whole FVP is ~30 us) the launch
+    // gaps are a fifth of the solve, so an identical repeated solve is captured once into a CUDA graph and replayed.
+    static const bool no_graph = getenv("TRPO_NO_GRAPH") != nullptr;
+    const int path = (c->path_req == TRPO_PATH_AUTO) ? (fused_eligible(c->net) ? TRPO_PATH_FUSED : TRPO_PATH_GEMM_CHAIN) : c->path_req;
+    const bool eligible = !no_graph && !c->comm && !c->ktime_on && !c->copy_inflight && path == TRPO_PATH_FUSED &&
+                          c->precision == TRPO_PRECISION_FP64 && c->d_obs && c->n_local;
+    if (eligible) {
+        trpo_ctx::CgKey key;
+        memset(&key, 0, sizeof(key));            // padding bytes take part in the memcmp below
+        key.db = db; key.dres = dResult; key.iters = MaxIter; key.th = ResidualTh; key.damping = damping;
+        key.obs = c->d_obs; key.n = c->n_local; key.st = c->stream; key.path = path;
+        const bool same = memcmp(&key, &c->cg_key, sizeof(key)) == 0;
+        if (same && c->cg_exec) {
+            CU(cudaGraphLaunch(c->cg_exec, c->stream));
+            c->launches += c->cg_graph_launches;
+            c->path_used = path;
+            return 0;
+        }
+        if (same && c->cg_key_seen >= 1) {
+            if (c->cg_exec) { cudaGraphExecDestroy(c->cg_exec); c->cg_exec = nullptr; }
+            const long long l0 = c->launches;
+            cudaGraph_t graph = nullptr;
+            CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+            const int rc = cg_enqueue(c, db, dResult, MaxIter, ResidualTh, damping);
+            const cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+            c->launches = l0;
+            if (rc == 0 && e == cudaSuccess && graph && cudaGraphInstantiate(&c->cg_exec, graph, 0) == cudaSuccess) {
+                c->cg_graph_launches = 3 * (long long)MaxIter + 1;
+                cudaGraphDestroy(graph);
+                CU(cudaGraphLaunch(c->cg_exec, c->stream));
+                c->launches += c->cg_graph_launches;
+                return 0;
+            }
+            if (graph) cudaGraphDestroy(graph);
+            c->cg_exec = nullptr;
+            cudaGetLastError();
+            c->cg_key_seen = -1000000;           // capture is not possible here: stay on direct launches
+        }
+        if (!same) { if (c->cg_exec) { cudaGraphExecDestroy(c->cg_exec); c->cg_exec = nullptr; } c->cg_key = key; c->cg_key_seen = 0; }
+        ++c->cg_key_seen;
+    }
+    if (cg_enqueue(c, db, dResult, MaxIter, ResidualTh, damping)) return -1;
     CU(cudaGetLastError());
     return 0;
 }
