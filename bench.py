@@ -34,6 +34,10 @@ DAMPING = 0.1
 # measured on this pool's B200 with tools/fp64_peak.cu (profiles/fp64_peak_r01.txt): DMMA.8x8x4 and DFMA share one
 # FP64 pipe, 37.1 TFLOP/s = 148 SMs x 64 FMA/clk x 2 x 1.96 GHz. MEASURED_PEAKS.json has no FP64 entry.
 FP64_PEAK_TFLOPS = 37.1
+try:
+    HBM_PEAK_GBPS = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+except Exception:
+    HBM_PEAK_GBPS = 6650.0        # fallback stated in B200_PROFILING.md
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_fvp_fused launch, ncu --set full (profiles/r01_summary.md)
 NCU_TRAFFIC_BYTES = {("mlp64", 1_000_000, "fused_dmma"): 136_495_872 + 4_343_808}
 WORKLOAD_INDEX = {"arm": 1, "mlp64": 2, "pendulum64": 2, "humanoid64": 2, "humanoid256": 3}
@@ -52,7 +56,7 @@ def flops_min_per_sample(layers):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms during the timed region."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -62,7 +66,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -293,6 +297,10 @@ def run_gpu_arm(args, pkg):
                          "traffic": NCU_TRAFFIC_BYTES.get((workload, n_local, path_used)),
                          "kernel": path_used, "kernel_avg_ms": k_avg_ms, "kernel_launches_timed": k_n,
                          "flops_per_sample": fl,
+                         "hbm_context": {"algorithmic_bytes_per_launch": n_local * layers[0] * 8,
+                                         "achieved_GBps": (n_local * layers[0] * 8 / (k_avg_ms * 1e-3) / 1e9) if k_n else None,
+                                         "measured_peak_GBps": HBM_PEAK_GBPS,
+                                         "note": "compute bound by design: 377 flop/B against a ridge of 5.7"},
                          "peak_source": "measured FP64 DMMA/DFMA pipe, profiles/fp64_peak_r01.txt (MEASURED_PEAKS.json has no FP64 entry)"},
             "theta": theta, "batch": batch, "vec": vec, "ac": ac,
         }
@@ -347,7 +355,7 @@ def run_gpu_arm(args, pkg):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="mlp64")
