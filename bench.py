@@ -300,7 +300,7 @@ def run_gpu_arm(args, pkg):
                          "hbm_context": {"algorithmic_bytes_per_launch": n_local * layers[0] * 8,
                                          "achieved_GBps": (n_local * layers[0] * 8 / (k_avg_ms * 1e-3) / 1e9) if k_n else None,
                                          "measured_peak_GBps": HBM_PEAK_GBPS,
-                                         "note": "compute bound by design: 377 flop/B against a ridge of 5.7"},
+                                         "note": f"compute bound by design: {fl / (8 * layers[0]):.0f} flop/B against a ridge of 5.7"},
                          "peak_source": "measured FP64 DMMA/DFMA pipe, profiles/fp64_peak_r01.txt (MEASURED_PEAKS.json has no FP64 entry)"},
             "theta": theta, "batch": batch, "vec": vec, "ac": ac,
         }
