@@ -138,6 +138,27 @@ def reference_cg_rate(pkg, layers, ac, theta, batch, vec, n_sample, steps, warmu
     return CG_ITERS * n_sample / t, t, ("reference" if use_ref else "port")
 
 
+def reference_thread_scaling(pkg, layers, ac, theta, batch, vec, tmpdir, n_small=256):
+    """The reference's OpenMP pragmas sit inside the per-sample layer loops (TRPO_FVP.c:790,864,889): more threads make it
+    slower. One FVPFast() on a few samples at 1 thread and at all host threads documents why the arm runs single-threaded."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_lib import Reference
+    if not Reference.available():
+        return None
+    ref = Reference(fast=True)
+    sl = {k: (v[:n_small] if k != "Std" else v) for k, v in batch.items()}
+    mf, df = os.path.join(tmpdir, "model_s.txt"), os.path.join(tmpdir, "data_s.txt")
+    pkg.textio.write_model(mf, theta)
+    pkg.textio.write_data(df, sl["Mean"], sl["Std"], sl["Observ"], sl["Action"], sl["Advantage"])
+    nthreads = os.cpu_count() or 1
+    out = {}
+    for nt in (1, nthreads):
+        _, t = ref.fvp_fast(mf, df, layers, ac, n_small, DAMPING, vec["v"], nt)
+        out[nt] = n_small / t
+    return {"states": n_small, "samples_per_s_1_thread": out[1], f"samples_per_s_{nthreads}_threads": out[nthreads],
+            "threads": nthreads}
+
+
 def run_reference_arm(args, pkg):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -148,6 +169,7 @@ def run_reference_arm(args, pkg):
     n_sample = int(min(n, max(512, 8.0 / (CG_ITERS * flops_ref * 1.3e-9))))
     with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as tmp:
         rate, t_step, kind = reference_cg_rate(pkg, layers, ac, theta, batch, vec, n_sample, args.steps, max(1, min(args.warmup, 1)), tmp)
+        scaling = reference_thread_scaling(pkg, layers, ac, theta, batch, vec, tmp)
     line = {
         "impl": "reference", "metric": "fvp_samples_per_sec", "value": rate, "unit": "samples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * 1e3,
@@ -159,6 +181,8 @@ def run_reference_arm(args, pkg):
                                    f"(its OpenMP sits inside the 64-wide layer loops and anti-scales, SURVEY.md section 6)"},
         "e2e": {"value": rate, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    if scaling:
+        line["cpu_baseline"]["openmp_thread_scaling_of_FVPFast"] = scaling
     print(json.dumps(line), flush=True)
 
 
