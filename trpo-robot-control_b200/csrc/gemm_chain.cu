@@ -8,11 +8,13 @@
 // The flat parameter layout already stores [W_i;B_i] as one (L_i+1) x L_{i+1} row-major matrix, so the bias is the
 // "ones" row of the augmented operand and no packing is needed.
 //
-// All three are one tiled GEMM on the FP64 tensor pipe (DMMA.8x8x4): CTA tile 128 x 64, k-step 16, 8 warps of 32 x 32
-// (4 x 4 MMA tiles), operands staged by 8-byte cp.async (zero-filled at the ragged edges, so odd sizes such as 15, 17,
-// 376 need no padding in HBM) into a double-buffered shared tile whose row strides (20 / 68 doubles) make every
-// fragment read bank-conflict-free. The forward kernel carries two accumulator sets (x and R{x}) and issues the three
-// products of the R-op per fragment pair; tanh runs branch-free on 8 values in lock step (dmma_common.cuh).
+// All three are one tiled GEMM on the FP64 tensor pipe (DMMA.8x8x4): CTA tile 128 x 64, operands staged by cp.async
+// (16-byte when the leading dimension is even, 8-byte otherwise; zero-filled at the ragged edges, so odd sizes such as
+// 15, 17, 376 need no padding in HBM) into a double-buffered shared tile whose row strides (20 / 36 / 68 doubles) make
+// every fragment read bank-conflict-free. The forward kernel carries two accumulator sets (x and R{x}) and issues the
+// three products of the R-op per fragment pair: 512 threads, 32 x 16 warp tiles, k-step 16 (122 registers, 16 warps per
+// SM). The single-product kernels (backward, outer) use 256 threads, 32 x 32 warp tiles, k-step 32 and run two CTAs
+// per SM (126-128 registers). tanh runs branch-free on 8 values in lock step (dmma_common.cuh).
 // Determinism: every output element has exactly one owner thread per (slice); slices are summed in fixed order.
 #include <stdint.h>
 
