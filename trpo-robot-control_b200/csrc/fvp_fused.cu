@@ -466,10 +466,11 @@ constexpr int FUSED_MAX_ROWS = 4 * FUSED_SMS;
 // (0.57 vs 0.51 ms per 10-iteration solve). The small-CTA variant stays selectable with TRPO_FUSED_ARM_VARIANT=4.
 using CfgArm  = Cfg<16, 16, 16, 8, 8, 1>;
 using CfgArm4 = Cfg<16, 16, 16, 8, 4, 4>;
+using CfgH32  = Cfg<32, 32, 32, 8, 8>;     // hidden <= 32, up to 32 inputs (e.g. 11-32-32-3)
 using CfgP64  = Cfg<4, 64, 64, 8, 8>;      // InvertedPendulum-size: 4-64-64-1
 using CfgM64  = Cfg<20, 64, 64, 8, 8>;     // 17-64-64-6 (and anything with L0 <= 20, hidden <= 64, A <= 8)
 
-enum FusedShape { SHAPE_NONE = 0, SHAPE_ARM, SHAPE_P64, SHAPE_M64 };
+enum FusedShape { SHAPE_NONE = 0, SHAPE_ARM, SHAPE_H32, SHAPE_P64, SHAPE_M64 };
 
 FusedShape pick_shape(const NetDesc &net) {
     if (net.K != 3) return SHAPE_NONE;
@@ -477,6 +478,7 @@ FusedShape pick_shape(const NetDesc &net) {
     const int L0 = net.L[0], L1 = net.L[1], L2 = net.L[2], L3 = net.L[3];
     if (L3 > 8) return SHAPE_NONE;
     if (L0 <= 16 && L1 <= 16 && L2 <= 16) return SHAPE_ARM;
+    if (L0 <= 32 && L1 <= 32 && L2 <= 32) return SHAPE_H32;
     if (L0 <= 4 && L1 <= 64 && L2 <= 64) return SHAPE_P64;
     if (L0 <= 20 && L1 <= 64 && L2 <= 64) return SHAPE_M64;
     return SHAPE_NONE;
@@ -530,6 +532,7 @@ int fused_fvp_accumulate(const NetDesc &net, const double *d_theta, const double
             rc = v4 ? launch_shape<CfgArm4>(a, st, &rows) : launch_shape<CfgArm>(a, st, &rows);
             break;
         }
+        case SHAPE_H32: rc = launch_shape<CfgH32>(a, st, &rows); break;
         case SHAPE_P64: rc = launch_shape<CfgP64>(a, st, &rows); break;
         case SHAPE_M64: rc = launch_shape<CfgM64>(a, st, &rows); break;
         default: return 1;
