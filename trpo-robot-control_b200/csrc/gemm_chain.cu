@@ -339,6 +339,143 @@ __global__ void __launch_bounds__(NT, 2) k_chain_outer(const double *__restrict_
     }
 }
 
+
+inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// tail: the LAST weight layer of the FVP when the action dimension is small (A <= 24) and the output activation is
+// linear / 0.1x (its pre-activation does not enter the FVP). One kernel does what forward(K-1) + backward(K) would do in two
+// 128 x 64-tile GEMM launches that are 4x too wide for a 17-column layer:
+//   Rx_K = Ry_{K-1} W + [y_{K-1},1] [VW;VB]      (TRPO_FVP.c:795-803)       k loop over H+1, 128 rows x 8*NTA columns per CTA
+//   RG_K = Rx_K f'^2 / sigma^2                   (:809-823, :852-854, :869-882)
+//   RG_{K-1} = (RG_K W^T) .* f'(y_{K-1})         (:890-899)                 contraction over the 8*NTA padded actions
+// A warp owns 16 rows; RG_K stays in its accumulator registers and is used directly as the A fragment of the second
+// product (contraction-index permutation, as in fvp_fused.cu), with W^T staged once per CTA in shared memory at a row
+// stride of HP + 2 doubles (2*stride % 16 == 4: conflict-free fragment reads).
+template <int NTA>
+__global__ void __launch_bounds__(NT, 1) k_chain_tail(const double *__restrict__ Y, const double *__restrict__ RY,
+                                                      const double *__restrict__ W, const double *__restrict__ VW,
+                                                      int rows, int H, int A, char act_prev, double d3,
+                                                      const double *__restrict__ inv_var,
+                                                      double *__restrict__ GK, double *__restrict__ Gprev,
+                                                      const int *__restrict__ done) {
+    if (done && *done) return;
+    extern __shared__ __align__(16) double smem[];
+    constexpr int BK = 16, RSA = Tile<BK>::RSA, AP = 8 * NTA, RSBT = AP + 4;
+    constexpr int A_TILE = BM * RSA, B_TILE = BK * RSBT, STAGE = 2 * A_TILE + 2 * B_TILE;
+    const int HP = (H + 7) & ~7, RST = HP + 2;
+    double *WT = smem + 2 * STAGE;                              // [AP][RST]
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
+    const int m0 = blockIdx.x * BM;
+    // W^T, zero padded: WT[k][j] = W[j][k]
+    for (int idx = tid; idx < AP * RST; idx += NT) WT[idx] = 0.0;
+    __syncthreads();
+    for (int idx = tid; idx < H * A; idx += NT) { const int j = idx / A, k = idx % A; WT[k * RST + j] = W[idx]; }
+
+    double rxa[2][NTA][2] = {}, rxb[2][NTA][2] = {};
+    const int nk = (H + 1 + BK - 1) / BK;
+    auto load = [&](int st, int k0) {
+        double *As = smem + st * STAGE, *RAs = As + A_TILE, *Bs = RAs + A_TILE, *VBs = Bs + B_TILE;
+        load_a_rowmajor<BK, NT>(As, Y, rows, H, m0, k0, true, 1.0, tid);
+        load_a_rowmajor<BK, NT>(RAs, RY, rows, H, m0, k0, false, 0.0, tid);
+        for (int idx = tid; idx < BK * AP; idx += NT) {
+            const int k = idx / AP, n = idx % AP, gk = k0 + k;
+            const bool in = gk <= H && n < A;
+            cp_async8(&Bs[k * RSBT + n], in ? &W[(size_t)gk * A + n] : W, in ? 8 : 0);
+            cp_async8(&VBs[k * RSBT + n], in ? &VW[(size_t)gk * A + n] : VW, in ? 8 : 0);
+        }
+        cp_async_commit();
+    };
+    load(0, 0);
+    for (int it = 0; it < nk; ++it) {
+        if (it + 1 < nk) { load((it + 1) & 1, (it + 1) * BK); cp_async_wait_group<1>(); }
+        else cp_async_wait_group<0>();
+        __syncthreads();
+        const double *As = smem + (it & 1) * STAGE, *RAs = As + A_TILE, *Bs = RAs + A_TILE, *VBs = Bs + B_TILE;
+#pragma unroll
+        for (int q = 0; q < BK / 4; ++q) {
+            double a[2], ra[2], b[NTA], vb[NTA];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                a[i] = As[(16 * w + 8 * i + g) * RSA + 4 * q + t];
+                ra[i] = RAs[(16 * w + 8 * i + g) * RSA + 4 * q + t];
+            }
+#pragma unroll
+            for (int j = 0; j < NTA; ++j) { b[j] = Bs[(4 * q + t) * RSBT + 8 * j + g]; vb[j] = VBs[(4 * q + t) * RSBT + 8 * j + g]; }
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < NTA; ++j) { dmma(rxa[i][j], ra[i], b[j]); dmma(rxb[i][j], a[i], vb[j]); }
+        }
+        __syncthreads();
+    }
+    // RG_K in accumulator layout; rows past the end of the chunk contribute nothing
+    double gk[2][NTA][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int gm = m0 + 16 * w + 8 * i + g;
+#pragma unroll
+        for (int j = 0; j < NTA; ++j)
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int col = 8 * j + 2 * t + r;
+                const double v = (gm < rows && col < A) ? (rxa[i][j][r] + rxb[i][j][r]) * d3 * inv_var[col] * d3 : 0.0;
+                gk[i][j][r] = v;
+                if (gm < rows && col < A) GK[(size_t)gm * A + col] = v;
+            }
+    }
+    // RG_{K-1} = (RG_K W^T) .* f'(y_{K-1}), 64 columns at a time
+    for (int n0 = 0; n0 < HP; n0 += 64) {
+        double acc[2][8][2] = {};
+#pragma unroll
+        for (int b = 0; b < NTA; ++b)
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const double *wrow = WT + (8 * b + 2 * t + r) * RST + n0 + g;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const double bf = (n0 + 8 * j < HP) ? wrow[8 * j] : 0.0;
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) dmma(acc[i][j], gk[i][b][r], bf);
+                }
+            }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int gm = m0 + 16 * w + 8 * i + g;
+            if (gm >= rows) continue;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    const int col = n0 + 8 * j + 2 * t + r;
+                    if (col >= H) continue;
+                    const size_t o = (size_t)gm * H + col;
+                    Gprev[o] = acc[i][j][r] * act_deriv(act_prev, Y[o]);
+                }
+        }
+    }
+}
+
+template <int NTA>
+size_t tail_smem_bytes(int H) {
+    constexpr int BK = 16, AP = 8 * NTA;
+    const int HP = (H + 7) & ~7;
+    return sizeof(double) * (2 * (2 * BM * Tile<BK>::RSA + 2 * BK * (AP + 4)) + (size_t)AP * (HP + 2));
+}
+
+template <int NTA>
+int launch_tail(const double *Y, const double *RY, const double *W, const double *VW, int rows, int H, int A, char act_prev,
+                double d3, const double *inv_var, double *GK, double *Gprev, const int *done, cudaStream_t st) {
+    const size_t bytes = tail_smem_bytes<NTA>(H);
+    static size_t configured = 0;
+    if (bytes > configured) {
+        if (cudaFuncSetAttribute(k_chain_tail<NTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return -1;
+        configured = bytes;
+    }
+    k_chain_tail<NTA><<<cdiv(rows, BM), NT, bytes, st>>>(Y, RY, W, VW, rows, H, A, act_prev, d3, inv_var, GK, Gprev, done);
+    return 0;
+}
+
 constexpr size_t SMEM_FWD_DUAL = sizeof(double) * 2 * (2 * Tile<BK_DUAL>::A + 2 * Tile<BK_DUAL>::B);
 constexpr size_t SMEM_FWD_L0   = sizeof(double) * 2 * (Tile<BK_DUAL>::A + 2 * Tile<BK_DUAL>::B);
 constexpr size_t SMEM_SINGLE   = sizeof(double) * 2 * (Tile<BK_SINGLE>::A + Tile<BK_SINGLE>::B);
@@ -371,7 +508,6 @@ __global__ void k_pg_seed(const double *__restrict__ mean, const double *__restr
     GL[idx] = adv[s] * (t * t - 1.0);
 }
 
-inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
 // split-K slices of one outer-product GEMM: about two CTAs per SM in total, never more than the partial rows available.
 // Wide layers get few slices (each CTA then amortises its 128 x 64 partial-tile read-modify-write over many samples);
@@ -403,8 +539,11 @@ int chain_accumulate(const NetDesc &net, const ChainScratch &sc, ChainMode mode,
     for (size_t c0 = 0; c0 < nsamples; c0 += sc.chunk, ++chunk_idx) {
         const int rows = (int)((nsamples - c0 < (size_t)sc.chunk) ? nsamples - c0 : sc.chunk);
         const int accumulate = chunk_idx > 0;
+        // the last layer of a narrow-action FVP goes through the fused tail kernel (forward(K-1) + seed + backward(K))
+        const bool tail = fvp && K >= 2 && A <= 24 && (net.ac[K] == 'l' || net.ac[K] == 'o') &&
+                          tail_smem_bytes<3>(net.L[K - 1]) <= 200 * 1024;
         // ---- forward ----
-        for (int i = 0; i < K; ++i) {
+        for (int i = 0; i < (tail ? K - 1 : K); ++i) {
             const double *Yin = (i == 0) ? d_obs + c0 * net.L[0] : sc.Y[i];
             const bool last = (i == K - 1);
             dim3 grid(cdiv(rows, BM), cdiv(net.L[i + 1], BN));
@@ -440,6 +579,17 @@ int chain_accumulate(const NetDesc &net, const ChainScratch &sc, ChainMode mode,
                                              sc.partial, net.P, net.logstd_off, accumulate, d_done);
             ++*launches;
         }
+        if (tail) {
+            const int H = net.L[K - 1];
+            const double d3 = net.ac[K] == 'o' ? 0.1 : 1.0;
+            const double *W = d_theta + net.w_off[K - 1], *VW = d_v + net.w_off[K - 1];
+            int rc;
+            if (A <= 8) rc = launch_tail<1>(sc.Y[K - 1], sc.RY[(K - 1) & 1], W, VW, rows, H, A, net.ac[K - 1], d3, d_inv_var, sc.G[K & 1], sc.G[(K - 1) & 1], d_done, st);
+            else if (A <= 16) rc = launch_tail<2>(sc.Y[K - 1], sc.RY[(K - 1) & 1], W, VW, rows, H, A, net.ac[K - 1], d3, d_inv_var, sc.G[K & 1], sc.G[(K - 1) & 1], d_done, st);
+            else rc = launch_tail<3>(sc.Y[K - 1], sc.RY[(K - 1) & 1], W, VW, rows, H, A, net.ac[K - 1], d3, d_inv_var, sc.G[K & 1], sc.G[(K - 1) & 1], d_done, st);
+            if (rc) return -1;
+            ++*launches;
+        }
         // ---- backward + outer products ----
         for (int i = K; i >= 1; --i) {
             const double *Yprev = (i == 1) ? d_obs + c0 * net.L[0] : sc.Y[i - 1];
@@ -450,7 +600,7 @@ int chain_accumulate(const NetDesc &net, const ChainScratch &sc, ChainMode mode,
             k_chain_outer<<<go, NT, SMEM_SINGLE, st>>>(Yprev, sc.G[i & 1], rows, M0, N, cdiv(cdiv(rows, ns), BK_SINGLE) * BK_SINGLE, tiles_n,
                                              sc.partial, net.P, net.w_off[i - 1], accumulate, d_done);
             ++*launches;
-            if (i > 1) {
+            if (i > 1 && !(tail && i == K)) {
                 dim3 gb(cdiv(rows, BM), cdiv(M0, BN));
                 k_chain_bwd<<<gb, NT, SMEM_SINGLE, st>>>(sc.G[i & 1], d_theta + net.w_off[i - 1], sc.Y[i - 1], rows, N, M0,
                                                net.ac[i - 1], sc.G[(i - 1) & 1], d_done);
