@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(DUAL ? 512 : NT, 1) k_chain_fwd(const double *
     constexpr int A_TILE = Tile<BK>::A, B_TILE = Tile<BK>::B;
     constexpr int STAGE = A_TILE * (DUAL && HAS_RA ? 2 : 1) + B_TILE * (DUAL ? 2 : 1);
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3, wm = w / WN, wn = w % WN;
-    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;     // the n-tiles of one row block run together: its A tile is read from L2 once
     double acc[4][NJ][2] = {}, racc[4][NJ][2] = {};
     __shared__ double exp2_tab[64];
     load_exp2_table(exp2_tab);                          // visible after the first barrier of the k loop
@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(NT, 2) k_chain_bwd(const double *__restrict__ 
     constexpr int BK = BK_SINGLE, A_TILE = Tile<BK>::A, B_TILE = Tile<BK>::B;
     constexpr int STAGE = A_TILE + B_TILE;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3, wm = w >> 1, wn = w & 1;
-    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;     // the n-tiles of one row block run together: its A tile is read from L2 once
     double acc[4][4][2] = {}, dummy[4][4][2];
     const int nk = (Kd + BK - 1) / BK;
     auto load = [&](int st, int k0) {
@@ -546,7 +546,7 @@ int chain_accumulate(const NetDesc &net, const ChainScratch &sc, ChainMode mode,
         for (int i = 0; i < (tail ? K - 1 : K); ++i) {
             const double *Yin = (i == 0) ? d_obs + c0 * net.L[0] : sc.Y[i];
             const bool last = (i == K - 1);
-            dim3 grid(cdiv(rows, BM), cdiv(net.L[i + 1], BN));
+            dim3 grid(cdiv(net.L[i + 1], BN), cdiv(rows, BM));
             if (fvp) {
                 const double *RYin = (i == 0) ? nullptr : sc.RY[i & 1];
                 const bool needY = !last || net.ac[K] == 't' || net.ac[K] == 's';
@@ -601,7 +601,7 @@ int chain_accumulate(const NetDesc &net, const ChainScratch &sc, ChainMode mode,
                                              sc.partial, net.P, net.w_off[i - 1], accumulate, d_done);
             ++*launches;
             if (i > 1 && !(tail && i == K)) {
-                dim3 gb(cdiv(rows, BM), cdiv(M0, BN));
+                dim3 gb(cdiv(M0, BN), cdiv(rows, BM));
                 k_chain_bwd<<<gb, NT, SMEM_SINGLE, st>>>(sc.G[i & 1], d_theta + net.w_off[i - 1], sc.Y[i - 1], rows, N, M0,
                                                net.ac[i - 1], sc.G[(i - 1) & 1], d_done);
                 ++*launches;
@@ -621,7 +621,7 @@ int chain_forward(const NetDesc &net, const ChainScratch &sc, const double *d_th
         for (int i = 0; i < K; ++i) {
             const double *Yin = (i == 0) ? d_obs + c0 * net.L[0] : sc.Y[i];
             double *Yout = (i == K - 1) ? d_mean_out + c0 * A : sc.Y[i + 1];
-            dim3 grid(cdiv(rows, BM), cdiv(net.L[i + 1], BN));
+            dim3 grid(cdiv(net.L[i + 1], BN), cdiv(rows, BM));
             k_chain_fwd<false, false><<<grid, NT, SMEM_SINGLE, st>>>(Yin, nullptr, d_theta + net.w_off[i], nullptr, rows, net.L[i],
                                                    net.L[i + 1], net.ac[i + 1], Yout, nullptr, nullptr, nullptr, nullptr);
             ++*launches;
