@@ -6,8 +6,9 @@
 // which keeps ~FP32 accuracy (a single TF32 product would lose 13 mantissa bits and miss the 1e-4 target).
 // Measured on this box (profiles/tf32_peak_r01.txt): mma.sync.m16n8k8.tf32 (SASS HMMA.1688.F32.TF32) 278 TFLOP/s, i.e.
 // 93 TFLOP/s effective for 3xTF32 against 37.1 for the FP64 tensor pipe and 71.7 for plain FFMA.
-// CTA tile 128 x 64, k-step 32, 8 warps of 32 x 32 (2 x 4 MMA tiles of 16 x 8), 4-byte cp.async with zero fill, shared
-// row strides 36 / 72 floats (conflict-free fragment reads). Per-slice partial sums are FP32; the fixed-order slice
+// CTA tile 128 x 64, k-step 32; the dual forward kernel runs 16 warps of 32 x 16, the single-product kernels 8 warps of
+// 32 x 32 at two CTAs per SM (as in gemm_chain.cu); 4-byte cp.async with zero fill, shared row strides 36 / 72 floats
+// (conflict-free fragment reads). Per-slice partial sums are FP32; the fixed-order slice
 // reduction and everything downstream (CG) are FP64.
 #include "trpo_internal.cuh"
 
@@ -60,11 +61,12 @@ __device__ __forceinline__ float act_deriv(char a, float y) {
     }
 }
 
+template <int NTH>
 __device__ __forceinline__ void load_a_rowmajor(float *As, const float *X, int rows, int ld, int m0, int k0,
                                                 bool aug, float ones_val, int tid) {
 #pragma unroll
-    for (int it = 0; it < BM * BK / NT; ++it) {
-        const int idx = tid + it * NT, m = idx / BK, k = idx % BK;
+    for (int it = 0; it < BM * BK / NTH; ++it) {
+        const int idx = tid + it * NTH, m = idx / BK, k = idx % BK;
         const int gm = m0 + m, gk = k0 + k;
         const bool in = X != nullptr && gm < rows && gk < ld;
         if (aug && gk == ld && gm < rows) As[m * RSA + k] = ones_val;
@@ -81,10 +83,11 @@ __device__ __forceinline__ void load_a_transposed(float *As, const float *Y, int
         else cp_async4(&As[m * RSA + k], in ? &Y[(size_t)gs * M0 + gm] : Y, in ? 4 : 0);
     }
 }
+template <int NTH>
 __device__ __forceinline__ void load_b_rowmajor(float *Bs, const float *M, int kdim, int N, int k0, int n0, int tid) {
 #pragma unroll
-    for (int it = 0; it < BK * BN / NT; ++it) {
-        const int idx = tid + it * NT, k = idx >> 6, n = idx & 63;
+    for (int it = 0; it < BK * BN / NTH; ++it) {
+        const int idx = tid + it * NTH, k = idx >> 6, n = idx & 63;
         const int gk = k0 + k, gn = n0 + n;
         const bool in = gk < kdim && gn < N;
         cp_async4(&Bs[k * RSB + n], in ? &M[(size_t)gk * N + gn] : M, in ? 4 : 0);
@@ -102,12 +105,12 @@ __device__ __forceinline__ void load_b_transposed(float *Bs, const float *W, int
 
 // one k-step (32) of a warp's 32 x 32 sub-tile. Fragment layout of m16n8k8 (lane = 4g + t):
 //   A: (g, t) (g+8, t) (g, t+4) (g+8, t+4)    B: (t, g) (t+4, g)    C: (g, 2t) (g, 2t+1) (g+8, 2t) (g+8, 2t+1)
-template <bool DUAL, bool HAS_RA>
-__device__ __forceinline__ void mma_stage(float (&acc)[2][4][4], float (&racc)[2][4][4], const float *As, const float *RAs,
+template <bool DUAL, bool HAS_RA, int NJ>
+__device__ __forceinline__ void mma_stage(float (&acc)[2][NJ][4], float (&racc)[2][NJ][4], const float *As, const float *RAs,
                                           const float *Bs, const float *VBs, int wm, int wn, int g, int t) {
 #pragma unroll
     for (int q = 0; q < BK / 8; ++q) {
-        unsigned ahi[2][4], alo[2][4], rhi[2][4], rlo[2][4], bhi[4][2], blo[4][2], vhi[4][2], vlo[4][2];
+        unsigned ahi[2][4], alo[2][4], rhi[2][4], rlo[2][4], bhi[NJ][2], blo[NJ][2], vhi[NJ][2], vlo[NJ][2];
 #pragma unroll
         for (int i = 0; i < 2; ++i)
 #pragma unroll
@@ -117,17 +120,17 @@ __device__ __forceinline__ void mma_stage(float (&acc)[2][4][4], float (&racc)[2
                 if (DUAL && HAS_RA) split_tf32(RAs[row * RSA + col], rhi[i][e], rlo[i][e]);
             }
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int j = 0; j < NJ; ++j)
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                const int row = 8 * q + t + 4 * e, col = 32 * wn + 8 * j + g;
+                const int row = 8 * q + t + 4 * e, col = 8 * NJ * wn + 8 * j + g;
                 split_tf32(Bs[row * RSB + col], bhi[j][e], blo[j][e]);
                 if (DUAL) split_tf32(VBs[row * RSB + col], vhi[j][e], vlo[j][e]);
             }
 #pragma unroll
         for (int i = 0; i < 2; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < NJ; ++j) {
                 mma3(acc[i][j], ahi[i], alo[i], bhi[j], blo[j]);
                 if (DUAL) {
                     if (HAS_RA) mma3(racc[i][j], rhi[i], rlo[i], bhi[j], blo[j]);
@@ -138,7 +141,7 @@ __device__ __forceinline__ void mma_stage(float (&acc)[2][4][4], float (&racc)[2
 }
 
 template <bool DUAL, bool HAS_RA>
-__global__ void __launch_bounds__(NT, 1) k_fwd(const float *__restrict__ Yin, const float *__restrict__ RYin,
+__global__ void __launch_bounds__(512, 1) k_fwd(const float *__restrict__ Yin, const float *__restrict__ RYin,
                                                const float *__restrict__ W, const float *__restrict__ VW,
                                                int rows, int Kd, int N, char act,
                                                float *__restrict__ Yout, float *__restrict__ RYout,
@@ -147,9 +150,10 @@ __global__ void __launch_bounds__(NT, 1) k_fwd(const float *__restrict__ Yin, co
     if (done && *done) return;
     extern __shared__ __align__(16) float smem_f[];
     constexpr int STAGE = A_TILE * (DUAL && HAS_RA ? 2 : 1) + B_TILE * (DUAL ? 2 : 1);
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3, wm = w >> 1, wn = w & 1;
-    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
-    float acc[2][4][4] = {}, racc[2][4][4] = {};
+    constexpr int NTH = 512, WN = 4, NJ = BN / 8 / WN;      // 16 warps: 4 (m) x 4 (n), 32 x 16 warp tiles
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3, wm = w / WN, wn = w % WN;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    float acc[2][NJ][4] = {}, racc[2][NJ][4] = {};
     const int nk = (Kd + 1 + BK - 1) / BK;
     auto stage_ptrs = [&](int st, float *&As, float *&RAs, float *&Bs, float *&VBs) {
         float *p = smem_f + st * STAGE;
@@ -161,11 +165,11 @@ __global__ void __launch_bounds__(NT, 1) k_fwd(const float *__restrict__ Yin, co
     auto load = [&](int st, int k0) {
         float *As, *RAs, *Bs, *VBs;
         stage_ptrs(st, As, RAs, Bs, VBs);
-        load_a_rowmajor(As, Yin, rows, Kd, m0, k0, true, 1.0f, tid);
-        load_b_rowmajor(Bs, W, Kd + 1, N, k0, n0, tid);
+        load_a_rowmajor<NTH>(As, Yin, rows, Kd, m0, k0, true, 1.0f, tid);
+        load_b_rowmajor<NTH>(Bs, W, Kd + 1, N, k0, n0, tid);
         if (DUAL) {
-            if (HAS_RA) load_a_rowmajor(RAs, RYin, rows, Kd, m0, k0, false, 0.0f, tid);
-            load_b_rowmajor(VBs, VW, Kd + 1, N, k0, n0, tid);
+            if (HAS_RA) load_a_rowmajor<NTH>(RAs, RYin, rows, Kd, m0, k0, false, 0.0f, tid);
+            load_b_rowmajor<NTH>(VBs, VW, Kd + 1, N, k0, n0, tid);
         }
         cp_commit();
     };
@@ -176,16 +180,16 @@ __global__ void __launch_bounds__(NT, 1) k_fwd(const float *__restrict__ Yin, co
         __syncthreads();
         float *As, *RAs, *Bs, *VBs;
         stage_ptrs(it & 1, As, RAs, Bs, VBs);
-        mma_stage<DUAL, HAS_RA>(acc, racc, As, RAs, Bs, VBs, wm, wn, g, t);
+        mma_stage<DUAL, HAS_RA, NJ>(acc, racc, As, RAs, Bs, VBs, wm, wn, g, t);
         __syncthreads();
     }
 #pragma unroll
     for (int i = 0; i < 2; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int j = 0; j < NJ; ++j)
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const int gm = m0 + 32 * wm + 16 * i + g + 8 * (e >> 1), gn = n0 + 32 * wn + 8 * j + 2 * t + (e & 1);
+                const int gm = m0 + 32 * wm + 16 * i + g + 8 * (e >> 1), gn = n0 + 8 * NJ * wn + 8 * j + 2 * t + (e & 1);
                 if (gm >= rows || gn >= N) continue;
                 const float y = act_apply(act, acc[i][j][e]);
                 const float d = act_deriv(act, y);
@@ -198,19 +202,19 @@ __global__ void __launch_bounds__(NT, 1) k_fwd(const float *__restrict__ Yin, co
             }
 }
 
-__global__ void __launch_bounds__(NT, 1) k_bwd(const float *__restrict__ Gin, const float *__restrict__ W,
+__global__ void __launch_bounds__(NT, 2) k_bwd(const float *__restrict__ Gin, const float *__restrict__ W,
                                                const float *__restrict__ Yprev, int rows, int Kd, int N, char act_prev,
                                                float *__restrict__ Gout, const int *__restrict__ done) {
     if (done && *done) return;
     extern __shared__ __align__(16) float smem_f[];
     constexpr int STAGE = A_TILE + B_TILE;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3, wm = w >> 1, wn = w & 1;
-    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     float acc[2][4][4] = {}, dummy[2][4][4];
     const int nk = (Kd + BK - 1) / BK;
     auto load = [&](int st, int k0) {
         float *As = smem_f + st * STAGE, *Bs = As + A_TILE;
-        load_a_rowmajor(As, Gin, rows, Kd, m0, k0, false, 0.0f, tid);
+        load_a_rowmajor<NT>(As, Gin, rows, Kd, m0, k0, false, 0.0f, tid);
         load_b_transposed(Bs, W, Kd, N, k0, n0, tid);
         cp_commit();
     };
@@ -220,7 +224,7 @@ __global__ void __launch_bounds__(NT, 1) k_bwd(const float *__restrict__ Gin, co
         else cp_wait<0>();
         __syncthreads();
         const float *As = smem_f + (it & 1) * STAGE, *Bs = As + A_TILE;
-        mma_stage<false, false>(acc, dummy, As, nullptr, Bs, nullptr, wm, wn, g, t);
+        mma_stage<false, false, 4>(acc, dummy, As, nullptr, Bs, nullptr, wm, wn, g, t);
         __syncthreads();
     }
 #pragma unroll
@@ -235,7 +239,7 @@ __global__ void __launch_bounds__(NT, 1) k_bwd(const float *__restrict__ Gin, co
             }
 }
 
-__global__ void __launch_bounds__(NT, 1) k_outer(const float *__restrict__ Yprev, const float *__restrict__ G,
+__global__ void __launch_bounds__(NT, 2) k_outer(const float *__restrict__ Yprev, const float *__restrict__ G,
                                                  int rows, int M0, int N, int per_slice, int tiles_n,
                                                  float *__restrict__ partial, int P, int out_off, int accumulate,
                                                  const int *__restrict__ done) {
@@ -252,7 +256,7 @@ __global__ void __launch_bounds__(NT, 1) k_outer(const float *__restrict__ Yprev
     auto load = [&](int st, int ks) {
         float *As = smem_f + st * STAGE, *Bs = As + A_TILE;
         load_a_transposed(As, Yprev, s1, M0, m0, ks, tid);
-        load_b_rowmajor(Bs, G + (size_t)ks * N, s1 - ks, N, 0, n0, tid);
+        load_b_rowmajor<NT>(Bs, G + (size_t)ks * N, s1 - ks, N, 0, n0, tid);
         cp_commit();
     };
     if (nk) load(0, s0);
@@ -261,7 +265,7 @@ __global__ void __launch_bounds__(NT, 1) k_outer(const float *__restrict__ Yprev
         else cp_wait<0>();
         __syncthreads();
         const float *As = smem_f + (it & 1) * STAGE, *Bs = As + A_TILE;
-        mma_stage<false, false>(acc, dummy, As, nullptr, Bs, nullptr, wm, wn, g, t);
+        mma_stage<false, false, 4>(acc, dummy, As, nullptr, Bs, nullptr, wm, wn, g, t);
         __syncthreads();
     }
     float *out = partial + (size_t)slice * P + out_off;
@@ -355,13 +359,13 @@ int chain_f32_accumulate(const NetDesc &net, const ChainScratchF32 &sc, const fl
             const float *Yin = (i == 0) ? f_obs + c0 * net.L[0] : sc.Y[i];
             const bool last = (i == K - 1);
             const bool needY = !last || net.ac[K] == 't' || net.ac[K] == 's';
-            dim3 grid(cdiv(rows, BM), cdiv(net.L[i + 1], BN));
+            dim3 grid(cdiv(net.L[i + 1], BN), cdiv(rows, BM));
             if (i == 0)
-                k_fwd<true, false><<<grid, NT, SMEM_L0, st>>>(Yin, nullptr, f_theta + net.w_off[i], f_v + net.w_off[i], rows,
+                k_fwd<true, false><<<grid, 512, SMEM_L0, st>>>(Yin, nullptr, f_theta + net.w_off[i], f_v + net.w_off[i], rows,
                         net.L[i], net.L[i + 1], net.ac[i + 1], needY ? sc.Y[i + 1] : nullptr,
                         last ? nullptr : sc.RY[(i + 1) & 1], last ? sc.G[K & 1] : nullptr, f_inv_var, d_done);
             else
-                k_fwd<true, true><<<grid, NT, SMEM_DUAL, st>>>(Yin, sc.RY[i & 1], f_theta + net.w_off[i], f_v + net.w_off[i], rows,
+                k_fwd<true, true><<<grid, 512, SMEM_DUAL, st>>>(Yin, sc.RY[i & 1], f_theta + net.w_off[i], f_v + net.w_off[i], rows,
                         net.L[i], net.L[i + 1], net.ac[i + 1], needY ? sc.Y[i + 1] : nullptr,
                         last ? nullptr : sc.RY[(i + 1) & 1], last ? sc.G[K & 1] : nullptr, f_inv_var, d_done);
             ++*launches;
@@ -376,7 +380,7 @@ int chain_f32_accumulate(const NetDesc &net, const ChainScratchF32 &sc, const fl
                                                 sc.partial, net.P, net.w_off[i - 1], accumulate, d_done);
             ++*launches;
             if (i > 1) {
-                dim3 gb(cdiv(rows, BM), cdiv(M0, BN));
+                dim3 gb(cdiv(M0, BN), cdiv(rows, BM));
                 k_bwd<<<gb, NT, SMEM_SINGLE, st>>>(sc.G[i & 1], f_theta + net.w_off[i - 1], sc.Y[i - 1], rows, N, M0,
                                                   net.ac[i - 1], sc.G[(i - 1) & 1], d_done);
                 ++*launches;
