@@ -166,7 +166,7 @@ __device__ __forceinline__ void mma_stage(double (&acc)[4][NJ][2], double (&racc
 // The dual (R-op) kernel carries two accumulator sets; to keep 16 warps per SM it runs 512 threads with 32 x 16 warp tiles
 // (64 accumulator registers per thread) instead of 256 threads with 32 x 32 tiles (128 registers, 8 warps per SM).
 template <bool DUAL, bool HAS_RA>
-__global__ void __launch_bounds__(DUAL ? 512 : NT, 1) k_chain_fwd(const double *__restrict__ Yin, const double *__restrict__ RYin,
+__global__ void __launch_bounds__(DUAL ? 512 : NT, DUAL ? 1 : 2) k_chain_fwd(const double *__restrict__ Yin, const double *__restrict__ RYin,
                                                      const double *__restrict__ W, const double *__restrict__ VW,
                                                      int rows, int Kd, int N, char act,
                                                      double *__restrict__ Yout, double *__restrict__ RYout,
