@@ -55,6 +55,12 @@ for shape in args.shapes.split(","):
         err = float(np.abs(u_gpu - u_ref).max() / np.abs(u_ref).max())
         for n in (int(x) for x in args.sizes.split(",")):
             b = {k: (np.ascontiguousarray(v[:n]) if k != "Std" else v) for k, v in full.items()}
+            try:            # a training loop reuses pinned staging buffers; pageable numpy arrays halve the copy rate
+                import torch
+                b = {k: (torch.from_numpy(v).pin_memory().numpy() if k != "Std" else v) for k, v in b.items()}
+                pinned = True
+            except Exception:
+                pinned = False
             times = []
             for rep in range(4):
                 t0 = time.perf_counter()
@@ -63,7 +69,7 @@ for shape in args.shapes.split(","):
                 times.append(time.perf_counter() - t0)
             t = min(times[1:])
             print(json.dumps({"shape": shape, "layers": layers, "N": n, "update_ms_e2e": t * 1e3,
-                              "states_per_s": n / t, "cg_iters": info.cg_iters, "ls_steps": info.ls_steps,
+                              "states_per_s": n / t, "pinned_host_buffers": pinned, "cg_iters": info.cg_iters, "ls_steps": info.ls_steps,
                               "ls_accepted": info.ls_accepted,
                               "cpu_port_states_per_s": ns / cpu_s, "cpu_sample": ns, "cpu_cg_iters": info_ref.cg_iters,
                               "parity_on_cpu_sample_max_rel": err}), flush=True)
