@@ -457,6 +457,338 @@ __global__ void __launch_bounds__(C::NTHREADS, C::CTAS_PER_SM) k_fvp_fused(const
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Warp-private variant for very small nets (hidden <= 16, e.g. the reference's armDOF_0 policy 15-16-16-3): all
+// parameter-gradient accumulators of the whole net fit in one warp's registers (30 doubles per thread), so a warp runs
+// phase A AND phase B on its own 8 samples and there is no block barrier inside the sample loop at all. Warps drift
+// apart, which keeps the FP64 pipe busy while others sit in tanh or wait for loads, and the work splits in 8-sample
+// units (50 k states over 1184 warps: 5.3 units each instead of 5.3 tiles of 64 per CTA with 2 of 8 warps doing the
+// outer products). The per-warp sums are added in fixed warp order at the end of the kernel.
+template <typename C, char ACT1, char ACT2>
+__global__ void __launch_bounds__(C::NTHREADS, 1) k_fvp_warp(const FusedArgs p) {
+    if (p.done && *p.done) return;
+    extern __shared__ __align__(16) double sm[];
+    constexpr int K0 = C::K0, H1 = C::H1, H2 = C::H2, AP = C::AP, NW = C::NW, NT = C::NTHREADS;
+    constexpr int Q0 = C::Q0, MT0 = C::MT0, NT1 = C::NT1, NT2 = C::NT2, NT3 = C::NT3;
+    constexpr int RS0 = C::RS0, RS1 = C::RS1, RS2 = C::RS2, RS3 = C::RS3, RSB = C::RSB;
+    constexpr int WS = 2 * (8 * RS0 + 8) + 8 * RS1 + 8 * RS2 + 8 * RSB + 8 * RS3;      // per-warp scratch (doubles)
+    double *W0f = sm + C::oW0, *VW0f = sm + C::oVW0, *W1s = sm + C::oW1, *VW1s = sm + C::oVW1;
+    double *W2s = sm + C::oW2, *VW2s = sm + C::oVW2, *B0s = sm + C::oB0, *VB0s = sm + C::oVB0;
+    double *B1s = sm + C::oB1, *VB1s = sm + C::oVB1, *VB2s = sm + C::oVB2, *IVs = sm + C::oIV;
+    double *Tab = sm + C::oY0;                              // the region after the weights is laid out locally
+    double *scratch = Tab + 64;
+
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
+    const int L0 = p.L0, L1 = p.L1, L2 = p.L2, L3 = p.L3;
+    const bool free_col = L0 < K0;
+    const int rows0 = L0 + (free_col ? 1 : 0);
+    for (int idx = tid; idx < K0 * H1; idx += NT) {
+        const int k = idx / H1, n = idx % H1;
+        const bool in = k < rows0 && n < L1;
+        const int dst = ((k >> 2) * NT1 + (n >> 3)) * 32 + (n & 7) * 4 + (k & 3);
+        W0f[dst]  = in ? p.theta[p.w_off0 + k * L1 + n] : 0.0;
+        VW0f[dst] = in ? p.v[p.w_off0 + k * L1 + n] : 0.0;
+    }
+    for (int idx = tid; idx < H1 * H2; idx += NT) {
+        const int j = idx / H2, n = idx % H2;
+        const bool in = j < L1 && n < L2;
+        const int dst = ((j >> 3) * NT2 + (n >> 3)) * 64 + swz(j & 7, n & 7);
+        W1s[dst]  = in ? p.theta[p.w_off1 + j * L2 + n] : 0.0;
+        VW1s[dst] = in ? p.v[p.w_off1 + j * L2 + n] : 0.0;
+    }
+    for (int idx = tid; idx < H2 * AP; idx += NT) {
+        const int j = idx / AP, n = idx % AP;
+        const bool in = j < L2 && n < L3;
+        const int dst = ((j >> 3) * NT3 + (n >> 3)) * 64 + swz(j & 7, n & 7);
+        W2s[dst]  = in ? p.theta[p.w_off2 + j * L3 + n] : 0.0;
+        VW2s[dst] = in ? p.v[p.w_off2 + j * L3 + n] : 0.0;
+    }
+    for (int n = tid; n < H1; n += NT) {
+        B0s[n]  = n < L1 ? p.theta[p.w_off0 + L0 * L1 + n] : 0.0;
+        VB0s[n] = n < L1 ? p.v[p.w_off0 + L0 * L1 + n] : 0.0;
+    }
+    for (int n = tid; n < H2; n += NT) {
+        B1s[n]  = n < L2 ? p.theta[p.w_off1 + L1 * L2 + n] : 0.0;
+        VB1s[n] = n < L2 ? p.v[p.w_off1 + L1 * L2 + n] : 0.0;
+    }
+    for (int n = tid; n < AP; n += NT) {
+        VB2s[n] = n < L3 ? p.v[p.w_off2 + L2 * L3 + n] : 0.0;
+        IVs[n]  = n < L3 ? p.inv_var[n] : 0.0;
+    }
+    load_exp2_table(Tab);
+    for (int i = tid; i < NW * WS; i += NT) scratch[i] = 0.0;
+    __syncthreads();
+
+    double *Y0w = scratch + w * WS;                         // [2][8*RS0 + 8]
+    double *Y1w = Y0w + 2 * (8 * RS0 + 8), *Y2w = Y1w + 8 * RS1, *Gw = Y2w + 8 * RS2, *G3w = Gw + 8 * RSB;
+    int sf[2], sb[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) { sf[r] = swz(2 * t + r, g); sb[r] = swz(g, 2 * t + r); }
+    const double d3 = (p.act3 == 'o') ? 0.1 : 1.0;
+    const double ones = (g == 0) ? 1.0 : 0.0;
+
+    double acc0[MT0][NT1][2], accb0[NT1][2], acc1[NT1][NT2][2], accb1[NT2][2], acc2[NT2][NT3][2], accb2[NT3][2];
+#pragma unroll
+    for (int m = 0; m < MT0; ++m)
+#pragma unroll
+        for (int j = 0; j < NT1; ++j) acc0[m][j][0] = acc0[m][j][1] = 0.0;
+#pragma unroll
+    for (int j = 0; j < NT1; ++j) accb0[j][0] = accb0[j][1] = 0.0;
+#pragma unroll
+    for (int m = 0; m < NT1; ++m)
+#pragma unroll
+        for (int j = 0; j < NT2; ++j) acc1[m][j][0] = acc1[m][j][1] = 0.0;
+#pragma unroll
+    for (int j = 0; j < NT2; ++j) accb1[j][0] = accb1[j][1] = 0.0;
+#pragma unroll
+    for (int m = 0; m < NT2; ++m)
+#pragma unroll
+        for (int c = 0; c < NT3; ++c) acc2[m][c][0] = acc2[m][c][1] = 0.0;
+#pragma unroll
+    for (int c = 0; c < NT3; ++c) accb2[c][0] = accb2[c][1] = 0.0;
+
+    // this warp's 8-sample units: u = blockIdx.x * NW + w, stride gridDim.x * NW
+    const long long nunits = (p.nsamples + 7) / 8;
+    const long long ustride = (long long)gridDim.x * NW;
+    auto stage_obs = [&](long long unit, int buf) {         // the warp stages its own 8 x K0 tile
+        double *dst = Y0w + buf * (8 * RS0 + 8);
+        const long long s0n = unit * 8;
+        wait_samples(p, (s0n + 8 < p.nsamples ? s0n + 8 : p.nsamples) - 1);
+        for (int idx = lane; idx < 8 * K0; idx += 32) {
+            const int row = idx / K0, col = idx % K0;
+            const long long gs = s0n + row;
+            const bool in = gs < p.nsamples && col < L0;
+            if (free_col && col == L0) dst[row * RS0 + col] = (gs < p.nsamples) ? 1.0 : 0.0;
+            else cp_async8(&dst[row * RS0 + col], in ? &p.obs[gs * L0 + col] : p.obs, in ? 8 : 0);
+        }
+    };
+    long long unit = (long long)blockIdx.x * NW + w;
+    if (unit < nunits) stage_obs(unit, 0);
+    cp_async_wait_all();
+    __syncwarp();
+    int buf = 0;
+    for (; unit < nunits; unit += ustride, buf ^= 1) {
+        const double *Y0c = Y0w + buf * (8 * RS0 + 8);
+        if (unit + ustride < nunits) stage_obs(unit + ustride, buf ^ 1);
+        // ---- phase A (as in k_fvp_fused, rows = g) ----
+        double y1[NT1][2], ry1[NT1][2];
+#pragma unroll
+        for (int c = 0; c < NT1; ++c)
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                y1[c][r] = free_col ? 0.0 : B0s[8 * c + 2 * t + r];
+                ry1[c][r] = free_col ? 0.0 : VB0s[8 * c + 2 * t + r];
+            }
+#pragma unroll
+        for (int q = 0; q < Q0; ++q) {
+            const double a = Y0c[g * RS0 + 4 * q + t];
+#pragma unroll
+            for (int c = 0; c < NT1; ++c) {
+                dmma(y1[c], a, W0f[(q * NT1 + c) * 32 + lane]);
+                dmma(ry1[c], a, VW0f[(q * NT1 + c) * 32 + lane]);
+            }
+        }
+        activate_tiles<ACT1, 0, NT1>(p.act1, y1, ry1, Tab);
+#pragma unroll
+        for (int c = 0; c < NT1; ++c)
+            *reinterpret_cast<double2 *>(&Y1w[g * RS1 + 8 * c + 2 * t]) = make_double2(y1[c][0], y1[c][1]);
+        double x2[NT2][2], rx2[NT2][2];
+#pragma unroll
+        for (int c = 0; c < NT2; ++c)
+#pragma unroll
+            for (int r = 0; r < 2; ++r) { x2[c][r] = B1s[8 * c + 2 * t + r]; rx2[c][r] = VB1s[8 * c + 2 * t + r]; }
+#pragma unroll
+        for (int b = 0; b < NT1; ++b)
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+                for (int c = 0; c < NT2; ++c) {
+                    const double bw = W1s[(b * NT2 + c) * 64 + sf[r]], bv = VW1s[(b * NT2 + c) * 64 + sf[r]];
+                    dmma(rx2[c], ry1[b][r], bw);
+                    dmma(x2[c], y1[b][r], bw);
+                    dmma(rx2[c], y1[b][r], bv);
+                }
+        activate_tiles<ACT2, 0, NT2>(p.act2, x2, rx2, Tab);
+#pragma unroll
+        for (int c = 0; c < NT2; ++c)
+            *reinterpret_cast<double2 *>(&Y2w[g * RS2 + 8 * c + 2 * t]) = make_double2(x2[c][0], x2[c][1]);
+        double rx3[NT3][2];
+#pragma unroll
+        for (int c = 0; c < NT3; ++c)
+#pragma unroll
+            for (int r = 0; r < 2; ++r) rx3[c][r] = VB2s[8 * c + 2 * t + r];
+#pragma unroll
+        for (int b = 0; b < NT2; ++b)
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+                for (int c = 0; c < NT3; ++c) {
+                    dmma(rx3[c], rx2[b][r], W2s[(b * NT3 + c) * 64 + sf[r]]);
+                    dmma(rx3[c], x2[b][r], VW2s[(b * NT3 + c) * 64 + sf[r]]);
+                }
+        const bool valid = (unit * 8 + g) < p.nsamples;
+        double g3[NT3][2];
+#pragma unroll
+        for (int c = 0; c < NT3; ++c) {
+#pragma unroll
+            for (int r = 0; r < 2; ++r) g3[c][r] = valid ? rx3[c][r] * d3 * IVs[8 * c + 2 * t + r] * d3 : 0.0;
+            *reinterpret_cast<double2 *>(&G3w[g * RS3 + 8 * c + 2 * t]) = make_double2(g3[c][0], g3[c][1]);
+        }
+        double g2[NT2][2];
+#pragma unroll
+        for (int b = 0; b < NT2; ++b) g2[b][0] = g2[b][1] = 0.0;
+#pragma unroll
+        for (int c = 0; c < NT3; ++c)
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+                for (int b = 0; b < NT2; ++b) dmma(g2[b], g3[c][r], W2s[(b * NT3 + c) * 64 + sb[r]]);
+#pragma unroll
+        for (int b = 0; b < NT2; ++b) {
+            g2[b][0] *= act_deriv_y<ACT2>(p.act2, x2[b][0]);
+            g2[b][1] *= act_deriv_y<ACT2>(p.act2, x2[b][1]);
+            *reinterpret_cast<double2 *>(&Gw[g * RSB + 8 * b + 2 * t]) = make_double2(g2[b][0], g2[b][1]);
+        }
+        double g1[NT1][2];
+#pragma unroll
+        for (int b = 0; b < NT1; ++b) g1[b][0] = g1[b][1] = 0.0;
+#pragma unroll
+        for (int c = 0; c < NT2; ++c)
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+                for (int b = 0; b < NT1; ++b) dmma(g1[b], g2[c][r], W1s[(b * NT2 + c) * 64 + sb[r]]);
+#pragma unroll
+        for (int b = 0; b < NT1; ++b) {
+            g1[b][0] *= act_deriv_y<ACT1>(p.act1, y1[b][0]);
+            g1[b][1] *= act_deriv_y<ACT1>(p.act1, y1[b][1]);
+        }
+        __syncwarp();
+        // ---- phase B on this warp's own 8 samples (2 k-steps) ----
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int srow = 4 * h + t;
+            double bg2[NT2], bg3[NT3];
+#pragma unroll
+            for (int j = 0; j < NT2; ++j) bg2[j] = Gw[srow * RSB + 8 * j + g];
+#pragma unroll
+            for (int c = 0; c < NT3; ++c) bg3[c] = G3w[srow * RS3 + 8 * c + g];
+#pragma unroll
+            for (int m = 0; m < NT1; ++m) {
+                const double a = Y1w[srow * RS1 + 8 * m + g];
+#pragma unroll
+                for (int j = 0; j < NT2; ++j) dmma(acc1[m][j], a, bg2[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < NT2; ++j) dmma(accb1[j], ones, bg2[j]);
+#pragma unroll
+            for (int m = 0; m < NT2; ++m) {
+                const double a = Y2w[srow * RS2 + 8 * m + g];
+#pragma unroll
+                for (int c = 0; c < NT3; ++c) dmma(acc2[m][c], a, bg3[c]);
+            }
+#pragma unroll
+            for (int c = 0; c < NT3; ++c) dmma(accb2[c], ones, bg3[c]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int b = 0; b < NT1; ++b)
+            *reinterpret_cast<double2 *>(&Gw[g * RSB + 8 * b + 2 * t]) = make_double2(g1[b][0], g1[b][1]);
+        __syncwarp();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int srow = 4 * h + t;
+            double bg1[NT1];
+#pragma unroll
+            for (int j = 0; j < NT1; ++j) bg1[j] = Gw[srow * RSB + 8 * j + g];
+#pragma unroll
+            for (int m = 0; m < MT0; ++m) {
+                const double a = Y0c[srow * RS0 + 8 * m + g];
+#pragma unroll
+                for (int j = 0; j < NT1; ++j) dmma(acc0[m][j], a, bg1[j]);
+            }
+            if (!free_col) {
+#pragma unroll
+                for (int j = 0; j < NT1; ++j) dmma(accb0[j], ones, bg1[j]);
+            }
+        }
+        cp_async_wait_all();
+        __syncwarp();
+    }
+
+    // ---- per-warp sums -> shared [NW][P] -> fixed-order sum over the warps -> this CTA's partial row ----
+    __syncthreads();
+    double *red = scratch;                                  // NW * P doubles (fits: P <= 1024 on this path)
+    double *mine = red + (size_t)w * p.P;
+    for (int i = lane; i < p.P; i += 32) mine[i] = 0.0;
+    __syncwarp();
+#pragma unroll
+    for (int m = 0; m < MT0; ++m)
+#pragma unroll
+        for (int j = 0; j < NT1; ++j)
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int row = 8 * m + g, col = 8 * j + 2 * t + r;
+                if (row < rows0 && col < L1) mine[p.w_off0 + row * L1 + col] = acc0[m][j][r];
+            }
+#pragma unroll
+    for (int j = 0; j < NT1; ++j)
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int col = 8 * j + 2 * t + r;
+            if (!free_col && g == 0 && col < L1) mine[p.w_off0 + L0 * L1 + col] = accb0[j][r];
+        }
+#pragma unroll
+    for (int m = 0; m < NT1; ++m)
+#pragma unroll
+        for (int j = 0; j < NT2; ++j)
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int row = 8 * m + g, col = 8 * j + 2 * t + r;
+                if (row < L1 && col < L2) mine[p.w_off1 + row * L2 + col] = acc1[m][j][r];
+            }
+#pragma unroll
+    for (int j = 0; j < NT2; ++j)
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int col = 8 * j + 2 * t + r;
+            if (g == 0 && col < L2) mine[p.w_off1 + L1 * L2 + col] = accb1[j][r];
+        }
+#pragma unroll
+    for (int m = 0; m < NT2; ++m)
+#pragma unroll
+        for (int c = 0; c < NT3; ++c)
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int row = 8 * m + g, col = 8 * c + 2 * t + r;
+                if (row < L2 && col < L3) mine[p.w_off2 + row * L3 + col] = acc2[m][c][r];
+            }
+#pragma unroll
+    for (int c = 0; c < NT3; ++c)
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int col = 8 * c + 2 * t + r;
+            if (g == 0 && col < L3) mine[p.w_off2 + L2 * L3 + col] = accb2[c][r];
+        }
+    __syncthreads();
+    double *out = p.partial + (size_t)blockIdx.x * p.P;
+    for (int i = tid; i < p.P; i += NT) {
+        double sum = red[i];
+#pragma unroll
+        for (int ww = 1; ww < NW; ++ww) sum += red[(size_t)ww * p.P + i];
+        out[i] = sum;
+    }
+}
+
+template <typename C>
+constexpr size_t warp_smem_bytes() {
+    constexpr int WS = 2 * (8 * C::RS0 + 8) + 8 * C::RS1 + 8 * C::RS2 + 8 * C::RSB + 8 * C::RS3;
+    constexpr int PMAX = (C::K0 + 1) * C::H1 + (C::H1 + 1) * C::H2 + (C::H2 + 1) * C::AP + C::AP;
+    constexpr int SCR = C::NW * (WS > PMAX ? WS : PMAX);
+    return sizeof(double) * (C::oY0 + 64 + SCR);
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int FUSED_SMS = 148;
 constexpr int FUSED_MAX_ROWS = 4 * FUSED_SMS;
@@ -496,6 +828,29 @@ int launch_cfg(const FusedArgs &a, int grid, cudaStream_t st) {
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
+template <typename C, char A1, char A2>
+int launch_warp_cfg(const FusedArgs &a, int grid, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(k_fvp_warp<C, A1, A2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)warp_smem_bytes<C>()) != cudaSuccess)
+            return -1;
+        configured = true;
+    }
+    k_fvp_warp<C, A1, A2><<<grid, C::NTHREADS, warp_smem_bytes<C>(), st>>>(a);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+// warp-private kernel: one 8-warp CTA per SM, every warp works through its own 8-sample units
+template <typename C>
+int launch_warp_shape(const FusedArgs &a, cudaStream_t st, int *rows) {
+    const long long nunits = (a.nsamples + 7) / 8;
+    const long long want = (nunits + C::NW - 1) / C::NW;
+    const int grid = (int)(want < FUSED_SMS ? want : FUSED_SMS);
+    *rows = grid;
+    if (a.act1 == 't' && a.act2 == 't') return launch_warp_cfg<C, 't', 't'>(a, grid, st);
+    return launch_warp_cfg<C, 0, 0>(a, grid, st);
+}
+
 template <typename C>
 int launch_shape(const FusedArgs &a, cudaStream_t st, int *rows) {
     const long long ntiles = (a.nsamples + C::S - 1) / C::S;
@@ -528,8 +883,11 @@ int fused_fvp_accumulate(const NetDesc &net, const double *d_theta, const double
     int rows = 0, rc = -1;
     switch (shape) {
         case SHAPE_ARM: {
-            static const bool v4 = getenv("TRPO_FUSED_ARM_VARIANT") && atoi(getenv("TRPO_FUSED_ARM_VARIANT")) == 4;
-            rc = v4 ? launch_shape<CfgArm4>(a, st, &rows) : launch_shape<CfgArm>(a, st, &rows);
+            // default: warp-private kernel (no block barriers); TRPO_FUSED_ARM_VARIANT=8 / 4 select the block-wide variants
+            static const int variant = getenv("TRPO_FUSED_ARM_VARIANT") ? atoi(getenv("TRPO_FUSED_ARM_VARIANT")) : 0;
+            rc = variant == 4 ? launch_shape<CfgArm4>(a, st, &rows)
+               : variant == 8 ? launch_shape<CfgArm>(a, st, &rows)
+                              : launch_warp_shape<CfgArm>(a, st, &rows);
             break;
         }
         case SHAPE_H32: rc = launch_shape<CfgH32>(a, st, &rows); break;
