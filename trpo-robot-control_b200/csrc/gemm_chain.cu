@@ -202,15 +202,18 @@ __global__ void __launch_bounds__(DUAL ? 512 : NT, DUAL ? 1 : 2) k_chain_fwd(con
         }
         cp_async_commit();
     };
-    load(0, 0);
+    // 3-stage cp.async pipeline, one block barrier per k-step: the barrier that publishes stage `it` also guarantees that
+    // everybody is done with stage it-1, whose buffer the load issued right after it overwrites
+    constexpr int NS = DUAL ? 3 : 2;
+#pragma unroll
+    for (int s0 = 0; s0 < NS - 1; ++s0) { if (s0 < nk) load(s0, s0 * BK); else cp_async_commit(); }
     for (int it = 0; it < nk; ++it) {
-        if (it + 1 < nk) { load((it + 1) & 1, (it + 1) * BK); cp_async_wait_group<1>(); }
-        else cp_async_wait_group<0>();
+        cp_async_wait_group<NS - 2>();
         __syncthreads();
+        if (it + NS - 1 < nk) load((it + NS - 1) % NS, (it + NS - 1) * BK); else cp_async_commit();
         double *As, *RAs, *Bs, *VBs;
-        stage_ptrs(it & 1, As, RAs, Bs, VBs);
+        stage_ptrs(it % NS, As, RAs, Bs, VBs);
         mma_stage<DUAL, HAS_RA, BK, NJ>(acc, racc, As, RAs, Bs, VBs, wm, wn, g, t);
-        __syncthreads();
     }
     // epilogue: activation, R{y} = R{x} f'(x), last layer: R-gradient seed RG_K = Ry_K / sigma^2 * f' (TRPO_FVP.c:852-882)
 #pragma unroll
@@ -268,13 +271,12 @@ __global__ void __launch_bounds__(NT, 2) k_chain_bwd(const double *__restrict__ 
         cp_async_commit();
     };
     load(0, 0);
-    for (int it = 0; it < nk; ++it) {
-        if (it + 1 < nk) { load((it + 1) & 1, (it + 1) * BK); cp_async_wait_group<1>(); }
-        else cp_async_wait_group<0>();
+    for (int it = 0; it < nk; ++it) {          // one barrier per k-step: it publishes stage `it` and frees the other buffer
+        cp_async_wait_group<0>();
         __syncthreads();
+        if (it + 1 < nk) load((it + 1) & 1, (it + 1) * BK);
         const double *As = smem + (it & 1) * STAGE, *Bs = As + A_TILE;
         mma_stage<false, false, BK, 4>(acc, dummy, As, nullptr, Bs, nullptr, wm, wn, g, t);
-        __syncthreads();
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -315,12 +317,11 @@ __global__ void __launch_bounds__(NT, 2) k_chain_outer(const double *__restrict_
     };
     if (nk) load(0, s0);
     for (int it = 0; it < nk; ++it) {
-        if (it + 1 < nk) { load((it + 1) & 1, s0 + (it + 1) * BK); cp_async_wait_group<1>(); }
-        else cp_async_wait_group<0>();
+        cp_async_wait_group<0>();
         __syncthreads();
+        if (it + 1 < nk) load((it + 1) & 1, s0 + (it + 1) * BK);
         const double *As = smem + (it & 1) * STAGE, *Bs = As + A_TILE;
         mma_stage<false, false, BK, 4>(acc, dummy, As, nullptr, Bs, nullptr, wm, wn, g, t);
-        __syncthreads();
     }
     double *out = partial + (size_t)slice * P + out_off;
 #pragma unroll
@@ -476,8 +477,8 @@ int launch_tail(const double *Y, const double *RY, const double *W, const double
     return 0;
 }
 
-constexpr size_t SMEM_FWD_DUAL = sizeof(double) * 2 * (2 * Tile<BK_DUAL>::A + 2 * Tile<BK_DUAL>::B);
-constexpr size_t SMEM_FWD_L0   = sizeof(double) * 2 * (Tile<BK_DUAL>::A + 2 * Tile<BK_DUAL>::B);
+constexpr size_t SMEM_FWD_DUAL = sizeof(double) * 3 * (2 * Tile<BK_DUAL>::A + 2 * Tile<BK_DUAL>::B);
+constexpr size_t SMEM_FWD_L0   = sizeof(double) * 3 * (Tile<BK_DUAL>::A + 2 * Tile<BK_DUAL>::B);
 constexpr size_t SMEM_SINGLE   = sizeof(double) * 2 * (Tile<BK_SINGLE>::A + Tile<BK_SINGLE>::B);
 
 bool configure_kernels() {
