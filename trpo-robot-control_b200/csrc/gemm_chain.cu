@@ -204,13 +204,42 @@ __global__ void __launch_bounds__(DUAL ? 512 : NT, DUAL ? 1 : 2) k_chain_fwd(con
     };
     // 3-stage cp.async pipeline, one block barrier per k-step: the barrier that publishes stage `it` also guarantees that
     // everybody is done with stage it-1, whose buffer the load issued right after it overwrites
+    // interior k-steps of an aligned, full-width tile take a branch-free loader (16-byte copies, no bounds on k, rows past the
+    // end zero-filled by src-size 0); only the last k-step(s) need the general one. The general loaders cost 11 % of this
+    // kernel's stall samples in index arithmetic and bound / augmented-column branches (profiles/r01_summary.md).
+    const bool fast_ok = (Kd & 1) == 0 && (N & 1) == 0 && n0 + BN <= N && (reinterpret_cast<uintptr_t>(Yin) & 15) == 0 &&
+                         (reinterpret_cast<uintptr_t>(W) & 15) == 0 &&
+                         (!DUAL || ((reinterpret_cast<uintptr_t>(VW) & 15) == 0 &&
+                                    (!HAS_RA || (reinterpret_cast<uintptr_t>(RYin) & 15) == 0)));
+    auto load_fast = [&](int st, int k0) {                  // requires k0 + BK <= Kd
+        double *As, *RAs, *Bs, *VBs;
+        stage_ptrs(st, As, RAs, Bs, VBs);
+        constexpr int RSA = Tile<BK>::RSA, CH = BK / 2;     // 16-byte chunks per tile row
+#pragma unroll
+        for (int it2 = 0; it2 < BM * CH / NTH; ++it2) {
+            const int idx = tid + it2 * NTH, m = idx / CH, k = (idx % CH) * 2, gm = m0 + m;
+            const int bytes = gm < rows ? 16 : 0;
+            const size_t off = (size_t)(gm < rows ? gm : rows - 1) * Kd + k0 + k;
+            cp_async16(&As[m * RSA + k], Yin + off, bytes);
+            if (DUAL && HAS_RA) cp_async16(&RAs[m * RSA + k], RYin + off, bytes);
+        }
+#pragma unroll
+        for (int it2 = 0; it2 < BK * (BN / 2) / NTH; ++it2) {
+            const int idx = tid + it2 * NTH, k = idx / (BN / 2), n = (idx % (BN / 2)) * 2;
+            const size_t off = (size_t)(k0 + k) * N + n0 + n;
+            cp_async16(&Bs[k * RSB + n], W + off, 16);
+            if (DUAL) cp_async16(&VBs[k * RSB + n], VW + off, 16);
+        }
+        cp_async_commit();
+    };
+    auto load_any = [&](int st, int k0) { if (fast_ok && k0 + BK <= Kd) load_fast(st, k0); else load(st, k0); };
     constexpr int NS = DUAL ? 3 : 2;
 #pragma unroll
-    for (int s0 = 0; s0 < NS - 1; ++s0) { if (s0 < nk) load(s0, s0 * BK); else cp_async_commit(); }
+    for (int s0 = 0; s0 < NS - 1; ++s0) { if (s0 < nk) load_any(s0, s0 * BK); else cp_async_commit(); }
     for (int it = 0; it < nk; ++it) {
         cp_async_wait_group<NS - 2>();
         __syncthreads();
-        if (it + NS - 1 < nk) load((it + NS - 1) % NS, (it + NS - 1) * BK); else cp_async_commit();
+        if (it + NS - 1 < nk) load_any((it + NS - 1) % NS, (it + NS - 1) * BK); else cp_async_commit();
         double *As, *RAs, *Bs, *VBs;
         stage_ptrs(it % NS, As, RAs, Bs, VBs);
         mma_stage<DUAL, HAS_RA, BK, NJ>(acc, racc, As, RAs, Bs, VBs, wm, wn, g, t);
