@@ -340,6 +340,14 @@ def run_gpu_arm(args, pkg):
                            "cg_solve_ms": a["ms_step_graph"], "cg_solve_ms_direct_launches_with_event_pairs": a["ms_step"],
                            "e2e_value": a["e2e_value"], "e2e_ms_per_step": a["e2e_ms"], "kernel_path": a["path"],
                            "roofline_frac": a["roofline"]["frac"], "kernel_avg_ms": a["roofline"]["kernel_avg_ms"]}
+        if world == 1 and rank == 0 and not args.no_cpu_baseline:
+            # the reference's CPU CG() on the whole 50 k-state arm batch (about 4 s on one core)
+            with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as tmp:
+                rate, t_step, kind = reference_cg_rate(pkg, a["layers"], a["ac"], a["theta"], a["batch"], a["vec"],
+                                                       a["n_total"], 1, 0, tmp)
+            also["arm_50k"]["cpu_baseline"] = {"value": rate, "unit": "samples/s", "cores": 1, "kind": kind,
+                                               "sample": f"one 10-iteration CG() of the unmodified reference on all "
+                                                         f"{a['n_total']} states ({t_step:.1f} s), NumThreads=1"}
 
     if rank == 0:
         layers, n_total, P = m["layers"], m["n_total"], m["P"]
