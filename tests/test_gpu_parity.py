@@ -345,3 +345,31 @@ def test_repeated_solves_replay_a_cuda_graph_bitwise(pkg, armtest):
     assert rel_err(xs[0], a["ref_cg_3150"])[0] < CG_TOL
     assert rel_err(x_other, 2.0 * a["ref_cg_3150"])[0] < 1e-6       # linear system: x scales with b (different early exit point)
     assert not np.array_equal(x_new_model, xs[0])
+
+
+@pytest.mark.parametrize("variant", ["8", "4"])
+def test_block_wide_variants_of_the_arm_kernel(variant, tmp_path):
+    """TRPO_FUSED_ARM_VARIANT selects the block-wide fused kernel (one 8-warp CTA, or four 4-warp CTAs per SM) instead of
+    the warp-private default for the 15-16-16-3 policy; the switch is read once per process, hence the subprocess."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, numpy as np\n"
+        f"sys.path.insert(0, {root!r}); sys.path.insert(0, {os.path.join(root, 'tests')!r})\n"
+        "from __graft_entry__ import load_package\n"
+        "pkg = load_package()\n"
+        f"a = dict(np.load({os.path.join(root, 'tests', 'golden', 'armtest.npz')!r}))\n"
+        "with pkg.Context([15, 16, 16, 3], 'lttl') as ctx:\n"
+        "    ctx.set_model(a['theta']); ctx.set_batch(a['Observ'], a['Std'])\n"
+        "    z = ctx.fvp(a['fvp_in'], 0.1); x, info = ctx.cg(a['cg_b'], 10, 1e-10, 0.1)\n"
+        "    assert ctx.path_used() == 2\n"
+        "e1 = np.abs(z - a['ref_fvpfast_3150']).max() / np.abs(a['ref_fvpfast_3150']).max()\n"
+        "e2 = np.abs(x - a['ref_cg_3150']).max() / np.abs(a['ref_cg_3150']).max()\n"
+        "print('ERR', e1, e2, info.cg_iters)\n"
+        "assert e1 < 1e-10 and e2 < 1e-8 and info.cg_iters == 8\n"
+    )
+    env = dict(os.environ, TRPO_FUSED_ARM_VARIANT=variant)
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-500:] + out.stderr[-1500:]
