@@ -125,3 +125,42 @@ def test_oracle_vs_live_reference(oracle, tmp_path):
     d = oracle.load_data(df, layers, ac, N)
     for k in ("Mean", "Std", "Observ", "Action", "Advantage"):
         assert np.array_equal(d[k], b[k])
+
+
+def test_fisher_matrix_is_positive_semidefinite_and_cg_solves_it(oracle):
+    """Properties the solve relies on: v.Fv >= 0, the LogStd block of F is 2 I (TRPO_FVP.c:918-921), and enough CG
+    iterations drive the residual of (F + damping I) x = b to rounding level."""
+    s = load_synth("net3")
+    L, ac = s["layers"], s["acfunc"]
+    P = s["theta"].size
+    rng = np.random.default_rng(3)
+    for _ in range(5):
+        v = rng.standard_normal(P)
+        Fv = oracle.fvp(L, ac, s["theta"], s["Std"], s["Observ"], 0.0, v)
+        assert v @ Fv >= -1e-12
+        assert np.allclose(Fv[-L[-1]:], 2.0 * v[-L[-1]:], rtol=1e-13)
+    x, nf, rd, _ = oracle.cg(L, ac, s["theta"], s["Std"], s["Observ"], 0.1, s["b"], 30, 1e-28)
+    resid = oracle.fvp(L, ac, s["theta"], s["Std"], s["Observ"], 0.1, x) - s["b"]
+    assert np.linalg.norm(resid) < 1e-8 * np.linalg.norm(s["b"])
+
+
+def test_damping_and_sample_count_enter_as_in_the_reference(oracle):
+    """Result = sum/N + damping*v (TRPO_FVP.c:928-931): damping is additive, and duplicating the batch changes nothing."""
+    s = load_synth("acts5")
+    L, ac = s["layers"], s["acfunc"]
+    F0 = oracle.fvp(L, ac, s["theta"], s["Std"], s["Observ"], 0.0, s["v"])
+    F1 = oracle.fvp(L, ac, s["theta"], s["Std"], s["Observ"], 0.25, s["v"])
+    assert np.allclose(F1, F0 + 0.25 * s["v"], rtol=1e-14, atol=1e-16)
+    twice = np.ascontiguousarray(np.concatenate([s["Observ"], s["Observ"]]))
+    F2 = oracle.fvp(L, ac, s["theta"], s["Std"], twice, 0.0, s["v"])
+    assert np.allclose(F2, F0, rtol=1e-13, atol=1e-16)
+
+
+def test_update_returns_step_direction_when_line_search_fails(oracle):
+    """The reference's quirk (TRPO_Update.c:852): with all-negative ... zero advantages no step is accepted and the
+    *step direction* (not the parameters) comes back; here b = 0, so CG stops at once and the direction is zero."""
+    s = load_synth("net3")
+    L, ac = s["layers"], s["acfunc"]
+    u, info = oracle.update(L, ac, s["theta"], s["Std"], s["Observ"], s["Mean"], s["Action"], np.zeros_like(s["Advantage"]), 0.1)
+    assert info.cg_iters == 0 and info.ls_accepted == 0
+    assert not np.isfinite(u).all() or not u.any()        # 0/0 in the Lagrange multiplier: NaNs or zeros, never theta
