@@ -373,3 +373,19 @@ def test_block_wide_variants_of_the_arm_kernel(variant, tmp_path):
     env = dict(os.environ, TRPO_FUSED_ARM_VARIANT=variant)
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-500:] + out.stderr[-1500:]
+
+
+def test_update_with_failed_line_search_returns_the_step_direction(pkg, oracle):
+    """TRPO_Update.c:852 quirk: when no line-search step is accepted the step direction is returned, not the parameters.
+    Zero advantages give b = 0: CG stops before its first FVP and the direction is the zero vector on both sides."""
+    s = load_synth("net3")
+    L, ac = s["layers"], s["acfunc"]
+    zero_adv = np.zeros_like(s["Advantage"])
+    u_ref, info_ref = oracle.update(L, ac, s["theta"], s["Std"], s["Observ"], s["Mean"], s["Action"], zero_adv, 0.1)
+    with pkg.Context(L, ac) as ctx:
+        ctx.set_model(s["theta"])
+        ctx.set_batch(s["Observ"], s["Std"], s["Mean"], s["Action"], zero_adv)
+        u, info = ctx.update(0.1)
+    assert info.cg_iters == info_ref.cg_iters == 0
+    assert info.ls_accepted == info_ref.ls_accepted == 0 and info.ls_steps == info_ref.ls_steps == 10
+    assert np.array_equal(np.nan_to_num(u), np.nan_to_num(u_ref)) and not np.nan_to_num(u).any()
