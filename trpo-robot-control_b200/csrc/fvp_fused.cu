@@ -110,6 +110,9 @@ struct FusedArgs {
     const int *ready;
     long long chunk_samples;
     int *error;
+    // policy-gradient mode (TRPO_Update.c:254-378): ordinary forward / backward with the surrogate-loss seed
+    const double *mean, *action, *adv;       // [N x A], [N x A], [N]
+    int logstd_off;
 };
 
 __device__ __forceinline__ int ld_volatile_i32(const int *p) {
@@ -128,7 +131,11 @@ __device__ __forceinline__ void wait_samples(const FusedArgs &p, long long last_
     }
 }
 
-template <typename C, char ACT1, char ACT2>
+// PG = true turns the same kernel into the policy-gradient kernel: no R{} quantities (a third of the forward DMMAs, no
+// layer-2 forward at all: the seed uses the rollout's own Mean), seed g3 = A (a - mu) / sigma^2 * f', and the LogStd
+// gradient sum_n A (((a - mu)/sigma)^2 - 1) accumulated per thread; backward pass and outer products are shared.
+// In PG mode p.inv_var holds 1/sigma = exp(-LogStd) of the CURRENT parameters (TRPO_Update.c:298-300), p.v is unused.
+template <typename C, char ACT1, char ACT2, bool PG>
 __global__ void __launch_bounds__(C::NTHREADS, C::CTAS_PER_SM) k_fvp_fused(const FusedArgs p) {
     if (p.done && *p.done) return;
     extern __shared__ __align__(16) double sm[];
@@ -155,32 +162,32 @@ __global__ void __launch_bounds__(C::NTHREADS, C::CTAS_PER_SM) k_fvp_fused(const
         const bool in = k < rows0 && n < L1;
         const int dst = ((k >> 2) * NT1 + (n >> 3)) * 32 + (n & 7) * 4 + (k & 3);
         W0f[dst]  = in ? p.theta[p.w_off0 + k * L1 + n] : 0.0;
-        VW0f[dst] = in ? p.v[p.w_off0 + k * L1 + n] : 0.0;
+        if (!PG) VW0f[dst] = in ? p.v[p.w_off0 + k * L1 + n] : 0.0;
     }
     for (int idx = tid; idx < H1 * H2; idx += NT) {
         const int j = idx / H2, n = idx % H2;
         const bool in = j < L1 && n < L2;
         const int dst = ((j >> 3) * NT2 + (n >> 3)) * 64 + swz(j & 7, n & 7);
         W1s[dst]  = in ? p.theta[p.w_off1 + j * L2 + n] : 0.0;
-        VW1s[dst] = in ? p.v[p.w_off1 + j * L2 + n] : 0.0;
+        if (!PG) VW1s[dst] = in ? p.v[p.w_off1 + j * L2 + n] : 0.0;
     }
     for (int idx = tid; idx < H2 * AP; idx += NT) {
         const int j = idx / AP, n = idx % AP;
         const bool in = j < L2 && n < L3;
         const int dst = ((j >> 3) * NT3 + (n >> 3)) * 64 + swz(j & 7, n & 7);
         W2s[dst]  = in ? p.theta[p.w_off2 + j * L3 + n] : 0.0;
-        VW2s[dst] = in ? p.v[p.w_off2 + j * L3 + n] : 0.0;
+        if (!PG) VW2s[dst] = in ? p.v[p.w_off2 + j * L3 + n] : 0.0;
     }
     for (int n = tid; n < H1; n += NT) {
         B0s[n]  = n < L1 ? p.theta[p.w_off0 + L0 * L1 + n] : 0.0;
-        VB0s[n] = n < L1 ? p.v[p.w_off0 + L0 * L1 + n] : 0.0;
+        VB0s[n] = (!PG && n < L1) ? p.v[p.w_off0 + L0 * L1 + n] : 0.0;
     }
     for (int n = tid; n < H2; n += NT) {
         B1s[n]  = n < L2 ? p.theta[p.w_off1 + L1 * L2 + n] : 0.0;
-        VB1s[n] = n < L2 ? p.v[p.w_off1 + L1 * L2 + n] : 0.0;
+        VB1s[n] = (!PG && n < L2) ? p.v[p.w_off1 + L1 * L2 + n] : 0.0;
     }
     for (int n = tid; n < AP; n += NT) {
-        VB2s[n] = n < L3 ? p.v[p.w_off2 + L2 * L3 + n] : 0.0;
+        VB2s[n] = (!PG && n < L3) ? p.v[p.w_off2 + L2 * L3 + n] : 0.0;
         IVs[n]  = n < L3 ? p.inv_var[n] : 0.0;
     }
     load_exp2_table(Tab);
@@ -218,6 +225,9 @@ __global__ void __launch_bounds__(C::NTHREADS, C::CTAS_PER_SM) k_fvp_fused(const
 #pragma unroll
     for (int i = 0; i < NT3; ++i) acc2[i][0] = acc2[i][1] = accb2[i][0] = accb2[i][1] = 0.0;
     accb0[0] = accb0[1] = accb1[0] = accb1[1] = 0.0;
+    double gl[NT3][2];                  // PG: this thread's share of the LogStd gradient (its row, its two columns per tile)
+#pragma unroll
+    for (int i = 0; i < NT3; ++i) gl[i][0] = gl[i][1] = 0.0;
 
     const long long ntiles = (p.nsamples + S - 1) / S;
     const int rowA = 8 * w + g;                          // this lane's sample row inside the tile (phase A)
@@ -246,7 +256,7 @@ __global__ void __launch_bounds__(C::NTHREADS, C::CTAS_PER_SM) k_fvp_fused(const
 #pragma unroll
                 for (int c = 0; c < NT1; ++c) {
                     dmma(y1[c], a, W0f[(q * NT1 + c) * 32 + lane]);
-                    dmma(ry1[c], a, VW0f[(q * NT1 + c) * 32 + lane]);
+                    if (!PG) dmma(ry1[c], a, VW0f[(q * NT1 + c) * 32 + lane]);
                 }
             }
             constexpr int ACH = NT1 < 4 ? NT1 : 4;       // activation chunk: 8 values in flight per thread
@@ -288,20 +298,21 @@ __global__ void __launch_bounds__(C::NTHREADS, C::CTAS_PER_SM) k_fvp_fused(const
 #pragma unroll
                     for (int cc = 0; cc < GRP; ++cc) {
                         bw[cc] = W1s[(b * NT2 + c0 + cc) * 64 + sf[r]];
-                        bv[cc] = VW1s[(b * NT2 + c0 + cc) * 64 + sf[r]];
+                        if (!PG) bv[cc] = VW1s[(b * NT2 + c0 + cc) * 64 + sf[r]];
                     }
 #pragma unroll
                     for (int cc = 0; cc < GRP; ++cc) {
-                        dmma(rx2[cc], ry1[b][r], bw[cc]);
+                        if (!PG) dmma(rx2[cc], ry1[b][r], bw[cc]);
                         dmma(x2[cc], y1[b][r], bw[cc]);
-                        dmma(rx2[cc], y1[b][r], bv[cc]);
+                        if (!PG) dmma(rx2[cc], y1[b][r], bv[cc]);
                     }
                 }
             activate_tiles<ACT2, 0, GRP>(p.act2, x2, rx2, Tab);
 #pragma unroll
             for (int cc = 0; cc < GRP; ++cc)
                 *reinterpret_cast<double2 *>(&BufC[rowA * RS2 + 8 * (c0 + cc) + 2 * t]) = make_double2(x2[cc][0], x2[cc][1]);
-            // layer 2 contribution of these k-blocks: Rx3 += Ry2*W2 + y2*VW2
+            // layer 2 contribution of these k-blocks: Rx3 += Ry2*W2 + y2*VW2 (the policy gradient needs no layer-2 forward)
+            if (!PG)
 #pragma unroll
             for (int r = 0; r < 2; ++r)
 #pragma unroll
@@ -325,12 +336,33 @@ __global__ void __launch_bounds__(C::NTHREADS, C::CTAS_PER_SM) k_fvp_fused(const
         // R-gradient seed: RG3 = Ry3 / sigma^2 (times the constant f' of the last layer, twice: Ry3 = f' Rx3, RG3 *= f')
         const bool valid = (s0 + rowA) < p.nsamples;     // rows past the end of the batch contribute nothing
         double g3[NT3][2];
+        if (PG) {
+            // surrogate-loss seed (TRPO_Update.c:297-301,310-324): t = (a - mu)/sigma, g = A t / sigma * f', dLogStd = A (t^2 - 1)
+            const long long gs = s0 + rowA;
+            const double adv = valid ? p.adv[gs] : 0.0;
 #pragma unroll
-        for (int c = 0; c < NT3; ++c) {
+            for (int c = 0; c < NT3; ++c)
 #pragma unroll
-            for (int r = 0; r < 2; ++r) g3[c][r] = valid ? rx3[c][r] * d3 * IVs[8 * c + 2 * t + r] * d3 : 0.0;
-            *reinterpret_cast<double2 *>(&BufD[rowA * RS3 + 8 * c + 2 * t]) = make_double2(g3[c][0], g3[c][1]);
+                for (int r = 0; r < 2; ++r) {
+                    const int col = 8 * c + 2 * t + r;
+                    double gv = 0.0;
+                    if (valid && col < L3) {
+                        const double is = IVs[col];
+                        const double tt = (p.action[gs * L3 + col] - p.mean[gs * L3 + col]) * is;
+                        gv = adv * tt * is * d3;
+                        gl[c][r] += adv * (tt * tt - 1.0);
+                    }
+                    g3[c][r] = gv;
+                }
+        } else {
+#pragma unroll
+            for (int c = 0; c < NT3; ++c)
+#pragma unroll
+                for (int r = 0; r < 2; ++r) g3[c][r] = valid ? rx3[c][r] * d3 * IVs[8 * c + 2 * t + r] * d3 : 0.0;
         }
+#pragma unroll
+        for (int c = 0; c < NT3; ++c)
+            *reinterpret_cast<double2 *>(&BufD[rowA * RS3 + 8 * c + 2 * t]) = make_double2(g3[c][0], g3[c][1]);
         // backward through layer 2: RG2 = (RG3 * W2^T) .* f'(y2)
         double g2[NT2][2];
 #pragma unroll
@@ -454,6 +486,28 @@ __global__ void __launch_bounds__(C::NTHREADS, C::CTAS_PER_SM) k_fvp_fused(const
                 const int col = 8 * c + 2 * t + r;
                 if (g == 0 && col < L3) out[p.w_off2 + L2 * L3 + col] = accb2[c][r];
             }
+    }
+    if (PG) {
+        // LogStd gradient: fixed-order sum over the 8 rows of a warp (shuffle tree), then over the warps
+        __syncthreads();
+        double *red = BufD;                                  // NW * AP doubles
+#pragma unroll
+        for (int c = 0; c < NT3; ++c)
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                double vsum = gl[c][r];
+                vsum += __shfl_xor_sync(0xffffffffu, vsum, 4);
+                vsum += __shfl_xor_sync(0xffffffffu, vsum, 8);
+                vsum += __shfl_xor_sync(0xffffffffu, vsum, 16);
+                if (g == 0) red[w * AP + 8 * c + 2 * t + r] = vsum;
+            }
+        __syncthreads();
+        if (tid < L3) {
+            double vsum = red[tid];
+#pragma unroll
+            for (int ww = 1; ww < NW; ++ww) vsum += red[ww * AP + tid];
+            out[p.logstd_off + tid] = vsum;
+        }
     }
 }
 
@@ -816,15 +870,15 @@ FusedShape pick_shape(const NetDesc &net) {
     return SHAPE_NONE;
 }
 
-template <typename C, char A1, char A2>
+template <typename C, char A1, char A2, bool PG>
 int launch_cfg(const FusedArgs &a, int grid, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(k_fvp_fused<C, A1, A2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES) != cudaSuccess)
+        if (cudaFuncSetAttribute(k_fvp_fused<C, A1, A2, PG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES) != cudaSuccess)
             return -1;
         configured = true;
     }
-    k_fvp_fused<C, A1, A2><<<grid, C::NTHREADS, C::SMEM_BYTES, st>>>(a);
+    k_fvp_fused<C, A1, A2, PG><<<grid, C::NTHREADS, C::SMEM_BYTES, st>>>(a);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
@@ -851,14 +905,14 @@ int launch_warp_shape(const FusedArgs &a, cudaStream_t st, int *rows) {
     return launch_warp_cfg<C, 0, 0>(a, grid, st);
 }
 
-template <typename C>
+template <typename C, bool PG = false>
 int launch_shape(const FusedArgs &a, cudaStream_t st, int *rows) {
     const long long ntiles = (a.nsamples + C::S - 1) / C::S;
     const int max_grid = FUSED_SMS * C::CTAS_PER_SM;
     const int grid = (int)(ntiles < max_grid ? ntiles : max_grid);
     *rows = grid;
-    if (a.act1 == 't' && a.act2 == 't') return launch_cfg<C, 't', 't'>(a, grid, st);
-    return launch_cfg<C, 0, 0>(a, grid, st);
+    if (a.act1 == 't' && a.act2 == 't') return launch_cfg<C, 't', 't', PG>(a, grid, st);
+    return launch_cfg<C, 0, 0, PG>(a, grid, st);
 }
 
 }  // namespace
@@ -880,6 +934,7 @@ int fused_fvp_accumulate(const NetDesc &net, const double *d_theta, const double
     a.P = net.P;
     a.act1 = net.ac[1]; a.act2 = net.ac[2]; a.act3 = net.ac[3];
     a.ready = stream_ready; a.chunk_samples = (long long)(stream_chunk ? stream_chunk : 1); a.error = stream_error;
+    a.mean = a.action = a.adv = nullptr; a.logstd_off = net.logstd_off;
     int rows = 0, rc = -1;
     switch (shape) {
         case SHAPE_ARM: {
@@ -898,5 +953,35 @@ int fused_fvp_accumulate(const NetDesc &net, const double *d_theta, const double
     if (rc) return -1;
     ++*launches;
     launch_reduce_partials(d_partial, rows, net.P, d_zsum, d_done, p2p, st, launches);
+    return 0;
+}
+
+// Policy-gradient sum (TRPO_Update.c:254-371) on the fused kernel: zsum = sum_n [GW, GB, ..., GLogStd].
+// d_inv_std = exp(-LogStd) of the current parameters.
+int fused_pg_accumulate(const NetDesc &net, const double *d_theta, const double *d_inv_std, const double *d_obs,
+                        const double *d_mean, const double *d_action, const double *d_adv, size_t nsamples,
+                        double *d_partial, double *d_zsum, cudaStream_t st, long long *launches) {
+    const FusedShape shape = pick_shape(net);
+    if (shape == SHAPE_NONE) return 1;
+    FusedArgs a;
+    a.theta = d_theta; a.v = nullptr; a.inv_var = d_inv_std; a.obs = d_obs; a.partial = d_partial; a.done = nullptr;
+    a.nsamples = (long long)nsamples;
+    a.L0 = net.L[0]; a.L1 = net.L[1]; a.L2 = net.L[2]; a.L3 = net.L[3];
+    a.w_off0 = net.w_off[0]; a.w_off1 = net.w_off[1]; a.w_off2 = net.w_off[2];
+    a.P = net.P;
+    a.act1 = net.ac[1]; a.act2 = net.ac[2]; a.act3 = net.ac[3];
+    a.ready = nullptr; a.chunk_samples = 1; a.error = nullptr;
+    a.mean = d_mean; a.action = d_action; a.adv = d_adv; a.logstd_off = net.logstd_off;
+    int rows = 0, rc = -1;
+    switch (shape) {
+        case SHAPE_ARM: rc = launch_shape<CfgArm, true>(a, st, &rows); break;
+        case SHAPE_H32: rc = launch_shape<CfgH32, true>(a, st, &rows); break;
+        case SHAPE_P64: rc = launch_shape<CfgP64, true>(a, st, &rows); break;
+        case SHAPE_M64: rc = launch_shape<CfgM64, true>(a, st, &rows); break;
+        default: return 1;
+    }
+    if (rc) return -1;
+    ++*launches;
+    launch_reduce_partials(d_partial, rows, net.P, d_zsum, nullptr, nullptr, st, launches);
     return 0;
 }

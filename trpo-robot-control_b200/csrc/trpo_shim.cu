@@ -66,6 +66,7 @@ struct trpo_ctx {
     long long launches;
 
     double *d_theta, *d_inv_var, *d_std;
+    double *d_inv_std_model;   // exp(-LogStd) of the current parameters (policy-gradient seed, TRPO_Update.c:298-300)
     // batch
     size_t n_local, n_total;
     double *d_obs, *d_mean, *d_action, *d_adv;
@@ -204,6 +205,7 @@ extern "C" trpo_ctx *trpo_ctx_create(const size_t *LayerSize, const char *AcFunc
     for (auto v : vecs) ok = ok && cudaMalloc(v, P * sizeof(double)) == cudaSuccess;
     ok = ok && cudaMalloc(&c->d_inv_var, A * sizeof(double)) == cudaSuccess;
     ok = ok && cudaMalloc(&c->d_std, A * sizeof(double)) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->d_inv_std_model, A * sizeof(double)) == cudaSuccess;
     ok = ok && cudaMalloc(&c->d_scal, 16 * sizeof(double)) == cudaSuccess;
     ok = ok && cudaMalloc(&c->d_blockpart, 1024 * sizeof(double)) == cudaSuccess;
     ok = ok && cudaMalloc(&c->d_state, sizeof(CgState)) == cudaSuccess;
@@ -243,7 +245,7 @@ extern "C" void trpo_ctx_destroy(trpo_ctx *c) {
     if (c->p2p_buf) cudaFree(c->p2p_buf);
     free_batch(c);
     double *vecs[] = {c->d_theta, c->d_in, c->d_out, c->d_zsum, c->d_x, c->d_r, c->d_p, c->d_z, c->d_b, c->d_xnew,
-                      c->d_inv_var, c->d_std, c->d_scal, c->d_blockpart, c->d_mean_new, c->sc_base, c->d_fused_partial};
+                      c->d_inv_var, c->d_std, c->d_inv_std_model, c->d_scal, c->d_blockpart, c->d_mean_new, c->sc_base, c->d_fused_partial};
     for (double *v : vecs) if (v) cudaFree(v);
     float *fvecs[] = {c->f_theta, c->f_v, c->f_inv_var, c->f_obs, c->scf_base};
     for (float *v : fvecs) if (v) cudaFree(v);
@@ -293,6 +295,14 @@ extern "C" int trpo_ctx_set_model(trpo_ctx *c, const double *theta) {
     if (!c || !theta) return fail("null argument");
     CU(cudaSetDevice(c->device));
     CU(cudaMemcpyAsync(c->d_theta, theta, c->net.P * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    {
+        const int A = c->net.L[c->net.K];
+        double is[TRPO_MAX_LAYERS * 64];
+        if (A > (int)(sizeof(is) / sizeof(is[0]))) return fail("action dimension too large");
+        for (int j = 0; j < A; ++j) is[j] = 1.0 / exp(theta[c->net.logstd_off + j]);
+        CU(cudaMemcpyAsync(c->d_inv_std_model, is, A * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        CU(cudaStreamSynchronize(c->stream));      // `is` is a stack buffer
+    }
     if (c->precision == TRPO_PRECISION_FP32) chain_f32_convert(c->d_theta, c->f_theta, c->net.P, c->stream, &c->launches);
     CU(cudaStreamSynchronize(c->stream));
     return 0;
@@ -624,9 +634,14 @@ static int policy_gradient_device(trpo_ctx *c) {
     if (!c->d_obs || !c->d_mean || !c->d_action || !c->d_adv) return fail("policy gradient needs Mean/Action/Advantage in the batch");
     if (c->copy_inflight) { CU(cudaStreamWaitEvent(c->stream, c->ev_copy, 0)); c->copy_inflight = false; }
     c->stream_first_fvp = false;
-    if (ensure_chain_scratch(c)) return -1;
-    if (chain_accumulate(c->net, c->sc, CHAIN_PG, c->d_theta, nullptr, nullptr, c->d_obs, c->d_mean, c->d_action, c->d_adv,
-                         c->n_local, c->d_zsum, nullptr, nullptr, c->stream, &c->launches))
+    if (ensure_chain_scratch(c)) return -1;      // the line search's forward pass uses it in any case
+    const bool fused_pg = fused_eligible(c->net) && c->path_req != TRPO_PATH_GEMM_CHAIN && c->precision == TRPO_PRECISION_FP64;
+    if (fused_pg) {
+        if (fused_pg_accumulate(c->net, c->d_theta, c->d_inv_std_model, c->d_obs, c->d_mean, c->d_action, c->d_adv, c->n_local,
+                                c->d_fused_partial, c->d_zsum, c->stream, &c->launches))
+            return fail("fused policy-gradient launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    } else if (chain_accumulate(c->net, c->sc, CHAIN_PG, c->d_theta, nullptr, nullptr, c->d_obs, c->d_mean, c->d_action, c->d_adv,
+                                c->n_local, c->d_zsum, nullptr, nullptr, c->stream, &c->launches))
         return fail("policy-gradient launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     if (c->comm) NC(g_nccl.AllReduce(c->d_zsum, c->d_zsum, c->net.P, ncclFloat64_, ncclSum_, c->comm, c->stream));
     // b = zsum / N: same kernel as the FVP finalise with no damping and no LogStd special case
