@@ -135,6 +135,9 @@ int trpo_ctx_set_batch_device(trpo_ctx *ctx, size_t NumSamples, const double *dO
 int trpo_ctx_fvp(trpo_ctx *ctx, const double *Input, double *Result, double CG_Damping);
 int trpo_ctx_cg(trpo_ctx *ctx, const double *b, double *Result, size_t MaxIter, double ResidualTh, double CG_Damping);
 int trpo_ctx_policy_gradient(trpo_ctx *ctx, double *b_out);
+/* Policy mean of every staged sample (ordinary forward pass, TRPO_Update.c:259-291 / the Mean column a rollout producer
+ * writes, TRPO_Lightweight_FPGA.c:548-556): Mean_out is NumSamples x A on the host. */
+int trpo_ctx_forward(trpo_ctx *ctx, double *Mean_out);
 int trpo_ctx_update(trpo_ctx *ctx, double *Result, double CG_Damping);
 int trpo_ctx_get_info(const trpo_ctx *ctx, trpo_info *info);
 

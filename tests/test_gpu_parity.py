@@ -389,3 +389,15 @@ def test_update_with_failed_line_search_returns_the_step_direction(pkg, oracle):
     assert info.cg_iters == info_ref.cg_iters == 0
     assert info.ls_accepted == info_ref.ls_accepted == 0 and info.ls_steps == info_ref.ls_steps == 10
     assert np.array_equal(np.nan_to_num(u), np.nan_to_num(u_ref)) and not np.nan_to_num(u).any()
+
+
+@pytest.mark.parametrize("name", ["acts5", "mlp64", "odd_tanh_out"])
+def test_forward_pass_matches_oracle(pkg, oracle, name):
+    """trpo_ctx_forward: the policy mean of every staged sample (TRPO_Update.c:259-291)."""
+    s = load_synth(name)
+    with pkg.Context(s["layers"], s["acfunc"]) as ctx:
+        ctx.set_model(s["theta"])
+        ctx.set_batch(s["Observ"], s["Std"])
+        mean = ctx.forward(s["Observ"].shape[0])
+    ref = oracle.forward(s["layers"], s["acfunc"], s["theta"], s["Observ"])
+    assert np.abs(mean - ref).max() < 1e-13 * max(1.0, np.abs(ref).max())

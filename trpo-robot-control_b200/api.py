@@ -80,6 +80,7 @@ def lib():
         L.trpo_ctx_fvp.argtypes = [C.c_void_p, c_double_p, c_double_p, C.c_double]
         L.trpo_ctx_cg.argtypes = [C.c_void_p, c_double_p, c_double_p, C.c_size_t, C.c_double, C.c_double]
         L.trpo_ctx_policy_gradient.argtypes = [C.c_void_p, c_double_p]
+        L.trpo_ctx_forward.argtypes = [C.c_void_p, c_double_p]
         L.trpo_ctx_update.argtypes = [C.c_void_p, c_double_p, C.c_double]
         L.trpo_ctx_get_info.argtypes = [C.c_void_p, C.POINTER(TrpoInfo)]
         L.trpo_ctx_fvp_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double]
@@ -245,6 +246,11 @@ class Context:
         out = np.zeros(self.P)
         _check(lib().trpo_ctx_cg(self.h, _dp(b), _dp(out), max_iter, residual_th, damping))
         return out, self.info()
+
+    def forward(self, num_samples):
+        out = np.zeros((num_samples, self.layers[-1]))
+        _check(lib().trpo_ctx_forward(self.h, _dp(out)))
+        return out
 
     def policy_gradient(self):
         out = np.zeros(self.P)

@@ -649,6 +649,27 @@ static int policy_gradient_device(trpo_ctx *c) {
     return 0;
 }
 
+extern "C" int trpo_ctx_forward(trpo_ctx *c, double *Mean_out) {
+    if (!c || !Mean_out) return fail("null argument");
+    if (!c->d_obs || c->n_local == 0) return fail("no batch staged: call trpo_ctx_set_batch first");
+    CU(cudaSetDevice(c->device));
+    if (c->copy_inflight) { CU(cudaStreamWaitEvent(c->stream, c->ev_copy, 0)); c->copy_inflight = false; }
+    c->stream_first_fvp = false;
+    if (ensure_chain_scratch(c)) return -1;
+    const size_t n = c->n_local * (size_t)c->net.L[c->net.K];
+    if (n > c->cap_mean_new) {
+        if (c->d_mean_new) cudaFree(c->d_mean_new);
+        c->d_mean_new = nullptr;
+        CU(cudaMalloc(&c->d_mean_new, n * sizeof(double)));
+        c->cap_mean_new = n;
+    }
+    if (chain_forward(c->net, c->sc, c->d_theta, c->d_obs, c->n_local, c->d_mean_new, c->stream, &c->launches))
+        return fail("forward launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    CU(cudaMemcpyAsync(Mean_out, c->d_mean_new, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
 extern "C" int trpo_ctx_policy_gradient(trpo_ctx *c, double *b_out) {
     if (!c || !b_out) return fail("null argument");
     CU(cudaSetDevice(c->device));
