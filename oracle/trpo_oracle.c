@@ -481,3 +481,189 @@ int oracle_update(const OracleNet *net, const double *theta0, const double *Std,
     scratch_free(s, &lo);
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Rows f-3 / f-4 of SURVEY.md section 8: what sits either side of the update inside the reference's training loop
+ * (TRPO_Lightweight.c:349-694, TRPO_Baseline.c:29-237).
+ * ------------------------------------------------------------------------------------------------------------------ */
+
+/* Value-function ("baseline") input of step `t`: the observation followed by t / EpLen (TRPO_Baseline.c:98-103). */
+static void vf_input(const Layout *lo, const double *Observ, size_t pos, size_t step, size_t EpLen, Scratch *s) {
+    const size_t O = lo->L[0] - 1;
+    for (size_t i = 0; i < O; ++i) s->y[0][i] = Observ[pos * O + i];
+    s->y[0][O] = (double)step / (double)EpLen;
+}
+
+int oracle_vf_predict(const OracleNet *vfnet, size_t NumEpBatch, size_t EpLen, const double *Observ, const double *x,
+                      double *Baseline) {
+    /* TRPO_Lightweight.c:582-625 */
+    Layout lo; if (make_layout(vfnet, &lo) || check_acfunc(vfnet)) return -1;
+    Scratch s; scratch_alloc(&s, &lo);
+    for (size_t ep = 0; ep < NumEpBatch; ++ep)
+        for (size_t t = 0; t < EpLen; ++t) {
+            const size_t pos = ep * EpLen + t;
+            vf_input(&lo, Observ, pos, t, EpLen, &s);
+            forward_one(&lo, vfnet->AcFunc, x, &s);
+            Baseline[pos] = s.y[lo.K][0];
+        }
+    scratch_free(&s, &lo);
+    return 0;
+}
+
+double oracle_vf_evaluate(const OracleNet *vfnet, size_t NumEpBatch, size_t EpLen, const double *Observ,
+                          const double *Target, const double *x, double *g, int n, double *Predict) {
+    /* TRPO_Baseline.c:29-237: 0.01*MSE + 0.001*|x|^2 and its gradient; x holds W,B per layer (no LogStd). */
+    Layout lo; if (make_layout(vfnet, &lo) || check_acfunc(vfnet)) return -1;
+    const char *ac = vfnet->AcFunc;
+    const size_t K = lo.K, NP = lo.logstd, N = NumEpBatch * EpLen;
+    Scratch sc; scratch_alloc(&sc, &lo); Scratch *s = &sc;
+    double *gw = (double *)calloc(NP, sizeof(double));
+    for (int i = 0; i < n; ++i) g[i] = 0;
+    for (size_t ep = 0; ep < NumEpBatch; ++ep)
+        for (size_t t = 0; t < EpLen; ++t) {
+            const size_t pos = ep * EpLen + t;
+            vf_input(&lo, Observ, pos, t, EpLen, s);
+            forward_one(&lo, ac, x, s);
+            Predict[pos] = s->y[K][0];
+            s->g[K][0] = 0.02 * (Predict[pos] - Target[pos]);
+            for (size_t i = K; i > 0; --i) {
+                const size_t cur = lo.L[i], prv = lo.L[i - 1];
+                const double *W = x + lo.w[i - 1];
+                for (size_t j = 0; j < cur; ++j) {
+                    if (ac[i] == 't') s->g[i][j] = s->g[i][j] * (1 - s->y[i][j] * s->y[i][j]);
+                    gw[lo.b[i - 1] + j] = s->g[i][j];
+                }
+                for (size_t j = 0; j < prv; ++j)
+                    for (size_t k = 0; k < cur; ++k) gw[lo.w[i - 1] + j * cur + k] = s->g[i][k] * s->y[i - 1][j];
+                for (size_t j = 0; j < prv; ++j) {
+                    s->g[i - 1][j] = 0;
+                    for (size_t k = 0; k < cur; ++k) s->g[i - 1][j] += s->g[i][k] * W[j * cur + k];
+                }
+            }
+            for (size_t q = 0; q < NP; ++q) g[q] += gw[q];
+        }
+    for (size_t q = 0; q < NP; ++q) g[q] = g[q] / (double)N + 0.002 * x[q];
+    double mse = 0;
+    for (size_t i = 0; i < N; ++i) mse += 0.01 * (Predict[i] - Target[i]) * (Predict[i] - Target[i]);
+    mse = mse / (double)N;
+    double l2 = 0;
+    for (size_t q = 0; q < NP; ++q) l2 += x[q] * x[q];
+    free(gw);
+    scratch_free(s, &lo);
+    return mse + 0.001 * l2;
+}
+
+void oracle_reward_stats(size_t NumEpBatch, size_t EpLen, const double *Reward, double *EpRewMean, double *EpRewStd) {
+    /* TRPO_Lightweight.c:545-558 */
+    double mean = 0;
+    for (size_t i = 0; i < NumEpBatch * EpLen; ++i) mean += Reward[i];
+    mean = mean / (double)NumEpBatch;
+    double var = 0;
+    for (size_t ep = 0; ep < NumEpBatch; ++ep) {
+        double r = 0;
+        for (size_t t = 0; t < EpLen; ++t) r += Reward[ep * EpLen + t];
+        var += (r - mean) * (r - mean);
+    }
+    *EpRewMean = mean;
+    *EpRewStd = sqrt(var / (double)NumEpBatch);
+}
+
+int oracle_gae(size_t NumEpBatch, size_t EpLen, double gamma, double lam, double *Reward, const double *Baseline,
+               double *Return, double *Advantage) {
+    /* TRPO_Lightweight.c:565-653, the reference's O(EpLen^2) pow() sums kept as they are; Reward is left holding the
+     * TD residuals, as in the reference. */
+    const size_t N = NumEpBatch * EpLen;
+    for (size_t ep = 0; ep < NumEpBatch; ++ep) {
+        double *R = Reward + ep * EpLen;
+        const double *V = Baseline + ep * EpLen;
+        for (size_t t = 0; t < EpLen; ++t) {
+            double ret = R[t];
+            for (size_t f = t + 1; f < EpLen; ++f) ret += R[f] * pow(gamma, (double)(int)(f - t));
+            Return[ep * EpLen + t] = ret;
+        }
+        for (size_t t = 0; t + 1 < EpLen; ++t) R[t] += gamma * V[t + 1] - V[t];
+        R[EpLen - 1] += (-1) * V[EpLen - 1];
+        for (size_t t = 0; t < EpLen; ++t) {
+            double adv = R[t];
+            for (size_t f = t + 1; f < EpLen; ++f) adv += R[f] * pow(gamma * lam, (double)(int)(f - t));
+            Advantage[ep * EpLen + t] = adv;
+        }
+    }
+    double mean = 0;
+    for (size_t i = 0; i < N; ++i) mean += Advantage[i];
+    mean = mean / (double)N;
+    double sd = 0;
+    for (size_t i = 0; i < N; ++i) sd += (Advantage[i] - mean) * (Advantage[i] - mean);
+    sd = sqrt(sd / (double)N);
+    for (size_t i = 0; i < N; ++i) Advantage[i] = (Advantage[i] - mean) / sd;
+    return 0;
+}
+
+/* Lightweight arm simulator (TRPO_Lightweight.c:349-540): three joint angles integrate the sampled action, forward
+ * kinematics give the link positions, reward = -100*|object - grip|^2 - |action|^2. Draws from rand() in the
+ * reference's order (3 per episode for the object, 2 per action component per step). */
+typedef struct { double dof2[3], wrist[3], grip[3]; } ArmPose;
+
+static void arm_kinematics(double t1, double t2, double t3, ArmPose *p) {
+    const double s1 = sin(t1), c1 = cos(t1), s2 = sin(t2), c2 = cos(t2), s3 = sin(t3), c3 = cos(t3);
+    const double c2c3 = c2 * c3, s2s3 = s2 * s3, c2s3 = c2 * s3, s2c3 = s2 * c3;
+    p->dof2[0] = 0.0575 * c1 * c2;
+    p->dof2[1] = 0.0575 * s1 * c2;
+    p->dof2[2] = 0.01768 - 0.0575 * s2;
+    p->wrist[0] = p->dof2[0] + 0.07375 * c1 * (c2c3 - s2s3);
+    p->wrist[1] = p->dof2[1] + 0.07375 * s1 * (c2c3 - s2s3);
+    p->wrist[2] = p->dof2[2] - 0.07375 * (c2s3 + s2c3);
+    p->grip[0] = p->dof2[0] + 0.11315 * c1 * (c2c3 - s2s3) - 0.0125 * c1 * (c2s3 + s2c3);
+    p->grip[1] = p->dof2[1] + 0.11315 * s1 * (c2c3 - s2s3) - 0.0125 * s1 * (c2s3 + s2c3);
+    p->grip[2] = p->dof2[2] - 0.11315 * (c2s3 + s2c3) + 0.0125 * (s2s3 - c2c3);
+}
+
+int oracle_arm_rollout(const OracleNet *net, const double *theta, size_t NumEpBatch, size_t EpLen,
+                       double *Observ, double *Mean, double *Std, double *Action, double *Reward) {
+    Layout lo; if (make_layout(net, &lo) || check_acfunc(net)) return -1;
+    const size_t K = lo.K, O = lo.L[0], A = lo.L[K];
+    if (O != 15 || A != 3) return -1;
+    const double pi = 3.1415926535897931, TimeStepLen = 0.02, coeff = 1;
+    const double *LogStd = theta + lo.logstd;
+    Scratch s; scratch_alloc(&s, &lo);
+    for (size_t ep = 0; ep < NumEpBatch; ++ep) {
+        double t1 = 0, t2 = -pi / 2.0, t3 = pi / 2.0;
+        const double dof1[3] = {0, 0, 0.01768};
+        ArmPose p = {{0, 0, 0.07518}, {0.07375, 0, 0.07518}, {0.11315, 0, 0.06268}};
+        double obj[3];
+        obj[0] = ((double)rand() / (double)RAND_MAX) * 0.076 + 0.084;
+        obj[1] = ((double)rand() / (double)RAND_MAX) * 0.100 - 0.05;
+        obj[2] = ((double)rand() / (double)RAND_MAX) * 0.100;
+        for (size_t t = 0; t < EpLen; ++t) {
+            const size_t row = ep * EpLen + t;
+            double *ob = Observ + row * O;
+            for (int i = 0; i < 3; ++i) {
+                ob[i] = dof1[i]; ob[3 + i] = p.dof2[i]; ob[6 + i] = p.wrist[i]; ob[9 + i] = p.grip[i]; ob[12 + i] = obj[i];
+            }
+            memcpy(s.y[0], ob, O * sizeof(double));
+            forward_one(&lo, net->AcFunc, theta, &s);
+            double ac[3];
+            for (size_t i = 0; i < A; ++i) Mean[row * A + i] = s.y[K][i];
+            for (size_t i = 0; i < A; ++i) Std[i] = exp(LogStd[i]);
+            for (size_t i = 0; i < A; ++i) {
+                const double u1 = ((double)rand() + 1.0) / ((double)RAND_MAX + 1.0);
+                const double u2 = ((double)rand() + 1.0) / ((double)RAND_MAX + 1.0);
+                const double z0 = sqrt(-2.0 * log(u1)) * cos(2 * pi * u2);
+                ac[i] = z0 * Std[i] + s.y[K][i];
+                Action[row * A + i] = ac[i];
+            }
+            t1 += ac[0] * coeff * TimeStepLen;
+            t2 += ac[1] * coeff * TimeStepLen;
+            t3 += ac[2] * coeff * TimeStepLen;
+            arm_kinematics(t1, t2, t3, &p);
+            double re = 0;
+            for (int i = 0; i < 3; ++i) {
+                re -= 100 * (obj[i] - p.grip[i]) * (obj[i] - p.grip[i]);
+                re -= ac[i] * ac[i];
+            }
+            Reward[row] = re;
+        }
+    }
+    scratch_free(&s, &lo);
+    return 0;
+}

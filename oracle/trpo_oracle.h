@@ -7,6 +7,8 @@
  *   CG           /root/reference/src/TRPO_CG.c:11-113
  *   TRPO_Update  /root/reference/src/TRPO_Update.c:10-1056
  *   NumParamsCalc/root/reference/src/TRPO_Util.c:7-17
+ *   evaluate (baseline objective)  /root/reference/src/TRPO_Baseline.c:29-237
+ *   rollout / return / GAE blocks  /root/reference/src/TRPO_Lightweight.c:349-653
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
  * load this library, and only as the checker. The product (libtrpo_b200.so) never links or calls it.
@@ -76,6 +78,31 @@ int oracle_policy_gradient(const OracleNet *net, const double *theta, const doub
 int oracle_update(const OracleNet *net, const double *theta, const double *Std, const double *Observ,
                   const double *Mean, const double *Action, const double *Advantage, size_t NumSamples,
                   double CG_Damping, double *Result, OracleUpdateInfo *info);
+
+/* ---- rows f-3 / f-4: the steps either side of the update in the training loop -------------------------------------
+ * vfnet describes the value-function ("baseline") network: LayerSize[0] = ObservSpaceDim + 1 (the observation followed
+ * by step/EpLen), last layer 1; x = [W0,B0,...] without a LogStd tail (TRPO_Lightweight.c:655-672). */
+
+/* Baseline prediction of every step (TRPO_Lightweight.c:582-625). */
+int oracle_vf_predict(const OracleNet *vfnet, size_t NumEpBatch, size_t EpLen, const double *Observ, const double *x,
+                      double *Baseline);
+
+/* libLBFGS objective callback restated (TRPO_Baseline.c:29-237): returns 0.01*MSE + 0.001*|x|^2, writes the gradient
+ * (n >= number of parameters; the padding is zeroed) and the predictions. */
+double oracle_vf_evaluate(const OracleNet *vfnet, size_t NumEpBatch, size_t EpLen, const double *Observ,
+                          const double *Target, const double *x, double *g, int n, double *Predict);
+
+/* Episode reward statistics printed per iteration (TRPO_Lightweight.c:545-558). */
+void oracle_reward_stats(size_t NumEpBatch, size_t EpLen, const double *Reward, double *EpRewMean, double *EpRewStd);
+
+/* Discounted return, GAE(gamma, lam) advantage and its standardisation (TRPO_Lightweight.c:565-653). Reward is
+ * overwritten with the TD residuals exactly as the reference does. */
+int oracle_gae(size_t NumEpBatch, size_t EpLen, double gamma, double lam, double *Reward, const double *Baseline,
+               double *Return, double *Advantage);
+
+/* One batch of rollouts of the lightweight arm simulator (TRPO_Lightweight.c:349-540); consumes rand(). */
+int oracle_arm_rollout(const OracleNet *net, const double *theta, size_t NumEpBatch, size_t EpLen,
+                       double *Observ, double *Mean, double *Std, double *Action, double *Reward);
 
 #ifdef __cplusplus
 }

@@ -1,7 +1,8 @@
 """ctypes bindings for the CHECKER libraries (test infrastructure only).
 
 * ``liboracle.so``        -- oracle/trpo_oracle.c, the in-memory C restatement
-* ``_ref/libtrpo_ref.so`` -- the unmodified reference sources (TRPO_FVP.c, TRPO_CG.c, TRPO_Update.c, TRPO_Util.c)
+* ``_ref/libtrpo_ref.so`` -- the unmodified reference sources (TRPO_FVP.c, TRPO_CG.c, TRPO_Update.c, TRPO_Util.c,
+                             TRPO_Baseline.c, TRPO_Lightweight.c and the vendored lbfgs.c)
                              compiled by oracle/Makefile; file-based API with ``TRPOparam`` by value
                              (/root/reference/src/include/TRPO.h:6-49,88-104).
 
@@ -41,6 +42,26 @@ class TRPOparam(C.Structure):
                 ("DataFile", C.c_char_p), ("NumLayers", C.c_size_t), ("AcFunc", C.c_char_p),
                 ("LayerSize", c_size_p), ("NumSamples", C.c_size_t), ("CG_Damping", C.c_double),
                 ("PaddedLayerSize", c_size_p), ("NumBlocks", c_size_p)]
+
+
+class TRPOBaselineParam(C.Structure):
+    """/root/reference/src/include/TRPO.h:51-77."""
+    _fields_ = [("NumLayers", C.c_size_t), ("ObservSpaceDim", C.c_size_t), ("NumEpBatch", C.c_size_t),
+                ("EpLen", C.c_size_t), ("NumSamples", C.c_size_t), ("NumParams", C.c_size_t),
+                ("PaddedParams", C.c_int), ("AcFunc", C.c_char_p), ("LayerSizeBase", c_size_p),
+                ("WBase", C.POINTER(c_double_p)), ("BBase", C.POINTER(c_double_p)), ("LayerBase", C.POINTER(c_double_p)),
+                ("GWBase", C.POINTER(c_double_p)), ("GBBase", C.POINTER(c_double_p)),
+                ("GLayerBase", C.POINTER(c_double_p)),
+                ("Observ", c_double_p), ("Target", c_double_p), ("Predict", c_double_p)]
+
+
+class LbfgsParameter(C.Structure):
+    """lbfgs_parameter_t of libLBFGS 1.10 (/root/reference/src/include/lbfgs.h:198-358), LBFGS_FLOAT = 64."""
+    _fields_ = [("m", C.c_int), ("epsilon", C.c_double), ("past", C.c_int), ("delta", C.c_double),
+                ("max_iterations", C.c_int), ("linesearch", C.c_int), ("max_linesearch", C.c_int),
+                ("min_step", C.c_double), ("max_step", C.c_double), ("ftol", C.c_double), ("wolfe", C.c_double),
+                ("gtol", C.c_double), ("xtol", C.c_double), ("orthantwise_c", C.c_double),
+                ("orthantwise_start", C.c_int), ("orthantwise_end", C.c_int)]
 
 
 def _dp(a):
@@ -138,6 +159,51 @@ class Oracle:
                                       _dp(advantage), C.c_size_t(N), C.c_double(damping), _dp(out), C.byref(info)) == 0
         return out, info
 
+    # ---- rows f-3 / f-4 -------------------------------------------------------------------------------------------
+    def vf_predict(self, vf_layers, acfunc, x, observ, num_ep, ep_len):
+        n = _Net(vf_layers, acfunc)
+        out = np.zeros(num_ep * ep_len)
+        assert self.lib.oracle_vf_predict(C.byref(n.net), C.c_size_t(num_ep), C.c_size_t(ep_len), _dp(observ), _dp(x),
+                                          _dp(out)) == 0
+        return out
+
+    def vf_evaluate(self, vf_layers, acfunc, x, observ, target, num_ep, ep_len, n_padded=None):
+        """(fx, g, Predict) of the baseline objective; x has num_params(vf_layers) - 1 entries (+ padding)."""
+        n = _Net(vf_layers, acfunc)
+        n_padded = n_padded or len(x)
+        g = np.zeros(n_padded)
+        pred = np.zeros(num_ep * ep_len)
+        self.lib.oracle_vf_evaluate.restype = C.c_double
+        fx = self.lib.oracle_vf_evaluate(C.byref(n.net), C.c_size_t(num_ep), C.c_size_t(ep_len), _dp(observ),
+                                         _dp(target), _dp(x), _dp(g), C.c_int(n_padded), _dp(pred))
+        return fx, g, pred
+
+    def reward_stats(self, reward, num_ep, ep_len):
+        m, s = C.c_double(), C.c_double()
+        self.lib.oracle_reward_stats.restype = None
+        self.lib.oracle_reward_stats(C.c_size_t(num_ep), C.c_size_t(ep_len), _dp(reward), C.byref(m), C.byref(s))
+        return m.value, s.value
+
+    def gae(self, reward, baseline, num_ep, ep_len, gamma, lam):
+        """Returns (Return, standardised Advantage); ``reward`` is left untouched (the C routine works on a copy)."""
+        r = np.array(reward, dtype=np.float64)
+        ret = np.zeros(num_ep * ep_len)
+        adv = np.zeros(num_ep * ep_len)
+        assert self.lib.oracle_gae(C.c_size_t(num_ep), C.c_size_t(ep_len), C.c_double(gamma), C.c_double(lam), _dp(r),
+                                   _dp(baseline), _dp(ret), _dp(adv)) == 0
+        return ret, adv
+
+    def arm_rollout(self, layers, acfunc, theta, num_ep, ep_len):
+        """One batch from the lightweight arm simulator; consumes the C library's rand() stream."""
+        n = _Net(layers, acfunc)
+        N, O, A = num_ep * ep_len, layers[0], layers[-1]
+        d = dict(Observ=np.zeros((N, O)), Mean=np.zeros((N, A)), Std=np.zeros(A), Action=np.zeros((N, A)),
+                 Reward=np.zeros(N))
+        assert self.lib.oracle_arm_rollout(C.byref(n.net), _dp(theta), C.c_size_t(num_ep), C.c_size_t(ep_len),
+                                           _dp(d["Observ"]), _dp(d["Mean"]), _dp(d["Std"]), _dp(d["Action"]),
+                                           _dp(d["Reward"])) == 0
+        return d
+
 
 class Reference:
     """The unmodified reference, compiled from /root/reference by oracle/Makefile (file-based API)."""
@@ -203,3 +269,86 @@ class Reference:
         out = np.zeros(num_params(layers))
         t = self.lib.TRPO_Update(p, _dp(out), threads)
         return out, t
+
+
+    # ---- rows f-3 / f-4 -------------------------------------------------------------------------------------------
+    def vf_evaluate(self, vf_layers, acfunc, x, observ, target, num_ep, ep_len, n_padded=None):
+        """The reference's libLBFGS callback ``evaluate`` (TRPO_Baseline.c:29) on in-memory data."""
+        K = len(vf_layers) - 1
+        n_padded = n_padded or len(x)
+        N = num_ep * ep_len
+        keep = []
+
+        def rows(sizes):
+            arrs = [np.zeros(max(1, sz)) for sz in sizes]
+            ptrs = (c_double_p * len(arrs))(*[_dp(a) for a in arrs])
+            keep.extend(arrs)
+            return ptrs
+
+        bp = TRPOBaselineParam()
+        ls = (C.c_size_t * len(vf_layers))(*vf_layers)
+        ac = C.c_char_p(acfunc.encode())
+        bp.NumLayers, bp.ObservSpaceDim, bp.NumEpBatch, bp.EpLen = len(vf_layers), vf_layers[0] - 1, num_ep, ep_len
+        bp.NumSamples, bp.NumParams, bp.PaddedParams = N, num_params(vf_layers) - 1, n_padded
+        bp.AcFunc, bp.LayerSizeBase = ac, C.cast(ls, c_size_p)
+        bp.WBase = rows([vf_layers[i] * vf_layers[i + 1] for i in range(K)])
+        bp.BBase = rows([vf_layers[i + 1] for i in range(K)])
+        bp.GWBase = rows([vf_layers[i] * vf_layers[i + 1] for i in range(K)])
+        bp.GBBase = rows([vf_layers[i + 1] for i in range(K)])
+        bp.LayerBase = rows(list(vf_layers))
+        bp.GLayerBase = rows(list(vf_layers))
+        pred = np.zeros(N)
+        obs = np.ascontiguousarray(observ)
+        tgt = np.ascontiguousarray(target)
+        bp.Observ, bp.Target, bp.Predict = _dp(obs), _dp(tgt), _dp(pred)
+        g = np.zeros(n_padded)
+        xx = np.ascontiguousarray(x)
+        self.lib.evaluate.restype = C.c_double
+        self.lib.evaluate.argtypes = [C.c_void_p, c_double_p, c_double_p, C.c_int, C.c_double]
+        fx = self.lib.evaluate(C.cast(C.byref(bp), C.c_void_p), _dp(xx), _dp(g), n_padded, 0.0)
+        return fx, g, pred
+
+    def lbfgs(self, x0, evaluate, max_iterations=25):
+        """Minimise with the libLBFGS the reference vendors (src/lbfgs.c), exactly as TRPO_Lightweight.c:325-327,675
+        drives it: default parameters, max_iterations = 25. ``evaluate(x, g) -> fx`` works on numpy views of the
+        solver's own buffers; alternatively pass ``(fnptr, instance)`` to hand libLBFGS a native callback."""
+        L = self.lib
+        n = len(x0)
+        L.lbfgs_malloc.restype = c_double_p
+        L.lbfgs_malloc.argtypes = [C.c_int]
+        L.lbfgs_free.argtypes = [c_double_p]
+        L.lbfgs_parameter_init.argtypes = [C.POINTER(LbfgsParameter)]
+        cb_t = C.CFUNCTYPE(C.c_double, C.c_void_p, c_double_p, c_double_p, C.c_int, C.c_double)
+        L.lbfgs.restype = C.c_int
+        L.lbfgs.argtypes = [C.c_int, c_double_p, c_double_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                            C.POINTER(LbfgsParameter)]
+        xbuf = L.lbfgs_malloc(n)
+        xv = np.ctypeslib.as_array(xbuf, shape=(n,))
+        xv[:] = x0
+        prm = LbfgsParameter()
+        L.lbfgs_parameter_init(C.byref(prm))
+        prm.max_iterations = max_iterations
+        fx = C.c_double()
+        if isinstance(evaluate, tuple):
+            fnptr, instance = evaluate
+            cb = None
+        else:
+            def _cb(_inst, xp, gp, nn, _step):
+                return float(evaluate(np.ctypeslib.as_array(xp, shape=(nn,)), np.ctypeslib.as_array(gp, shape=(nn,))))
+            cb = cb_t(_cb)
+            fnptr, instance = C.cast(cb, C.c_void_p), None
+        rc = L.lbfgs(n, xbuf, C.byref(fx), fnptr, None, instance, C.byref(prm))
+        out = np.array(xv)
+        L.lbfgs_free(xbuf)
+        return out, fx.value, rc
+
+    def lightweight(self, model_file, baseline_file, result_prefix, layers, acfunc, damping, iters, threads=1):
+        """TRPO_Lightweight (TRPO_Lightweight.c:12): the whole training loop, srand(0), 20 episodes x 150 steps; writes
+        ``<result_prefix>%03d.txt`` for the last iteration (the prefix must stay under 23 characters, :1469-1473)."""
+        keep = []
+        p = self.param(model_file, "", layers, acfunc, 3000, damping, keep)
+        p.BaselineFile = baseline_file.encode()
+        p.ResultFile = result_prefix.encode()
+        self.lib.TRPO_Lightweight.restype = C.c_double
+        self.lib.TRPO_Lightweight.argtypes = [TRPOparam, C.c_int, C.c_size_t]
+        return self.lib.TRPO_Lightweight(p, iters, threads)
