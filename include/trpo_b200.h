@@ -153,6 +153,62 @@ int     trpo_memcpy_h2d(double *dst_dev, const double *src_host, size_t n_double
 int     trpo_memcpy_d2h(double *dst_host, const double *src_dev, size_t n_doubles);
 
 /* ------------------------------------------------------------------------------------------------
+ * The training loop around the update: what TRPO_Lightweight.c:541-694 does
+ * between the rollouts and the TRPO update, on the batch already staged in HBM.
+ * ---------------------------------------------------------------------------------------------- */
+/* Stage one batch of rollouts: NumEpBatch episodes of EpLen steps, row = ep*EpLen + step; Reward has one entry per row
+ * (the arrays TRPO_Lightweight.c:112-118 fills, or the streams TRPO_RunLightweight returns,
+ * TRPO_Lightweight_FPGA.c:548-556). The advantage is produced on the device by trpo_vf_advantage. */
+int trpo_ctx_set_rollout(trpo_ctx *ctx, size_t NumEpBatch, size_t EpLen, const double *Observ, const double *Std,
+                         const double *Mean, const double *Action, const double *Reward);
+
+/* Value-function ("baseline") network on the policy context's device and stream. LayerSizeBase[0] must be
+ * ObservSpaceDim + 1 (observation followed by step/EpLen), the last layer 1 (TRPO_Lightweight.c:36, TRPO_Baseline.c:98-103).
+ * Its parameter vector x is [W0,B0,...] WITHOUT a LogStd tail: trpo_vf_num_params == NumParamsCalc(LayerSizeBase) - 1
+ * (TRPO_Lightweight.c:44). Shares the policy context's communicator in multi-GPU mode. */
+typedef struct trpo_vf trpo_vf;
+trpo_vf *trpo_vf_create(trpo_ctx *policy, const size_t *LayerSizeBase, const char *AcFunc, size_t NumLayers);
+void     trpo_vf_destroy(trpo_vf *vf);
+size_t   trpo_vf_num_params(const trpo_vf *vf);
+/* (Re)build the time-augmented observation matrix from the batch staged in the policy context; call after every
+ * trpo_ctx_set_batch / set_rollout (trpo_vf_advantage does it itself). NumSamples must be a multiple of EpLen. */
+int trpo_vf_bind_batch(trpo_vf *vf, size_t EpLen);
+int trpo_vf_set_target(trpo_vf *vf, const double *Target);                 /* NumSamples doubles on the host */
+int trpo_vf_predict(trpo_vf *vf, const double *x, double *Predict_out);    /* TRPO_Lightweight.c:582-625 */
+/* Return, GAE(gamma, lam) advantage and its standardisation (TRPO_Lightweight.c:565-653) with the baseline predicted
+ * from x. The standardised advantage becomes the policy context's Advantage (ready for trpo_ctx_update), the return
+ * becomes this network's target (ready for trpo_vf_evaluate). Return_out / Advantage_out may be NULL. */
+int trpo_vf_advantage(trpo_vf *vf, const double *x, double gamma, double lam, double *Return_out, double *Advantage_out);
+/* libLBFGS objective callback, a drop-in for the reference's `evaluate` (TRPO_Baseline.c:29, lbfgs.h lbfgs_evaluate_t):
+ *     lbfgs(PaddedParams, x, &fx, trpo_vf_evaluate, NULL, vf, &param);
+ * returns 0.01*MSE + 0.001*|x|^2 and writes g = d/dx (n >= trpo_vf_num_params; the padding of g is zeroed).
+ * Returns -1 after a failure (see trpo_last_error), like the reference does for an unsupported activation. */
+double trpo_vf_evaluate(void *vf, const double *x, double *g, const int n, const double step);
+
+/* Binary replacement for the text data file (TRPO_FVP.c:731-762 re-parses N x (3A+O+1) decimal numbers on every call):
+ * a 64-byte header {"TRPOB200", version, flags, N, O, A} followed by Std[A], Observ[N*O], Mean[N*A], Action[N*A],
+ * Advantage[N] as little-endian doubles. FVP_GPU / CG_GPU / TRPO_Update_GPU accept either format in param.DataFile. */
+typedef struct {
+    char               magic[8];        /* "TRPOB200" */
+    unsigned int       version;         /* 1 */
+    unsigned int       flags;           /* bit 0: Mean / Action / Advantage sections present */
+    unsigned long long NumSamples, ObservSpaceDim, ActionSpaceDim;
+    unsigned long long reserved[3];
+} trpo_batch_file_header;               /* 64 bytes */
+int trpo_batch_file_write(const char *path, size_t NumSamples, size_t ObservSpaceDim, size_t ActionSpaceDim,
+                          const double *Observ, const double *Std, const double *Mean, const double *Action,
+                          const double *Advantage);
+int trpo_batch_file_from_text(const char *text_path, const char *bin_path, size_t NumSamples, size_t ObservSpaceDim,
+                              size_t ActionSpaceDim);
+/* Read the header of a binary batch file; returns -1 (and leaves *hdr zeroed) if path is not one. */
+int trpo_batch_file_probe(const char *path, trpo_batch_file_header *hdr);
+/* Read the first NumSamples rows into caller-allocated host arrays (Mean/Action/Advantage may be NULL). */
+int trpo_batch_file_read(const char *path, size_t NumSamples, double *Observ, double *Std, double *Mean, double *Action,
+                         double *Advantage);
+/* Stage the first NumSamples rows (0 = all) of a binary batch file through pinned buffers. */
+int trpo_ctx_set_batch_file(trpo_ctx *ctx, const char *path, size_t NumSamples);
+
+/* ------------------------------------------------------------------------------------------------
  * Multi-GPU: one process (or thread) per GPU. Samples are sharded; each FVP ends with ONE all-reduce of the
  * P-length un-normalised sum (ncclDouble, ncclSum) before the replicated CG update.
  * Rank 0 creates the id and ships the 128 bytes to the others by any means (bench.py: torch.distributed).

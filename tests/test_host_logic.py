@@ -64,3 +64,31 @@ def test_branch_free_tanh_algorithm_accuracy():
         y = y + y * (1.0 - s * y)
     got = np.copysign(1.0 - 2.0 * y, x)
     assert np.abs(got - np.tanh(x)).max() < 4e-16
+
+
+def test_binary_batch_file_round_trip_and_text_conversion(pkg, tmp_path):
+    """The binary data file (include/trpo_b200.h, host/trpo_batch_file.c) holds exactly what the text file parses to."""
+    s = load_synth("net3")
+    N, O, A = s["Observ"].shape[0], s["Observ"].shape[1], s["Std"].size
+    bf = str(tmp_path / "d.bin")
+    pkg.api.batch_file_write(bf, s["Observ"], s["Std"], s["Mean"], s["Action"], s["Advantage"])
+    import os
+    assert os.path.getsize(bf) == 64 + 8 * (A + N * O + 2 * N * A + N)
+    d = pkg.api.batch_file_read(bf, N, O, A)
+    for k in ("Mean", "Std", "Observ", "Action", "Advantage"):
+        assert np.array_equal(d[k], s[k]), k
+    # a prefix of the rows, as TRPOparam.NumSamples < file rows does with the text file
+    d = pkg.api.batch_file_read(bf, 17, O, A)
+    assert np.array_equal(d["Observ"], s["Observ"][:17]) and np.array_equal(d["Advantage"], s["Advantage"][:17])
+    assert np.array_equal(d["Action"], s["Action"][:17])
+    # text -> binary conversion parses the reference's row format (TRPO_FVP.c:739-760)
+    df, bf2 = str(tmp_path / "d.txt"), str(tmp_path / "d2.bin")
+    pkg.textio.write_data(df, s["Mean"], s["Std"], s["Observ"], s["Action"], s["Advantage"])
+    pkg.api.batch_file_from_text(df, bf2, N, O, A)
+    assert open(bf, "rb").read() == open(bf2, "rb").read()
+    # asking for more rows than the file holds fails like a short text file does
+    import pytest
+    with pytest.raises(RuntimeError):
+        pkg.api.batch_file_read(bf, N + 1, O, A)
+    with pytest.raises(RuntimeError):
+        pkg.api.batch_file_read(df, N, O, A)          # a text file is not a binary batch file

@@ -7,4 +7,5 @@ text formats (``textio``) and the synthetic batch generator (``synth``). There i
 The directory name is not a Python identifier; load it with ``__graft_entry__.load_package()``.
 """
 from . import api, synth, textio  # noqa: F401
-from .api import CG_GPU, FVP_GPU, TRPO_Update_GPU, Context, TRPOparam, build_library, library_path  # noqa: F401
+from .api import (CG_GPU, FVP_GPU, TRPO_Update_GPU, Context, TRPOparam, ValueFunction, build_library,  # noqa: F401
+                  library_path)

@@ -85,6 +85,22 @@ def lib():
         L.trpo_ctx_get_info.argtypes = [C.c_void_p, C.POINTER(TrpoInfo)]
         L.trpo_ctx_fvp_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double]
         L.trpo_ctx_cg_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_double, C.c_double]
+        L.trpo_ctx_set_rollout.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t] + [c_double_p] * 5
+        L.trpo_vf_create.restype = C.c_void_p
+        L.trpo_vf_create.argtypes = [C.c_void_p, c_size_p, C.c_char_p, C.c_size_t]
+        L.trpo_vf_destroy.argtypes = [C.c_void_p]
+        L.trpo_vf_num_params.restype = C.c_size_t
+        L.trpo_vf_num_params.argtypes = [C.c_void_p]
+        L.trpo_vf_bind_batch.argtypes = [C.c_void_p, C.c_size_t]
+        L.trpo_vf_set_target.argtypes = [C.c_void_p, c_double_p]
+        L.trpo_vf_predict.argtypes = [C.c_void_p, c_double_p, c_double_p]
+        L.trpo_vf_advantage.argtypes = [C.c_void_p, c_double_p, C.c_double, C.c_double, c_double_p, c_double_p]
+        L.trpo_vf_evaluate.restype = C.c_double
+        L.trpo_vf_evaluate.argtypes = [C.c_void_p, c_double_p, c_double_p, C.c_int, C.c_double]
+        L.trpo_batch_file_write.argtypes = [C.c_char_p, C.c_size_t, C.c_size_t, C.c_size_t] + [c_double_p] * 5
+        L.trpo_batch_file_from_text.argtypes = [C.c_char_p, C.c_char_p, C.c_size_t, C.c_size_t, C.c_size_t]
+        L.trpo_batch_file_read.argtypes = [C.c_char_p, C.c_size_t] + [c_double_p] * 5
+        L.trpo_ctx_set_batch_file.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
         L.trpo_nccl_unique_id.argtypes = [C.c_char_p]
         L.trpo_ctx_init_comm.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int]
         L.trpo_ctx_p2p_export.argtypes = [C.c_void_p, C.c_char_p]
@@ -235,6 +251,15 @@ class Context:
                                                C.c_void_p(d_mean or None), C.c_void_p(d_action or None),
                                                C.c_void_p(d_advantage or None)))
 
+    def set_rollout(self, num_ep, ep_len, observ, std, mean, action, reward):
+        """Stage one batch of rollouts (row = ep * ep_len + step); the advantage comes from ValueFunction.advantage."""
+        arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (observ, std, mean, action, reward)]
+        assert arrs[0].shape[0] == num_ep * ep_len
+        _check(lib().trpo_ctx_set_rollout(self.h, num_ep, ep_len, *[_dp(a) for a in arrs]))
+
+    def set_batch_file(self, path, num_samples=0):
+        _check(lib().trpo_ctx_set_batch_file(self.h, path.encode(), num_samples))
+
     def fvp(self, v, damping):
         v = np.ascontiguousarray(v, dtype=np.float64)
         out = np.zeros(self.P)
@@ -292,6 +317,83 @@ class Context:
 
     def global_samples(self):
         return lib().trpo_ctx_global_samples(self.h)
+
+
+class ValueFunction:
+    """Baseline network bound to a policy Context (TRPO_Baseline.c / TRPO_Lightweight.c:565-694 on the GPU)."""
+
+    def __init__(self, policy, vf_layers, acfunc):
+        self.policy = policy
+        self.layers = list(vf_layers)
+        ls = (C.c_size_t * len(vf_layers))(*vf_layers)
+        self.h = lib().trpo_vf_create(policy.h, ls, acfunc.encode(), len(vf_layers))
+        if not self.h:
+            raise RuntimeError(f"libtrpo_b200: {last_error()}")
+        self.num_params = lib().trpo_vf_num_params(self.h)
+
+    def close(self):
+        if self.h:
+            lib().trpo_vf_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def bind_batch(self, ep_len):
+        _check(lib().trpo_vf_bind_batch(self.h, ep_len))
+
+    def set_target(self, target):
+        target = np.ascontiguousarray(target, dtype=np.float64)
+        _check(lib().trpo_vf_set_target(self.h, _dp(target)))
+
+    def predict(self, x, num_samples):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        out = np.zeros(num_samples)
+        _check(lib().trpo_vf_predict(self.h, _dp(x), _dp(out)))
+        return out
+
+    def advantage(self, x, num_samples, gamma, lam):
+        """(Return, standardised Advantage); also installs them as the baseline target / the policy batch's Advantage."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        ret, adv = np.zeros(num_samples), np.zeros(num_samples)
+        _check(lib().trpo_vf_advantage(self.h, _dp(x), gamma, lam, _dp(ret), _dp(adv)))
+        return ret, adv
+
+    def evaluate(self, x, n_padded=None):
+        """(fx, g) of the baseline objective -- the libLBFGS callback called from Python."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        g = np.zeros(n_padded or x.size)
+        fx = lib().trpo_vf_evaluate(self.h, _dp(x), _dp(g), g.size, 0.0)
+        if fx == -1.0:                       # the objective itself is >= 0
+            raise RuntimeError(f"libtrpo_b200: {last_error()}")
+        return fx, g
+
+    def callback_pointer(self):
+        """(function pointer, instance) to hand to a native libLBFGS: lbfgs(n, x, &fx, fn, NULL, instance, &param)."""
+        return C.cast(lib().trpo_vf_evaluate, C.c_void_p), C.c_void_p(self.h)
+
+
+def batch_file_write(path, observ, std, mean=None, action=None, advantage=None):
+    observ = np.ascontiguousarray(observ, dtype=np.float64)
+    std = np.ascontiguousarray(std, dtype=np.float64)
+    arrs = [None if a is None else np.ascontiguousarray(a, dtype=np.float64) for a in (mean, action, advantage)]
+    _check(lib().trpo_batch_file_write(path.encode(), observ.shape[0], observ.shape[1], std.size, _dp(observ), _dp(std),
+                                       *[_dp(a) for a in arrs]))
+
+
+def batch_file_from_text(text_path, bin_path, num_samples, obs_dim, act_dim):
+    _check(lib().trpo_batch_file_from_text(text_path.encode(), bin_path.encode(), num_samples, obs_dim, act_dim))
+
+
+def batch_file_read(path, num_samples, obs_dim, act_dim):
+    d = dict(Observ=np.zeros((num_samples, obs_dim)), Std=np.zeros(act_dim), Mean=np.zeros((num_samples, act_dim)),
+             Action=np.zeros((num_samples, act_dim)), Advantage=np.zeros(num_samples))
+    _check(lib().trpo_batch_file_read(path.encode(), num_samples, _dp(d["Observ"]), _dp(d["Std"]), _dp(d["Mean"]),
+                                      _dp(d["Action"]), _dp(d["Advantage"])))
+    return d
 
 
 def nccl_unique_id():

@@ -119,3 +119,17 @@ void launch_surrogate(const double *d_mean_new, const double *d_mean_old, const 
                       const double *d_std_old, const double *d_logstd_new, int A, size_t nsamples,
                       double *d_block_partials, double *d_out, cudaStream_t st, long long *launches);
 void launch_sum(const double *d_a, size_t n, double *d_block_partials, double *d_out, cudaStream_t st, long long *launches);
+
+// ---- rollout_kernels.cu (rows f-3 / f-4: advantage estimation and the baseline objective) ------------------------------
+// out[n][0..O) = obs[n][0..O), out[n][O] = (n mod EpLen)/EpLen: the baseline network's input (TRPO_Baseline.c:98-103)
+void launch_vf_augment(const double *d_obs, size_t n, int O, size_t ep_len, double *d_out, cudaStream_t st, long long *launches);
+// discounted return and GAE(gamma, lam) advantage of every episode (TRPO_Lightweight.c:565-641), un-standardised
+void launch_gae(const double *d_reward, const double *d_baseline, size_t num_ep, int ep_len, double gamma, double lam,
+                double *d_ret, double *d_adv, cudaStream_t st, long long *launches);
+// out[0] = sum_i (a[i] - c_i)^2, c_i = b[i] if b != NULL else *d_shift_sum / shift_div; fixed-order
+void launch_sqdiff(const double *d_a, const double *d_b, const double *d_shift_sum, double shift_div, size_t n,
+                   double *d_block_partials, double *d_out, cudaStream_t st, long long *launches);
+// a = (a - sum/N) / sqrt(sqdev/N)  (TRPO_Lightweight.c:645-653)
+void launch_standardise(double *d_a, size_t n, const double *d_sum, const double *d_sqdev, double n_total, cudaStream_t st,
+                        long long *launches);
+void launch_fill(double *d_a, double v, size_t n, cudaStream_t st, long long *launches);

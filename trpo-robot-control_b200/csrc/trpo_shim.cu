@@ -72,6 +72,9 @@ struct trpo_ctx {
     double *d_obs, *d_mean, *d_action, *d_adv;
     bool own_batch;
     size_t cap_obs, cap_mean, cap_adv;
+    // rollout staging (rows f-3/f-4): per-step rewards of the staged batch and its episode length
+    double *d_reward;
+    size_t cap_reward, ep_len;
     // work vectors (P each)
     double *d_in, *d_out, *d_zsum, *d_x, *d_r, *d_p, *d_z, *d_b, *d_xnew;
     double *d_scal;            // small scalar scratch (16 doubles)
@@ -100,6 +103,7 @@ struct trpo_ctx {
     cudaEvent_t *ktime_ev;     // 2 * KTIME_MAX events
     // comm
     ncclComm_t comm;
+    bool borrowed_comm;        // comm belongs to another context (the value-function network shares the policy's)
     int rank, world;
     // streamed staging of the observation matrix (pinned host source, fused path): the first FVP after set_batch
     // overlaps the host-to-device copy, the kernel polling d_ready for the chunks it needs
@@ -240,12 +244,13 @@ extern "C" void trpo_ctx_destroy(trpo_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    if (c->comm && !c->borrowed_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     for (int r = 0; r < TRPO_MAX_RANKS; ++r) if (c->p2p_peer[r]) cudaIpcCloseMemHandle(c->p2p_peer[r]);
     if (c->p2p_buf) cudaFree(c->p2p_buf);
     free_batch(c);
     double *vecs[] = {c->d_theta, c->d_in, c->d_out, c->d_zsum, c->d_x, c->d_r, c->d_p, c->d_z, c->d_b, c->d_xnew,
-                      c->d_inv_var, c->d_std, c->d_inv_std_model, c->d_scal, c->d_blockpart, c->d_mean_new, c->sc_base, c->d_fused_partial};
+                      c->d_inv_var, c->d_std, c->d_inv_std_model, c->d_scal, c->d_blockpart, c->d_mean_new, c->sc_base, c->d_fused_partial,
+                      c->d_reward};
     for (double *v : vecs) if (v) cudaFree(v);
     float *fvecs[] = {c->f_theta, c->f_v, c->f_inv_var, c->f_obs, c->scf_base};
     for (float *v : fvecs) if (v) cudaFree(v);
@@ -407,6 +412,74 @@ extern "C" int trpo_ctx_set_batch_device(trpo_ctx *c, size_t N, const double *dO
     c->d_obs = (double *)dObserv; c->d_mean = (double *)dMean; c->d_action = (double *)dAction; c->d_adv = (double *)dAdvantage;
     c->n_local = N;
     if (set_std(c, Std_host)) return -1;
+    return update_global_samples(c);
+}
+
+
+// Stage a binary batch file (host/trpo_batch_file.c) section by section through two pinned 32 MB buffers: the read of
+// one piece overlaps the host-to-device copy of the previous one.
+extern "C" int trpo_ctx_set_batch_file(trpo_ctx *c, const char *path, size_t N) {
+    if (!c || !path) return fail("null argument");
+    trpo_batch_file_header h;
+    if (trpo_batch_file_probe(path, &h)) {
+        fprintf(stderr, "[ERROR] Cannot open Data File [%s]. \n", path);
+        return fail("%s is not a binary batch file", path);
+    }
+    const size_t O = c->net.L[0], A = c->net.L[c->net.K], NF = (size_t)h.NumSamples;
+    if (h.ObservSpaceDim != O || h.ActionSpaceDim != A) return fail("batch file is %llux%llu, the network needs %zux%zu", h.ObservSpaceDim, h.ActionSpaceDim, O, A);
+    if (N == 0) N = NF;
+    if (N > NF) return fail("batch file holds %zu samples, %zu requested", NF, N);
+    CU(cudaSetDevice(c->device));
+    if (c->copy_inflight) { CU(cudaStreamWaitEvent(c->stream, c->ev_copy, 0)); c->copy_inflight = false; }
+    c->stream_first_fvp = false;
+    if (!c->own_batch) free_batch(c);
+    c->own_batch = true;
+    const bool full = (h.flags & 1u) != 0;
+    if (N * O > c->cap_obs) { cudaFree(c->d_obs); c->d_obs = nullptr; CU(cudaMalloc(&c->d_obs, N * O * sizeof(double))); c->cap_obs = N * O; }
+    if (full) {
+        if (N * A > c->cap_mean) {
+            cudaFree(c->d_mean); cudaFree(c->d_action); c->d_mean = c->d_action = nullptr;
+            CU(cudaMalloc(&c->d_mean, N * A * sizeof(double)));
+            CU(cudaMalloc(&c->d_action, N * A * sizeof(double)));
+            c->cap_mean = N * A;
+        }
+        if (N > c->cap_adv) { cudaFree(c->d_adv); c->d_adv = nullptr; CU(cudaMalloc(&c->d_adv, N * sizeof(double))); c->cap_adv = N; }
+    }
+    FILE *f = fopen(path, "rb");
+    if (!f) return fail("cannot open %s", path);
+    const size_t PIECE = (32u << 20) / sizeof(double);
+    double *pin[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    bool used[2] = {false, false};
+    int rc = 0, which = 0;
+    for (int i = 0; i < 2 && !rc; ++i)
+        if (cudaMallocHost(&pin[i], PIECE * sizeof(double)) != cudaSuccess || cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess)
+            rc = fail("pinned staging allocation failed");
+    double std_host[TRPO_MAX_LAYERS * 64];
+    if (!rc && A > sizeof(std_host) / sizeof(std_host[0])) rc = fail("action dimension too large");
+    if (!rc && (fseek(f, (long)sizeof(h), SEEK_SET) != 0 || fread(std_host, sizeof(double), A, f) != A)) rc = fail("short batch file");
+    struct Section { double *dst; size_t count, file_count; };
+    const Section secs[4] = {{c->d_obs, N * O, NF * O}, {c->d_mean, N * A, NF * A}, {c->d_action, N * A, NF * A}, {c->d_adv, N, NF}};
+    long off = (long)(sizeof(h) + A * sizeof(double));
+    for (int sidx = 0; sidx < (full ? 4 : 1) && !rc; ++sidx) {
+        if (fseek(f, off, SEEK_SET) != 0) { rc = fail("short batch file"); break; }
+        for (size_t done = 0; done < secs[sidx].count && !rc; done += PIECE) {
+            const size_t n = secs[sidx].count - done < PIECE ? secs[sidx].count - done : PIECE;
+            if (used[which] && cudaEventSynchronize(ev[which]) != cudaSuccess) { rc = fail("staging copy failed"); break; }
+            if (fread(pin[which], sizeof(double), n, f) != n) { rc = fail("short batch file"); break; }
+            if (cudaMemcpyAsync(secs[sidx].dst + done, pin[which], n * sizeof(double), cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
+                cudaEventRecord(ev[which], c->stream) != cudaSuccess) { rc = fail("staging copy failed"); break; }
+            used[which] = true;
+            which ^= 1;
+        }
+        off += (long)(secs[sidx].file_count * sizeof(double));
+    }
+    fclose(f);
+    cudaStreamSynchronize(c->stream);
+    for (int i = 0; i < 2; ++i) { if (pin[i]) cudaFreeHost(pin[i]); if (ev[i]) cudaEventDestroy(ev[i]); }
+    if (rc) return rc;
+    c->n_local = N;
+    if (set_std(c, std_host)) return -1;
     return update_global_samples(c);
 }
 
@@ -744,6 +817,187 @@ extern "C" int trpo_ctx_update(trpo_ctx *c, double *Result, double damping) {
     CU(cudaMemcpyAsync(Result, d_result, P * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return 0;
+}
+
+
+// --------------------------------------------------------------------------------------------------------------
+// Rows f-3 / f-4: rollout staging, advantage estimation and the baseline ("value function") objective.
+extern "C" int trpo_ctx_set_rollout(trpo_ctx *c, size_t NumEpBatch, size_t EpLen, const double *Observ, const double *Std,
+                                    const double *Mean, const double *Action, const double *Reward) {
+    if (!c || !Observ || !Std || !Mean || !Action || !Reward || NumEpBatch == 0 || EpLen == 0) return fail("bad rollout arguments");
+    const size_t N = NumEpBatch * EpLen;
+    // Reward is staged twice: once as the (not yet valid) Advantage so that all batch buffers exist, once on its own
+    if (trpo_ctx_set_batch(c, N, Observ, Std, Mean, Action, Reward)) return -1;
+    if (N > c->cap_reward) {
+        if (c->d_reward) cudaFree(c->d_reward);
+        c->d_reward = nullptr;
+        CU(cudaMalloc(&c->d_reward, N * sizeof(double)));
+        c->cap_reward = N;
+    }
+    CU(cudaMemcpyAsync(c->d_reward, c->d_adv, N * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    c->ep_len = EpLen;
+    return 0;
+}
+
+struct trpo_vf {
+    trpo_ctx *pol, *net;       // policy context (borrowed) and the baseline network's own context
+    size_t npar;               // parameters of the baseline network (no LogStd tail)
+    size_t n, ep_len;          // bound batch
+    double *d_aug;             // [n x (O+1)] observation + step/EpLen
+    double *d_pred, *d_target, *d_coef;   // [n] prediction, regression target, constant gradient seed factor
+    size_t cap_aug, cap_n;
+    double *h_theta, *h_g;     // host staging (npar + 1)
+    bool target_set;
+};
+
+extern "C" trpo_vf *trpo_vf_create(trpo_ctx *pol, const size_t *LayerSizeBase, const char *AcFunc, size_t NumLayers) {
+    if (!pol || !LayerSizeBase || !AcFunc || NumLayers < 2) { fail("bad value-function description"); return nullptr; }
+    if (LayerSizeBase[0] != (size_t)pol->net.L[0] + 1) { fail("LayerSizeBase[0] must be ObservSpaceDim + 1 (observation, step/EpLen)"); return nullptr; }
+    if (LayerSizeBase[NumLayers - 1] != 1) { fail("the value-function network must have one output"); return nullptr; }
+    for (size_t i = 1; i < NumLayers; ++i)
+        if (AcFunc[i] != 'l' && AcFunc[i] != 't') {
+            // TRPO_Baseline.c:126-129,152-156: only linear and tanh layers exist for the baseline
+            fprintf(stderr, "[ERROR] Activation Function for Layer [%zu] is %c. Unsupported.\n", i, AcFunc[i]);
+            fail("unsupported baseline activation '%c'", AcFunc[i]);
+            return nullptr;
+        }
+    trpo_ctx *net = trpo_ctx_create(LayerSizeBase, AcFunc, NumLayers, pol->device, TRPO_PRECISION_FP64);
+    if (!net) return nullptr;
+    trpo_vf *vf = (trpo_vf *)calloc(1, sizeof(trpo_vf));
+    vf->pol = pol; vf->net = net;
+    vf->npar = (size_t)net->net.logstd_off;
+    vf->h_theta = (double *)calloc(vf->npar + 1, sizeof(double));
+    vf->h_g = (double *)calloc(vf->npar + 1, sizeof(double));
+    return vf;
+}
+
+extern "C" void trpo_vf_destroy(trpo_vf *vf) {
+    if (!vf) return;
+    cudaSetDevice(vf->net->device);
+    cudaStreamSynchronize(vf->net->stream);
+    trpo_ctx_destroy(vf->net);                   // adopted batch pointers are not freed by the context
+    double *bufs[] = {vf->d_aug, vf->d_pred, vf->d_target, vf->d_coef};
+    for (double *b : bufs) if (b) cudaFree(b);
+    free(vf->h_theta); free(vf->h_g);
+    free(vf);
+}
+
+extern "C" size_t trpo_vf_num_params(const trpo_vf *vf) { return vf ? vf->npar : 0; }
+
+extern "C" int trpo_vf_bind_batch(trpo_vf *vf, size_t EpLen) {
+    if (!vf) return fail("null value function");
+    trpo_ctx *pol = vf->pol, *net = vf->net;
+    if (!pol->d_obs || pol->n_local == 0) return fail("no batch staged in the policy context");
+    if (EpLen == 0 || pol->n_local % EpLen) return fail("NumSamples (%zu) is not a multiple of EpLen (%zu)", pol->n_local, EpLen);
+    CU(cudaSetDevice(pol->device));
+    if (pol->copy_inflight) { CU(cudaStreamWaitEvent(pol->stream, pol->ev_copy, 0)); pol->copy_inflight = false; }
+    pol->stream_first_fvp = false;
+    if (net->stream != pol->stream && trpo_ctx_set_stream(net, pol->stream)) return -1;
+    net->comm = pol->comm; net->borrowed_comm = true; net->rank = pol->rank; net->world = pol->world;
+    net->path_req = (pol->path_req == TRPO_PATH_GEMM_CHAIN) ? TRPO_PATH_GEMM_CHAIN : TRPO_PATH_AUTO;   // follow the policy's choice
+    const size_t n = pol->n_local, O = pol->net.L[0];
+    if (n * (O + 1) > vf->cap_aug) {
+        if (vf->d_aug) cudaFree(vf->d_aug);
+        vf->d_aug = nullptr;
+        CU(cudaMalloc(&vf->d_aug, n * (O + 1) * sizeof(double)));
+        vf->cap_aug = n * (O + 1);
+    }
+    if (n > vf->cap_n) {
+        double **bufs[] = {&vf->d_pred, &vf->d_target, &vf->d_coef};
+        for (double **b : bufs) { if (*b) cudaFree(*b); *b = nullptr; CU(cudaMalloc(b, n * sizeof(double))); }
+        vf->cap_n = n;
+        vf->target_set = false;
+    }
+    launch_vf_augment(pol->d_obs, n, (int)O, EpLen, vf->d_aug, pol->stream, &net->launches);
+    // gradient seed 0.02 * (Predict - Target) (TRPO_Baseline.c:141) == Advantage * (Action - Mean) / sigma^2 of the policy
+    // gradient (TRPO_Update.c:298-300) with Action := Target, Mean := Predict, Advantage := -0.02, sigma := 1
+    launch_fill(vf->d_coef, -0.02, n, pol->stream, &net->launches);
+    const double one = 1.0;
+    if (trpo_ctx_set_batch_device(net, n, vf->d_aug, &one, vf->d_pred, vf->d_target, vf->d_coef)) return -1;
+    vf->n = n; vf->ep_len = EpLen;
+    return 0;
+}
+
+extern "C" int trpo_vf_set_target(trpo_vf *vf, const double *Target) {
+    if (!vf || !Target) return fail("null argument");
+    if (vf->n == 0) return fail("trpo_vf_bind_batch first");
+    CU(cudaSetDevice(vf->net->device));
+    CU(cudaMemcpyAsync(vf->d_target, Target, vf->n * sizeof(double), cudaMemcpyHostToDevice, vf->net->stream));
+    CU(cudaStreamSynchronize(vf->net->stream));
+    vf->target_set = true;
+    return 0;
+}
+
+// forward pass of the baseline network for parameters x into vf->d_pred (stays on the stream)
+static int vf_forward(trpo_vf *vf, const double *x) {
+    trpo_ctx *net = vf->net;
+    if (vf->n == 0) return fail("trpo_vf_bind_batch first");
+    memcpy(vf->h_theta, x, vf->npar * sizeof(double));
+    vf->h_theta[vf->npar] = 0.0;                 // LogStd slot of the embedding context: sigma = 1
+    if (trpo_ctx_set_model(net, vf->h_theta)) return -1;
+    if (ensure_chain_scratch(net)) return -1;
+    if (chain_forward(net->net, net->sc, net->d_theta, vf->d_aug, vf->n, vf->d_pred, net->stream, &net->launches))
+        return fail("baseline forward launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return 0;
+}
+
+extern "C" int trpo_vf_predict(trpo_vf *vf, const double *x, double *Predict_out) {
+    if (!vf || !x || !Predict_out) return fail("null argument");
+    CU(cudaSetDevice(vf->net->device));
+    if (vf_forward(vf, x)) return -1;
+    CU(cudaMemcpyAsync(Predict_out, vf->d_pred, vf->n * sizeof(double), cudaMemcpyDeviceToHost, vf->net->stream));
+    CU(cudaStreamSynchronize(vf->net->stream));
+    return 0;
+}
+
+extern "C" int trpo_vf_advantage(trpo_vf *vf, const double *x, double gamma, double lam, double *Return_out, double *Advantage_out) {
+    if (!vf || !x) return fail("null argument");
+    trpo_ctx *pol = vf->pol;
+    if (!pol->d_reward || pol->ep_len == 0) return fail("no rollout staged: call trpo_ctx_set_rollout first");
+    CU(cudaSetDevice(pol->device));
+    if (trpo_vf_bind_batch(vf, pol->ep_len)) return -1;
+    if (vf_forward(vf, x)) return -1;
+    const size_t n = vf->n;
+    cudaStream_t st = pol->stream;
+    launch_gae(pol->d_reward, vf->d_pred, n / pol->ep_len, (int)pol->ep_len, gamma, lam, vf->d_target, pol->d_adv, st, &pol->launches);
+    vf->target_set = true;
+    // standardise over the whole (global) batch: mean, then the squared deviations, both fixed-order
+    launch_sum(pol->d_adv, n, pol->d_blockpart, pol->d_scal + 8, st, &pol->launches);
+    if (allreduce_scalars(pol, pol->d_scal + 8, 1)) return -1;
+    launch_sqdiff(pol->d_adv, nullptr, pol->d_scal + 8, (double)pol->n_total, n, pol->d_blockpart, pol->d_scal + 9, st, &pol->launches);
+    if (allreduce_scalars(pol, pol->d_scal + 9, 1)) return -1;
+    launch_standardise(pol->d_adv, n, pol->d_scal + 8, pol->d_scal + 9, (double)pol->n_total, st, &pol->launches);
+    if (Return_out) CU(cudaMemcpyAsync(Return_out, vf->d_target, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (Advantage_out) CU(cudaMemcpyAsync(Advantage_out, pol->d_adv, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
+extern "C" double trpo_vf_evaluate(void *instance, const double *x, double *g, const int n, const double step) {
+    (void)step;
+    trpo_vf *vf = (trpo_vf *)instance;
+    if (!vf || !x || !g) { fail("null argument"); return -1.0; }
+    if ((size_t)n < vf->npar) { fail("n (%d) is smaller than the number of baseline parameters (%zu)", n, vf->npar); return -1.0; }
+    if (!vf->target_set) { fail("no regression target: trpo_vf_set_target or trpo_vf_advantage first"); return -1.0; }
+    trpo_ctx *net = vf->net;
+    if (cudaSetDevice(net->device) != cudaSuccess) { fail("cudaSetDevice failed"); return -1.0; }
+    if (vf_forward(vf, x)) return -1.0;
+    if (policy_gradient_device(net)) return -1.0;                        // net->d_b = (1/N) sum_n dLoss_n/dx
+    launch_sqdiff(vf->d_pred, vf->d_target, nullptr, 1.0, vf->n, net->d_blockpart, net->d_scal, net->stream, &net->launches);
+    if (allreduce_scalars(net, net->d_scal, 1)) return -1.0;
+    if (cudaMemcpyAsync(vf->h_g, net->d_b, vf->npar * sizeof(double), cudaMemcpyDeviceToHost, net->stream) != cudaSuccess ||
+        cudaMemcpyAsync(net->h_scal, net->d_scal, sizeof(double), cudaMemcpyDeviceToHost, net->stream) != cudaSuccess ||
+        cudaStreamSynchronize(net->stream) != cudaSuccess) {
+        fail("baseline objective failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return -1.0;
+    }
+    double l2 = 0.0;
+    for (size_t i = 0; i < vf->npar; ++i) {
+        g[i] = vf->h_g[i] + 0.002 * x[i];                                // TRPO_Baseline.c:205-214
+        l2 += x[i] * x[i];
+    }
+    for (int i = (int)vf->npar; i < n; ++i) g[i] = 0.0;
+    return 0.01 * net->h_scal[0] / (double)net->n_total + 0.001 * l2;    // TRPO_Baseline.c:220-235
 }
 
 // --------------------------------------------------------------------------------------------------------------

@@ -57,6 +57,18 @@ static int host_batch_load(const TRPOparam *param, HostBatch *hb) {
     hb->Observ = (double *)calloc(N * O, sizeof(double));
     hb->Action = (double *)calloc(N * A, sizeof(double));
     hb->Advantage = (double *)calloc(N, sizeof(double));
+    trpo_batch_file_header bh;
+    if (trpo_batch_file_probe(param->DataFile, &bh) == 0) {
+        /* binary batch file (trpo_batch_file.c): same content, no decimal parsing */
+        fclose(df);
+        if (bh.ObservSpaceDim != O || bh.ActionSpaceDim != A || !(bh.flags & 1u) ||
+            trpo_batch_file_read(param->DataFile, N, hb->Observ, hb->Std, hb->Mean, hb->Action, hb->Advantage)) {
+            fprintf(stderr, "[ERROR] Data File [%s] does not match the network or holds fewer than %zu samples. \n", param->DataFile, N);
+            host_batch_free(hb);
+            return -1;
+        }
+        return 0;
+    }
     int ok = 1;
     for (size_t n = 0; n < N && ok; ++n) {
         for (size_t j = 0; j < A; ++j) ok &= fscanf(df, "%lf", &hb->Mean[n * A + j]) == 1;
