@@ -355,9 +355,13 @@ class ValueFunction:
         _check(lib().trpo_vf_predict(self.h, _dp(x), _dp(out)))
         return out
 
-    def advantage(self, x, num_samples, gamma, lam):
-        """(Return, standardised Advantage); also installs them as the baseline target / the policy batch's Advantage."""
+    def advantage(self, x, num_samples, gamma, lam, fetch=True):
+        """(Return, standardised Advantage); also installs them as the baseline target / the policy batch's Advantage.
+        fetch=False leaves both on the device (nothing is copied back) and returns None."""
         x = np.ascontiguousarray(x, dtype=np.float64)
+        if not fetch:
+            _check(lib().trpo_vf_advantage(self.h, _dp(x), gamma, lam, None, None))
+            return None
         ret, adv = np.zeros(num_samples), np.zeros(num_samples)
         _check(lib().trpo_vf_advantage(self.h, _dp(x), gamma, lam, _dp(ret), _dp(adv)))
         return ret, adv
