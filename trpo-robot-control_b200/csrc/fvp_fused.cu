@@ -113,6 +113,9 @@ struct FusedArgs {
     // policy-gradient mode (TRPO_Update.c:254-378): ordinary forward / backward with the surrogate-loss seed
     const double *mean, *action, *adv;       // [N x A], [N x A], [N]
     int logstd_off;
+    // mean == NULL: the kernel forms the network output itself (one more DMMA step per sample) and, when mean_out is
+    // set, stores it -- the baseline objective's Predict (TRPO_Baseline.c:134) and its gradient in ONE pass
+    double *mean_out;
 };
 
 __device__ __forceinline__ int ld_volatile_i32(const int *p) {
@@ -187,7 +190,7 @@ __global__ void __launch_bounds__(C::NTHREADS, C::CTAS_PER_SM) k_fvp_fused(const
         VB1s[n] = (!PG && n < L2) ? p.v[p.w_off1 + L1 * L2 + n] : 0.0;
     }
     for (int n = tid; n < AP; n += NT) {
-        VB2s[n] = (!PG && n < L3) ? p.v[p.w_off2 + L2 * L3 + n] : 0.0;
+        VB2s[n] = n >= L3 ? 0.0 : (PG ? p.theta[p.w_off2 + L2 * L3 + n] : p.v[p.w_off2 + L2 * L3 + n]);   // PG: plain bias B2
         IVs[n]  = n < L3 ? p.inv_var[n] : 0.0;
     }
     load_exp2_table(Tab);
@@ -283,6 +286,7 @@ __global__ void __launch_bounds__(C::NTHREADS, C::CTAS_PER_SM) k_fvp_fused(const
             for (int c = 0; c < NT3; ++c)
 #pragma unroll
                 for (int r = 0; r < 2; ++r) rx3p[cc][c][r] = (cc == 0) ? VB2s[8 * c + 2 * t + r] : 0.0;
+        const bool self_mean = PG && p.mean == nullptr;      // uniform: x3 = y2*W2 + B2 accumulates in rx3p
 #pragma unroll
         for (int c0 = 0; c0 < NT2; c0 += GRP) {
             double x2[GRP][2], rx2[GRP][2];
@@ -312,7 +316,7 @@ __global__ void __launch_bounds__(C::NTHREADS, C::CTAS_PER_SM) k_fvp_fused(const
             for (int cc = 0; cc < GRP; ++cc)
                 *reinterpret_cast<double2 *>(&BufC[rowA * RS2 + 8 * (c0 + cc) + 2 * t]) = make_double2(x2[cc][0], x2[cc][1]);
             // layer 2 contribution of these k-blocks: Rx3 += Ry2*W2 + y2*VW2 (the policy gradient needs no layer-2 forward)
-            if (!PG)
+            if (!PG) {
 #pragma unroll
             for (int r = 0; r < 2; ++r)
 #pragma unroll
@@ -322,6 +326,14 @@ __global__ void __launch_bounds__(C::NTHREADS, C::CTAS_PER_SM) k_fvp_fused(const
 #pragma unroll
                     for (int cc = 0; cc < GRP; ++cc) dmma(rx3p[cc][c], x2[cc][r], VW2s[((c0 + cc) * NT3 + c) * 64 + sf[r]]);
                 }
+            } else if (self_mean) {
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+                for (int c = 0; c < NT3; ++c)
+#pragma unroll
+                    for (int cc = 0; cc < GRP; ++cc) dmma(rx3p[cc][c], x2[cc][r], W2s[((c0 + cc) * NT3 + c) * 64 + sf[r]]);
+            }
         }
         double rx3[NT3][2];
 #pragma unroll
@@ -348,7 +360,12 @@ __global__ void __launch_bounds__(C::NTHREADS, C::CTAS_PER_SM) k_fvp_fused(const
                     double gv = 0.0;
                     if (valid && col < L3) {
                         const double is = IVs[col];
-                        const double tt = (p.action[gs * L3 + col] - p.mean[gs * L3 + col]) * is;
+                        double mu;
+                        if (self_mean) {
+                            mu = rx3[c][r] * d3;             // last layer is 'l' (y = x) or 'o' (y = 0.1 x)
+                            if (p.mean_out) p.mean_out[gs * L3 + col] = mu;
+                        } else mu = p.mean[gs * L3 + col];
+                        const double tt = (p.action[gs * L3 + col] - mu) * is;
                         gv = adv * tt * is * d3;
                         gl[c][r] += adv * (tt * tt - 1.0);
                     }
@@ -934,7 +951,7 @@ int fused_fvp_accumulate(const NetDesc &net, const double *d_theta, const double
     a.P = net.P;
     a.act1 = net.ac[1]; a.act2 = net.ac[2]; a.act3 = net.ac[3];
     a.ready = stream_ready; a.chunk_samples = (long long)(stream_chunk ? stream_chunk : 1); a.error = stream_error;
-    a.mean = a.action = a.adv = nullptr; a.logstd_off = net.logstd_off;
+    a.mean = a.action = a.adv = nullptr; a.logstd_off = net.logstd_off; a.mean_out = nullptr;
     int rows = 0, rc = -1;
     switch (shape) {
         case SHAPE_ARM: {
@@ -960,7 +977,7 @@ int fused_fvp_accumulate(const NetDesc &net, const double *d_theta, const double
 // d_inv_std = exp(-LogStd) of the current parameters.
 int fused_pg_accumulate(const NetDesc &net, const double *d_theta, const double *d_inv_std, const double *d_obs,
                         const double *d_mean, const double *d_action, const double *d_adv, size_t nsamples,
-                        double *d_partial, double *d_zsum, cudaStream_t st, long long *launches) {
+                        double *d_partial, double *d_zsum, double *d_mean_out, cudaStream_t st, long long *launches) {
     const FusedShape shape = pick_shape(net);
     if (shape == SHAPE_NONE) return 1;
     FusedArgs a;
@@ -971,7 +988,7 @@ int fused_pg_accumulate(const NetDesc &net, const double *d_theta, const double 
     a.P = net.P;
     a.act1 = net.ac[1]; a.act2 = net.ac[2]; a.act3 = net.ac[3];
     a.ready = nullptr; a.chunk_samples = 1; a.error = nullptr;
-    a.mean = d_mean; a.action = d_action; a.adv = d_adv; a.logstd_off = net.logstd_off;
+    a.mean = d_mean; a.action = d_action; a.adv = d_adv; a.logstd_off = net.logstd_off; a.mean_out = d_mean_out;
     int rows = 0, rc = -1;
     switch (shape) {
         case SHAPE_ARM: rc = launch_shape<CfgArm, true>(a, st, &rows); break;

@@ -94,9 +94,10 @@ int  fused_fvp_accumulate(const NetDesc &net, const double *d_theta, const doubl
                           const int *d_done, const P2PComm *p2p, const int *stream_ready, size_t stream_chunk,
                           int *stream_error, cudaStream_t st, long long *launches);
 
+// d_mean == NULL: the kernel computes the network output itself and stores it to d_mean_out (if not NULL)
 int  fused_pg_accumulate(const NetDesc &net, const double *d_theta, const double *d_inv_std, const double *d_obs,
                          const double *d_mean, const double *d_action, const double *d_adv, size_t nsamples,
-                         double *d_partial, double *d_zsum, cudaStream_t st, long long *launches);
+                         double *d_partial, double *d_zsum, double *d_mean_out, cudaStream_t st, long long *launches);
 
 // ---- cg_kernels.cu ------------------------------------------------------------------------------------------------
 // p2p != NULL: the fixed-order row sum is pushed straight into every rank's slot (fused reduce + all-reduce send)

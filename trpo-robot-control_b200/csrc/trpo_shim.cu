@@ -702,16 +702,22 @@ extern "C" int trpo_ctx_get_info(const trpo_ctx *c, trpo_info *info) {
     return 0;
 }
 
-// policy gradient b = (1/N) sum_n grad (TRPO_Update.c:254-378) into c->d_b
-static int policy_gradient_device(trpo_ctx *c) {
+// policy gradient b = (1/N) sum_n grad (TRPO_Update.c:254-378) into c->d_b.
+// own_mean_out != NULL (fused path only): the seed uses the network's own output instead of the batch's Mean column and
+// the output is stored there -- prediction and gradient of the baseline objective in one pass.
+static bool fused_pg_eligible(const trpo_ctx *c) {
+    return fused_eligible(c->net) && c->path_req != TRPO_PATH_GEMM_CHAIN && c->precision == TRPO_PRECISION_FP64;
+}
+static int policy_gradient_device(trpo_ctx *c, double *own_mean_out = nullptr) {
     if (!c->d_obs || !c->d_mean || !c->d_action || !c->d_adv) return fail("policy gradient needs Mean/Action/Advantage in the batch");
     if (c->copy_inflight) { CU(cudaStreamWaitEvent(c->stream, c->ev_copy, 0)); c->copy_inflight = false; }
     c->stream_first_fvp = false;
     if (ensure_chain_scratch(c)) return -1;      // the line search's forward pass uses it in any case
-    const bool fused_pg = fused_eligible(c->net) && c->path_req != TRPO_PATH_GEMM_CHAIN && c->precision == TRPO_PRECISION_FP64;
+    const bool fused_pg = fused_pg_eligible(c);
+    if (own_mean_out && !fused_pg) return fail("internal: own-mean policy gradient needs the fused kernel");
     if (fused_pg) {
-        if (fused_pg_accumulate(c->net, c->d_theta, c->d_inv_std_model, c->d_obs, c->d_mean, c->d_action, c->d_adv, c->n_local,
-                                c->d_fused_partial, c->d_zsum, c->stream, &c->launches))
+        if (fused_pg_accumulate(c->net, c->d_theta, c->d_inv_std_model, c->d_obs, own_mean_out ? nullptr : c->d_mean, c->d_action,
+                                c->d_adv, c->n_local, c->d_fused_partial, c->d_zsum, own_mean_out, c->stream, &c->launches))
             return fail("fused policy-gradient launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     } else if (chain_accumulate(c->net, c->sc, CHAIN_PG, c->d_theta, nullptr, nullptr, c->d_obs, c->d_mean, c->d_action, c->d_adv,
                                 c->n_local, c->d_zsum, nullptr, nullptr, c->stream, &c->launches))
@@ -981,8 +987,18 @@ extern "C" double trpo_vf_evaluate(void *instance, const double *x, double *g, c
     if (!vf->target_set) { fail("no regression target: trpo_vf_set_target or trpo_vf_advantage first"); return -1.0; }
     trpo_ctx *net = vf->net;
     if (cudaSetDevice(net->device) != cudaSuccess) { fail("cudaSetDevice failed"); return -1.0; }
-    if (vf_forward(vf, x)) return -1.0;
-    if (policy_gradient_device(net)) return -1.0;                        // net->d_b = (1/N) sum_n dLoss_n/dx
+    // net->d_b = (1/N) sum_n dLoss_n/dx. Shapes the fused kernel takes: prediction and gradient in one pass over the
+    // batch; otherwise a forward GEMM chain for the prediction, then the chain's gradient pass.
+    if (fused_pg_eligible(net)) {
+        if (vf->n == 0) { fail("trpo_vf_bind_batch first"); return -1.0; }
+        memcpy(vf->h_theta, x, vf->npar * sizeof(double));
+        vf->h_theta[vf->npar] = 0.0;
+        if (trpo_ctx_set_model(net, vf->h_theta)) return -1.0;
+        if (policy_gradient_device(net, vf->d_pred)) return -1.0;
+    } else {
+        if (vf_forward(vf, x)) return -1.0;
+        if (policy_gradient_device(net)) return -1.0;
+    }
     launch_sqdiff(vf->d_pred, vf->d_target, nullptr, 1.0, vf->n, net->d_blockpart, net->d_scal, net->stream, &net->launches);
     if (allreduce_scalars(net, net->d_scal, 1)) return -1.0;
     if (cudaMemcpyAsync(vf->h_g, net->d_b, vf->npar * sizeof(double), cudaMemcpyDeviceToHost, net->stream) != cudaSuccess ||
