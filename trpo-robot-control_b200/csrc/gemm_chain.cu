@@ -553,7 +553,6 @@ inline int layer_slices(int tiles, int max_slices) {
 size_t chain_scratch_bytes(const NetDesc &net, int chunk, int nslices) {
     size_t maxL = 0, sumL = 0;
     for (int i = 1; i <= net.K; ++i) { sumL += net.L[i]; if ((size_t)net.L[i] > maxL) maxL = net.L[i]; }
-    if ((size_t)net.L[0] > maxL) maxL = net.L[0];
     return sizeof(double) * ((size_t)chunk * (sumL + 4 * maxL) + (size_t)nslices * net.P);
 }
 

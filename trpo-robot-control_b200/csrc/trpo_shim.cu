@@ -137,7 +137,8 @@ static int ensure_chain_scratch(trpo_ctx *c) {
     // chunk: several whole waves of CTAs per kernel so the fixed per-launch cost (first-tile latency, epilogue, tail) is
     // amortised; up to 512 MB of scratch. Wide layers are compute bound even from HBM (>= 100 flop/B), so the chunk does not
     // have to stay L2 resident.
-    size_t maxL = c->net.L[0], sumL = 0;
+    // the R{y} / gradient ping-pong buffers only ever hold layers 1..K (Ry0 = 0, no gradient w.r.t. the observations)
+    size_t maxL = 1, sumL = 0;
     for (int i = 1; i <= c->net.K; ++i) { sumL += c->net.L[i]; if ((size_t)c->net.L[i] > maxL) maxL = c->net.L[i]; }
     size_t per_sample = 8 * (sumL + 4 * maxL);
     // rows per chunk = 128 * m with m * (n-tiles of the widest layer) a multiple of the 148 SMs: whole waves of CTAs
