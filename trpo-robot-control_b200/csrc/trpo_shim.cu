@@ -134,8 +134,8 @@ extern "C" size_t trpo_num_params(const size_t *LayerSize, size_t NumLayers) {
 }
 
 static int ensure_chain_scratch(trpo_ctx *c) {
-    // chunk: several whole waves of CTAs per kernel so the fixed per-launch cost (first-tile latency, epilogue, tail) is
-    // amortised; up to 512 MB of scratch. Wide layers are compute bound even from HBM (>= 100 flop/B), so the chunk does not
+    // chunk: many whole waves of CTAs per kernel so the fixed per-launch cost (first-tile latency, epilogue, tail, ~10 us
+    // per kernel measured) is amortised; up to 4 GB of scratch (of 180 GB). Wide layers are compute bound even from HBM (>= 100 flop/B), so the chunk does not
     // have to stay L2 resident.
     // the R{y} / gradient ping-pong buffers only ever hold layers 1..K (Ry0 = 0, no gradient w.r.t. the observations)
     size_t maxL = 1, sumL = 0;
@@ -148,10 +148,15 @@ static int ensure_chain_scratch(trpo_ctx *c) {
     size_t gcd = 148, b = tiles_n;
     while (b) { size_t r = gcd % b; gcd = b; b = r; }
     const size_t unit = 128 * (148 / gcd);
-    size_t chunk = ((512u << 20) / per_sample / unit) * unit;
+    size_t chunk = (((size_t)4 << 30) / per_sample / unit) * unit;
     if (chunk < unit) chunk = unit;
-    if (chunk > 8 * unit) chunk = 8 * unit;
-    if (chunk > 131072) chunk = (131072 / unit) * unit;
+    if (chunk > 64 * unit) chunk = 64 * unit;
+    if (chunk > 1048576) chunk = (1048576 / unit) * unit;
+    {   // the GEMM kernels index rows * width with 32-bit ints
+        size_t widest = c->net.L[0] + 1;
+        for (int i = 1; i <= c->net.K; ++i) if ((size_t)c->net.L[i] + 1 > widest) widest = c->net.L[i] + 1;
+        while (chunk > unit && chunk * widest >= ((size_t)1 << 31)) chunk -= unit;
+    }
     if (c->n_local && chunk > ((c->n_local + 127) / 128) * 128) chunk = ((c->n_local + 127) / 128) * 128;
     int nslices = 148;
     if ((size_t)nslices * 16 > chunk) nslices = (int)(chunk / 16);
