@@ -332,7 +332,7 @@ inline int layer_slices(int tiles, int max_slices) {
 }  // namespace
 
 size_t chain_f32_scratch_floats(const NetDesc &net, int chunk, int nslices) {
-    size_t maxL = net.L[0], sumL = 0;
+    size_t maxL = 1, sumL = 0;
     for (int i = 1; i <= net.K; ++i) { sumL += net.L[i]; if ((size_t)net.L[i] > maxL) maxL = net.L[i]; }
     return (size_t)chunk * (sumL + 4 * maxL) + (size_t)nslices * net.P + 2 * (size_t)net.P + 64;
 }

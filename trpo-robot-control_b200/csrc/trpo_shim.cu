@@ -521,7 +521,7 @@ extern "C" double trpo_ctx_kernel_time_ms(trpo_ctx *c, int *launches) {
 
 // un-normalised FVP sum of the local shard into d_zsum, then the cross-GPU sum
 static int ensure_f32_scratch(trpo_ctx *c) {
-    size_t maxL = c->net.L[0], sumL = 0, maxH = 1;
+    size_t maxL = 1, sumL = 0, maxH = 1;           // same sizing rules as ensure_chain_scratch
     for (int i = 1; i <= c->net.K; ++i) {
         sumL += c->net.L[i];
         if ((size_t)c->net.L[i] > maxL) maxL = c->net.L[i];
@@ -532,10 +532,15 @@ static int ensure_f32_scratch(trpo_ctx *c) {
     size_t gcd = 148, b = tiles_n;
     while (b) { size_t r = gcd % b; gcd = b; b = r; }
     const size_t unit = 128 * (148 / gcd);
-    size_t chunk = ((512u << 20) / per_sample / unit) * unit;
+    size_t chunk = (((size_t)2 << 30) / per_sample / unit) * unit;
     if (chunk < unit) chunk = unit;
-    if (chunk > 8 * unit) chunk = 8 * unit;
-    if (chunk > 131072) chunk = (131072 / unit) * unit;
+    if (chunk > 64 * unit) chunk = 64 * unit;
+    if (chunk > 1048576) chunk = (1048576 / unit) * unit;
+    {
+        size_t widest = c->net.L[0] + 1;
+        for (int i = 1; i <= c->net.K; ++i) if ((size_t)c->net.L[i] + 1 > widest) widest = c->net.L[i] + 1;
+        while (chunk > unit && chunk * widest >= ((size_t)1 << 31)) chunk -= unit;
+    }
     if (c->n_local && chunk > ((c->n_local + 127) / 128) * 128) chunk = ((c->n_local + 127) / 128) * 128;
     int nslices = 148;
     if ((size_t)nslices * 32 > chunk) nslices = (int)(chunk / 32);
