@@ -187,6 +187,65 @@ def run_reference_arm(args, pkg):
 
 
 # ------------------------------------------------------------------------------------------------------------------
+def measure_loop_body(pkg, m, steps, torch):
+    """SURVEY.md section 8 rows f-3/f-4 beside the headline: everything the reference's training loop does between the
+    rollouts and the next rollouts (TRPO_Lightweight.c:541-1461) on the headline batch, through the host-buffer C-ABI
+    with pinned HOST arrays: stage the rollouts, baseline prediction + return + GAE + standardisation, 30 baseline
+    objective/gradient evaluations (what a 25-iteration L-BFGS fit asks for; the L-BFGS vector work itself is the
+    caller's libLBFGS and not in here) and the TRPO update. Wall clock, every call synchronises."""
+    layers, ac, n = m["layers"], m["ac"], m["n_total"]
+    ep_len = 1000
+    num_ep = n // ep_len
+    n = num_ep * ep_len
+    b = m["batch"]
+    vf_layers = [layers[0] + 1] + layers[1:-1] + [1]
+    npar = sum(vf_layers[i] * vf_layers[i + 1] + vf_layers[i + 1] for i in range(len(vf_layers) - 1))
+    x = np.zeros((npar + 15) // 16 * 16)
+    x[:npar] = pkg.synth.make_model(vf_layers, 92)[:npar]
+    rng = np.random.default_rng(5)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    obs, mean, act = pin(b["Observ"][:n]), pin(b["Mean"][:n]), pin(b["Action"][:n])
+    rew = pin(-np.abs(rng.standard_normal(n)) * 3)
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    with pkg.Context(layers, ac) as ctx, pkg.ValueFunction(ctx, vf_layers, ac) as vf:
+        ctx.set_model(m["theta"])
+        parts = {"stage": 0.0, "advantage": 0.0, "objective_x30": 0.0, "update": 0.0}
+
+        def step(record):
+            t0 = time.perf_counter()
+            ctx.set_rollout(num_ep, ep_len, obs, b["Std"], mean, act, rew)
+            ctx.sync()
+            t1 = time.perf_counter()
+            vf.advantage(x, n, 0.995, 0.98, fetch=False)
+            t2 = time.perf_counter()
+            for _ in range(30):
+                vf.evaluate(x)
+            t3 = time.perf_counter()
+            saved = os.dup(1)                      # trpo_ctx_update prints nothing, the C host entry points may
+            os.dup2(devnull, 1)
+            try:
+                ctx.update(DAMPING)
+            finally:
+                os.dup2(saved, 1)
+                os.close(saved)
+            t4 = time.perf_counter()
+            if record:
+                for k, v in zip(parts, (t1 - t0, t2 - t1, t3 - t2, t4 - t3)):
+                    parts[k] += v * 1e3 / steps
+        step(False)
+        l0 = ctx.launch_count()
+        for _ in range(steps):
+            step(True)
+        launches = ctx.launch_count() - l0
+    os.close(devnull)
+    total = sum(parts.values())
+    return {"workload": f"{'-'.join(map(str, layers))} policy + {'-'.join(map(str, vf_layers))} baseline, {n} steps "
+                        f"({num_ep} episodes x {ep_len}), pinned host buffers",
+            "ms_per_iteration": total, "ms": parts, "steps_per_sec": n / (total * 1e-3),
+            "h2d_bytes_per_iteration": n * (layers[0] + 2 * layers[-1] + 2) * 8,
+            "policy_ctx_launches_per_iteration": launches / steps}
+
+
 def run_gpu_arm(args, pkg):
     import torch
     import torch.distributed as dist
@@ -348,6 +407,9 @@ def run_gpu_arm(args, pkg):
             also["arm_50k"]["cpu_baseline"] = {"value": rate, "unit": "samples/s", "cores": 1, "kind": kind,
                                                "sample": f"one 10-iteration CG() of the unmodified reference on all "
                                                          f"{a['n_total']} states ({t_step:.1f} s), NumThreads=1"}
+
+        if world == 1:
+            also["loop_body_1m"] = measure_loop_body(pkg, m, args.steps, torch)
 
     if rank == 0:
         layers, n_total, P = m["layers"], m["n_total"], m["P"]

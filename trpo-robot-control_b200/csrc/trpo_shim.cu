@@ -297,6 +297,7 @@ extern "C" int trpo_ctx_get_path(const trpo_ctx *c) { return c ? c->path_used : 
 extern "C" int trpo_ctx_sync(trpo_ctx *c) {
     if (!c) return fail("null context");
     CU(cudaSetDevice(c->device));
+    if (c->copy_inflight) CU(cudaEventSynchronize(c->ev_copy));      // a streamed batch copy counts as work of this context
     CU(cudaStreamSynchronize(c->stream));
     return 0;
 }
