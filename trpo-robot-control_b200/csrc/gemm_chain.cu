@@ -95,6 +95,37 @@ __device__ __forceinline__ void load_a_transposed(double *As, const double *Y, i
         else cp_async8(&As[m * RSA + k], in ? &Y[(size_t)gs * M0 + gm] : Y, in ? 8 : 0);
     }
 }
+// The same operand in its NATURAL orientation: An[k][m] = Yprev[(s0+k)*M0 + m0+m] (1.0 for m == M0), row stride RSN.
+// No transposition on the way in: 16-byte copies along m (8 per thread and stage instead of 16 element copies), and the
+// m8n8k4 A fragment (lane (g,t) holds A[m=g][k=t]) reads An[(4q+t)*RSN + m] -- per half warp t*RSN + g covers 16
+// distinct banks because RSN % 16 == 4.
+constexpr int RSN = BM + 4;
+template <int BK>
+__device__ __forceinline__ void load_a_natural(double *An, const double *Y, int s_end, int M0, int m0, int s0, int tid) {
+    if (Y != nullptr && (M0 & 1) == 0 && (reinterpret_cast<uintptr_t>(Y) & 15) == 0) {
+#pragma unroll
+        for (int it = 0; it < BK * BM / 2 / NT; ++it) {
+            const int idx = tid + it * NT, k = idx >> 6, m = (idx & 63) * 2;
+            const int gm = m0 + m, gs = s0 + k;
+            if (gm == M0) {                                  // bias-gradient column of the augmented matrix
+                An[k * RSN + m] = gs < s_end ? 1.0 : 0.0;
+                An[k * RSN + m + 1] = 0.0;
+            } else {
+                const bool in = gm < M0 && gs < s_end;
+                cp_async16(&An[k * RSN + m], in ? &Y[(size_t)gs * M0 + gm] : Y, in ? 16 : 0);
+            }
+        }
+        return;
+    }
+#pragma unroll 2
+    for (int it = 0; it < BK * BM / NT; ++it) {
+        const int idx = tid + it * NT, k = idx >> 7, m = idx & 127;
+        const int gm = m0 + m, gs = s0 + k;
+        const bool in = Y != nullptr && gm < M0 && gs < s_end;
+        if (gm == M0) An[k * RSN + m] = gs < s_end ? 1.0 : 0.0;
+        else cp_async8(&An[k * RSN + m], in ? &Y[(size_t)gs * M0 + gm] : Y, in ? 8 : 0);
+    }
+}
 // B tile from a row-major matrix M[kdim x N]: Bs[k][n] = M[(k0+k)*N + n0+n]
 template <int BK, int NTH>
 __device__ __forceinline__ void load_b_rowmajor(double *Bs, const double *M, int kdim, int N, int k0, int n0, int tid) {
@@ -133,7 +164,7 @@ __device__ __forceinline__ void load_b_transposed(double *Bs, const double *W, i
 }
 
 // one k-step (16) of a warp's 32 x 32 sub-tile: acc += A*B [, racc += RA*B + A*VB]
-template <bool DUAL, bool HAS_RA, int BK, int NJ>
+template <bool DUAL, bool HAS_RA, int BK, int NJ, bool ANAT = false>
 __device__ __forceinline__ void mma_stage(double (&acc)[4][NJ][2], double (&racc)[4][NJ][2], const double *As,
                                           const double *RAs, const double *Bs, const double *VBs, int wm, int wn, int g, int t) {
     constexpr int RSA = Tile<BK>::RSA;
@@ -142,7 +173,7 @@ __device__ __forceinline__ void mma_stage(double (&acc)[4][NJ][2], double (&racc
         double a[4], ra[4], b[NJ], vb[NJ];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            a[i] = As[(32 * wm + 8 * i + g) * RSA + 4 * q + t];
+            a[i] = ANAT ? As[(4 * q + t) * RSN + 32 * wm + 8 * i + g] : As[(32 * wm + 8 * i + g) * RSA + 4 * q + t];
             if (DUAL && HAS_RA) ra[i] = RAs[(32 * wm + 8 * i + g) * RSA + 4 * q + t];
         }
 #pragma unroll
@@ -329,8 +360,9 @@ __global__ void __launch_bounds__(NT, 2) k_chain_outer(const double *__restrict_
                                                        const int *__restrict__ done) {
     if (done && *done) return;
     extern __shared__ __align__(16) double smem[];
-    constexpr int BK = BK_SINGLE, A_TILE = Tile<BK>::A, B_TILE = Tile<BK>::B;
+    constexpr int BK = BK_SINGLE, A_TILE = BK * RSN, B_TILE = Tile<BK>::B;       // A in its natural orientation
     constexpr int STAGE = A_TILE + B_TILE;
+    static_assert(A_TILE <= Tile<BK>::A && (A_TILE & 1) == 0, "natural A tile must fit the single-product stage and keep B 16-byte aligned");
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3, wm = w >> 1, wn = w & 1;
     const int m0 = (blockIdx.x / tiles_n) * BM, n0 = (blockIdx.x % tiles_n) * BN;
     const int slice = blockIdx.y;
@@ -340,7 +372,7 @@ __global__ void __launch_bounds__(NT, 2) k_chain_outer(const double *__restrict_
     const int nk = s1 > s0 ? (s1 - s0 + BK - 1) / BK : 0;
     auto load = [&](int st, int ks) {
         double *As = smem + st * STAGE, *Bs = As + A_TILE;
-        load_a_transposed<BK>(As, Yprev, s1, M0, m0, ks, tid);
+        load_a_natural<BK>(As, Yprev, s1, M0, m0, ks, tid);
         load_b_rowmajor<BK, NT>(Bs, G + (size_t)ks * N, s1 - ks, N, 0, n0, tid);
         cp_async_commit();
     };
@@ -350,7 +382,7 @@ __global__ void __launch_bounds__(NT, 2) k_chain_outer(const double *__restrict_
         __syncthreads();
         if (it + 1 < nk) load((it + 1) & 1, s0 + (it + 1) * BK);
         const double *As = smem + (it & 1) * STAGE, *Bs = As + A_TILE;
-        mma_stage<false, false, BK, 4>(acc, dummy, As, nullptr, Bs, nullptr, wm, wn, g, t);
+        mma_stage<false, false, BK, 4, true>(acc, dummy, As, nullptr, Bs, nullptr, wm, wn, g, t);
     }
     double *out = partial + (size_t)slice * P + out_off;
 #pragma unroll
