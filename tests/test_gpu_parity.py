@@ -294,7 +294,10 @@ def test_fp32_mode_humanoid_width(pkg, oracle):
 
 @pytest.mark.parametrize("layers,ac", [([5, 3], "ll"), ([9, 4], "lt"), ([6, 7, 8, 9, 10, 3], "ltstol"),
                                        ([20, 64, 64, 8], "lttl"), ([3, 130, 70, 2], "ltsl"),
-                                       ([11, 32, 32, 3], "lttl"), ([32, 24, 32, 8], "lsto"), ([16, 16, 16, 8], "ltto")])
+                                       ([11, 32, 32, 3], "lttl"), ([32, 24, 32, 8], "lsto"), ([16, 16, 16, 8], "ltto"),
+                                       # widths that are whole tiles / whole k-steps: bias as accumulator start value
+                                       # (forward) and as column sums (outer product) instead of an augmented row
+                                       ([128, 256, 128, 5], "ltsl"), ([32, 128, 3], "ltl")])
 def test_unusual_depths_and_widths(pkg, oracle, layers, ac):
     """NumLayers 2 and 6, widths that straddle the tile sizes, shapes at the fused kernel's eligibility limits."""
     seed = 1000 + sum(layers)

@@ -214,7 +214,22 @@ __global__ void __launch_bounds__(DUAL ? 512 : NT, DUAL ? 1 : 2) k_chain_fwd(con
     double acc[4][NJ][2] = {}, racc[4][NJ][2] = {};
     __shared__ double exp2_tab[64];
     load_exp2_table(exp2_tab);                          // visible after the first barrier of the k loop
-    const int nk = (Kd + 1 + BK - 1) / BK;              // augmented contraction length Kd + 1 (bias row)
+    // augmented contraction length Kd + 1 (bias row) -- unless Kd is a whole number of k-steps: then the bias row would cost
+    // a k-step of its own (17 instead of 16 for a 256-wide layer), so the accumulators start from [B ; VB] instead
+    const bool bias_init = (Kd % BK) == 0;
+    const int nk = bias_init ? Kd / BK : (Kd + 1 + BK - 1) / BK;
+    if (bias_init) {
+#pragma unroll
+        for (int j = 0; j < NJ; ++j)
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int gn = n0 + 8 * NJ * wn + 8 * j + 2 * t + r;
+                const double bw = gn < N ? W[(size_t)Kd * N + gn] : 0.0;
+                const double bv = (DUAL && gn < N) ? VW[(size_t)Kd * N + gn] : 0.0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { acc[i][j][r] = bw; racc[i][j][r] = bv; }
+            }
+    }
     auto stage_ptrs = [&](int st, double *&As, double *&RAs, double *&Bs, double *&VBs) {
         double *p = smem + st * STAGE;
         As = p; p += A_TILE;
@@ -354,10 +369,13 @@ __global__ void __launch_bounds__(NT, 2) k_chain_bwd(const double *__restrict__ 
 }
 
 // outer: out[slice][m*N + n] (+)= sum_{s in slice} [Yprev,1][s][m] * G[s][n],  m in [0, M0]  (row M0 = bias gradient)
+// bias_colsum: the grid's m-tiles cover rows [0, M0) only (M0 a multiple of the tile height: a 257th row would cost a whole
+// extra 128-row tile) and the bias-gradient row = column sums of G is formed by the m-tile-0 CTAs from the B tiles they
+// stage anyway (fixed order: 4 k-phases per column, then the phases).
 __global__ void __launch_bounds__(NT, 2) k_chain_outer(const double *__restrict__ Yprev, const double *__restrict__ G,
                                                        int rows, int M0, int N, int per_slice, int tiles_n,
                                                        double *__restrict__ partial, int P, int out_off, int accumulate,
-                                                       const int *__restrict__ done) {
+                                                       int bias_colsum, const int *__restrict__ done) {
     if (done && *done) return;
     extern __shared__ __align__(16) double smem[];
     constexpr int BK = BK_SINGLE, A_TILE = BK * RSN, B_TILE = Tile<BK>::B;       // A in its natural orientation
@@ -369,6 +387,8 @@ __global__ void __launch_bounds__(NT, 2) k_chain_outer(const double *__restrict_
     const int s0 = slice * per_slice;
     const int s1 = min(rows, s0 + per_slice);
     double acc[4][4][2] = {}, dummy[4][4][2];
+    const bool colsum = bias_colsum && m0 == 0;
+    double bsum = 0.0;
     const int nk = s1 > s0 ? (s1 - s0 + BK - 1) / BK : 0;
     auto load = [&](int st, int ks) {
         double *As = smem + st * STAGE, *Bs = As + A_TILE;
@@ -383,8 +403,23 @@ __global__ void __launch_bounds__(NT, 2) k_chain_outer(const double *__restrict_
         if (it + 1 < nk) load((it + 1) & 1, s0 + (it + 1) * BK);
         const double *As = smem + (it & 1) * STAGE, *Bs = As + A_TILE;
         mma_stage<false, false, BK, 4, true>(acc, dummy, As, nullptr, Bs, nullptr, wm, wn, g, t);
+        if (colsum) {
+#pragma unroll
+            for (int kk = 0; kk < BK / 4; ++kk) bsum += Bs[(4 * kk + (tid >> 6)) * RSB + (tid & 63)];
+        }
     }
     double *out = partial + (size_t)slice * P + out_off;
+    if (colsum) {
+        __syncthreads();                                   // everybody is done with the stage buffers
+        smem[tid] = bsum;
+        __syncthreads();
+        const int gn = n0 + tid;
+        if (tid < BN && gn < N) {
+            const double sum = ((smem[tid] + smem[tid + 64]) + smem[tid + 128]) + smem[tid + 192];
+            const size_t o = (size_t)M0 * N + gn;
+            out[o] = accumulate ? out[o] + sum : sum;
+        }
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int gm = m0 + 32 * wm + 8 * i + g;
@@ -637,7 +672,7 @@ int chain_accumulate(const NetDesc &net, const ChainScratch &sc, ChainMode mode,
             const int tl = cdiv(1, BM) * cdiv(A, BN), nsl = layer_slices(tl, sc.nslices);
             dim3 g1(tl, nsl);
             k_chain_outer<<<g1, NT, SMEM_SINGLE, st>>>(nullptr, sc.RY[0], rows, 0, A, cdiv(cdiv(rows, nsl), BK_SINGLE) * BK_SINGLE, cdiv(A, BN),
-                                             sc.partial, net.P, net.logstd_off, accumulate, d_done);
+                                             sc.partial, net.P, net.logstd_off, accumulate, 0, d_done);
             ++*launches;
         }
         if (tail) {
@@ -655,11 +690,12 @@ int chain_accumulate(const NetDesc &net, const ChainScratch &sc, ChainMode mode,
         for (int i = K; i >= 1; --i) {
             const double *Yprev = (i == 1) ? d_obs + c0 * net.L[0] : sc.Y[i - 1];
             const int M0 = net.L[i - 1], N = net.L[i];
-            const int tiles_m = cdiv(M0 + 1, BM), tiles_n = cdiv(N, BN);
+            const int bias_colsum = (M0 % BM) == 0;      // the bias row would open a tile of its own: column sums instead
+            const int tiles_m = bias_colsum ? M0 / BM : cdiv(M0 + 1, BM), tiles_n = cdiv(N, BN);
             const int ns = layer_slices(tiles_m * tiles_n, sc.nslices);
             dim3 go(tiles_m * tiles_n, ns);
             k_chain_outer<<<go, NT, SMEM_SINGLE, st>>>(Yprev, sc.G[i & 1], rows, M0, N, cdiv(cdiv(rows, ns), BK_SINGLE) * BK_SINGLE, tiles_n,
-                                             sc.partial, net.P, net.w_off[i - 1], accumulate, d_done);
+                                             sc.partial, net.P, net.w_off[i - 1], accumulate, bias_colsum, d_done);
             ++*launches;
             if (i > 1 && !(tail && i == K)) {
                 dim3 gb(cdiv(M0, BN), cdiv(rows, BM));
