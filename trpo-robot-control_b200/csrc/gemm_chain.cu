@@ -369,8 +369,8 @@ __global__ void __launch_bounds__(NT, 2) k_chain_bwd(const double *__restrict__ 
 }
 
 // outer: out[slice][m*N + n] (+)= sum_{s in slice} [Yprev,1][s][m] * G[s][n],  m in [0, M0]  (row M0 = bias gradient)
-// bias_colsum: the grid's m-tiles cover rows [0, M0) only (M0 a multiple of the tile height: a 257th row would cost a whole
-// extra 128-row tile) and the bias-gradient row = column sums of G is formed by the m-tile-0 CTAs from the B tiles they
+// bias_colsum: the grid's m-tiles cover rows [0, M0) only (M0 a multiple of the 32-row warp tile: a 257th row would cost a
+// whole extra 128-row CTA tile, a 65th one a third warp row) and the bias-gradient row = column sums of G is formed by the m-tile-0 CTAs from the B tiles they
 // stage anyway (fixed order: 4 k-phases per column, then the phases).
 __global__ void __launch_bounds__(NT, 2) k_chain_outer(const double *__restrict__ Yprev, const double *__restrict__ G,
                                                        int rows, int M0, int N, int per_slice, int tiles_n,
@@ -389,6 +389,9 @@ __global__ void __launch_bounds__(NT, 2) k_chain_outer(const double *__restrict_
     double acc[4][4][2] = {}, dummy[4][4][2];
     const bool colsum = bias_colsum && m0 == 0;
     double bsum = 0.0;
+    // warps whose 32 x 32 sub-tile lies entirely outside the matrix (64-wide layers in a 128-row tile, a 17-column action
+    // layer in a 64-column tile) issue no DMMAs; they still help with the copies
+    const bool active = m0 + 32 * wm < M0 + (bias_colsum ? 0 : 1) && n0 + 32 * wn < N;
     const int nk = s1 > s0 ? (s1 - s0 + BK - 1) / BK : 0;
     auto load = [&](int st, int ks) {
         double *As = smem + st * STAGE, *Bs = As + A_TILE;
@@ -402,7 +405,7 @@ __global__ void __launch_bounds__(NT, 2) k_chain_outer(const double *__restrict_
         __syncthreads();
         if (it + 1 < nk) load((it + 1) & 1, s0 + (it + 1) * BK);
         const double *As = smem + (it & 1) * STAGE, *Bs = As + A_TILE;
-        mma_stage<false, false, BK, 4, true>(acc, dummy, As, nullptr, Bs, nullptr, wm, wn, g, t);
+        if (active) mma_stage<false, false, BK, 4, true>(acc, dummy, As, nullptr, Bs, nullptr, wm, wn, g, t);
         if (colsum) {
 #pragma unroll
             for (int kk = 0; kk < BK / 4; ++kk) bsum += Bs[(4 * kk + (tid >> 6)) * RSB + (tid & 63)];
@@ -423,7 +426,7 @@ __global__ void __launch_bounds__(NT, 2) k_chain_outer(const double *__restrict_
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int gm = m0 + 32 * wm + 8 * i + g;
-        if (gm > M0) continue;
+        if (gm >= M0 + (bias_colsum ? 0 : 1)) continue;      // with bias_colsum the row M0 belongs to the column sums above
 #pragma unroll
         for (int j = 0; j < 4; ++j)
 #pragma unroll
@@ -690,8 +693,9 @@ int chain_accumulate(const NetDesc &net, const ChainScratch &sc, ChainMode mode,
         for (int i = K; i >= 1; --i) {
             const double *Yprev = (i == 1) ? d_obs + c0 * net.L[0] : sc.Y[i - 1];
             const int M0 = net.L[i - 1], N = net.L[i];
-            const int bias_colsum = (M0 % BM) == 0;      // the bias row would open a tile of its own: column sums instead
-            const int tiles_m = bias_colsum ? M0 / BM : cdiv(M0 + 1, BM), tiles_n = cdiv(N, BN);
+            // the bias row would open a 32-row warp tile (or a whole 128-row CTA tile) of its own: column sums instead
+            const int bias_colsum = (M0 % 32) == 0;
+            const int tiles_m = bias_colsum ? cdiv(M0, BM) : cdiv(M0 + 1, BM), tiles_n = cdiv(N, BN);
             const int ns = layer_slices(tiles_m * tiles_n, sc.nslices);
             dim3 go(tiles_m * tiles_n, ns);
             k_chain_outer<<<go, NT, SMEM_SINGLE, st>>>(Yprev, sc.G[i & 1], rows, M0, N, cdiv(cdiv(rows, ns), BK_SINGLE) * BK_SINGLE, tiles_n,
