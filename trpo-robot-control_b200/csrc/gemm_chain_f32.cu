@@ -154,7 +154,21 @@ __global__ void __launch_bounds__(512, 1) k_fwd(const float *__restrict__ Yin, c
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3, wm = w / WN, wn = w % WN;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     float acc[2][NJ][4] = {}, racc[2][NJ][4] = {};
-    const int nk = (Kd + 1 + BK - 1) / BK;
+    // as in gemm_chain.cu: a width that is a whole number of k-steps takes its bias as the accumulators' start value
+    const bool bias_init = (Kd % BK) == 0;
+    const int nk = bias_init ? Kd / BK : (Kd + 1 + BK - 1) / BK;
+    if (bias_init) {
+#pragma unroll
+        for (int j = 0; j < NJ; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int gn = n0 + 8 * NJ * wn + 8 * j + 2 * t + (e & 1);
+                const float bw = gn < N ? W[(size_t)Kd * N + gn] : 0.0f;
+                const float bv = (DUAL && gn < N) ? VW[(size_t)Kd * N + gn] : 0.0f;
+#pragma unroll
+                for (int i = 0; i < 2; ++i) { acc[i][j][e] = bw; racc[i][j][e] = bv; }
+            }
+    }
     auto stage_ptrs = [&](int st, float *&As, float *&RAs, float *&Bs, float *&VBs) {
         float *p = smem_f + st * STAGE;
         As = p; p += A_TILE;
@@ -242,7 +256,7 @@ __global__ void __launch_bounds__(NT, 2) k_bwd(const float *__restrict__ Gin, co
 __global__ void __launch_bounds__(NT, 2) k_outer(const float *__restrict__ Yprev, const float *__restrict__ G,
                                                  int rows, int M0, int N, int per_slice, int tiles_n,
                                                  float *__restrict__ partial, int P, int out_off, int accumulate,
-                                                 const int *__restrict__ done) {
+                                                 int bias_colsum, const int *__restrict__ done) {
     if (done && *done) return;
     extern __shared__ __align__(16) float smem_f[];
     constexpr int STAGE = A_TILE + B_TILE;
@@ -252,6 +266,10 @@ __global__ void __launch_bounds__(NT, 2) k_outer(const float *__restrict__ Yprev
     const int s0 = slice * per_slice;
     const int s1 = min(rows, s0 + per_slice);
     float acc[2][4][4] = {}, dummy[2][4][4];
+    // bias gradient as column sums of the staged G tiles, idle warps outside the matrix: see gemm_chain.cu k_chain_outer
+    const bool colsum = bias_colsum && m0 == 0;
+    const bool active = m0 + 32 * wm < M0 + (bias_colsum ? 0 : 1) && n0 + 32 * wn < N;
+    float bsum = 0.0f;
     const int nk = s1 > s0 ? (s1 - s0 + BK - 1) / BK : 0;
     auto load = [&](int st, int ks) {
         float *As = smem_f + st * STAGE, *Bs = As + A_TILE;
@@ -265,10 +283,24 @@ __global__ void __launch_bounds__(NT, 2) k_outer(const float *__restrict__ Yprev
         else cp_wait<0>();
         __syncthreads();
         const float *As = smem_f + (it & 1) * STAGE, *Bs = As + A_TILE;
-        mma_stage<false, false, 4>(acc, dummy, As, nullptr, Bs, nullptr, wm, wn, g, t);
+        if (active) mma_stage<false, false, 4>(acc, dummy, As, nullptr, Bs, nullptr, wm, wn, g, t);
+        if (colsum) {
+#pragma unroll
+            for (int kk = 0; kk < BK / 4; ++kk) bsum += Bs[(4 * kk + (tid >> 6)) * RSB + (tid & 63)];
+        }
         __syncthreads();
     }
     float *out = partial + (size_t)slice * P + out_off;
+    if (colsum) {
+        smem_f[tid] = bsum;
+        __syncthreads();
+        const int gn = n0 + tid;
+        if (tid < BN && gn < N) {
+            const float sum = ((smem_f[tid] + smem_f[tid + 64]) + smem_f[tid + 128]) + smem_f[tid + 192];
+            const size_t o = (size_t)M0 * N + gn;
+            out[o] = accumulate ? out[o] + sum : sum;
+        }
+    }
 #pragma unroll
     for (int i = 0; i < 2; ++i)
 #pragma unroll
@@ -276,7 +308,7 @@ __global__ void __launch_bounds__(NT, 2) k_outer(const float *__restrict__ Yprev
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const int gm = m0 + 32 * wm + 16 * i + g + 8 * (e >> 1), gn = n0 + 32 * wn + 8 * j + 2 * t + (e & 1);
-                if (gm > M0 || gn >= N) continue;
+                if (gm >= M0 + (bias_colsum ? 0 : 1) || gn >= N) continue;
                 const size_t o = (size_t)gm * N + gn;
                 out[o] = accumulate ? out[o] + acc[i][j][e] : acc[i][j][e];
             }
@@ -373,11 +405,12 @@ int chain_f32_accumulate(const NetDesc &net, const ChainScratchF32 &sc, const fl
         for (int i = K; i >= 1; --i) {
             const float *Yprev = (i == 1) ? f_obs + c0 * net.L[0] : sc.Y[i - 1];
             const int M0 = net.L[i - 1], N = net.L[i];
-            const int tiles_m = cdiv(M0 + 1, BM), tiles_n = cdiv(N, BN);
+            const int bias_colsum = (M0 % 32) == 0;
+            const int tiles_m = bias_colsum ? cdiv(M0, BM) : cdiv(M0 + 1, BM), tiles_n = cdiv(N, BN);
             const int ns = layer_slices(tiles_m * tiles_n, sc.nslices);
             dim3 go(tiles_m * tiles_n, ns);
             k_outer<<<go, NT, SMEM_SINGLE, st>>>(Yprev, sc.G[i & 1], rows, M0, N, cdiv(cdiv(rows, ns), BK) * BK, tiles_n,
-                                                sc.partial, net.P, net.w_off[i - 1], accumulate, d_done);
+                                                sc.partial, net.P, net.w_off[i - 1], accumulate, bias_colsum, d_done);
             ++*launches;
             if (i > 1) {
                 dim3 gb(cdiv(M0, BN), cdiv(rows, BM));
