@@ -162,6 +162,17 @@ int     trpo_memcpy_d2h(double *dst_host, const double *src_dev, size_t n_double
 int trpo_ctx_set_rollout(trpo_ctx *ctx, size_t NumEpBatch, size_t EpLen, const double *Observ, const double *Std,
                          const double *Mean, const double *Action, const double *Reward);
 
+/* Rollout PRODUCER on the device: the reference's lightweight arm simulator (TRPO_Lightweight.c:349-540; the role
+ * TRPO_RunLightweight plays on the FPGA, TRPO_Lightweight_FPGA.c:548-556) driven by the model last given to
+ * trpo_ctx_set_model, one warp per episode; Observ / Mean / Action / Reward land in the context's batch exactly as after
+ * trpo_ctx_set_rollout, Std = exp(LogStd). RandDraws (host) holds the raw rand() values in the reference's order --
+ * per episode 3 (object position), then per step 2 per action component: NumEpBatch * (3 + 6 * EpLen) ints -- which makes
+ * the batch the one the reference would have produced from the same stream; NULL selects a counter-based generator
+ * seeded by Seed. The policy must be 15-...-3 with hidden widths <= 32. */
+int trpo_ctx_rollout_arm(trpo_ctx *ctx, size_t NumEpBatch, size_t EpLen, const int *RandDraws, unsigned long long Seed);
+/* Copy the staged rollout back to the host (any pointer may be NULL). */
+int trpo_ctx_get_rollout(trpo_ctx *ctx, double *Observ, double *Mean, double *Action, double *Reward);
+
 /* Value-function ("baseline") network on the policy context's device and stream. LayerSizeBase[0] must be
  * ObservSpaceDim + 1 (observation followed by step/EpLen), the last layer 1 (TRPO_Lightweight.c:36, TRPO_Baseline.c:98-103).
  * Its parameter vector x is [W0,B0,...] WITHOUT a LogStd tail: trpo_vf_num_params == NumParamsCalc(LayerSizeBase) - 1

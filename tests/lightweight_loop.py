@@ -39,6 +39,13 @@ class OracleBackend:
         return out
 
 
+def libc_rand_draws(n):
+    """The next n values of the C library's rand() stream (what the reference's simulator would consume)."""
+    libc = C.CDLL(None)
+    libc.rand.restype = C.c_int
+    return np.fromiter((libc.rand() for _ in range(n)), dtype=np.int32, count=n)
+
+
 def run(backend, oracle, reference, theta0, x_base0, iters, damping=0.1, seed=0, trace=None):
     """Returns the policy parameters after ``iters`` iterations (what TRPO_Lightweight writes to its result file)."""
     C.CDLL(None).srand(seed)                                           # TRPO_Lightweight.c:66
@@ -46,7 +53,10 @@ def run(backend, oracle, reference, theta0, x_base0, iters, damping=0.1, seed=0,
     x = np.zeros(PADDED)
     x[:len(x_base0)] = x_base0
     for it in range(iters):
-        batch = oracle.arm_rollout(ARM_LAYERS, ARM_ACFUNC, theta, NUM_EP, EP_LEN)
+        if hasattr(backend, "rollout"):                                # device-side producer fed with the same rand() stream
+            batch = backend.rollout(theta)
+        else:
+            batch = oracle.arm_rollout(ARM_LAYERS, ARM_ACFUNC, theta, NUM_EP, EP_LEN)
         ret, adv = backend.advantage(batch, x)
         x, fx, rc = reference.lbfgs(x, backend.vf_callback(batch, ret), max_iterations=25)
         theta = backend.update(theta, batch, adv, damping)

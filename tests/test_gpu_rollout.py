@@ -195,6 +195,87 @@ def test_training_loop_body_matches_the_reference_result_files(pkg, oracle, gold
         assert e < 1e-8, (i, e)
 
 
+def test_rollout_producer_matches_the_reference_batch(pkg, gold):
+    """trpo_ctx_rollout_arm fed with the rand() stream of srand(0) reproduces the first batch of the reference's run
+    (tests/golden/lightweight.npz holds the oracle's copy, pinned by the result files)."""
+    import ctypes as C
+    C.CDLL(None).srand(0)
+    draws = lw.libc_rand_draws(lw.NUM_EP * (3 + 6 * lw.EP_LEN))
+    N = lw.NUM_EP * lw.EP_LEN
+    with pkg.Context(lw.ARM_LAYERS, lw.ARM_ACFUNC) as ctx:
+        ctx.set_model(gold["theta0"])
+        ctx.rollout_arm(lw.NUM_EP, lw.EP_LEN, draws)
+        b = ctx.get_rollout(N)
+        for k in ("Observ", "Mean", "Action", "Reward"):
+            err = np.abs(b[k] - gold["it0_" + k]).max() / np.abs(gold["it0_" + k]).max()
+            assert err < TOL, (k, err)
+        # the produced batch is staged: advantage and update run on it without any host copy of the observations
+        with pkg.ValueFunction(ctx, lw.ARM_VF_LAYERS, lw.ARM_ACFUNC) as vf:
+            ret, adv = vf.advantage(_padded(gold["x_base0"]), N, lw.GAMMA, lw.LAM)
+        assert rel_err(ret, gold["it0_Return"])[0] < 1e-9 and rel_err(adv, gold["it0_Advantage"])[0] < 1e-9
+        theta1, info = ctx.update(0.1)
+    assert np.abs(theta1 - gold["ref_theta_iter1"]).max() < 1e-8
+
+
+def test_rollout_producer_device_generator(pkg, gold):
+    """Counter-based generator: deterministic per seed, different across seeds, and the sampled actions are
+    Mean + Std * N(0,1) with the object inside the simulator's box (TRPO_Lightweight.c:391-393)."""
+    num_ep, ep_len = 2000, 50
+    N = num_ep * ep_len
+    with pkg.Context(lw.ARM_LAYERS, lw.ARM_ACFUNC) as ctx:
+        ctx.set_model(gold["theta0"])
+        ctx.rollout_arm(num_ep, ep_len, None, seed=7)
+        a = ctx.get_rollout(N)
+        ctx.rollout_arm(num_ep, ep_len, None, seed=7)
+        a2 = ctx.get_rollout(N)
+        ctx.rollout_arm(num_ep, ep_len, None, seed=8)
+        b = ctx.get_rollout(N)
+    for k in a:
+        assert np.array_equal(a[k], a2[k])
+    assert not np.array_equal(a["Action"], b["Action"])
+    std = np.exp(gold["theta0"][-3:])
+    z = (a["Action"] - a["Mean"]) / std
+    assert abs(z.mean()) < 0.01 and abs(z.std() - 1) < 0.01
+    obj = a["Observ"][:, 12:15]
+    assert obj[:, 0].min() >= 0.084 and obj[:, 0].max() <= 0.16 and obj[:, 1].min() >= -0.05 and obj[:, 1].max() <= 0.05
+    assert obj[:, 2].min() >= 0 and obj[:, 2].max() <= 0.1
+    assert np.all(a["Reward"] < 0) and np.isfinite(a["Reward"]).all()
+    # the first step of every episode starts from the reset pose (TRPO_Lightweight.c:357-385)
+    first = a["Observ"][::ep_len]
+    assert np.allclose(first[:, :12], [0, 0, 0.01768, 0, 0, 0.07518, 0.07375, 0, 0.07518, 0.11315, 0, 0.06268])
+
+
+class GpuProducerBackend(GpuBackend):
+    """Rollouts produced on the device too: only the rand() draws and the P-length vectors cross PCIe."""
+
+    def rollout(self, theta):
+        self.ctx.set_model(theta)
+        self.ctx.rollout_arm(lw.NUM_EP, lw.EP_LEN, lw.libc_rand_draws(lw.NUM_EP * (3 + 6 * lw.EP_LEN)))
+        b = self.ctx.get_rollout(lw.NUM_EP * lw.EP_LEN)         # for the trace only
+        b["Std"] = np.exp(theta[-3:])
+        return b
+
+    def advantage(self, batch, x_base):
+        return self.vf.advantage(x_base, lw.NUM_EP * lw.EP_LEN, lw.GAMMA, lw.LAM)
+
+
+@pytest.mark.skipif(not Reference.available(), reason="oracle/_ref (the reference's vendored libLBFGS) not built")
+def test_training_loop_with_device_rollouts_matches_the_reference_result_files(pkg, oracle, gold):
+    """The whole loop of TRPO_Lightweight -- simulator, advantage, baseline fit, TRPO update -- with every compute step on
+    the GPU, fed with the rand() stream the reference consumes: same parameters after 3 iterations."""
+    ref = Reference()
+    be = GpuProducerBackend(pkg)
+    trace = []
+    try:
+        lw.run(be, oracle, ref, gold["theta0"], gold["x_base0"], 3, trace=trace)
+    finally:
+        be.close()
+    assert np.abs(trace[0]["batch"]["Observ"] - gold["it0_Observ"]).max() < 1e-10
+    for i in (1, 2, 3):
+        e = np.abs(trace[i - 1]["theta"] - gold[f"ref_theta_iter{i}"]).max()
+        assert e < 1e-7, (i, e)
+
+
 def test_binary_batch_file_staging(pkg, tmp_path):
     """trpo_ctx_set_batch_file and a binary DataFile behind the file-based entry points give the same bits as the text
     file / host arrays."""

@@ -86,6 +86,8 @@ def lib():
         L.trpo_ctx_fvp_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double]
         L.trpo_ctx_cg_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_double, C.c_double]
         L.trpo_ctx_set_rollout.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t] + [c_double_p] * 5
+        L.trpo_ctx_rollout_arm.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.POINTER(C.c_int), C.c_ulonglong]
+        L.trpo_ctx_get_rollout.argtypes = [C.c_void_p] + [c_double_p] * 4
         L.trpo_vf_create.restype = C.c_void_p
         L.trpo_vf_create.argtypes = [C.c_void_p, c_size_p, C.c_char_p, C.c_size_t]
         L.trpo_vf_destroy.argtypes = [C.c_void_p]
@@ -256,6 +258,23 @@ class Context:
         arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (observ, std, mean, action, reward)]
         assert arrs[0].shape[0] == num_ep * ep_len
         _check(lib().trpo_ctx_set_rollout(self.h, num_ep, ep_len, *[_dp(a) for a in arrs]))
+
+    def rollout_arm(self, num_ep, ep_len, rand_draws=None, seed=0):
+        """Produce one batch of rollouts of the lightweight arm simulator on the device with the current model.
+        rand_draws: int32 array of raw rand() values in the reference's order (num_ep * (3 + 6 * ep_len)), or None."""
+        ptr = None
+        if rand_draws is not None:
+            rand_draws = np.ascontiguousarray(rand_draws, dtype=np.int32)
+            assert rand_draws.size == num_ep * (3 + 2 * self.layers[-1] * ep_len)
+            ptr = rand_draws.ctypes.data_as(C.POINTER(C.c_int))
+        _check(lib().trpo_ctx_rollout_arm(self.h, num_ep, ep_len, ptr, seed))
+
+    def get_rollout(self, num_samples):
+        O, A = self.layers[0], self.layers[-1]
+        d = dict(Observ=np.zeros((num_samples, O)), Mean=np.zeros((num_samples, A)), Action=np.zeros((num_samples, A)),
+                 Reward=np.zeros(num_samples))
+        _check(lib().trpo_ctx_get_rollout(self.h, _dp(d["Observ"]), _dp(d["Mean"]), _dp(d["Action"]), _dp(d["Reward"])))
+        return d
 
     def set_batch_file(self, path, num_samples=0):
         _check(lib().trpo_ctx_set_batch_file(self.h, path.encode(), num_samples))

@@ -152,3 +152,154 @@ void launch_fill(double *d_a, double v, size_t n, cudaStream_t st, long long *la
     k_fill<<<grid_for(n), RB_THREADS, 0, st>>>(d_a, v, n);
     ++*launches;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Rollout producer: the reference's lightweight arm simulator (TRPO_Lightweight.c:349-540; on the FPGA build the role of
+// TRPO_RunLightweight, TRPO_Lightweight_FPGA.c:548-556). One WARP per episode: lane j owns neuron j of every layer (all
+// widths <= 32), the activations of the previous layer are broadcast by shuffles in the reference's summation order
+// (bias first, then k ascending), the scalar simulator state (joint angles, link positions, reward) is computed
+// redundantly by every lane -- SIMT issues it once per warp either way. Random numbers: either the caller's raw rand()
+// draws in the reference's order (3 per episode for the object position, then 2 per action component per step), which
+// makes the batch comparable to the reference's, or a counter-based generator (splitmix64 of seed + draw index).
+namespace {
+
+constexpr int ROLL_MAX_LAYERS = 8;
+struct RolloutNet {
+    int K;
+    int L[ROLL_MAX_LAYERS + 1];
+    int w_off[ROLL_MAX_LAYERS];
+    int logstd_off, P;
+    char ac[ROLL_MAX_LAYERS + 1];
+};
+
+__device__ __forceinline__ double roll_act(char a, double x) {
+    switch (a) {
+        case 't': return tanh(x);
+        case 'o': return 0.1 * x;
+        case 's': return 1.0 / (1.0 + exp(-x));
+        default:  return x;
+    }
+}
+
+__device__ __forceinline__ int roll_draw(const int *__restrict__ draws, unsigned long long seed, size_t idx) {
+    if (draws) return draws[idx];
+    unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(idx + 1);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (int)(z >> 33);                                  // 31 bits, the range of glibc's rand()
+}
+
+constexpr double ROLL_RAND_MAX = 2147483647.0;
+
+__global__ void __launch_bounds__(128) k_arm_rollout(RolloutNet net, const double *__restrict__ theta,
+                                                     const int *__restrict__ draws, unsigned long long seed,
+                                                     size_t num_ep, int ep_len,
+                                                     double *__restrict__ observ, double *__restrict__ mean,
+                                                     double *__restrict__ action, double *__restrict__ reward) {
+    extern __shared__ double sm[];
+    double *th = sm;                                        // the whole parameter vector
+    double *obs_sm = sm + net.P + (threadIdx.x >> 5) * 16;  // 15 observation components of this warp's current step
+    for (int i = threadIdx.x; i < net.P; i += blockDim.x) th[i] = theta[i];
+    __syncthreads();
+    const size_t ep = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (ep >= num_ep) return;
+    const int K = net.K, O = net.L[0], A = net.L[K];
+    const double pi = 3.1415926535897931, TimeStepLen = 0.02, coeff = 1;
+    const size_t per_ep = 3 + (size_t)2 * A * ep_len;
+    const size_t d0 = ep * per_ep;
+    double t1 = 0, t2 = -pi / 2.0, t3 = pi / 2.0;
+    double dof2x = 0, dof2y = 0, dof2z = 0.07518, wrx = 0.07375, wry = 0, wrz = 0.07518, grx = 0.11315, gry = 0, grz = 0.06268;
+    const double objx = ((double)roll_draw(draws, seed, d0 + 0) / ROLL_RAND_MAX) * 0.076 + 0.084;
+    const double objy = ((double)roll_draw(draws, seed, d0 + 1) / ROLL_RAND_MAX) * 0.100 - 0.05;
+    const double objz = ((double)roll_draw(draws, seed, d0 + 2) / ROLL_RAND_MAX) * 0.100;
+    const double sd = lane < A ? exp(th[net.logstd_off + lane]) : 1.0;
+    for (int step = 0; step < ep_len; ++step) {
+        const size_t row = ep * (size_t)ep_len + step;
+        if (lane == 0) {
+            obs_sm[0] = 0; obs_sm[1] = 0; obs_sm[2] = 0.01768;
+            obs_sm[3] = dof2x; obs_sm[4] = dof2y; obs_sm[5] = dof2z;
+            obs_sm[6] = wrx; obs_sm[7] = wry; obs_sm[8] = wrz;
+            obs_sm[9] = grx; obs_sm[10] = gry; obs_sm[11] = grz;
+            obs_sm[12] = objx; obs_sm[13] = objy; obs_sm[14] = objz;
+        }
+        __syncwarp();
+        if (lane < O) observ[row * O + lane] = obs_sm[lane];
+        // policy forward: lane j = neuron j
+        double y = 0.0;
+        {
+            const int N = net.L[1];
+            const double *W = th + net.w_off[0];
+            double x = lane < N ? W[O * N + lane] : 0.0;
+            for (int k = 0; k < O; ++k) x += obs_sm[k] * (lane < N ? W[k * N + lane] : 0.0);
+            y = roll_act(net.ac[1], x);
+        }
+        for (int i = 1; i < K; ++i) {
+            const int M = net.L[i], N = net.L[i + 1];
+            const double *W = th + net.w_off[i];
+            double x = lane < N ? W[M * N + lane] : 0.0;
+            for (int k = 0; k < M; ++k) {
+                const double yk = __shfl_sync(0xffffffffu, y, k);
+                x += yk * (lane < N ? W[k * N + lane] : 0.0);
+            }
+            y = roll_act(net.ac[i + 1], x);
+        }
+        __syncwarp();                                       // obs_sm is rewritten at the top of the next step
+        // sample the action (Box-Muller on two draws per component, TRPO_Lightweight.c:463-474)
+        double ac = 0.0;
+        if (lane < A) {
+            const size_t di = d0 + 3 + (size_t)2 * A * step + 2 * lane;
+            const double u1 = ((double)roll_draw(draws, seed, di) + 1.0) / (ROLL_RAND_MAX + 1.0);
+            const double u2 = ((double)roll_draw(draws, seed, di + 1) + 1.0) / (ROLL_RAND_MAX + 1.0);
+            const double z0 = sqrt(-2.0 * log(u1)) * cos(2 * pi * u2);
+            ac = z0 * sd + y;
+            mean[row * A + lane] = y;
+            action[row * A + lane] = ac;
+        }
+        const double a0 = __shfl_sync(0xffffffffu, ac, 0), a1 = __shfl_sync(0xffffffffu, ac, 1), a2 = __shfl_sync(0xffffffffu, ac, 2);
+        t1 += a0 * coeff * TimeStepLen;
+        t2 += a1 * coeff * TimeStepLen;
+        t3 += a2 * coeff * TimeStepLen;
+        const double s1 = sin(t1), c1 = cos(t1), s2 = sin(t2), c2 = cos(t2), s3 = sin(t3), c3 = cos(t3);
+        const double c2c3 = c2 * c3, s2s3 = s2 * s3, c2s3 = c2 * s3, s2c3 = s2 * c3;
+        dof2x = 0.0575 * c1 * c2;
+        dof2y = 0.0575 * s1 * c2;
+        dof2z = 0.01768 - 0.0575 * s2;
+        wrx = dof2x + 0.07375 * c1 * (c2c3 - s2s3);
+        wry = dof2y + 0.07375 * s1 * (c2c3 - s2s3);
+        wrz = dof2z - 0.07375 * (c2s3 + s2c3);
+        grx = dof2x + 0.11315 * c1 * (c2c3 - s2s3) - 0.0125 * c1 * (c2s3 + s2c3);
+        gry = dof2y + 0.11315 * s1 * (c2c3 - s2s3) - 0.0125 * s1 * (c2s3 + s2c3);
+        grz = dof2z - 0.11315 * (c2s3 + s2c3) + 0.0125 * (s2s3 - c2c3);
+        double re = 0;
+        re -= 100 * (objx - grx) * (objx - grx); re -= a0 * a0;
+        re -= 100 * (objy - gry) * (objy - gry); re -= a1 * a1;
+        re -= 100 * (objz - grz) * (objz - grz); re -= a2 * a2;
+        if (lane == 0) reward[row] = re;
+    }
+}
+
+}  // namespace
+
+int launch_arm_rollout(const NetDesc &net, const double *d_theta, const int *d_draws, unsigned long long seed, size_t num_ep,
+                       int ep_len, double *d_obs, double *d_mean, double *d_action, double *d_reward, cudaStream_t st,
+                       long long *launches) {
+    if (net.K > ROLL_MAX_LAYERS || net.L[0] != 15 || net.L[net.K] != 3) return 1;     // the simulator's observation / action layout
+    RolloutNet rn;
+    rn.K = net.K; rn.logstd_off = net.logstd_off; rn.P = net.P;
+    for (int i = 0; i <= net.K; ++i) { if (i && net.L[i] > 32) return 1; rn.L[i] = net.L[i]; rn.ac[i] = net.ac[i]; }
+    for (int i = 0; i < net.K; ++i) rn.w_off[i] = net.w_off[i];
+    const int threads = 128, warps = threads / 32;
+    const size_t smem = sizeof(double) * ((size_t)net.P + 16 * warps);
+    if (smem > 200 * 1024) return 1;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(k_arm_rollout, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return -1;
+        configured = true;
+    }
+    const unsigned blocks = (unsigned)((num_ep + warps - 1) / warps);
+    k_arm_rollout<<<blocks, threads, smem, st>>>(rn, d_theta, d_draws, seed, num_ep, ep_len, d_obs, d_mean, d_action, d_reward);
+    ++*launches;
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}

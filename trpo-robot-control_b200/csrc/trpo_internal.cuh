@@ -134,3 +134,9 @@ void launch_sqdiff(const double *d_a, const double *d_b, const double *d_shift_s
 void launch_standardise(double *d_a, size_t n, const double *d_sum, const double *d_sqdev, double n_total, cudaStream_t st,
                         long long *launches);
 void launch_fill(double *d_a, double v, size_t n, cudaStream_t st, long long *launches);
+// Rollout producer for the lightweight arm simulator (TRPO_Lightweight.c:349-540): one warp per episode. d_draws = raw rand()
+// values in the reference's order, or NULL for the counter-based generator. Returns 1 if the network is not a
+// 15-...-3 policy with hidden widths <= 32.
+int launch_arm_rollout(const NetDesc &net, const double *d_theta, const int *d_draws, unsigned long long seed, size_t num_ep,
+                       int ep_len, double *d_obs, double *d_mean, double *d_action, double *d_reward, cudaStream_t st,
+                       long long *launches);

@@ -75,6 +75,9 @@ struct trpo_ctx {
     // rollout staging (rows f-3/f-4): per-step rewards of the staged batch and its episode length
     double *d_reward;
     size_t cap_reward, ep_len;
+    int *d_draws;              // raw rand() draws of the rollout producer
+    size_t cap_draws;
+    double *h_logstd;          // LogStd block of the last trpo_ctx_set_model (host copy, A entries)
     // work vectors (P each)
     double *d_in, *d_out, *d_zsum, *d_x, *d_r, *d_p, *d_z, *d_b, *d_xnew;
     double *d_scal;            // small scalar scratch (16 doubles)
@@ -207,6 +210,7 @@ extern "C" trpo_ctx *trpo_ctx_create(const size_t *LayerSize, const char *AcFunc
     c->net.P = pos + c->net.L[c->net.K];
     c->world = 1;
     c->precision = precision;
+    c->h_logstd = (double *)calloc((size_t)c->net.L[c->net.K], sizeof(double));
     if (precision == TRPO_PRECISION_FP32) c->path_req = TRPO_PATH_GEMM_CHAIN;      // the FP32 mode is a GEMM-chain mode
     const size_t P = c->net.P, A = c->net.L[c->net.K];
     bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
@@ -260,6 +264,8 @@ extern "C" void trpo_ctx_destroy(trpo_ctx *c) {
     for (double *v : vecs) if (v) cudaFree(v);
     float *fvecs[] = {c->f_theta, c->f_v, c->f_inv_var, c->f_obs, c->scf_base};
     for (float *v : fvecs) if (v) cudaFree(v);
+    if (c->d_draws) cudaFree(c->d_draws);
+    free(c->h_logstd);
     if (c->d_state) cudaFree(c->d_state);
     if (c->h_state) cudaFreeHost(c->h_state);
     if (c->h_scal) cudaFreeHost(c->h_scal);
@@ -311,7 +317,7 @@ extern "C" int trpo_ctx_set_model(trpo_ctx *c, const double *theta) {
         const int A = c->net.L[c->net.K];
         double is[TRPO_MAX_LAYERS * 64];
         if (A > (int)(sizeof(is) / sizeof(is[0]))) return fail("action dimension too large");
-        for (int j = 0; j < A; ++j) is[j] = 1.0 / exp(theta[c->net.logstd_off + j]);
+        for (int j = 0; j < A; ++j) { is[j] = 1.0 / exp(theta[c->net.logstd_off + j]); c->h_logstd[j] = theta[c->net.logstd_off + j]; }
         CU(cudaMemcpyAsync(c->d_inv_std_model, is, A * sizeof(double), cudaMemcpyHostToDevice, c->stream));
         CU(cudaStreamSynchronize(c->stream));      // `is` is a stack buffer
     }
@@ -854,6 +860,60 @@ extern "C" int trpo_ctx_set_rollout(trpo_ctx *c, size_t NumEpBatch, size_t EpLen
     }
     CU(cudaMemcpyAsync(c->d_reward, c->d_adv, N * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
     c->ep_len = EpLen;
+    return 0;
+}
+
+// Rollout producer on the device (the role TRPO_RunLightweight plays for the FPGA build, TRPO_Lightweight_FPGA.c:548-556):
+// the lightweight arm simulator driven by the CURRENT model, writing Observ / Mean / Action / Reward straight into the
+// context's batch buffers -- nothing but the random draws crosses PCIe.
+extern "C" int trpo_ctx_rollout_arm(trpo_ctx *c, size_t NumEpBatch, size_t EpLen, const int *RandDraws, unsigned long long Seed) {
+    if (!c || NumEpBatch == 0 || EpLen == 0) return fail("bad rollout arguments");
+    if (EpLen > 0x7fffffff) return fail("episode too long");
+    CU(cudaSetDevice(c->device));
+    const size_t N = NumEpBatch * EpLen, O = c->net.L[0], A = c->net.L[c->net.K];
+    if (c->copy_inflight) { CU(cudaStreamWaitEvent(c->stream, c->ev_copy, 0)); c->copy_inflight = false; }
+    c->stream_first_fvp = false;
+    if (!c->own_batch) free_batch(c);
+    c->own_batch = true;
+    if (N * O > c->cap_obs) { cudaFree(c->d_obs); c->d_obs = nullptr; CU(cudaMalloc(&c->d_obs, N * O * sizeof(double))); c->cap_obs = N * O; }
+    if (N * A > c->cap_mean) {
+        cudaFree(c->d_mean); cudaFree(c->d_action); c->d_mean = c->d_action = nullptr;
+        CU(cudaMalloc(&c->d_mean, N * A * sizeof(double)));
+        CU(cudaMalloc(&c->d_action, N * A * sizeof(double)));
+        c->cap_mean = N * A;
+    }
+    if (N > c->cap_adv) { cudaFree(c->d_adv); c->d_adv = nullptr; CU(cudaMalloc(&c->d_adv, N * sizeof(double))); c->cap_adv = N; }
+    if (N > c->cap_reward) { cudaFree(c->d_reward); c->d_reward = nullptr; CU(cudaMalloc(&c->d_reward, N * sizeof(double))); c->cap_reward = N; }
+    const int *d_draws = nullptr;
+    if (RandDraws) {
+        const size_t nd = NumEpBatch * (3 + 2 * A * EpLen);
+        if (nd > c->cap_draws) { cudaFree(c->d_draws); c->d_draws = nullptr; CU(cudaMalloc(&c->d_draws, nd * sizeof(int))); c->cap_draws = nd; }
+        CU(cudaMemcpyAsync(c->d_draws, RandDraws, nd * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        d_draws = c->d_draws;
+    }
+    const int rc = launch_arm_rollout(c->net, c->d_theta, d_draws, Seed, NumEpBatch, (int)EpLen, c->d_obs, c->d_mean, c->d_action,
+                                      c->d_reward, c->stream, &c->launches);
+    if (rc > 0) return fail("the arm simulator needs a 15-...-3 policy with hidden widths <= 32");
+    if (rc < 0) return fail("rollout launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    c->n_local = N;
+    c->ep_len = EpLen;
+    double std_host[TRPO_MAX_LAYERS * 64];
+    for (size_t j = 0; j < A; ++j) std_host[j] = exp(c->h_logstd[j]);              // TRPO_Lightweight.c:460
+    if (set_std(c, std_host)) return -1;                                           // synchronises: RandDraws may be reused
+    return update_global_samples(c);
+}
+
+extern "C" int trpo_ctx_get_rollout(trpo_ctx *c, double *Observ, double *Mean, double *Action, double *Reward) {
+    if (!c) return fail("null context");
+    if (!c->d_obs || !c->d_reward || c->n_local == 0) return fail("no rollout staged");
+    CU(cudaSetDevice(c->device));
+    if (c->copy_inflight) { CU(cudaStreamWaitEvent(c->stream, c->ev_copy, 0)); c->copy_inflight = false; }
+    const size_t N = c->n_local, O = c->net.L[0], A = c->net.L[c->net.K];
+    if (Observ) CU(cudaMemcpyAsync(Observ, c->d_obs, N * O * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (Mean) CU(cudaMemcpyAsync(Mean, c->d_mean, N * A * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (Action) CU(cudaMemcpyAsync(Action, c->d_action, N * A * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (Reward) CU(cudaMemcpyAsync(Reward, c->d_reward, N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
     return 0;
 }
 
