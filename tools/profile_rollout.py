@@ -81,6 +81,12 @@ for shape in args.shapes.split(","):
             ctx.set_model(theta)
             stage = lambda: (ctx.set_rollout(num_ep, ep_len, hb["Observ"], hb["Std"], hb["Mean"], hb["Action"], h_reward), ctx.sync())
             out["stage_ms"] = timed(stage, args.reps)
+            if layers[0] == 15 and layers[-1] == 3:
+                # the device-side producer instead of staging host rollouts: counter-based generator / host rand() draws
+                out["rollout_arm_device_rng_ms"] = timed(lambda: (ctx.rollout_arm(num_ep, ep_len, None, 1), ctx.sync()), args.reps)
+                draws = np.random.default_rng(3).integers(0, 2**31 - 1, num_ep * (3 + 6 * ep_len), dtype=np.int32)
+                out["rollout_arm_host_draws_ms"] = timed(lambda: (ctx.rollout_arm(num_ep, ep_len, draws, 0), ctx.sync()), args.reps)
+                stage()
             out["advantage_ms"] = timed(lambda: vf.advantage(x0, n, GAMMA, LAM, fetch=False), args.reps)
             out["vf_evaluate_ms"] = timed(lambda: vf.evaluate(x0), args.reps)
             if ref is not None:
