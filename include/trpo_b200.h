@@ -61,10 +61,23 @@ double CG_GPU(TRPOparam param, double *Result, double *b, size_t MaxIter, double
 /* GPU counterpart of TRPO_Update (TRPO_Update.c:10): policy gradient, CG, shs FVP, line search. */
 double TRPO_Update_GPU(TRPOparam param, double *Result, size_t NumThreads);
 
-/* The reference's own symbol names, so that Test_FVP_FPGA / Test_CG_FPGA (TRPOCpuCode.c:189,273) link unchanged.
+/* GPU counterpart of TRPO_Lightweight / TRPO_Lightweight_FPGA (TRPO_Lightweight.c:12, TRPO_Lightweight_FPGA.c:12,
+ * prototypes TRPO.h:110,113): the whole training loop on the lightweight arm simulator -- rollouts, return / GAE,
+ * baseline fit, TRPO update -- for NumIter iterations; reads param.ModelFile / param.BaselineFile, writes
+ * `<param.ResultFile>%03d.txt` every 100 iterations and after the last one, prints the reference's log lines, returns the
+ * loop's wall-clock seconds or -1. The rollouts consume the C library's rand() stream after srand(0) exactly as the
+ * reference's loop does. The L-BFGS of the baseline fit is the CALLER's libLBFGS (the reference vendors src/lbfgs.c):
+ * `lbfgs` / `lbfgs_parameter_init` are taken from the process's loaded symbols or from the shared object named by the
+ * environment variable TRPO_LBFGS_LIB. _ex exposes the constants the reference hard-codes (:32-33,52-55). */
+double TRPO_Lightweight_GPU(TRPOparam param, const int NumIter, const size_t NumThreads);
+double TRPO_Lightweight_GPU_ex(TRPOparam param, const int NumIter, size_t NumEpBatch, size_t EpLen, double gamma, double lam);
+
+/* The reference's own symbol names, so that Test_FVP_FPGA / Test_CG_FPGA / Test_TRPO_Lightweight_FPGA
+ * (TRPOCpuCode.c:189,273,457) link unchanged.
  * Compiled only into libtrpo_b200_dropin.so (they would clash with the MaxCompiler build otherwise). */
 double FVP_FPGA(TRPOparam param, double *Result, double *Input);
 double CG_FPGA(TRPOparam param, double *Result, double *b, size_t MaxIter, double ResidualTh, size_t NumThreads);
+double TRPO_Lightweight_FPGA(TRPOparam param, const int NumIter, const size_t NumThreads);
 
 /* NumParamsCalc (TRPO_Util.c:7-17) under a non-clashing name. */
 size_t trpo_num_params(const size_t *LayerSize, size_t NumLayers);

@@ -276,6 +276,37 @@ def test_training_loop_with_device_rollouts_matches_the_reference_result_files(p
         assert e < 1e-7, (i, e)
 
 
+@pytest.mark.skipif(not Reference.available(), reason="oracle/_ref (the reference's TRPO_Lightweight and libLBFGS) not built")
+def test_trpo_lightweight_gpu_entry_point_writes_the_reference_result_files(pkg, gold, tmp_path, monkeypatch, capfd):
+    """TRPO_Lightweight_GPU (drop-in for TRPO_Lightweight / TRPO_Lightweight_FPGA, TRPO.h:110,113) against the unmodified
+    reference run here from the same model / baseline files: same result files, same log lines."""
+    import oracle_lib
+    mf, bf = str(tmp_path / "model.txt"), str(tmp_path / "base.txt")
+    pkg.textio.write_model(mf, gold["theta0"])
+    pkg.textio.write_model(bf, gold["x_base0"])
+    monkeypatch.setenv("TRPO_LBFGS_LIB", os.path.join(oracle_lib.ORACLE_DIR, "_ref", "libtrpo_ref.so"))
+    monkeypatch.chdir(tmp_path)                     # the reference's result-file name buffer is 30 bytes: keep it short
+    t_ref = Reference().lightweight(mf, bf, "ref", lw.ARM_LAYERS, lw.ARM_ACFUNC, 0.1, 3)
+    out_ref = capfd.readouterr().out
+    t_gpu = pkg.api.TRPO_Lightweight_GPU(mf, bf, "gpu", lw.ARM_LAYERS, lw.ARM_ACFUNC, 0.1, 3)
+    out_gpu = capfd.readouterr().out
+    assert t_ref > 0 and t_gpu > 0
+    ref = np.loadtxt(tmp_path / "ref002.txt")
+    got = np.loadtxt(tmp_path / "gpu002.txt")
+    assert np.abs(ref - gold["ref_theta_iter3"]).max() == 0
+    assert np.abs(got - ref).max() < 1e-7
+    assert os.path.exists(tmp_path / "gpu000.txt") and not os.path.exists(tmp_path / "gpu001.txt")   # iter % 100 == 0, last
+    # same log: three reward lines with the same statistics, same number of CG lines, same line-search outcomes
+    rew_ref = [l for l in out_ref.splitlines() if l.startswith("[INFO] Iteration")]
+    rew_gpu = [l for l in out_gpu.splitlines() if l.startswith("[INFO] Iteration")]
+    assert rew_ref == rew_gpu and len(rew_gpu) == 3
+    assert out_ref.count("CG Iter[") == out_gpu.count("CG Iter[")
+    assert out_ref.count("a/e/r") == out_gpu.count("a/e/r")
+    # a missing baseline file fails like the reference: message + -1
+    t = pkg.api.TRPO_Lightweight_GPU(mf, str(tmp_path / "nope.txt"), "gpu", lw.ARM_LAYERS, lw.ARM_ACFUNC, 0.1, 1)
+    assert t == -1.0 and "[ERROR] Cannot open BaselineFile" in capfd.readouterr().err
+
+
 def test_binary_batch_file_staging(pkg, tmp_path):
     """trpo_ctx_set_batch_file and a binary DataFile behind the file-based entry points give the same bits as the text
     file / host arrays."""

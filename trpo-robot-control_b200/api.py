@@ -111,8 +111,10 @@ def lib():
         L.trpo_ctx_comm_error.argtypes = [C.c_void_p]
         L.trpo_ctx_global_samples.restype = C.c_size_t
         L.trpo_ctx_global_samples.argtypes = [C.c_void_p]
-        for name in ("FVP_GPU", "CG_GPU", "TRPO_Update_GPU"):
+        for name in ("FVP_GPU", "CG_GPU", "TRPO_Update_GPU", "TRPO_Lightweight_GPU", "TRPO_Lightweight_GPU_ex"):
             getattr(L, name).restype = C.c_double
+        L.TRPO_Lightweight_GPU.argtypes = [TRPOparam, C.c_int, C.c_size_t]
+        L.TRPO_Lightweight_GPU_ex.argtypes = [TRPOparam, C.c_int, C.c_size_t, C.c_size_t, C.c_double, C.c_double]
         L.FVP_GPU.argtypes = [TRPOparam, c_double_p, c_double_p]
         L.CG_GPU.argtypes = [TRPOparam, c_double_p, c_double_p, C.c_size_t, C.c_double, C.c_size_t]
         L.TRPO_Update_GPU.argtypes = [TRPOparam, c_double_p, C.c_size_t]
@@ -181,6 +183,18 @@ def TRPO_Update_GPU(model_file, data_file, layers, acfunc, num_samples, damping,
     out = np.zeros(num_params(layers))
     t = lib().TRPO_Update_GPU(p, _dp(out), threads)
     return out, t
+
+
+def TRPO_Lightweight_GPU(model_file, baseline_file, result_prefix, layers, acfunc, damping, iters, threads=1,
+                         num_ep=None, ep_len=None, gamma=0.995, lam=0.98):
+    """The reference's all-in-one training loop on the GPU; num_ep / ep_len select the _ex entry point."""
+    keep = []
+    p = make_param(model_file, "", layers, acfunc, 0, damping, keep)
+    p.BaselineFile = baseline_file.encode()
+    p.ResultFile = result_prefix.encode()
+    if num_ep is None:
+        return lib().TRPO_Lightweight_GPU(p, iters, threads)
+    return lib().TRPO_Lightweight_GPU_ex(p, iters, num_ep, ep_len, gamma, lam)
 
 
 class Context:
