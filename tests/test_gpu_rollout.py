@@ -307,6 +307,30 @@ def test_trpo_lightweight_gpu_entry_point_writes_the_reference_result_files(pkg,
     assert t == -1.0 and "[ERROR] Cannot open BaselineFile" in capfd.readouterr().err
 
 
+@pytest.mark.skipif(not Reference.available(), reason="oracle/_ref (the reference's libLBFGS) not built")
+def test_c_harness_lightweight_mode(pkg, gold, tmp_path):
+    """host/trpo_test_main.c in the shape of Test_TRPO_Lightweight_FPGA (TRPOCpuCode.c:433-465): a plain C program, the
+    C-ABI library and the reference's libLBFGS -- no Python in the loop."""
+    import subprocess
+    import oracle_lib
+    exe = os.path.join(os.path.dirname(pkg.api.library_path()), "trpo_test_gpu")
+    mf, bf = str(tmp_path / "model.txt"), str(tmp_path / "base.txt")
+    pkg.textio.write_model(mf, gold["theta0"])
+    pkg.textio.write_model(bf, gold["x_base0"])
+    env = dict(os.environ, TRPO_LBFGS_LIB=os.path.join(oracle_lib.ORACLE_DIR, "_ref", "libtrpo_ref.so"))
+    out = subprocess.run([exe, "lightweight", mf, bf, str(tmp_path / "res"), "2"], capture_output=True, text=True,
+                         timeout=300, env=env)
+    assert out.returncode == 0, out.stderr
+    assert "[INFO] Iteration 1, Episode Rewards Mean = -476.223178, Std = 55.417171" in out.stdout   # the reference's own log
+    got = np.loadtxt(tmp_path / "res001.txt")
+    assert np.abs(got - gold["ref_theta_iter2"]).max() < 1e-7
+    # without a libLBFGS in reach the entry point says so and fails
+    env.pop("TRPO_LBFGS_LIB")
+    out = subprocess.run([exe, "lightweight", mf, bf, str(tmp_path / "res"), "1"], capture_output=True, text=True,
+                         timeout=300, env=env)
+    assert out.returncode != 0 and "libLBFGS not found" in out.stderr
+
+
 def test_binary_batch_file_staging(pkg, tmp_path):
     """trpo_ctx_set_batch_file and a binary DataFile behind the file-based entry points give the same bits as the text
     file / host arrays."""

@@ -7,6 +7,7 @@
  *   trpo_test_gpu fvp    <model> <data> <N> <vectors.txt>
  *   trpo_test_gpu cg     <model> <data> <N> <vectors.txt>
  *   trpo_test_gpu update <model> <data> <N> <expected_model.txt>
+ *   trpo_test_gpu lightweight <model> <baseline> <result-prefix> <NumIter>     (Test_TRPO_Lightweight_FPGA, :433-465)
  * Network: ArmDOF_0-v0, 15-16-16-3, {'l','t','t','l'}, CG_Damping 0.1 (TRPOCpuCode.c:142-160) unless
  * TRPO_LAYERS="17,64,64,6" TRPO_ACFUNC="lttl" are set in the environment.
  */
@@ -35,9 +36,34 @@ static void report(const char *what, const double *got, const double *expect, si
     printf("[INFO] %s max|d|/max|ref| = %.3e, rel-L2 = %.3e\n", what, maxabs / maxref, sqrt(num / den));
 }
 
-int main(int argc, char **argv) {
+/* Test_TRPO_Lightweight_FPGA (TRPOCpuCode.c:433-465): the whole training loop, NumIter iterations */
+static int run_lightweight(int argc, char **argv) {
     if (argc < 6) {
-        fprintf(stderr, "usage: %s fvp|cg|update <model> <data> <N> <vectors>\n", argv[0]);
+        fprintf(stderr, "usage: %s lightweight <model> <baseline> <result-prefix> <NumIter>   (TRPO_LBFGS_LIB names libLBFGS)\n", argv[0]);
+        return 2;
+    }
+    size_t LayerSize[4] = {15, 16, 16, 3};
+    char AcFunc[4] = {'l', 't', 't', 'l'};
+    TRPOparam Param;
+    memset(&Param, 0, sizeof(Param));
+    Param.ModelFile = argv[2];
+    Param.BaselineFile = argv[3];
+    Param.ResultFile = argv[4];
+    Param.NumLayers = 4;
+    Param.AcFunc = AcFunc;
+    Param.LayerSize = LayerSize;
+    Param.CG_Damping = 0.1;
+    const int NumIter = atoi(argv[5]);
+    const double compTime = TRPO_Lightweight_GPU(Param, NumIter, 1);
+    if (compTime < 0) fprintf(stderr, "[ERROR] TRPO Lightweight Failed.\n");
+    else printf("[INFO] TRPO Lightweight GPU: %d iterations in %f seconds.\n", NumIter, compTime);
+    return compTime < 0;
+}
+
+int main(int argc, char **argv) {
+    if (argc >= 2 && strcmp(argv[1], "lightweight") == 0) return run_lightweight(argc, argv);
+    if (argc < 6) {
+        fprintf(stderr, "usage: %s fvp|cg|update <model> <data> <N> <vectors>\n       %s lightweight <model> <baseline> <result-prefix> <NumIter>\n", argv[0], argv[0]);
         return 2;
     }
     size_t LayerSize[16] = {15, 16, 16, 3};
