@@ -158,3 +158,29 @@ def test_two_gpu_sharded_training_loop_body(tmp_path):
     assert np.array_equal(r0["g"], r0["g_again"]) and r0["fx"] == r0["fx_again"]
     for k in ("theta1", "theta1_p2p"):
         assert np.abs(r0[k] - g["ref_theta_iter1"]).max() < 1e-9
+
+
+def test_one_process_driving_two_devices():
+    """One process, two contexts on two GPUs (the thread-per-GPU deployment of INTEGRATION.md section 4): kernel attributes
+    such as the > 48 KB dynamic shared memory opt-in are per device and must be set on each."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    sys.path.insert(0, ROOT)
+    from __graft_entry__ import load_package
+    from conftest import load_synth, rel_err
+    pkg = load_package()
+    for name in ("mlp64", "arm_sigma", "acts5"):
+        s = load_synth(name)
+        outs = []
+        for dev in (0, 1):
+            for path in (pkg.api.PATH_AUTO, pkg.api.PATH_GEMM_CHAIN):
+                with pkg.Context(s["layers"], s["acfunc"], device=dev) as ctx:
+                    ctx.set_path(path)
+                    ctx.set_model(s["theta"])
+                    ctx.set_batch(s["Observ"], s["Std"], s["Mean"], s["Action"], s["Advantage"])
+                    z = ctx.fvp(s["v"], 0.1)
+                    u, _ = ctx.update(0.1)
+                assert rel_err(z, s["ref_fvpfast"])[0] < 1e-10, (name, dev, path)
+                assert rel_err(u, s["ref_update"])[0] < 1e-8, (name, dev, path)
+                outs.append((path, z))
+        assert np.array_equal(outs[0][1], outs[2][1]) and np.array_equal(outs[1][1], outs[3][1])   # same bits on both GPUs

@@ -889,11 +889,11 @@ FusedShape pick_shape(const NetDesc &net) {
 
 template <typename C, char A1, char A2, bool PG>
 int launch_cfg(const FusedArgs &a, int grid, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (configured.pending()) {
         if (cudaFuncSetAttribute(k_fvp_fused<C, A1, A2, PG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES) != cudaSuccess)
             return -1;
-        configured = true;
+        configured.mark();
     }
     k_fvp_fused<C, A1, A2, PG><<<grid, C::NTHREADS, C::SMEM_BYTES, st>>>(a);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
@@ -901,11 +901,11 @@ int launch_cfg(const FusedArgs &a, int grid, cudaStream_t st) {
 
 template <typename C, char A1, char A2>
 int launch_warp_cfg(const FusedArgs &a, int grid, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (configured.pending()) {
         if (cudaFuncSetAttribute(k_fvp_warp<C, A1, A2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)warp_smem_bytes<C>()) != cudaSuccess)
             return -1;
-        configured = true;
+        configured.mark();
     }
     k_fvp_warp<C, A1, A2><<<grid, C::NTHREADS, warp_smem_bytes<C>(), st>>>(a);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;

@@ -567,11 +567,8 @@ template <int NTA>
 int launch_tail(const double *Y, const double *RY, const double *W, const double *VW, int rows, int H, int A, char act_prev,
                 double d3, const double *inv_var, double *GK, double *Gprev, const int *done, cudaStream_t st) {
     const size_t bytes = tail_smem_bytes<NTA>(H);
-    static size_t configured = 0;
-    if (bytes > configured) {
-        if (cudaFuncSetAttribute(k_chain_tail<NTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return -1;
-        configured = bytes;
-    }
+    // size depends on the layer width and the attribute is per device: set it on every launch (host-side only, ~1 us)
+    if (cudaFuncSetAttribute(k_chain_tail<NTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return -1;
     k_chain_tail<NTA><<<cdiv(rows, BM), NT, bytes, st>>>(Y, RY, W, VW, rows, H, A, act_prev, d3, inv_var, GK, Gprev, done);
     return 0;
 }
@@ -581,15 +578,15 @@ constexpr size_t SMEM_FWD_L0   = sizeof(double) * 3 * (Tile<BK_DUAL>::A + 2 * Ti
 constexpr size_t SMEM_SINGLE   = sizeof(double) * 2 * (Tile<BK_SINGLE>::A + Tile<BK_SINGLE>::B);
 
 bool configure_kernels() {
-    static bool ok = false;
-    if (ok) return true;
+    static DeviceOnce once;
+    if (!once.pending()) return true;
     bool r = true;
     r = r && cudaFuncSetAttribute(k_chain_fwd<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_FWD_DUAL) == cudaSuccess;
     r = r && cudaFuncSetAttribute(k_chain_fwd<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_FWD_L0) == cudaSuccess;
     r = r && cudaFuncSetAttribute(k_chain_fwd<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_SINGLE) == cudaSuccess;
     r = r && cudaFuncSetAttribute(k_chain_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_SINGLE) == cudaSuccess;
     r = r && cudaFuncSetAttribute(k_chain_outer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_SINGLE) == cudaSuccess;
-    ok = r;
+    if (r) once.mark();
     return r;
 }
 

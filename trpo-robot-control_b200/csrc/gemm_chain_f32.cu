@@ -343,14 +343,14 @@ constexpr size_t SMEM_L0 = sizeof(float) * 2 * (A_TILE + 2 * B_TILE);
 constexpr size_t SMEM_SINGLE = sizeof(float) * 2 * (A_TILE + B_TILE);
 
 bool configure() {
-    static bool ok = false;
-    if (ok) return true;
+    static DeviceOnce once;
+    if (!once.pending()) return true;
     bool r = true;
     r = r && cudaFuncSetAttribute(k_fwd<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_DUAL) == cudaSuccess;
     r = r && cudaFuncSetAttribute(k_fwd<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_L0) == cudaSuccess;
     r = r && cudaFuncSetAttribute(k_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_SINGLE) == cudaSuccess;
     r = r && cudaFuncSetAttribute(k_outer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_SINGLE) == cudaSuccess;
-    ok = r;
+    if (r) once.mark();
     return r;
 }
 

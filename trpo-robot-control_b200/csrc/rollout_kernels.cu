@@ -293,11 +293,9 @@ int launch_arm_rollout(const NetDesc &net, const double *d_theta, const int *d_d
     const int threads = 128, warps = threads / 32;
     const size_t smem = sizeof(double) * ((size_t)net.P + 16 * warps);
     if (smem > 200 * 1024) return 1;
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(k_arm_rollout, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return -1;
-        configured = true;
-    }
+    // per device, so set on every launch (a process may drive several GPUs); only deep 32-wide policies exceed 48 KB
+    if (smem > 48 * 1024 &&
+        cudaFuncSetAttribute(k_arm_rollout, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
     const unsigned blocks = (unsigned)((num_ep + warps - 1) / warps);
     k_arm_rollout<<<blocks, threads, smem, st>>>(rn, d_theta, d_draws, seed, num_ep, ep_len, d_obs, d_mean, d_action, d_reward);
     ++*launches;

@@ -7,6 +7,17 @@
 
 #define TRPO_MAX_LAYERS 16
 
+#ifdef __cplusplus
+#include <atomic>
+// cudaFuncSetAttribute applies to the CURRENT device only; a process may drive several GPUs (one thread per GPU), so the
+// "already configured" memo of a kernel set is kept per device.
+struct DeviceOnce {
+    std::atomic<unsigned long long> mask{0};
+    bool pending() const { int d = 0; cudaGetDevice(&d); return !((mask.load() >> (d & 63)) & 1ull); }
+    void mark() { int d = 0; cudaGetDevice(&d); mask.fetch_or(1ull << (d & 63)); }
+};
+#endif
+
 // Network description in device-friendly form. The flat parameter vector (TRPO_FVP.c:704-725) is, per weight layer i,
 // an augmented row-major matrix [(L_i + 1) x L_{i+1}] at offset w_off[i]: L_i rows of W[i] followed by the row B[i].
 struct NetDesc {
