@@ -331,6 +331,29 @@ def test_c_harness_lightweight_mode(pkg, gold, tmp_path):
     assert out.returncode != 0 and "libLBFGS not found" in out.stderr
 
 
+def test_rollout_api_argument_errors(pkg, gold, tmp_path):
+    """Bad arguments fail loudly (RuntimeError carrying trpo_last_error) and leave the context usable."""
+    with pkg.Context([17, 64, 64, 6], "lttl") as ctx:
+        ctx.set_model(pkg.synth.make_model([17, 64, 64, 6], 3))
+        with pytest.raises(RuntimeError, match="15-...-3"):
+            ctx.rollout_arm(4, 10, None, 1)                 # the simulator's observation / action layout
+    with pkg.Context(lw.ARM_LAYERS, lw.ARM_ACFUNC) as ctx:
+        ctx.set_model(gold["theta0"])
+        with pytest.raises(RuntimeError):
+            ctx.rollout_arm(0, 10, None, 1)
+        with pytest.raises(RuntimeError):
+            ctx.get_rollout(10)                             # nothing staged yet
+        with pytest.raises(RuntimeError):
+            ctx.set_batch_file(str(tmp_path / "missing.bin"))
+        with pkg.ValueFunction(ctx, lw.ARM_VF_LAYERS, lw.ARM_ACFUNC) as vf:
+            with pytest.raises(RuntimeError, match="set_rollout"):
+                vf.advantage(_padded(gold["x_base0"]), 10, lw.GAMMA, lw.LAM)      # no rollout staged
+            with pytest.raises(RuntimeError):
+                vf.predict(_padded(gold["x_base0"]), 10)                          # not bound to a batch
+        ctx.rollout_arm(2, 5, None, 3)                      # still works afterwards
+        assert np.isfinite(ctx.get_rollout(10)["Reward"]).all()
+
+
 def test_binary_batch_file_staging(pkg, tmp_path):
     """trpo_ctx_set_batch_file and a binary DataFile behind the file-based entry points give the same bits as the text
     file / host arrays."""
