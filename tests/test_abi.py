@@ -20,7 +20,9 @@ def declared_functions():
 def test_header_declares_the_reference_entry_points():
     names = declared_functions()
     for must in ("FVP_GPU", "CG_GPU", "TRPO_Update_GPU", "FVP_FPGA", "CG_FPGA", "trpo_ctx_create", "trpo_ctx_fvp",
-                 "trpo_ctx_cg", "trpo_ctx_update", "trpo_ctx_init_comm"):
+                 "trpo_ctx_cg", "trpo_ctx_update", "trpo_ctx_init_comm", "TRPO_Lightweight_GPU", "TRPO_Lightweight_FPGA",
+                 "trpo_ctx_rollout_arm", "trpo_ctx_set_rollout", "trpo_vf_advantage", "trpo_vf_evaluate",
+                 "trpo_batch_file_write", "trpo_ctx_set_batch_file"):
         assert must in names
 
 
