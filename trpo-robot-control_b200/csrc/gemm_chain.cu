@@ -17,6 +17,7 @@
 // per SM (126-128 registers). tanh runs branch-free on 8 values in lock step (dmma_common.cuh).
 // Determinism: every output element has exactly one owner thread per (slice); slices are summed in fixed order.
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "trpo_internal.cuh"
 #include "dmma_common.cuh"
@@ -51,14 +52,14 @@ __device__ __forceinline__ double act_deriv(char a, double y) {   // f'(x) expre
 // ---- tile loaders (all 256 threads; 8-byte cp.async, src-size 0 = zero fill) --------------------------------------
 // A tile from row-major activations X[rows x ld]: As[m][k] = X[(m0+m)*ld + k0+k]; column k == ld is the augmented
 // "ones" column (value ones_val) when aug is set.
-template <int BK, int NTH>
+template <int BK, int NTH, int TM = BM>
 __device__ __forceinline__ void load_a_rowmajor(double *As, const double *X, int rows, int ld, int m0, int k0,
                                                 bool aug, double ones_val, int tid) {
     constexpr int RSA = Tile<BK>::RSA;
     if (X != nullptr && (ld & 1) == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0) {
         // even leading dimension: 16-byte copies (half the LDGSTS instructions); k0 and RSA are even
 #pragma unroll
-        for (int it = 0; it < BM * BK / 2 / NTH; ++it) {
+        for (int it = 0; it < TM * BK / 2 / NTH; ++it) {
             const int idx = tid + it * NTH, m = idx / (BK / 2), k = (idx % (BK / 2)) * 2;
             const int gm = m0 + m, gk = k0 + k;
             double *dst = &As[m * RSA + k];
@@ -71,7 +72,7 @@ __device__ __forceinline__ void load_a_rowmajor(double *As, const double *X, int
         return;
     }
 #pragma unroll
-    for (int it = 0; it < BM * BK / NTH; ++it) {
+    for (int it = 0; it < TM * BK / NTH; ++it) {
         const int idx = tid + it * NTH, m = idx / BK, k = idx % BK;
         const int gm = m0 + m, gk = k0 + k;
         const bool in = X != nullptr && gm < rows && gk < ld;
@@ -196,8 +197,11 @@ __device__ __forceinline__ void mma_stage(double (&acc)[4][NJ][2], double (&racc
 // forward: DUAL = also propagate R{} (FVP); HAS_RA = the incoming R{y} is non-zero (false for layer 0).
 // The dual (R-op) kernel carries two accumulator sets; to keep 16 warps per SM it runs 512 threads with 32 x 16 warp tiles
 // (64 accumulator registers per thread) instead of 256 threads with 32 x 32 tiles (128 registers, 8 warps per SM).
-template <bool DUAL, bool HAS_RA>
-__global__ void __launch_bounds__(DUAL ? 512 : NT, DUAL ? 1 : 2) k_chain_fwd(const double *__restrict__ Yin, const double *__restrict__ RYin,
+// TM = rows per CTA tile. The dual kernel exists as 128 rows x 512 threads (one CTA per SM) and as 64 rows x 256 threads (two
+// CTAs per SM, same 32 x 16 warp tiles): with two independent CTAs the first global loads and the tanh / store epilogue of
+// one overlap the main loop of the other, and a block barrier only stops 8 warps.
+template <bool DUAL, bool HAS_RA, int TM = BM>
+__global__ void __launch_bounds__(DUAL ? (TM == BM ? 512 : 256) : NT, (DUAL && TM == BM) ? 1 : 2) k_chain_fwd(const double *__restrict__ Yin, const double *__restrict__ RYin,
                                                      const double *__restrict__ W, const double *__restrict__ VW,
                                                      int rows, int Kd, int N, char act,
                                                      double *__restrict__ Yout, double *__restrict__ RYout,
@@ -206,11 +210,12 @@ __global__ void __launch_bounds__(DUAL ? 512 : NT, DUAL ? 1 : 2) k_chain_fwd(con
     if (done && *done) return;
     extern __shared__ __align__(16) double smem[];
     constexpr int BK = DUAL ? BK_DUAL : BK_SINGLE;
-    constexpr int NTH = DUAL ? 512 : NT, WN = NTH / 128, NJ = BN / 8 / WN;     // warps along n, n-tiles per warp
-    constexpr int A_TILE = Tile<BK>::A, B_TILE = Tile<BK>::B;
+    constexpr int NTH = DUAL ? (TM == BM ? 512 : 256) : NT, WN = DUAL ? 4 : 2, NJ = BN / 8 / WN;     // warps along n, n-tiles per warp
+    static_assert(NTH / 32 / WN * 32 == TM, "warp rows must cover the tile");
+    constexpr int A_TILE = TM * Tile<BK>::RSA, B_TILE = Tile<BK>::B;
     constexpr int STAGE = A_TILE * (DUAL && HAS_RA ? 2 : 1) + B_TILE * (DUAL ? 2 : 1);
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3, wm = w / WN, wn = w % WN;
-    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;     // the n-tiles of one row block run together: its A tile is read from L2 once
+    const int m0 = blockIdx.y * TM, n0 = blockIdx.x * BN;     // the n-tiles of one row block run together: its A tile is read from L2 once
     double acc[4][NJ][2] = {}, racc[4][NJ][2] = {};
     __shared__ double exp2_tab[64];
     load_exp2_table(exp2_tab);                          // visible after the first barrier of the k loop
@@ -240,10 +245,10 @@ __global__ void __launch_bounds__(DUAL ? 512 : NT, DUAL ? 1 : 2) k_chain_fwd(con
     auto load = [&](int st, int k0) {
         double *As, *RAs, *Bs, *VBs;
         stage_ptrs(st, As, RAs, Bs, VBs);
-        load_a_rowmajor<BK, NTH>(As, Yin, rows, Kd, m0, k0, true, 1.0, tid);
+        load_a_rowmajor<BK, NTH, TM>(As, Yin, rows, Kd, m0, k0, true, 1.0, tid);
         load_b_rowmajor<BK, NTH>(Bs, W, Kd + 1, N, k0, n0, tid);
         if (DUAL) {
-            if (HAS_RA) load_a_rowmajor<BK, NTH>(RAs, RYin, rows, Kd, m0, k0, false, 0.0, tid);
+            if (HAS_RA) load_a_rowmajor<BK, NTH, TM>(RAs, RYin, rows, Kd, m0, k0, false, 0.0, tid);
             load_b_rowmajor<BK, NTH>(VBs, VW, Kd + 1, N, k0, n0, tid);
         }
         cp_async_commit();
@@ -262,7 +267,7 @@ __global__ void __launch_bounds__(DUAL ? 512 : NT, DUAL ? 1 : 2) k_chain_fwd(con
         stage_ptrs(st, As, RAs, Bs, VBs);
         constexpr int RSA = Tile<BK>::RSA, CH = BK / 2;     // 16-byte chunks per tile row
 #pragma unroll
-        for (int it2 = 0; it2 < BM * CH / NTH; ++it2) {
+        for (int it2 = 0; it2 < TM * CH / NTH; ++it2) {
             const int idx = tid + it2 * NTH, m = idx / CH, k = (idx % CH) * 2, gm = m0 + m;
             const int bytes = gm < rows ? 16 : 0;
             const size_t off = (size_t)(gm < rows ? gm : rows - 1) * Kd + k0 + k;
@@ -576,6 +581,9 @@ int launch_tail(const double *Y, const double *RY, const double *W, const double
 constexpr size_t SMEM_FWD_DUAL = sizeof(double) * 3 * (2 * Tile<BK_DUAL>::A + 2 * Tile<BK_DUAL>::B);
 constexpr size_t SMEM_FWD_L0   = sizeof(double) * 3 * (Tile<BK_DUAL>::A + 2 * Tile<BK_DUAL>::B);
 constexpr size_t SMEM_SINGLE   = sizeof(double) * 2 * (Tile<BK_SINGLE>::A + Tile<BK_SINGLE>::B);
+constexpr int TM_HALF = 64;
+constexpr size_t SMEM_FWD_DUAL_H = sizeof(double) * 3 * (2 * TM_HALF * Tile<BK_DUAL>::RSA + 2 * Tile<BK_DUAL>::B);
+constexpr size_t SMEM_FWD_L0_H   = sizeof(double) * 3 * (TM_HALF * Tile<BK_DUAL>::RSA + 2 * Tile<BK_DUAL>::B);
 
 bool configure_kernels() {
     static DeviceOnce once;
@@ -583,6 +591,8 @@ bool configure_kernels() {
     bool r = true;
     r = r && cudaFuncSetAttribute(k_chain_fwd<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_FWD_DUAL) == cudaSuccess;
     r = r && cudaFuncSetAttribute(k_chain_fwd<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_FWD_L0) == cudaSuccess;
+    r = r && cudaFuncSetAttribute(k_chain_fwd<true, true, TM_HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_FWD_DUAL_H) == cudaSuccess;
+    r = r && cudaFuncSetAttribute(k_chain_fwd<true, false, TM_HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_FWD_L0_H) == cudaSuccess;
     r = r && cudaFuncSetAttribute(k_chain_fwd<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_SINGLE) == cudaSuccess;
     r = r && cudaFuncSetAttribute(k_chain_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_SINGLE) == cudaSuccess;
     r = r && cudaFuncSetAttribute(k_chain_outer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_SINGLE) == cudaSuccess;
@@ -646,16 +656,23 @@ int chain_accumulate(const NetDesc &net, const ChainScratch &sc, ChainMode mode,
             if (fvp) {
                 const double *RYin = (i == 0) ? nullptr : sc.RY[i & 1];
                 const bool needY = !last || net.ac[K] == 't' || net.ac[K] == 's';
-                if (i == 0)
-                    k_chain_fwd<true, false><<<grid, 512, SMEM_FWD_L0, st>>>(Yin, nullptr, d_theta + net.w_off[i], d_v + net.w_off[i], rows,
-                                                      net.L[i], net.L[i + 1], net.ac[i + 1],
-                                                      needY ? sc.Y[i + 1] : nullptr, last ? nullptr : sc.RY[(i + 1) & 1],
-                                                      last ? sc.G[K & 1] : nullptr, d_inv_var, d_done);
+                // two 64-row CTAs per SM by default; TRPO_CHAIN_FWD_TM=128 selects the one-CTA-per-SM 128-row variant
+                static const bool half_tiles = !(getenv("TRPO_CHAIN_FWD_TM") && atoi(getenv("TRPO_CHAIN_FWD_TM")) == 128);
+                dim3 grid_h(cdiv(net.L[i + 1], BN), cdiv(rows, TM_HALF));
+                double *Yo = needY ? sc.Y[i + 1] : nullptr, *RYo = last ? nullptr : sc.RY[(i + 1) & 1], *Go = last ? sc.G[K & 1] : nullptr;
+                const double *Wl = d_theta + net.w_off[i], *VWl = d_v + net.w_off[i];
+                if (i == 0 && half_tiles)
+                    k_chain_fwd<true, false, TM_HALF><<<grid_h, 256, SMEM_FWD_L0_H, st>>>(Yin, nullptr, Wl, VWl, rows, net.L[i], net.L[i + 1],
+                                                                                     net.ac[i + 1], Yo, RYo, Go, d_inv_var, d_done);
+                else if (i == 0)
+                    k_chain_fwd<true, false><<<grid, 512, SMEM_FWD_L0, st>>>(Yin, nullptr, Wl, VWl, rows, net.L[i], net.L[i + 1],
+                                                                              net.ac[i + 1], Yo, RYo, Go, d_inv_var, d_done);
+                else if (half_tiles)
+                    k_chain_fwd<true, true, TM_HALF><<<grid_h, 256, SMEM_FWD_DUAL_H, st>>>(Yin, RYin, Wl, VWl, rows, net.L[i], net.L[i + 1],
+                                                                                      net.ac[i + 1], Yo, RYo, Go, d_inv_var, d_done);
                 else
-                    k_chain_fwd<true, true><<<grid, 512, SMEM_FWD_DUAL, st>>>(Yin, RYin, d_theta + net.w_off[i], d_v + net.w_off[i], rows,
-                                                      net.L[i], net.L[i + 1], net.ac[i + 1],
-                                                      needY ? sc.Y[i + 1] : nullptr, last ? nullptr : sc.RY[(i + 1) & 1],
-                                                      last ? sc.G[K & 1] : nullptr, d_inv_var, d_done);
+                    k_chain_fwd<true, true><<<grid, 512, SMEM_FWD_DUAL, st>>>(Yin, RYin, Wl, VWl, rows, net.L[i], net.L[i + 1],
+                                                                               net.ac[i + 1], Yo, RYo, Go, d_inv_var, d_done);
             } else {
                 k_chain_fwd<false, false><<<grid, NT, SMEM_SINGLE, st>>>(Yin, nullptr, d_theta + net.w_off[i], nullptr, rows,
                                                        net.L[i], net.L[i + 1], net.ac[i + 1], sc.Y[i + 1], nullptr,
