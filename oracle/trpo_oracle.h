@@ -16,6 +16,9 @@
  * Parity pinning: bit-exact against the compiled, unmodified reference (oracle/_ref/, built by
  * oracle/Makefile with -ffp-contract=off) on the ArmTest vectors and on synthetic cases; the
  * %.17g outputs of that reference run are committed under tests/golden/ (see tests/golden/make_golden.py).
+ * The rollout / GAE / baseline-objective restatements are pinned against the reference's exported `evaluate` callback
+ * (bit-exact) and against the result files the unmodified TRPO_Lightweight writes after 1-3 iterations
+ * (tests/golden/make_golden_lightweight.py, tests/test_oracle_rollout.py).
  */
 #ifndef TRPO_ORACLE_H
 #define TRPO_ORACLE_H
