@@ -89,3 +89,47 @@ def test_product_does_not_reference_the_oracle():
             if f.endswith((".cu", ".cuh", ".c", ".h", ".py")) or f == "Makefile":
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "liboracle" not in text and "trpo_oracle" not in text and "oracle_lib" not in text, f
+
+
+def test_header_compiles_as_c_and_cxx_and_after_the_reference_header(tmp_path):
+    """include/trpo_b200.h is plain C (gnu11 and c99), has C linkage under C++, and can follow the reference's own TRPO.h
+    (it then reuses that TRPOparam instead of redefining it)."""
+    import subprocess
+    inc = os.path.join(ROOT, "include")
+    src = tmp_path / "t.c"
+    src.write_text('#include "trpo_b200.h"\nint main(void) { TRPOparam p; (void)p; return (int)sizeof(trpo_batch_file_header) - 64; }\n')
+    for cmd in (["gcc", "-std=gnu11", "-Wall", "-Werror"], ["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror"],
+                ["g++", "-std=c++17", "-x", "c++", "-Wall", "-Werror"]):
+        r = subprocess.run(cmd + ["-fsyntax-only", "-I", inc, str(src)], capture_output=True, text=True)
+        assert r.returncode == 0, (cmd, r.stderr)
+    ref_inc = "/root/reference/src/include"
+    if os.path.exists(os.path.join(ref_inc, "TRPO.h")):
+        src2 = tmp_path / "t2.c"
+        src2.write_text('#include "TRPO.h"\n#include "trpo_b200.h"\n'
+                        'double f(TRPOparam p, double *r, double *b) { return CG_GPU(p, r, b, 10, 1e-10, 1) + CG_FPGA(p, r, b, 10, 1e-10, 1); }\n')
+        r = subprocess.run(["gcc", "-std=gnu11", "-w", "-fsyntax-only", "-I", ref_inc, "-I", inc, str(src2)],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+
+
+def test_reference_style_caller_links_against_the_dropin_library(pkg, tmp_path):
+    """The link line of INTEGRATION.md section 1: a C caller written against the reference's prototypes (TRPO.h:98,101,113)
+    links to libtrpo_b200_dropin.so with no other glue."""
+    import subprocess
+    libdir = os.path.dirname(pkg.api.library_path())
+    src = tmp_path / "caller.c"
+    src.write_text(
+        '#include <stddef.h>\n'
+        'typedef struct { char *ModelFile, *BaselineFile, *ResultFile, *DataFile; size_t NumLayers; char *AcFunc; size_t *LayerSize;\n'
+        '                 size_t NumSamples; double CG_Damping; size_t *PaddedLayerSize, *NumBlocks; } TRPOparam;\n'
+        'double FVP_FPGA(TRPOparam param, double *Result, double *Input);\n'
+        'double CG_FPGA(TRPOparam param, double *Result, double *b, size_t MaxIter, double ResidualTh, size_t NumThreads);\n'
+        'double TRPO_Lightweight_FPGA(TRPOparam param, const int NumIter, const size_t NumThreads);\n'
+        'int main(int argc, char **argv) { TRPOparam p = {0}; double r[4], b[4];\n'
+        '  if (argc > 99) return (int)(FVP_FPGA(p, r, b) + CG_FPGA(p, r, b, 10, 1e-10, 1) + TRPO_Lightweight_FPGA(p, 1, 1));\n'
+        '  return 0; }\n')
+    exe = tmp_path / "caller"
+    r = subprocess.run(["gcc", "-std=gnu11", str(src), "-L", libdir, "-ltrpo_b200_dropin", f"-Wl,-rpath,{libdir}", "-lm", "-o", str(exe)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert subprocess.run([str(exe)], capture_output=True).returncode == 0      # loads (CUDA runtime and all) and exits

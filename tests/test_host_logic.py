@@ -92,3 +92,45 @@ def test_binary_batch_file_round_trip_and_text_conversion(pkg, tmp_path):
         pkg.api.batch_file_read(bf, N + 1, O, A)
     with pytest.raises(RuntimeError):
         pkg.api.batch_file_read(df, N, O, A)          # a text file is not a binary batch file
+
+
+def test_chunked_scan_of_the_return_and_advantage_recurrences(oracle):
+    """The algorithm of k_gae (csrc/rollout_kernels.cu) emulated lane by lane: 32-step chunks walked backwards, a 5-step
+    shuffle scan inside a chunk, the carry from the chunk behind weighted a^(32 - lane). It must agree with the
+    reference's O(EpLen^2) pow() sums (oracle_gae) for episode lengths around the chunk size."""
+    gamma, lam = 0.995, 0.98
+    rng = np.random.default_rng(0)
+
+    def scan_episode(d, a):
+        n = len(d)
+        out = np.zeros(n)
+        carry = 0.0
+        for t0 in range(((n - 1) // 32) * 32, -1, -32):
+            x = np.zeros(32)
+            m = min(32, n - t0)
+            x[:m] = d[t0:t0 + m]
+            p, off = a, 1
+            while off < 32:
+                y = np.concatenate([x[off:], np.zeros(off)])        # __shfl_down, lanes past the end masked out
+                x = x + p * y
+                p, off = p * p, off * 2
+            x = x + a ** (32 - np.arange(32)) * carry
+            out[t0:t0 + m] = x[:m]
+            carry = x[0]
+        return out
+
+    for num_ep, ep_len in ((3, 1), (2, 31), (2, 32), (3, 33), (2, 150), (1, 257)):
+        N = num_ep * ep_len
+        reward, base = rng.normal(size=N) * 2 - 1, rng.normal(size=N)
+        ret = np.zeros(N)
+        adv = np.zeros(N)
+        for ep in range(num_ep):
+            r, v = reward[ep * ep_len:(ep + 1) * ep_len], base[ep * ep_len:(ep + 1) * ep_len]
+            delta = r + gamma * np.concatenate([v[1:], [0.0]]) - v
+            ret[ep * ep_len:(ep + 1) * ep_len] = scan_episode(r, gamma)
+            adv[ep * ep_len:(ep + 1) * ep_len] = scan_episode(delta, gamma * lam)
+        if N > 1:
+            adv = (adv - adv.mean()) / adv.std()
+            r_ref, a_ref = oracle.gae(reward, base, num_ep, ep_len, gamma, lam)
+            assert np.abs(ret - r_ref).max() < 1e-12 * max(1.0, np.abs(r_ref).max())
+            assert np.abs(adv - a_ref).max() < 1e-11
