@@ -410,6 +410,14 @@ def run_gpu_arm(args, pkg):
 
         if world == 1:
             also["loop_body_1m"] = measure_loop_body(pkg, m, args.steps, torch)
+            # BASELINE configs[3] (Humanoid-size 376-256-256-17: the wide-layer GEMM-chain path) on 200 k states, so that the
+            # default run also carries a roofline figure for the kernels that serve wide policies
+            h = measure("humanoid256", 200000, max(2, args.steps // 3), 2, False)
+            also["humanoid256_200k"] = {"workload": "humanoid256: 376-256-256-17 policy, 200000 synthetic states, 10-iteration CG",
+                                        "value": h["value"], "unit": "samples/s", "cg_solve_ms": h["ms_step"],
+                                        "e2e_value": h["e2e_value"], "e2e_ms_per_step": h["e2e_ms"], "kernel_path": h["path"],
+                                        "roofline_frac": h["roofline"]["frac"], "fvp_ms": h["roofline"]["kernel_avg_ms"],
+                                        "flops_per_sample": h["roofline"]["flops_per_sample"]}
 
     if rank == 0:
         layers, n_total, P = m["layers"], m["n_total"], m["P"]
