@@ -10,6 +10,8 @@
 // 32 x 32 at two CTAs per SM (as in gemm_chain.cu); 4-byte cp.async with zero fill, shared row strides 36 / 72 floats
 // (conflict-free fragment reads). Per-slice partial sums are FP32; the fixed-order slice
 // reduction and everything downstream (CG) are FP64.
+#include <stdint.h>
+
 #include "trpo_internal.cuh"
 
 namespace {
@@ -21,6 +23,10 @@ constexpr int A_TILE = BM * RSA, B_TILE = BK * RSB;     // floats per operand ti
 __device__ __forceinline__ void cp_async4(float *dst_smem, const float *src, int src_bytes) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" :: "r"(d), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async16(float *dst_smem, const float *src, int src_bytes) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" :: "r"(d), "l"(src), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
@@ -64,6 +70,22 @@ __device__ __forceinline__ float act_deriv(char a, float y) {
 template <int NTH>
 __device__ __forceinline__ void load_a_rowmajor(float *As, const float *X, int rows, int ld, int m0, int k0,
                                                 bool aug, float ones_val, int tid) {
+    if (X != nullptr && (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0) {
+        // leading dimension a multiple of 4 floats: 16-byte copies, a quarter of the copy instructions and index arithmetic
+        // (the kernel is instruction-issue bound: the 3xTF32 splits already cost ~2 ALU instructions per fragment element)
+#pragma unroll
+        for (int it = 0; it < BM * BK / 4 / NTH; ++it) {
+            const int idx = tid + it * NTH, m = idx / (BK / 4), k = (idx % (BK / 4)) * 4;
+            const int gm = m0 + m, gk = k0 + k;
+            float *dst = &As[m * RSA + k];
+            if (aug && gk == ld && gm < rows) { dst[0] = ones_val; dst[1] = dst[2] = dst[3] = 0.0f; }
+            else {
+                const bool in = gm < rows && gk < ld;      // ld % 4 == 0: gk < ld implies gk + 3 < ld
+                cp_async16(dst, in ? &X[(size_t)gm * ld + gk] : X, in ? 16 : 0);
+            }
+        }
+        return;
+    }
 #pragma unroll
     for (int it = 0; it < BM * BK / NTH; ++it) {
         const int idx = tid + it * NTH, m = idx / BK, k = idx % BK;
@@ -73,18 +95,45 @@ __device__ __forceinline__ void load_a_rowmajor(float *As, const float *X, int r
         else cp_async4(&As[m * RSA + k], in ? &X[(size_t)gm * ld + gk] : X, in ? 4 : 0);
     }
 }
-__device__ __forceinline__ void load_a_transposed(float *As, const float *Y, int s_end, int M0, int m0, int s0, int tid) {
+// The outer product's A operand in its natural orientation (see gemm_chain.cu): An[k][m] = Yprev[(s0+k)*M0 + m0+m], 1 for
+// m == M0. Row stride RSN % 32 == 8: the m16n8k8 A fragment (rows g / g+8, columns t / t+4) reads (t)*RSN + g -> 32 banks.
+constexpr int RSN = BM + 8;
+__device__ __forceinline__ void load_a_natural(float *An, const float *Y, int s_end, int M0, int m0, int s0, int tid) {
+    if (Y != nullptr && (M0 & 3) == 0 && (reinterpret_cast<uintptr_t>(Y) & 15) == 0) {
 #pragma unroll
-    for (int it = 0; it < BM * BK / NT; ++it) {
+        for (int it = 0; it < BK * BM / 4 / NT; ++it) {
+            const int idx = tid + it * NT, k = idx >> 5, m = (idx & 31) * 4;
+            const int gm = m0 + m, gs = s0 + k;
+            float *dst = &An[k * RSN + m];
+            if (gm == M0) { dst[0] = gs < s_end ? 1.0f : 0.0f; dst[1] = dst[2] = dst[3] = 0.0f; }
+            else {
+                const bool in = gm < M0 && gs < s_end;
+                cp_async16(dst, in ? &Y[(size_t)gs * M0 + gm] : Y, in ? 16 : 0);
+            }
+        }
+        return;
+    }
+#pragma unroll 2
+    for (int it = 0; it < BK * BM / NT; ++it) {
         const int idx = tid + it * NT, k = idx >> 7, m = idx & 127;
         const int gm = m0 + m, gs = s0 + k;
         const bool in = Y != nullptr && gm < M0 && gs < s_end;
-        if (gm == M0 && gs < s_end) As[m * RSA + k] = 1.0f;
-        else cp_async4(&As[m * RSA + k], in ? &Y[(size_t)gs * M0 + gm] : Y, in ? 4 : 0);
+        if (gm == M0) An[k * RSN + m] = gs < s_end ? 1.0f : 0.0f;
+        else cp_async4(&An[k * RSN + m], in ? &Y[(size_t)gs * M0 + gm] : Y, in ? 4 : 0);
     }
 }
 template <int NTH>
 __device__ __forceinline__ void load_b_rowmajor(float *Bs, const float *M, int kdim, int N, int k0, int n0, int tid) {
+    if ((N & 3) == 0 && (reinterpret_cast<uintptr_t>(M) & 15) == 0) {
+#pragma unroll
+        for (int it = 0; it < BK * BN / 4 / NTH; ++it) {
+            const int idx = tid + it * NTH, k = idx >> 4, n = (idx & 15) * 4;
+            const int gk = k0 + k, gn = n0 + n;
+            const bool in = gk < kdim && gn < N;
+            cp_async16(&Bs[k * RSB + n], in ? &M[(size_t)gk * N + gn] : M, in ? 16 : 0);
+        }
+        return;
+    }
 #pragma unroll
     for (int it = 0; it < BK * BN / NTH; ++it) {
         const int idx = tid + it * NTH, k = idx >> 6, n = idx & 63;
@@ -105,7 +154,7 @@ __device__ __forceinline__ void load_b_transposed(float *Bs, const float *W, int
 
 // one k-step (32) of a warp's 32 x 32 sub-tile. Fragment layout of m16n8k8 (lane = 4g + t):
 //   A: (g, t) (g+8, t) (g, t+4) (g+8, t+4)    B: (t, g) (t+4, g)    C: (g, 2t) (g, 2t+1) (g+8, 2t) (g+8, 2t+1)
-template <bool DUAL, bool HAS_RA, int NJ>
+template <bool DUAL, bool HAS_RA, int NJ, bool ANAT = false>
 __device__ __forceinline__ void mma_stage(float (&acc)[2][NJ][4], float (&racc)[2][NJ][4], const float *As, const float *RAs,
                                           const float *Bs, const float *VBs, int wm, int wn, int g, int t) {
 #pragma unroll
@@ -116,7 +165,7 @@ __device__ __forceinline__ void mma_stage(float (&acc)[2][NJ][4], float (&racc)[
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const int row = 32 * wm + 16 * i + g + 8 * (e & 1), col = 8 * q + t + 4 * (e >> 1);
-                split_tf32(As[row * RSA + col], ahi[i][e], alo[i][e]);
+                split_tf32(ANAT ? As[col * RSN + row] : As[row * RSA + col], ahi[i][e], alo[i][e]);
                 if (DUAL && HAS_RA) split_tf32(RAs[row * RSA + col], rhi[i][e], rlo[i][e]);
             }
 #pragma unroll
@@ -259,6 +308,8 @@ __global__ void __launch_bounds__(NT, 2) k_outer(const float *__restrict__ Yprev
                                                  int bias_colsum, const int *__restrict__ done) {
     if (done && *done) return;
     extern __shared__ __align__(16) float smem_f[];
+    constexpr int AN_TILE = BK * RSN;                       // natural-orientation A tile
+    static_assert(AN_TILE <= A_TILE && (AN_TILE & 3) == 0, "natural A tile must fit the stage and keep B 16-byte aligned");
     constexpr int STAGE = A_TILE + B_TILE;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3, wm = w >> 1, wn = w & 1;
     const int m0 = (blockIdx.x / tiles_n) * BM, n0 = (blockIdx.x % tiles_n) * BN;
@@ -273,7 +324,7 @@ __global__ void __launch_bounds__(NT, 2) k_outer(const float *__restrict__ Yprev
     const int nk = s1 > s0 ? (s1 - s0 + BK - 1) / BK : 0;
     auto load = [&](int st, int ks) {
         float *As = smem_f + st * STAGE, *Bs = As + A_TILE;
-        load_a_transposed(As, Yprev, s1, M0, m0, ks, tid);
+        load_a_natural(As, Yprev, s1, M0, m0, ks, tid);
         load_b_rowmajor<NT>(Bs, G + (size_t)ks * N, s1 - ks, N, 0, n0, tid);
         cp_commit();
     };
@@ -283,7 +334,7 @@ __global__ void __launch_bounds__(NT, 2) k_outer(const float *__restrict__ Yprev
         else cp_wait<0>();
         __syncthreads();
         const float *As = smem_f + (it & 1) * STAGE, *Bs = As + A_TILE;
-        if (active) mma_stage<false, false, 4>(acc, dummy, As, nullptr, Bs, nullptr, wm, wn, g, t);
+        if (active) mma_stage<false, false, 4, true>(acc, dummy, As, nullptr, Bs, nullptr, wm, wn, g, t);
         if (colsum) {
 #pragma unroll
             for (int kk = 0; kk < BK / 4; ++kk) bsum += Bs[(4 * kk + (tid >> 6)) * RSB + (tid & 63)];
