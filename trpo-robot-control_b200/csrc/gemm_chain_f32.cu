@@ -32,10 +32,13 @@ __device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_grou
 template <int N>
 __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(N) : "memory"); }
 
+// x = hi + lo with hi = x truncated to TF32's 10 mantissa bits (one LOP3) and lo = x - hi (exact in FP32; the tensor core
+// ignores its low 13 mantissa bits, an error of <= 2^-20 |x|). cvt.rna.tf32.f32 has no native SASS form on sm_100a -- it
+// expands to ~6 instructions each (FSETP/FMUL/FFMA/LOP3) and the kernel is instruction-issue bound; round-to-nearest
+// splits bought ~2 bits that the stated 1e-4 tolerance does not need.
 __device__ __forceinline__ void split_tf32(float x, unsigned &hi, unsigned &lo) {
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
-    const float rest = x - __uint_as_float(hi);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(rest));
+    hi = __float_as_uint(x) & 0xffffe000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
 }
 __device__ __forceinline__ void mma_tf32(float (&c)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
     asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
