@@ -11,6 +11,7 @@
 // (conflict-free fragment reads). Per-slice partial sums are FP32; the fixed-order slice
 // reduction and everything downstream (CG) are FP64.
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "trpo_internal.cuh"
 
@@ -70,14 +71,14 @@ __device__ __forceinline__ float act_deriv(char a, float y) {
     }
 }
 
-template <int NTH>
+template <int NTH, int TM = BM>
 __device__ __forceinline__ void load_a_rowmajor(float *As, const float *X, int rows, int ld, int m0, int k0,
                                                 bool aug, float ones_val, int tid) {
     if (X != nullptr && (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0) {
         // leading dimension a multiple of 4 floats: 16-byte copies, a quarter of the copy instructions and index arithmetic
         // (the kernel is instruction-issue bound: the 3xTF32 splits already cost ~2 ALU instructions per fragment element)
 #pragma unroll
-        for (int it = 0; it < BM * BK / 4 / NTH; ++it) {
+        for (int it = 0; it < TM * BK / 4 / NTH; ++it) {
             const int idx = tid + it * NTH, m = idx / (BK / 4), k = (idx % (BK / 4)) * 4;
             const int gm = m0 + m, gk = k0 + k;
             float *dst = &As[m * RSA + k];
@@ -90,7 +91,7 @@ __device__ __forceinline__ void load_a_rowmajor(float *As, const float *X, int r
         return;
     }
 #pragma unroll
-    for (int it = 0; it < BM * BK / NTH; ++it) {
+    for (int it = 0; it < TM * BK / NTH; ++it) {
         const int idx = tid + it * NTH, m = idx / BK, k = idx % BK;
         const int gm = m0 + m, gk = k0 + k;
         const bool in = X != nullptr && gm < rows && gk < ld;
@@ -192,8 +193,9 @@ __device__ __forceinline__ void mma_stage(float (&acc)[2][NJ][4], float (&racc)[
     }
 }
 
-template <bool DUAL, bool HAS_RA>
-__global__ void __launch_bounds__(512, 1) k_fwd(const float *__restrict__ Yin, const float *__restrict__ RYin,
+// TM = rows per CTA tile: 128 rows x 512 threads (one CTA per SM) or 64 rows x 256 threads (two per SM), see gemm_chain.cu
+template <bool DUAL, bool HAS_RA, int TM = BM>
+__global__ void __launch_bounds__(TM == BM ? 512 : 256, TM == BM ? 1 : 2) k_fwd(const float *__restrict__ Yin, const float *__restrict__ RYin,
                                                const float *__restrict__ W, const float *__restrict__ VW,
                                                int rows, int Kd, int N, char act,
                                                float *__restrict__ Yout, float *__restrict__ RYout,
@@ -201,10 +203,12 @@ __global__ void __launch_bounds__(512, 1) k_fwd(const float *__restrict__ Yin, c
                                                const int *__restrict__ done) {
     if (done && *done) return;
     extern __shared__ __align__(16) float smem_f[];
-    constexpr int STAGE = A_TILE * (DUAL && HAS_RA ? 2 : 1) + B_TILE * (DUAL ? 2 : 1);
-    constexpr int NTH = 512, WN = 4, NJ = BN / 8 / WN;      // 16 warps: 4 (m) x 4 (n), 32 x 16 warp tiles
+    constexpr int AT = TM * RSA;                             // floats per A tile of this variant
+    constexpr int STAGE = AT * (DUAL && HAS_RA ? 2 : 1) + B_TILE * (DUAL ? 2 : 1);
+    constexpr int NTH = TM == BM ? 512 : 256, WN = 4, NJ = BN / 8 / WN;      // (TM / 32) x 4 warps, 32 x 16 warp tiles
+    static_assert(NTH / 32 / WN * 32 == TM, "warp rows must cover the tile");
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3, wm = w / WN, wn = w % WN;
-    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int m0 = blockIdx.y * TM, n0 = blockIdx.x * BN;
     float acc[2][NJ][4] = {}, racc[2][NJ][4] = {};
     // as in gemm_chain.cu: a width that is a whole number of k-steps takes its bias as the accumulators' start value
     const bool bias_init = (Kd % BK) == 0;
@@ -223,18 +227,18 @@ __global__ void __launch_bounds__(512, 1) k_fwd(const float *__restrict__ Yin, c
     }
     auto stage_ptrs = [&](int st, float *&As, float *&RAs, float *&Bs, float *&VBs) {
         float *p = smem_f + st * STAGE;
-        As = p; p += A_TILE;
-        RAs = p; if (DUAL && HAS_RA) p += A_TILE;
+        As = p; p += AT;
+        RAs = p; if (DUAL && HAS_RA) p += AT;
         Bs = p; p += B_TILE;
         VBs = p;
     };
     auto load = [&](int st, int k0) {
         float *As, *RAs, *Bs, *VBs;
         stage_ptrs(st, As, RAs, Bs, VBs);
-        load_a_rowmajor<NTH>(As, Yin, rows, Kd, m0, k0, true, 1.0f, tid);
+        load_a_rowmajor<NTH, TM>(As, Yin, rows, Kd, m0, k0, true, 1.0f, tid);
         load_b_rowmajor<NTH>(Bs, W, Kd + 1, N, k0, n0, tid);
         if (DUAL) {
-            if (HAS_RA) load_a_rowmajor<NTH>(RAs, RYin, rows, Kd, m0, k0, false, 0.0f, tid);
+            if (HAS_RA) load_a_rowmajor<NTH, TM>(RAs, RYin, rows, Kd, m0, k0, false, 0.0f, tid);
             load_b_rowmajor<NTH>(VBs, VW, Kd + 1, N, k0, n0, tid);
         }
         cp_commit();
@@ -394,6 +398,9 @@ __global__ void __launch_bounds__(256) k_reduce_f32(const float *__restrict__ pa
 
 constexpr size_t SMEM_DUAL = sizeof(float) * 2 * (2 * A_TILE + 2 * B_TILE);
 constexpr size_t SMEM_L0 = sizeof(float) * 2 * (A_TILE + 2 * B_TILE);
+constexpr int TM_HALF = 64;
+constexpr size_t SMEM_DUAL_H = sizeof(float) * 2 * (2 * TM_HALF * RSA + 2 * B_TILE);
+constexpr size_t SMEM_L0_H = sizeof(float) * 2 * (TM_HALF * RSA + 2 * B_TILE);
 constexpr size_t SMEM_SINGLE = sizeof(float) * 2 * (A_TILE + B_TILE);
 
 bool configure() {
@@ -402,6 +409,8 @@ bool configure() {
     bool r = true;
     r = r && cudaFuncSetAttribute(k_fwd<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_DUAL) == cudaSuccess;
     r = r && cudaFuncSetAttribute(k_fwd<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_L0) == cudaSuccess;
+    r = r && cudaFuncSetAttribute(k_fwd<true, true, TM_HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_DUAL_H) == cudaSuccess;
+    r = r && cudaFuncSetAttribute(k_fwd<true, false, TM_HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_L0_H) == cudaSuccess;
     r = r && cudaFuncSetAttribute(k_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_SINGLE) == cudaSuccess;
     r = r && cudaFuncSetAttribute(k_outer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_SINGLE) == cudaSuccess;
     if (r) once.mark();
@@ -446,14 +455,23 @@ int chain_f32_accumulate(const NetDesc &net, const ChainScratchF32 &sc, const fl
             const bool last = (i == K - 1);
             const bool needY = !last || net.ac[K] == 't' || net.ac[K] == 's';
             dim3 grid(cdiv(net.L[i + 1], BN), cdiv(rows, BM));
-            if (i == 0)
-                k_fwd<true, false><<<grid, 512, SMEM_L0, st>>>(Yin, nullptr, f_theta + net.w_off[i], f_v + net.w_off[i], rows,
-                        net.L[i], net.L[i + 1], net.ac[i + 1], needY ? sc.Y[i + 1] : nullptr,
-                        last ? nullptr : sc.RY[(i + 1) & 1], last ? sc.G[K & 1] : nullptr, f_inv_var, d_done);
+            // two 64-row CTAs per SM by default (TRPO_CHAIN_FWD_TM=128: one 128-row CTA), as in the FP64 chain
+            static const bool half_tiles = !(getenv("TRPO_CHAIN_FWD_TM") && atoi(getenv("TRPO_CHAIN_FWD_TM")) == 128);
+            dim3 grid_h(cdiv(net.L[i + 1], BN), cdiv(rows, TM_HALF));
+            float *Yo = needY ? sc.Y[i + 1] : nullptr, *RYo = last ? nullptr : sc.RY[(i + 1) & 1], *Go = last ? sc.G[K & 1] : nullptr;
+            const float *Wl = f_theta + net.w_off[i], *VWl = f_v + net.w_off[i];
+            if (i == 0 && half_tiles)
+                k_fwd<true, false, TM_HALF><<<grid_h, 256, SMEM_L0_H, st>>>(Yin, nullptr, Wl, VWl, rows, net.L[i], net.L[i + 1], net.ac[i + 1],
+                                                                          Yo, RYo, Go, f_inv_var, d_done);
+            else if (i == 0)
+                k_fwd<true, false><<<grid, 512, SMEM_L0, st>>>(Yin, nullptr, Wl, VWl, rows, net.L[i], net.L[i + 1], net.ac[i + 1],
+                                                                Yo, RYo, Go, f_inv_var, d_done);
+            else if (half_tiles)
+                k_fwd<true, true, TM_HALF><<<grid_h, 256, SMEM_DUAL_H, st>>>(Yin, sc.RY[i & 1], Wl, VWl, rows, net.L[i], net.L[i + 1],
+                                                                           net.ac[i + 1], Yo, RYo, Go, f_inv_var, d_done);
             else
-                k_fwd<true, true><<<grid, 512, SMEM_DUAL, st>>>(Yin, sc.RY[i & 1], f_theta + net.w_off[i], f_v + net.w_off[i], rows,
-                        net.L[i], net.L[i + 1], net.ac[i + 1], needY ? sc.Y[i + 1] : nullptr,
-                        last ? nullptr : sc.RY[(i + 1) & 1], last ? sc.G[K & 1] : nullptr, f_inv_var, d_done);
+                k_fwd<true, true><<<grid, 512, SMEM_DUAL, st>>>(Yin, sc.RY[i & 1], Wl, VWl, rows, net.L[i], net.L[i + 1], net.ac[i + 1],
+                                                                 Yo, RYo, Go, f_inv_var, d_done);
             ++*launches;
         }
         for (int i = K; i >= 1; --i) {
