@@ -100,8 +100,8 @@ enum { TRPO_PATH_AUTO = 0, TRPO_PATH_GEMM_CHAIN = 1, TRPO_PATH_FUSED = 2 };
 /* Diagnostics of the last CG / update on a context. */
 typedef struct {
     int    cg_iters;            /* FVPs executed by the last CG */
-    double cg_rdotr[34];        /* value printed as "Residual Norm" at iteration i (i <= MaxIter <= 32) */
-    double cg_xnorm[34];        /* value printed as "Soln Norm" */
+    double cg_rdotr[34];        /* value printed as "Residual Norm" at iteration i: the first 34 entries of the trace */
+    double cg_xnorm[34];        /* value printed as "Soln Norm"; trpo_ctx_get_cg_trace returns the whole trace      */
     double shs, lm, gnorm, fval;
     int    ls_steps, ls_accepted;
     double ls_actual[16], ls_expected[16], ls_ratio[16];
@@ -119,6 +119,11 @@ int    trpo_ctx_set_stream(trpo_ctx *ctx, void *cuda_stream);
 void  *trpo_ctx_get_stream(const trpo_ctx *ctx);
 int    trpo_ctx_set_path(trpo_ctx *ctx, int path);
 int    trpo_ctx_get_path(const trpo_ctx *ctx);      /* the path the last launch actually used */
+/* GEMM-chain path: samples per pass over the kernel chain (rounded up to a multiple of 128). 0 = automatic: as many whole
+ * waves of CTAs as fit 4 GB of activation scratch. A batch larger than the chunk is processed in several passes whose
+ * per-slice partial sums accumulate in place (the sum TRPO_FVP.c:903-921 forms sample by sample). */
+int    trpo_ctx_set_chunk(trpo_ctx *ctx, size_t chunk_samples);
+size_t trpo_ctx_get_chunk(const trpo_ctx *ctx);     /* chunk of the last GEMM-chain launch (0 before the first) */
 int    trpo_ctx_sync(trpo_ctx *ctx);
 /* Number of kernels launched by this context since creation (bench.py's gpu_launches). */
 long long trpo_ctx_launch_count(const trpo_ctx *ctx);
@@ -153,6 +158,9 @@ int trpo_ctx_policy_gradient(trpo_ctx *ctx, double *b_out);
 int trpo_ctx_forward(trpo_ctx *ctx, double *Mean_out);
 int trpo_ctx_update(trpo_ctx *ctx, double *Result, double CG_Damping);
 int trpo_ctx_get_info(const trpo_ctx *ctx, trpo_info *info);
+/* Whole per-iteration trace of the last CG (entries 0..cg_iters: what TRPO_CG.c:56 prints); MaxIter is unbounded as in the
+ * reference (TRPO_CG.c:45). Copies at most max_entries values into each array (either may be NULL); returns the count. */
+int trpo_ctx_get_cg_trace(const trpo_ctx *ctx, double *rdotr_out, double *xnorm_out, size_t max_entries);
 
 /* Asynchronous device-buffer calls: enqueue on the context stream and return (inputs/outputs are device
  * pointers to P doubles). The CG state never leaves the device; trpo_ctx_get_info after trpo_ctx_sync. */
@@ -164,6 +172,9 @@ double *trpo_device_alloc(size_t n_doubles);
 void    trpo_device_free(double *p);
 int     trpo_memcpy_h2d(double *dst_dev, const double *src_host, size_t n_doubles);
 int     trpo_memcpy_d2h(double *dst_host, const double *src_dev, size_t n_doubles);
+/* Page-locked host arrays: with a pinned Observ source trpo_ctx_set_batch streams the copy under the first FVP. */
+double *trpo_host_alloc_pinned(size_t n_doubles);
+void    trpo_host_free_pinned(double *p);
 
 /* ------------------------------------------------------------------------------------------------
  * The training loop around the update: what TRPO_Lightweight.c:541-694 does
@@ -208,6 +219,11 @@ int trpo_vf_advantage(trpo_vf *vf, const double *x, double gamma, double lam, do
  * returns 0.01*MSE + 0.001*|x|^2 and writes g = d/dx (n >= trpo_vf_num_params; the padding of g is zeroed).
  * Returns -1 after a failure (see trpo_last_error), like the reference does for an unsupported activation. */
 double trpo_vf_evaluate(void *vf, const double *x, double *g, const int n, const double step);
+/* libLBFGS cannot tell a failed evaluation from a low objective, so a failure is also recorded on the network: the callback
+ * then returns +inf with a zero gradient, and this returns 1 once (and clears the record). Check it after lbfgs() returns.
+ * Lifetime: a trpo_vf borrows its policy context's stream and communicator -- destroy it BEFORE the policy context and
+ * re-bind (trpo_vf_bind_batch / trpo_vf_advantage) after trpo_ctx_set_stream on the policy context. */
+int trpo_vf_failed(trpo_vf *vf);
 
 /* Binary replacement for the text data file (TRPO_FVP.c:731-762 re-parses N x (3A+O+1) decimal numbers on every call):
  * a 64-byte header {"TRPOB200", version, flags, N, O, A} followed by Std[A], Observ[N*O], Mean[N*A], Action[N*A],
@@ -248,7 +264,10 @@ int trpo_ctx_p2p_export(trpo_ctx *ctx, char handle_out[64]);
 int trpo_ctx_p2p_attach(trpo_ctx *ctx, const char *handles /* world_size x 64 bytes */);
 enum { TRPO_COMM_NCCL = 0, TRPO_COMM_P2P = 1 };
 int trpo_ctx_set_comm_mode(trpo_ctx *ctx, int mode);       /* P2P becomes the default once attached */
-int trpo_ctx_comm_error(trpo_ctx *ctx);                    /* non-zero if a peer / staging wait timed out (synchronises) */
+/* Non-zero if a peer / staging wait has timed out and no call has reported it yet (synchronises). The synchronous host-buffer
+ * calls (trpo_ctx_fvp / _cg / _update / trpo_vf_evaluate) check the same flags themselves: they fail with -1, reset the flag, and
+ * the device results of that call are poisoned (NaN) / the solve stopped. Callers of the asynchronous *_device calls poll this. */
+int trpo_ctx_comm_error(trpo_ctx *ctx);
 
 /* Total sample count over all ranks (the 1/N of TRPO_FVP.c:930). Computed by init_comm+set_batch via all-reduce. */
 size_t trpo_ctx_global_samples(const trpo_ctx *ctx);

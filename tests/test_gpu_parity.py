@@ -404,3 +404,137 @@ def test_forward_pass_matches_oracle(pkg, oracle, name):
         mean = ctx.forward(s["Observ"].shape[0])
     ref = oracle.forward(s["layers"], s["acfunc"], s["theta"], s["Observ"])
     assert np.abs(mean - ref).max() < 1e-13 * max(1.0, np.abs(ref).max())
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# round 2: the parity holes the round-1 review named
+
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+@pytest.mark.parametrize("layers,ac,n,chunk", [([17, 64, 64, 6], "lttl", 2500, 1024),        # 3 passes, ragged last (452)
+                                               ([376, 256, 256, 17], "lttl", 1100, 384),     # Humanoid width: 384+384+332
+                                               ([6, 7, 8, 9, 10, 3], "ltstol", 1000, 256),   # 4 passes, 6 layers, no tail kernel
+                                               ([9, 40, 30], "ltt", 700, 128)])              # tanh output layer: Y_K is kept
+def test_multi_chunk_gemm_chain(pkg, oracle, layers, ac, n, chunk, precision):
+    """A batch larger than the GEMM-chain chunk runs as several passes whose per-slice partial sums accumulate in place
+    (chain_accumulate's `accumulate = chunk_idx > 0`; the sum the reference forms sample by sample, TRPO_FVP.c:903-921).
+    trpo_ctx_set_chunk forces >= 3 passes with a ragged last one: FVP, policy gradient and the whole update against the
+    oracle, and against the same context's single-pass result."""
+    seed = 500 + sum(layers)
+    theta = pkg.synth.make_model(layers, seed)
+    batch = pkg.synth.make_batch(layers, ac, theta, n, seed)
+    batch["Mean"] = oracle.forward(layers, ac, theta, batch["Observ"])
+    vec = pkg.synth.make_vectors(layers, seed)
+    z_ref = oracle.fvp(layers, ac, theta, batch["Std"], batch["Observ"], 0.1, vec["v"])
+    pg_ref = oracle.policy_gradient(layers, ac, theta, batch["Observ"], batch["Mean"], batch["Action"], batch["Advantage"])
+    u_ref, uinfo = oracle.update(layers, ac, theta, batch["Std"], batch["Observ"], batch["Mean"], batch["Action"],
+                                 batch["Advantage"], 0.1)
+    fp32 = precision == "fp32"
+    out = {}
+    for tag, ch in (("multi", chunk), ("single", 0)):
+        with pkg.Context(layers, ac, precision=pkg.api.PRECISION_FP32 if fp32 else pkg.api.PRECISION_FP64) as ctx:
+            ctx.set_path(pkg.api.PATH_GEMM_CHAIN)
+            ctx.set_chunk(ch)
+            ctx.set_model(theta)
+            ctx.set_batch(batch["Observ"], batch["Std"], batch["Mean"], batch["Action"], batch["Advantage"])
+            z = ctx.fvp(vec["v"], 0.1)
+            used = ctx.chunk_used()
+            pg = ctx.policy_gradient()
+            u, ginfo = ctx.update(0.1)
+            out[tag] = (z, pg, u, ginfo.ls_steps, ginfo.ls_accepted)
+        if tag == "multi":
+            assert used == (chunk + 127) // 128 * 128 and (n + used - 1) // used >= 3, (used, n)
+        else:
+            assert used >= n
+    fvp_tol = FP32_TOL if fp32 else FVP_TOL
+    for tag in out:
+        z, pg, u, steps, acc = out[tag]
+        e = rel_err(z, z_ref)
+        assert e[0] < fvp_tol and e[1] < fvp_tol, (tag, layers, precision, e)
+        assert rel_err(pg, pg_ref)[0] < FVP_TOL, (tag, rel_err(pg, pg_ref))          # the policy gradient is FP64 in both modes
+        if not fp32:
+            cg_tol = CG_TOL if theta.size < n else 1e-4                              # see test_unusual_depths_and_widths
+            assert steps == uinfo.ls_steps and acc == uinfo.ls_accepted
+            assert rel_err(u, u_ref)[0] < cg_tol, (tag, layers, rel_err(u, u_ref))
+        else:
+            assert np.isfinite(u).all()
+    # several passes only change the order in which slices receive their samples
+    assert rel_err(out["multi"][0], out["single"][0])[0] < (FP32_TOL if fp32 else 1e-12)
+    assert rel_err(out["multi"][1], out["single"][1])[0] < 1e-12
+
+
+def test_batch_without_mean_action_advantage_invalidates_the_old_ones(pkg):
+    """A second trpo_ctx_set_batch WITHOUT Mean/Action/Advantage must not leave the previous (smaller) arrays paired with
+    the new rows: the policy gradient / update then fail instead of reading stale or out-of-bounds memory."""
+    s = load_synth("mlp64")
+    L, ac = s["layers"], s["acfunc"]
+    n = s["Observ"].shape[0]
+    with pkg.Context(L, ac) as ctx:
+        ctx.set_model(s["theta"])
+        ctx.set_batch(s["Observ"][: n // 2], s["Std"], s["Mean"][: n // 2], s["Action"][: n // 2], s["Advantage"][: n // 2])
+        ctx.policy_gradient()
+        ctx.set_batch(s["Observ"], s["Std"])                       # more rows, observations only
+        assert rel_err(ctx.fvp(s["v"], 0.1), s["ref_fvpfast"])[0] < FVP_TOL
+        with pytest.raises(RuntimeError, match="Mean/Action/Advantage"):
+            ctx.policy_gradient()
+        with pytest.raises(RuntimeError, match="Mean/Action/Advantage"):
+            ctx.update(0.1)
+        ctx.set_batch(s["Observ"], s["Std"], s["Mean"], s["Action"], s["Advantage"])
+        u, _ = ctx.update(0.1)
+    assert rel_err(u, s["ref_update"])[0] < CG_TOL
+
+
+def test_max_iter_is_unbounded_like_the_reference(pkg, oracle, armtest, tmp_path, capfd):
+    """TRPO_CG.c:45 loops `for iter = 0 .. MaxIter` with no upper bound on MaxIter; round 1 refused MaxIter > 32."""
+    a = armtest
+    with pkg.Context(ARM_LAYERS, ARM_AC) as ctx:
+        ctx.set_model(a["theta"])
+        ctx.set_batch(a["Observ"], a["Std"])
+        x, info = ctx.cg(a["cg_b"], 1000, 1e-10, 0.1)               # early exit at iteration 8, as with MaxIter = 10
+        assert info.cg_iters == 8 and rel_err(x, a["ref_cg_3150"])[0] < CG_TOL
+        x40, info = ctx.cg(a["cg_b"], 40, 0.0, 0.1)                 # ResidualTh = 0: all 40 FVPs run
+        assert info.cg_iters == 40
+        rd, xn = ctx.cg_trace()
+        assert len(rd) == 41 and len(xn) == 41 and np.isfinite(rd).all() and np.isfinite(xn).all()
+        assert np.allclose(rd[:8], a["cg_trace_rdotr_3150"][:8], rtol=1e-7)
+        assert np.array_equal(np.array(info.cg_rdotr[:34]), rd[:34])
+    ref40, nf, _, _ = oracle.cg(ARM_LAYERS, ARM_AC, a["theta"], a["Std"], a["Observ"], 0.1, a["cg_b"], 40, 0.0)
+    assert nf == 40 and rel_err(x40, ref40)[0] < 1e-6              # 30 further iterations on a converged system
+    mf, df = str(tmp_path / "m.txt"), str(tmp_path / "d.txt")
+    pkg.textio.write_model(mf, a["theta"])
+    pkg.textio.write_data(df, a["Mean"], a["Std"], a["Observ"], a["Action"], a["Advantage"])
+    capfd.readouterr()
+    x, t = pkg.CG_GPU(mf, df, ARM_LAYERS, ARM_AC, 3150, 0.1, a["cg_b"], 40, 0.0, 1)
+    out = capfd.readouterr().out
+    assert t >= 0 and "CG Iter[40] Residual Norm=" in out and "CG Iter[41]" not in out
+
+
+def test_reference_own_harness_against_the_dropin(pkg, armtest, tmp_path):
+    """The reference's OWN Test_FVP_FPGA / Test_CG_FPGA (/root/reference/src/TRPOCpuCode.c:138-311), compiled unmodified by
+    oracle/Makefile into oracle/_ref/ref_harness and linked against libtrpo_b200_dropin.so in the FPGA library's place: it
+    runs the reference's CPU FVP() / CG() beside FVP_FPGA / CG_FPGA on the ArmTest files and prints its MAPE."""
+    import os
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "oracle", "_ref", "ref_harness")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/ref_harness was not built (needs /root/reference at build time)")
+    a = armtest
+    pkg.textio.write_model(str(tmp_path / "ArmTestModel.txt"), a["theta"])
+    pkg.textio.write_data(str(tmp_path / "ArmTestData.txt"), a["Mean"], a["Std"], a["Observ"], a["Action"], a["Advantage"])
+    for fname, vin, vexp in (("ArmTestFVP.txt", a["fvp_in"], a["ref_fvpfast_3150"]), ("ArmTestCG.txt", a["cg_b"], a["cg_expected"])):
+        with open(tmp_path / fname, "w") as f:
+            for x, e in zip(vin, vexp):
+                f.write(f"{float(x)!r} {float(e)!r}\n")
+    out = subprocess.run([exe, "all"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-800:] + out.stderr[-800:]
+    assert "[ERROR]" not in out.stderr, out.stderr[-800:]
+    m_fvp = re.search(r"Test FPGA -+\n\[INFO\] FPGA Computing Time = ([0-9.e+-]+) seconds\n\[INFO\] Mean Absolute Percentage Error = ([0-9.e+-]+)%", out.stdout)
+    m_cg = re.search(r"Mean Absolute Percentage Error = ([0-9.e+-]+)%, Max Percentage Error = ([0-9.e+-]+)%", out.stdout)
+    assert m_fvp and m_cg, out.stdout[-1500:]
+    # the harness's own metric, in percent: FVP elements agree to ~1e-12 %, CG (8 iterations) to ~1e-8 %
+    assert float(m_fvp.group(2)) < 1e-8, out.stdout[-1500:]
+    assert float(m_cg.group(1)) < 1e-6 and float(m_cg.group(2)) < 1e-4, out.stdout[-1500:]
+    assert "Difference" not in out.stdout                           # no element off by more than 1 %
+    # both CG traces were printed: the GPU's (from CG_FPGA) and the reference's (from CG)
+    assert out.stdout.count("CG Iter[8] Residual Norm=") == 2

@@ -68,6 +68,14 @@ def lib():
         L.trpo_ctx_get_stream.argtypes = [C.c_void_p]
         L.trpo_ctx_set_path.argtypes = [C.c_void_p, C.c_int]
         L.trpo_ctx_get_path.argtypes = [C.c_void_p]
+        L.trpo_ctx_set_chunk.argtypes = [C.c_void_p, C.c_size_t]
+        L.trpo_ctx_get_chunk.restype = C.c_size_t
+        L.trpo_ctx_get_chunk.argtypes = [C.c_void_p]
+        L.trpo_ctx_get_cg_trace.argtypes = [C.c_void_p, c_double_p, c_double_p, C.c_size_t]
+        L.trpo_host_alloc_pinned.restype = C.c_void_p
+        L.trpo_host_alloc_pinned.argtypes = [C.c_size_t]
+        L.trpo_host_free_pinned.argtypes = [C.c_void_p]
+        L.trpo_vf_failed.argtypes = [C.c_void_p]
         L.trpo_ctx_sync.argtypes = [C.c_void_p]
         L.trpo_ctx_launch_count.restype = C.c_longlong
         L.trpo_ctx_launch_count.argtypes = [C.c_void_p]
@@ -212,8 +220,9 @@ class Context:
 
     def close(self):
         if self.h:
-            lib().trpo_ctx_destroy(self.h)
+            lib().trpo_ctx_destroy(self.h)          # synchronises: no copy can still be reading the kept source
             self.h = None
+        self._keep = []
 
     def __del__(self):
         try:
@@ -235,6 +244,20 @@ class Context:
 
     def path_used(self):
         return lib().trpo_ctx_get_path(self.h)
+
+    def set_chunk(self, chunk_samples):
+        """GEMM-chain path: samples per pass over the kernel chain (0 = automatic)."""
+        _check(lib().trpo_ctx_set_chunk(self.h, chunk_samples))
+
+    def chunk_used(self):
+        return lib().trpo_ctx_get_chunk(self.h)
+
+    def cg_trace(self):
+        """(rdotr, xnorm) of every iteration of the last CG -- the values TRPO_CG.c:56 prints."""
+        n = self.info().cg_iters + 1
+        rd, xn = np.zeros(n), np.zeros(n)
+        got = lib().trpo_ctx_get_cg_trace(self.h, _dp(rd), _dp(xn), n)
+        return rd[:got], xn[:got]
 
     def sync(self):
         _check(lib().trpo_ctx_sync(self.h))
@@ -259,6 +282,8 @@ class Context:
         observ = np.ascontiguousarray(observ, dtype=np.float64)
         std = np.ascontiguousarray(std, dtype=np.float64)
         arrs = [None if a is None else np.ascontiguousarray(a, dtype=np.float64) for a in (mean, action, advantage)]
+        # a pinned source is copied asynchronously (the first FVP overlaps the DMA): keep it alive until the next batch
+        self._keep = [observ]
         _check(lib().trpo_ctx_set_batch(self.h, observ.shape[0], _dp(observ), _dp(std), *[_dp(a) for a in arrs]))
 
     def set_batch_device(self, num_samples, d_observ, std, d_mean=0, d_action=0, d_advantage=0):
@@ -271,6 +296,7 @@ class Context:
         """Stage one batch of rollouts (row = ep * ep_len + step); the advantage comes from ValueFunction.advantage."""
         arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (observ, std, mean, action, reward)]
         assert arrs[0].shape[0] == num_ep * ep_len
+        self._keep = [arrs[0]]
         _check(lib().trpo_ctx_set_rollout(self.h, num_ep, ep_len, *[_dp(a) for a in arrs]))
 
     def rollout_arm(self, num_ep, ep_len, rand_draws=None, seed=0):

@@ -111,16 +111,18 @@ __global__ void __launch_bounds__(RED_COLS * RED_GROUPS) k_reduce_partials_push(
 }
 
 // Receive side: wait until every rank's contribution number `seq` has landed in OUR memory. Called by one block's
-// threads r < world; a bounded spin (about 4 s) records an error instead of hanging the GPU.
-__device__ __forceinline__ void p2p_wait(const P2PComm &c, unsigned long long seq) {
+// threads r < world; a bounded spin (about 20 s: ranks may arrive seconds apart after rollouts or a lazy module load)
+// records an error instead of hanging the GPU. Returns false after a timeout: the caller must NOT consume the slots.
+__device__ __forceinline__ bool p2p_wait(const P2PComm &c, unsigned long long seq) {
     if ((int)threadIdx.x < c.world) {
         const unsigned long long *f = &c.flags[c.rank][(seq & 1) * c.world + threadIdx.x];
         const long long t0 = clock64();
         while (ld_acquire_sys(f) < seq) {
-            if (clock64() - t0 > 8000000000LL) { *c.error = 1; break; }
+            if (clock64() - t0 > 40000000000LL) { *(volatile int *)c.error = 1; break; }
         }
     }
     __syncthreads();
+    return *(volatile int *)c.error == 0;
 }
 __device__ __forceinline__ double p2p_sum(const P2PComm &c, unsigned long long seq, int e) {
     const double *base = c.slots[c.rank] + (size_t)(seq & 1) * c.world * c.P;
@@ -133,9 +135,10 @@ __device__ __forceinline__ double p2p_sum(const P2PComm &c, unsigned long long s
 __global__ void k_fvp_finalise_p2p(const double *__restrict__ v, double *__restrict__ out, int logstd_off,
                                    double n_total, double damping, const P2PComm c) {
     const unsigned long long seq = *c.seq_dev + 1;
-    p2p_wait(c, seq);
+    const bool ok = p2p_wait(c, seq);
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= c.P) return;
+    if (!ok) { out[e] = __longlong_as_double(0x7ff8000000000000LL); return; }     // poisoned: the host call fails as well
     const double mean = (e >= logstd_off) ? 2.0 * v[e] : p2p_sum(c, seq, e) / n_total;
     out[e] = mean + damping * v[e];
 }
@@ -152,7 +155,8 @@ __global__ void k_fvp_finalise(const double *__restrict__ zsum, const double *__
 
 __global__ void __launch_bounds__(CG_THREADS) k_cg_init(const double *__restrict__ b, double *__restrict__ x,
                                                         double *__restrict__ r, double *__restrict__ p, int P,
-                                                        double residual_th, CgState *st) {
+                                                        double residual_th, CgState *st, double *__restrict__ trace,
+                                                        int trace_cap) {
     __shared__ double red[32];
     double acc = 0.0;
     for (int i = threadIdx.x; i < P; i += blockDim.x) {
@@ -163,7 +167,7 @@ __global__ void __launch_bounds__(CG_THREADS) k_cg_init(const double *__restrict
     const double rdotr = block_sum(acc, red);
     if (threadIdx.x == 0) {
         st->rdotr = rdotr; st->pdotz = 0.0; st->xnorm = 0.0; st->iters = 0;
-        st->trace_rdotr[0] = rdotr; st->trace_xnorm[0] = 0.0;
+        trace[0] = rdotr; trace[trace_cap] = 0.0;
         st->done = (rdotr < residual_th) ? 1 : 0;
     }
 }
@@ -174,11 +178,18 @@ template <bool P2P>
 __global__ void __launch_bounds__(CG_THREADS) k_cg_update(const double *__restrict__ zsum, double *__restrict__ x,
                                                           double *__restrict__ r, double *__restrict__ p,
                                                           double *__restrict__ z, int P, int logstd_off, double n_total,
-                                                          double damping, double residual_th, CgState *st, const P2PComm c) {
+                                                          double damping, double residual_th, CgState *st,
+                                                          double *__restrict__ trace, int trace_cap, const P2PComm c) {
     if (st->done) return;
     __shared__ double red[32];
     unsigned long long seq = 0;
-    if (P2P) { seq = *c.seq_dev + 1; p2p_wait(c, seq); }
+    if (P2P) {
+        seq = *c.seq_dev + 1;
+        if (!p2p_wait(c, seq)) {          // a peer never arrived: stop the solve, poison the residual, keep seq where it was
+            if (threadIdx.x == 0) { st->done = 1; st->rdotr = __longlong_as_double(0x7ff8000000000000LL); }
+            return;
+        }
+    }
     const double rdotr = st->rdotr;
     double acc = 0.0;
     for (int i = threadIdx.x; i < P; i += blockDim.x) {
@@ -206,7 +217,7 @@ __global__ void __launch_bounds__(CG_THREADS) k_cg_update(const double *__restri
         const int it = st->iters + 1;
         st->iters = it;
         st->rdotr = newrdotr; st->pdotz = pdotz; st->xnorm = sqrt(xx);
-        if (it < 34) { st->trace_rdotr[it] = newrdotr; st->trace_xnorm[it] = sqrt(xx); }
+        if (it < trace_cap) { trace[it] = newrdotr; trace[trace_cap + it] = sqrt(xx); }
         if (newrdotr < residual_th) st->done = 1;
         if (P2P) *c.seq_dev = seq;
     }
@@ -289,18 +300,18 @@ void launch_fvp_finalise(const double *d_zsum, const double *d_v, double *d_out,
 }
 
 void launch_cg_init(const double *d_b, double *d_x, double *d_r, double *d_p, int P, double residual_th,
-                    CgState *d_state, cudaStream_t st, long long *launches) {
-    k_cg_init<<<1, CG_THREADS, 0, st>>>(d_b, d_x, d_r, d_p, P, residual_th, d_state);
+                    CgState *d_state, double *d_trace, int trace_cap, cudaStream_t st, long long *launches) {
+    k_cg_init<<<1, CG_THREADS, 0, st>>>(d_b, d_x, d_r, d_p, P, residual_th, d_state, d_trace, trace_cap);
     ++*launches;
 }
 
 void launch_cg_update(const double *d_zsum, double *d_x, double *d_r, double *d_p, double *d_z, int P, int logstd_off,
-                      double n_total, double damping, double residual_th, CgState *d_state, const P2PComm *p2p,
-                      cudaStream_t st, long long *launches) {
+                      double n_total, double damping, double residual_th, CgState *d_state, double *d_trace, int trace_cap,
+                      const P2PComm *p2p, cudaStream_t st, long long *launches) {
     if (p2p && p2p->world > 1)
-        k_cg_update<true><<<1, CG_THREADS, 0, st>>>(d_zsum, d_x, d_r, d_p, d_z, P, logstd_off, n_total, damping, residual_th, d_state, *p2p);
+        k_cg_update<true><<<1, CG_THREADS, 0, st>>>(d_zsum, d_x, d_r, d_p, d_z, P, logstd_off, n_total, damping, residual_th, d_state, d_trace, trace_cap, *p2p);
     else
-        k_cg_update<false><<<1, CG_THREADS, 0, st>>>(d_zsum, d_x, d_r, d_p, d_z, P, logstd_off, n_total, damping, residual_th, d_state, P2PComm{});
+        k_cg_update<false><<<1, CG_THREADS, 0, st>>>(d_zsum, d_x, d_r, d_p, d_z, P, logstd_off, n_total, damping, residual_th, d_state, d_trace, trace_cap, P2PComm{});
     ++*launches;
 }
 

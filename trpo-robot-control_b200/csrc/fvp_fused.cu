@@ -123,14 +123,15 @@ __device__ __forceinline__ int ld_volatile_i32(const int *p) {
     asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-// Block until the chunk holding sample `last_sample` has been copied in (bounded spin: ~4 s, then flag an error).
+// Block until the chunk holding sample `last_sample` has been copied in (bounded spin: ~4 s, then flag an error; the
+// host entry points read the flag after their synchronisation and fail the call).
 __device__ __forceinline__ void wait_samples(const FusedArgs &p, long long last_sample) {
     if (p.ready == nullptr) return;
     const int need = (int)(last_sample / p.chunk_samples) + 1;
     if (ld_volatile_i32(p.ready) >= need) return;
     const long long t0 = clock64();
     while (ld_volatile_i32(p.ready) < need) {
-        if (clock64() - t0 > 8000000000LL) { *p.error = 2; break; }
+        if (clock64() - t0 > 8000000000LL) { *(volatile int *)p.error = 2; break; }
     }
 }
 

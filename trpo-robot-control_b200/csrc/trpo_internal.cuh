@@ -36,9 +36,10 @@ struct CgState {
     double xnorm;
     int    done;        // set when rdotr < ResidualTh: the remaining iterations become no-ops
     int    iters;       // FVPs executed
-    double trace_rdotr[34];
-    double trace_xnorm[34];
 };
+// The per-iteration trace ("Residual Norm" / "Soln Norm" of TRPO_CG.c:56) lives in a separate device buffer of
+// 2 * trace_cap doubles (rdotr[0..cap), xnorm[0..cap)) that the context grows to MaxIter + 2: the reference places no
+// bound on MaxIter (TRPO_CG.c:45).
 
 // Scratch for the GEMM-chain path: activations of one sample chunk, row-major [chunk x L_i].
 struct ChainScratch {
@@ -118,10 +119,10 @@ void launch_reduce_partials(const double *d_partial, int rows, int P, double *d_
 void launch_fvp_finalise(const double *d_zsum, const double *d_v, double *d_out, int P, int logstd_off,
                          double n_total, double damping, const P2PComm *p2p, cudaStream_t st, long long *launches);
 void launch_cg_init(const double *d_b, double *d_x, double *d_r, double *d_p, int P, double residual_th,
-                    CgState *d_state, cudaStream_t st, long long *launches);
+                    CgState *d_state, double *d_trace, int trace_cap, cudaStream_t st, long long *launches);
 void launch_cg_update(const double *d_zsum, double *d_x, double *d_r, double *d_p, double *d_z, int P, int logstd_off,
-                      double n_total, double damping, double residual_th, CgState *d_state, const P2PComm *p2p,
-                      cudaStream_t st, long long *launches);
+                      double n_total, double damping, double residual_th, CgState *d_state, double *d_trace, int trace_cap,
+                      const P2PComm *p2p, cudaStream_t st, long long *launches);
 // out[0] = sum_i a[i]*b[i] with the same fixed-order reduction (used for shs, gnorm, b.x)
 void launch_dot(const double *d_a, const double *d_b, int n, double *d_out, cudaStream_t st, long long *launches);
 void launch_axpby(double *d_out, const double *d_x, double a, const double *d_y, double b, int n,

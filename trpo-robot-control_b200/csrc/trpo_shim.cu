@@ -72,6 +72,8 @@ struct trpo_ctx {
     double *d_obs, *d_mean, *d_action, *d_adv;
     bool own_batch;
     size_t cap_obs, cap_mean, cap_adv;
+    size_t n_full;             // rows for which Mean / Action / Advantage are staged (0: the batch carries observations only)
+    size_t chunk_override;     // trpo_ctx_set_chunk: samples per GEMM-chain pass (0 = automatic)
     // rollout staging (rows f-3/f-4): per-step rewards of the staged batch and its episode length
     double *d_reward;
     size_t cap_reward, ep_len;
@@ -86,6 +88,9 @@ struct trpo_ctx {
     size_t cap_mean_new;
     CgState *d_state;
     CgState *h_state;          // pinned
+    double *d_trace, *h_trace; // per-iteration CG trace: rdotr[0..trace_cap), xnorm[0..trace_cap) (h_trace pinned)
+    int trace_cap;
+    int *h_flags;              // pinned: [0] peer-memory wait error, [1] streamed-staging wait error (read back after a sync)
     double *h_scal;            // pinned
     // gemm-chain scratch
     ChainScratch sc;
@@ -160,6 +165,7 @@ static int ensure_chain_scratch(trpo_ctx *c) {
         for (int i = 1; i <= c->net.K; ++i) if ((size_t)c->net.L[i] + 1 > widest) widest = c->net.L[i] + 1;
         while (chunk > unit && chunk * widest >= ((size_t)1 << 31)) chunk -= unit;
     }
+    if (c->chunk_override) chunk = ((c->chunk_override + 127) / 128) * 128;      // trpo_ctx_set_chunk (tests, memory-tight callers)
     if (c->n_local && chunk > ((c->n_local + 127) / 128) * 128) chunk = ((c->n_local + 127) / 128) * 128;
     int nslices = 148;
     if ((size_t)nslices * 16 > chunk) nslices = (int)(chunk / 16);
@@ -225,6 +231,10 @@ extern "C" trpo_ctx *trpo_ctx_create(const size_t *LayerSize, const char *AcFunc
     ok = ok && cudaMalloc(&c->d_state, sizeof(CgState)) == cudaSuccess;
     ok = ok && cudaMallocHost(&c->h_state, sizeof(CgState)) == cudaSuccess;
     ok = ok && cudaMallocHost(&c->h_scal, 16 * sizeof(double)) == cudaSuccess;
+    ok = ok && cudaMallocHost(&c->h_flags, 2 * sizeof(int)) == cudaSuccess;
+    c->trace_cap = 64;
+    ok = ok && cudaMalloc(&c->d_trace, 2 * (size_t)c->trace_cap * sizeof(double)) == cudaSuccess;
+    ok = ok && cudaMallocHost(&c->h_trace, 2 * (size_t)c->trace_cap * sizeof(double)) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&c->ev_compute, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming) == cudaSuccess;
@@ -247,6 +257,7 @@ static void free_batch(trpo_ctx *c) {
     if (c->own_batch) { cudaFree(c->d_obs); cudaFree(c->d_mean); cudaFree(c->d_action); cudaFree(c->d_adv); }
     c->d_obs = c->d_mean = c->d_action = c->d_adv = nullptr;
     c->cap_obs = c->cap_mean = c->cap_adv = 0;
+    c->n_full = 0;
     c->own_batch = false;
 }
 
@@ -269,6 +280,9 @@ extern "C" void trpo_ctx_destroy(trpo_ctx *c) {
     if (c->d_state) cudaFree(c->d_state);
     if (c->h_state) cudaFreeHost(c->h_state);
     if (c->h_scal) cudaFreeHost(c->h_scal);
+    if (c->h_flags) cudaFreeHost(c->h_flags);
+    if (c->d_trace) cudaFree(c->d_trace);
+    if (c->h_trace) cudaFreeHost(c->h_trace);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     if (c->ev_compute) cudaEventDestroy(c->ev_compute);
     if (c->ev_copy) cudaEventDestroy(c->ev_copy);
@@ -300,6 +314,15 @@ extern "C" int trpo_ctx_set_path(trpo_ctx *c, int path) {
     return 0;
 }
 extern "C" int trpo_ctx_get_path(const trpo_ctx *c) { return c ? c->path_used : 0; }
+extern "C" int trpo_ctx_set_chunk(trpo_ctx *c, size_t chunk_samples) {
+    if (!c) return fail("null context");
+    c->chunk_override = chunk_samples;
+    return 0;
+}
+extern "C" size_t trpo_ctx_get_chunk(const trpo_ctx *c) {
+    if (!c) return 0;
+    return c->precision == TRPO_PRECISION_FP32 ? (size_t)c->scf.chunk : (size_t)c->sc.chunk;
+}
 extern "C" int trpo_ctx_sync(trpo_ctx *c) {
     if (!c) return fail("null context");
     CU(cudaSetDevice(c->device));
@@ -381,9 +404,12 @@ extern "C" int trpo_ctx_set_batch(trpo_ctx *c, size_t N, const double *Observ, c
         // pinned source: DMA in STAGE_CHUNKS pieces on the copy stream, bumping the device-side chunk counter after each
         // piece; the compute stream is not made to wait (the fused kernel polls the counter, see wait_samples)
         c->stage_chunk = ((N + STAGE_CHUNKS - 1) / STAGE_CHUNKS + 63) / 64 * 64;
+        // The chunk counter is reset on the COMPUTE stream: the copy stream waits on ev_compute, so the reset is ordered
+        // before every chunk bump, and the polling kernel is launched on the compute stream after it -- a reset issued on
+        // the copy stream had no ordering against that kernel (it could still see the previous batch's final count).
+        CU(cudaMemsetAsync(c->d_ready, 0, sizeof(int), c->stream));
         CU(cudaEventRecord(c->ev_compute, c->stream));
         CU(cudaStreamWaitEvent(c->copy_stream, c->ev_compute, 0));          // do not overwrite rows still being read
-        CU(cudaMemcpyAsync(c->d_ready, &c->h_ready_vals[0], sizeof(int), cudaMemcpyHostToDevice, c->copy_stream));
         int landed = 0;
         for (size_t s0 = 0; s0 < N; s0 += c->stage_chunk) {
             const size_t n = (N - s0 < c->stage_chunk) ? N - s0 : c->stage_chunk;
@@ -408,6 +434,9 @@ extern "C" int trpo_ctx_set_batch(trpo_ctx *c, size_t N, const double *Observ, c
         CU(cudaMemcpyAsync(c->d_mean, Mean, N * A * sizeof(double), cudaMemcpyHostToDevice, c->stream));
         CU(cudaMemcpyAsync(c->d_action, Action, N * A * sizeof(double), cudaMemcpyHostToDevice, c->stream));
         CU(cudaMemcpyAsync(c->d_adv, Advantage, N * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        c->n_full = N;
+    } else {
+        c->n_full = 0;         // stale Mean / Action / Advantage of an earlier batch must not be paired with these rows
     }
     c->n_local = N;
     if (set_std(c, Std)) return -1;
@@ -424,6 +453,7 @@ extern "C" int trpo_ctx_set_batch_device(trpo_ctx *c, size_t N, const double *dO
     c->own_batch = false;
     c->d_obs = (double *)dObserv; c->d_mean = (double *)dMean; c->d_action = (double *)dAction; c->d_adv = (double *)dAdvantage;
     c->n_local = N;
+    c->n_full = (dMean && dAction && dAdvantage) ? N : 0;
     if (set_std(c, Std_host)) return -1;
     return update_global_samples(c);
 }
@@ -492,6 +522,7 @@ extern "C" int trpo_ctx_set_batch_file(trpo_ctx *c, const char *path, size_t N) 
     for (int i = 0; i < 2; ++i) { if (pin[i]) cudaFreeHost(pin[i]); if (ev[i]) cudaEventDestroy(ev[i]); }
     if (rc) return rc;
     c->n_local = N;
+    c->n_full = full ? N : 0;
     if (set_std(c, std_host)) return -1;
     return update_global_samples(c);
 }
@@ -500,6 +531,7 @@ extern "C" int trpo_ctx_set_batch_file(trpo_ctx *c, const char *path, size_t N) 
 static inline const P2PComm *active_p2p(const trpo_ctx *c) {
     return (c->p2p_on && c->p2p.world > 1 && c->precision == TRPO_PRECISION_FP64) ? &c->p2p : nullptr;
 }
+static inline bool active_p2p_ctx(const trpo_ctx *c) { return active_p2p(c) != nullptr; }
 
 extern "C" int trpo_ctx_kernel_timing(trpo_ctx *c, int enable) {
     if (!c) return fail("null context");
@@ -548,6 +580,7 @@ static int ensure_f32_scratch(trpo_ctx *c) {
         for (int i = 1; i <= c->net.K; ++i) if ((size_t)c->net.L[i] + 1 > widest) widest = c->net.L[i] + 1;
         while (chunk > unit && chunk * widest >= ((size_t)1 << 31)) chunk -= unit;
     }
+    if (c->chunk_override) chunk = ((c->chunk_override + 127) / 128) * 128;
     if (c->n_local && chunk > ((c->n_local + 127) / 128) * 128) chunk = ((c->n_local + 127) / 128) * 128;
     int nslices = 148;
     if ((size_t)nslices * 32 > chunk) nslices = (int)(chunk / 32);
@@ -624,11 +657,11 @@ extern "C" int trpo_ctx_fvp_device(trpo_ctx *c, const double *dInput, double *dR
 }
 
 static int cg_enqueue(trpo_ctx *c, const double *db, double *dResult, size_t MaxIter, double ResidualTh, double damping) {
-    launch_cg_init(db, c->d_x, c->d_r, c->d_p, c->net.P, ResidualTh, c->d_state, c->stream, &c->launches);
+    launch_cg_init(db, c->d_x, c->d_r, c->d_p, c->net.P, ResidualTh, c->d_state, c->d_trace, c->trace_cap, c->stream, &c->launches);
     for (size_t it = 0; it < MaxIter; ++it) {
         if (fvp_sum(c, c->d_p, &c->d_state->done)) return -1;
         launch_cg_update(c->d_zsum, c->d_x, c->d_r, c->d_p, c->d_z, c->net.P, c->net.logstd_off, (double)c->n_total, damping,
-                         ResidualTh, c->d_state, active_p2p(c), c->stream, &c->launches);
+                         ResidualTh, c->d_state, c->d_trace, c->trace_cap, active_p2p(c), c->stream, &c->launches);
     }
     CU(cudaMemcpyAsync(dResult, c->d_x, c->net.P * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
     return 0;
@@ -636,8 +669,20 @@ static int cg_enqueue(trpo_ctx *c, const double *db, double *dResult, size_t Max
 
 extern "C" int trpo_ctx_cg_device(trpo_ctx *c, const double *db, double *dResult, size_t MaxIter, double ResidualTh, double damping) {
     if (!c || !db || !dResult) return fail("null argument");
-    if (MaxIter > 32) return fail("MaxIter > 32 not supported by the device trace buffer");
+    if (MaxIter > (size_t)1 << 20) return fail("MaxIter %zu is not a sensible iteration count", MaxIter);
     CU(cudaSetDevice(c->device));
+    if ((size_t)c->trace_cap < MaxIter + 2) {
+        // the reference places no bound on MaxIter (TRPO_CG.c:45): grow the per-iteration trace buffers
+        int cap = c->trace_cap;
+        while ((size_t)cap < MaxIter + 2) cap *= 2;
+        CU(cudaStreamSynchronize(c->stream));
+        if (c->cg_exec) { cudaGraphExecDestroy(c->cg_exec); c->cg_exec = nullptr; c->cg_key_seen = 0; memset(&c->cg_key, 0, sizeof(c->cg_key)); }
+        cudaFree(c->d_trace); cudaFreeHost(c->h_trace);
+        c->d_trace = c->h_trace = nullptr;
+        CU(cudaMalloc(&c->d_trace, 2 * (size_t)cap * sizeof(double)));
+        CU(cudaMallocHost(&c->h_trace, 2 * (size_t)cap * sizeof(double)));
+        c->trace_cap = cap;
+    }
     // A solve is 3 launches per iteration; for small batches (armDOF_0 x 50 k states: a whole FVP is ~30 us) the launch
     // gaps are a fifth of the solve, so an identical repeated solve is captured once into a CUDA graph and replayed.
     static const bool no_graph = getenv("TRPO_NO_GRAPH") != nullptr;
@@ -684,12 +729,55 @@ extern "C" int trpo_ctx_cg_device(trpo_ctx *c, const double *db, double *dResult
     return 0;
 }
 
+// Synchronise the context stream and fail the call if a device-side wait timed out since the last check: a peer that
+// never pushed its FVP sum (peer-memory all-reduce) or a staged chunk that never landed. The flags are reset, the results
+// of the call are not to be used (the kernels poison them with NaN / stop the solve).
+static int sync_and_check(trpo_ctx *c) {
+    c->h_flags[0] = c->h_flags[1] = 0;
+    if (c->p2p_buf) CU(cudaMemcpyAsync(&c->h_flags[0], c->p2p_buf + 268, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(&c->h_flags[1], c->d_ready + 1, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->h_flags[0] || c->h_flags[1]) {
+        const int e0 = c->h_flags[0], e1 = c->h_flags[1];
+        if (e0) cudaMemsetAsync(c->p2p_buf + 268, 0, sizeof(int), c->stream);
+        if (e1) cudaMemsetAsync(c->d_ready + 1, 0, sizeof(int), c->stream);
+        cudaStreamSynchronize(c->stream);
+        return fail(e0 ? "peer-memory all-reduce timed out: a rank never delivered its FVP sum (results discarded)"
+                       : "streamed batch staging timed out: a chunk of the observation matrix never landed (results discarded)");
+    }
+    return 0;
+}
+
 static int fetch_cg_info(trpo_ctx *c) {
     CU(cudaMemcpyAsync(c->h_state, c->d_state, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaMemcpyAsync(c->h_trace, c->d_trace, 2 * (size_t)c->trace_cap * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (sync_and_check(c)) return -1;
     c->info.cg_iters = c->h_state->iters;
-    memcpy(c->info.cg_rdotr, c->h_state->trace_rdotr, sizeof(c->info.cg_rdotr));
-    memcpy(c->info.cg_xnorm, c->h_state->trace_xnorm, sizeof(c->info.cg_xnorm));
+    const int keep = (int)(sizeof(c->info.cg_rdotr) / sizeof(double));
+    for (int i = 0; i < keep; ++i) {
+        const bool have = i <= c->h_state->iters && i < c->trace_cap;
+        c->info.cg_rdotr[i] = have ? c->h_trace[i] : 0.0;
+        c->info.cg_xnorm[i] = have ? c->h_trace[c->trace_cap + i] : 0.0;
+    }
+    return 0;
+}
+
+extern "C" int trpo_ctx_get_cg_trace(const trpo_ctx *c, double *rdotr_out, double *xnorm_out, size_t max_entries) {
+    if (!c) return -1;
+    const size_t have = (size_t)c->info.cg_iters + 1 < (size_t)c->trace_cap ? (size_t)c->info.cg_iters + 1 : (size_t)c->trace_cap;
+    const size_t n = have < max_entries ? have : max_entries;
+    for (size_t i = 0; i < n; ++i) {
+        if (rdotr_out) rdotr_out[i] = c->h_trace[i];
+        if (xnorm_out) xnorm_out[i] = c->h_trace[c->trace_cap + i];
+    }
+    return (int)n;
+}
+
+// Host-buffer entry points with the peer-memory exchange: one tiny NCCL all-reduce first, so that ranks which enter
+// seconds apart (rollouts, L-BFGS, first-use module loads) are aligned before any kernel starts its bounded spin.
+static int p2p_align_ranks(trpo_ctx *c) {
+    if (!c->comm || !active_p2p_ctx(c)) return 0;
+    NC(g_nccl.AllReduce(c->d_scal + 15, c->d_scal + 15, 1, ncclFloat64_, ncclSum_, c->comm, c->stream));
     return 0;
 }
 
@@ -698,10 +786,10 @@ extern "C" int trpo_ctx_fvp(trpo_ctx *c, const double *Input, double *Result, do
     CU(cudaSetDevice(c->device));
     const size_t bytes = c->net.P * sizeof(double);
     CU(cudaMemcpyAsync(c->d_in, Input, bytes, cudaMemcpyHostToDevice, c->stream));
+    if (p2p_align_ranks(c)) return -1;
     if (trpo_ctx_fvp_device(c, c->d_in, c->d_out, damping)) return -1;
     CU(cudaMemcpyAsync(Result, c->d_out, bytes, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    return 0;
+    return sync_and_check(c);
 }
 
 extern "C" int trpo_ctx_cg(trpo_ctx *c, const double *b, double *Result, size_t MaxIter, double ResidualTh, double damping) {
@@ -709,6 +797,7 @@ extern "C" int trpo_ctx_cg(trpo_ctx *c, const double *b, double *Result, size_t 
     CU(cudaSetDevice(c->device));
     const size_t bytes = c->net.P * sizeof(double);
     CU(cudaMemcpyAsync(c->d_b, b, bytes, cudaMemcpyHostToDevice, c->stream));
+    if (p2p_align_ranks(c)) return -1;
     if (trpo_ctx_cg_device(c, c->d_b, c->d_out, MaxIter, ResidualTh, damping)) return -1;
     CU(cudaMemcpyAsync(Result, c->d_out, bytes, cudaMemcpyDeviceToHost, c->stream));
     return fetch_cg_info(c);
@@ -727,7 +816,8 @@ static bool fused_pg_eligible(const trpo_ctx *c) {
     return fused_eligible(c->net) && c->path_req != TRPO_PATH_GEMM_CHAIN && c->precision == TRPO_PRECISION_FP64;
 }
 static int policy_gradient_device(trpo_ctx *c, double *own_mean_out = nullptr) {
-    if (!c->d_obs || !c->d_mean || !c->d_action || !c->d_adv) return fail("policy gradient needs Mean/Action/Advantage in the batch");
+    if (!c->d_obs || !c->d_mean || !c->d_action || !c->d_adv || c->n_full != c->n_local || c->n_local == 0)
+        return fail("policy gradient needs Mean/Action/Advantage in the batch (the current batch was staged without them)");
     if (c->copy_inflight) { CU(cudaStreamWaitEvent(c->stream, c->ev_copy, 0)); c->copy_inflight = false; }
     c->stream_first_fvp = false;
     if (ensure_chain_scratch(c)) return -1;      // the line search's forward pass uses it in any case
@@ -795,6 +885,7 @@ extern "C" int trpo_ctx_update(trpo_ctx *c, double *Result, double damping) {
     const size_t MaxIter = 10, MaxBackTracks = 10;
     const int P = c->net.P, A = c->net.L[c->net.K];
     memset(&c->info, 0, sizeof(c->info));
+    if (p2p_align_ranks(c)) return -1;
     if (policy_gradient_device(c)) return -1;
     if (trpo_ctx_cg_device(c, c->d_b, c->d_out, MaxIter, ResidualTh, damping)) return -1;   // d_x = stepdir
     if (trpo_ctx_fvp_device(c, c->d_x, c->d_z, damping)) return -1;                          // z = F x + damping x
@@ -839,8 +930,7 @@ extern "C" int trpo_ctx_update(trpo_ctx *c, double *Result, double damping) {
         if (ratio > AcceptRatio && actual > 0) { c->info.ls_accepted = 1; d_result = c->d_xnew; break; }
     }
     CU(cudaMemcpyAsync(Result, d_result, P * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    return 0;
+    return sync_and_check(c);
 }
 
 
@@ -896,6 +986,7 @@ extern "C" int trpo_ctx_rollout_arm(trpo_ctx *c, size_t NumEpBatch, size_t EpLen
     if (rc > 0) return fail("the arm simulator needs a 15-...-3 policy with hidden widths <= 32");
     if (rc < 0) return fail("rollout launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     c->n_local = N;
+    c->n_full = N;
     c->ep_len = EpLen;
     double std_host[TRPO_MAX_LAYERS * 64];
     for (size_t j = 0; j < A; ++j) std_host[j] = exp(c->h_logstd[j]);              // TRPO_Lightweight.c:460
@@ -926,6 +1017,7 @@ struct trpo_vf {
     size_t cap_aug, cap_n;
     double *h_theta, *h_g;     // host staging (npar + 1)
     bool target_set;
+    int failed;                // sticky: an objective evaluation failed (L-BFGS cannot tell -1.0 from a low objective value)
 };
 
 extern "C" trpo_vf *trpo_vf_create(trpo_ctx *pol, const size_t *LayerSizeBase, const char *AcFunc, size_t NumLayers) {
@@ -1051,9 +1143,28 @@ extern "C" int trpo_vf_advantage(trpo_vf *vf, const double *x, double gamma, dou
     return 0;
 }
 
+extern "C" int trpo_vf_failed(trpo_vf *vf) {
+    if (!vf) return 1;
+    const int f = vf->failed;
+    vf->failed = 0;
+    return f;
+}
+
+static double vf_evaluate_impl(trpo_vf *vf, const double *x, double *g, const int n);
 extern "C" double trpo_vf_evaluate(void *instance, const double *x, double *g, const int n, const double step) {
     (void)step;
     trpo_vf *vf = (trpo_vf *)instance;
+    const double fx = vf_evaluate_impl(vf, x, g, n);
+    if (vf && fx < 0.0) {
+        // the objective 0.01*MSE + 0.001*|x|^2 is never negative: -1 is the failure value. Make it sticky and hand L-BFGS
+        // an infinite objective so that the line search backs off instead of accepting a "lower" value.
+        vf->failed = 1;
+        if (g) for (int i = 0; i < n; ++i) g[i] = 0.0;
+        return HUGE_VAL;
+    }
+    return fx;
+}
+static double vf_evaluate_impl(trpo_vf *vf, const double *x, double *g, const int n) {
     if (!vf || !x || !g) { fail("null argument"); return -1.0; }
     if ((size_t)n < vf->npar) { fail("n (%d) is smaller than the number of baseline parameters (%zu)", n, vf->npar); return -1.0; }
     if (!vf->target_set) { fail("no regression target: trpo_vf_set_target or trpo_vf_advantage first"); return -1.0; }
@@ -1075,7 +1186,7 @@ extern "C" double trpo_vf_evaluate(void *instance, const double *x, double *g, c
     if (allreduce_scalars(net, net->d_scal, 1)) return -1.0;
     if (cudaMemcpyAsync(vf->h_g, net->d_b, vf->npar * sizeof(double), cudaMemcpyDeviceToHost, net->stream) != cudaSuccess ||
         cudaMemcpyAsync(net->h_scal, net->d_scal, sizeof(double), cudaMemcpyDeviceToHost, net->stream) != cudaSuccess ||
-        cudaStreamSynchronize(net->stream) != cudaSuccess) {
+        sync_and_check(net) != 0) {
         fail("baseline objective failed: %s", cudaGetErrorString(cudaGetLastError()));
         return -1.0;
     }
@@ -1095,6 +1206,13 @@ extern "C" double *trpo_device_alloc(size_t n) {
     return p;
 }
 extern "C" void trpo_device_free(double *p) { if (p) cudaFree(p); }
+// page-locked host arrays for C callers (a pinned Observ source lets trpo_ctx_set_batch stream the copy under the first FVP)
+extern "C" double *trpo_host_alloc_pinned(size_t n) {
+    double *p = nullptr;
+    if (cudaMallocHost(&p, (n ? n : 1) * sizeof(double)) != cudaSuccess) { cudaGetLastError(); fail("cudaMallocHost failed"); return nullptr; }
+    return p;
+}
+extern "C" void trpo_host_free_pinned(double *p) { if (p) cudaFreeHost(p); }
 extern "C" int trpo_memcpy_h2d(double *dst, const double *src, size_t n) { CU(cudaMemcpy(dst, src, n * sizeof(double), cudaMemcpyHostToDevice)); return 0; }
 extern "C" int trpo_memcpy_d2h(double *dst, const double *src, size_t n) { CU(cudaMemcpy(dst, src, n * sizeof(double), cudaMemcpyDeviceToHost)); return 0; }
 

@@ -22,10 +22,12 @@ static double now_s(void) {
 typedef struct {
     size_t N, O, A, P;
     double *theta, *Mean, *Std, *Observ, *Action, *Advantage;
+    int observ_pinned;        /* Observ is page-locked: trpo_ctx_set_batch streams it in chunks under the first FVP */
 } HostBatch;
 
 static void host_batch_free(HostBatch *hb) {
-    free(hb->theta); free(hb->Mean); free(hb->Std); free(hb->Observ); free(hb->Action); free(hb->Advantage);
+    free(hb->theta); free(hb->Mean); free(hb->Std); free(hb->Action); free(hb->Advantage);
+    if (hb->observ_pinned) trpo_host_free_pinned(hb->Observ); else free(hb->Observ);
     memset(hb, 0, sizeof(*hb));
 }
 
@@ -54,7 +56,10 @@ static int host_batch_load(const TRPOparam *param, HostBatch *hb) {
     const size_t N = hb->N, O = hb->O, A = hb->A;
     hb->Mean = (double *)calloc(N * A, sizeof(double));
     hb->Std = (double *)calloc(A, sizeof(double));
-    hb->Observ = (double *)calloc(N * O, sizeof(double));
+    hb->Observ = trpo_host_alloc_pinned(N * O);          /* NULL without a GPU: the calls fail later with the proper message */
+    hb->observ_pinned = hb->Observ != NULL;
+    if (hb->Observ == NULL) hb->Observ = (double *)calloc(N * O, sizeof(double));
+    else memset(hb->Observ, 0, N * O * sizeof(double));
     hb->Action = (double *)calloc(N * A, sizeof(double));
     hb->Advantage = (double *)calloc(N, sizeof(double));
     trpo_batch_file_header bh;
@@ -116,10 +121,15 @@ double FVP_GPU(TRPOparam param, double *Result, double *Input) {
     return rc ? -1 : t1 - t0;
 }
 
-static void print_cg_trace(const trpo_info *info) {
+static void print_cg_trace(const trpo_ctx *ctx, const trpo_info *info) {
     /* same line as TRPO_CG.c:56, one per executed iteration plus the terminating one */
-    for (int i = 0; i <= info->cg_iters; ++i)
-        printf("CG Iter[%d] Residual Norm=%.12e, Soln Norm=%.12e\n", i, info->cg_rdotr[i], info->cg_xnorm[i]);
+    const size_t n = (size_t)info->cg_iters + 1;
+    double *rd = (double *)calloc(2 * n, sizeof(double));
+    if (rd == NULL) return;
+    const int got = trpo_ctx_get_cg_trace(ctx, rd, rd + n, n);
+    for (int i = 0; i < got; ++i)
+        printf("CG Iter[%d] Residual Norm=%.12e, Soln Norm=%.12e\n", i, rd[i], rd[n + i]);
+    free(rd);
 }
 
 double CG_GPU(TRPOparam param, double *Result, double *b, size_t MaxIter, double ResidualTh, size_t NumThreads) {
@@ -136,7 +146,7 @@ double CG_GPU(TRPOparam param, double *Result, double *b, size_t MaxIter, double
     } else {
         trpo_info info;
         trpo_ctx_get_info(ctx, &info);
-        print_cg_trace(&info);
+        print_cg_trace(ctx, &info);
     }
     trpo_ctx_destroy(ctx);
     host_batch_free(&hb);
@@ -158,7 +168,7 @@ double TRPO_Update_GPU(TRPOparam param, double *Result, size_t NumThreads) {
         /* the reference's log lines (TRPO_Update.c:410,819,832,890,998) */
         trpo_info info;
         trpo_ctx_get_info(ctx, &info);
-        print_cg_trace(&info);
+        print_cg_trace(ctx, &info);
         printf("shs: %.14f\n", info.shs);
         printf("lagrange multiplier: %.14f, gnorm: %.14f\n", info.lm, info.gnorm);
         printf("fval before %.14e\n", info.fval);

@@ -129,7 +129,11 @@ double TRPO_Lightweight_GPU_ex(TRPOparam param, const int NumIter, size_t NumEpB
         failed = trpo_vf_advantage(vf, x, gamma, lam, NULL, NULL);
         if (failed) break;
         double fx = 0;
-        lbfgs_fn(PaddedParamsBase, x, &fx, trpo_vf_evaluate, NULL, vf, &prm);      /* TRPO_Lightweight.c:675 */
+        const int lb = lbfgs_fn(PaddedParamsBase, x, &fx, trpo_vf_evaluate, NULL, vf, &prm);   /* TRPO_Lightweight.c:675 */
+        /* the reference ignores lbfgs()'s status (a line-search or iteration-limit stop is normal); a failed objective
+         * evaluation on the GPU is not: the fit would continue from a corrupted x */
+        (void)lb;
+        if (trpo_vf_failed(vf)) { failed = 1; break; }
         failed = trpo_ctx_update(ctx, theta_new, param.CG_Damping);
         if (failed) break;
         trpo_info info;
