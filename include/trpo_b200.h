@@ -217,7 +217,8 @@ int trpo_vf_advantage(trpo_vf *vf, const double *x, double gamma, double lam, do
 /* libLBFGS objective callback, a drop-in for the reference's `evaluate` (TRPO_Baseline.c:29, lbfgs.h lbfgs_evaluate_t):
  *     lbfgs(PaddedParams, x, &fx, trpo_vf_evaluate, NULL, vf, &param);
  * returns 0.01*MSE + 0.001*|x|^2 and writes g = d/dx (n >= trpo_vf_num_params; the padding of g is zeroed).
- * Returns -1 after a failure (see trpo_last_error), like the reference does for an unsupported activation. */
+ * After a failure (see trpo_last_error; the reference returns -1 for an unsupported activation, which L-BFGS would take for a
+ * very good objective value) it returns +inf with a zero gradient and records the failure: see trpo_vf_failed. */
 double trpo_vf_evaluate(void *vf, const double *x, double *g, const int n, const double step);
 /* libLBFGS cannot tell a failed evaluation from a low objective, so a failure is also recorded on the network: the callback
  * then returns +inf with a zero gradient, and this returns 1 once (and clears the record). Check it after lbfgs() returns.

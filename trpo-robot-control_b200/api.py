@@ -430,7 +430,7 @@ class ValueFunction:
         x = np.ascontiguousarray(x, dtype=np.float64)
         g = np.zeros(n_padded or x.size)
         fx = lib().trpo_vf_evaluate(self.h, _dp(x), _dp(g), g.size, 0.0)
-        if fx == -1.0:                       # the objective itself is >= 0
+        if lib().trpo_vf_failed(self.h):     # a failed evaluation returns +inf to L-BFGS and is recorded on the network
             raise RuntimeError(f"libtrpo_b200: {last_error()}")
         return fx, g
 

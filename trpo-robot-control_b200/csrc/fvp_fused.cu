@@ -19,6 +19,7 @@
 
 #include "trpo_internal.cuh"
 #include "dmma_common.cuh"
+#include "tmem_scratch.cuh"
 
 namespace {
 
@@ -78,22 +79,36 @@ __host__ __device__ __forceinline__ int swz(int rr, int cc) {
     return (a & 1) + 2 * (cq & 1) + 4 * ((a >> 1) ^ rp) + 8 * (cp ^ (cq >> 1)) + 16 * rp + 32 * (cq >> 1);
 }
 
-template <int K0_, int H1_, int H2_, int AP_, int NW_, int CTAS_PER_SM_ = 1>
+// NG = number of independent warp groups inside the CTA. NG = 1: the whole CTA works on one tile of S = 8 * NW samples and
+// its phases are separated by block barriers. NG = 2: two groups of WG = NW / 2 warps (one warp of each group per SM
+// sub-partition) share the staged weights but own separate activation buffers, tiles of SG = 8 * WG samples and named
+// barriers, so the two warps of a scheduler are at DIFFERENT places of the per-tile instruction stream (with NG = 1 they
+// run in lock step and stall together: the same net is 18 % faster as two independent 4-warp CTAs, profiles/r02_summary.md).
+// Each group then needs the full set of parameter-gradient accumulators over half as many warps; they are parked in
+// Tensor Memory while phase A runs (tmem_scratch.cuh).
+template <int K0_, int H1_, int H2_, int AP_, int NW_, int CTAS_PER_SM_ = 1, int NG_ = 1>
 struct Cfg {
-    static constexpr int K0 = K0_, H1 = H1_, H2 = H2_, AP = AP_, NW = NW_, CTAS_PER_SM = CTAS_PER_SM_;
+    static constexpr int K0 = K0_, H1 = H1_, H2 = H2_, AP = AP_, NW = NW_, CTAS_PER_SM = CTAS_PER_SM_, NG = NG_;
     static constexpr int S = 8 * NW, NTHREADS = 32 * NW;
+    static constexpr int WG = NW / NG, SG = 8 * WG;                       // warps / samples per group tile
     static constexpr int Q0 = K0 / 4, MT0 = (K0 + 7) / 8;
     static constexpr int NT1 = H1 / 8, NT2 = H2 / 8, NT3 = AP / 8;
+    static constexpr int R1 = (NT1 + WG - 1) / WG, R2 = (NT2 + WG - 1) / WG;   // output tile rows a warp owns in phase B
     static constexpr int RS0 = pad_rs(K0), RS1 = H1 + 4, RS2 = H2 + 4, RS3 = AP + 4, RSB = cmax(RS1, RS2);
-    // shared memory carve-up (in doubles)
+    // shared memory carve-up (in doubles): weights and direction (shared by the groups), then per group the observation
+    // double buffer and the activation exchange buffers, then the exp2 table
     static constexpr int oW0 = 0, oVW0 = oW0 + K0 * H1, oW1 = oVW0 + K0 * H1, oVW1 = oW1 + H1 * H2,
                          oW2 = oVW1 + H1 * H2, oVW2 = oW2 + H2 * AP, oB0 = oVW2 + H2 * AP, oVB0 = oB0 + H1,
                          oB1 = oVB0 + H1, oVB1 = oB1 + H2, oVB2 = oVB1 + H2, oIV = oVB2 + AP,
-                         oY0 = oIV + AP, Y0SZ = S * RS0 + 8, oA = oY0 + 2 * Y0SZ, oC = oA + S * RS1, oB = oC + S * RS2,
-                         oD = oB + S * RSB, oTab = oD + S * RS3, TOTAL = oTab + 64;
+                         oY0 = oIV + AP, Y0SZ = SG * RS0 + 8,
+                         gA = 2 * Y0SZ, gC = gA + SG * RS1, gB = gC + SG * RS2, gD = gB + SG * RSB, GSZ = gD + SG * RS3,
+                         oTab = oY0 + NG * GSZ, TOTAL = oTab + 64;
     static constexpr size_t SMEM_BYTES = sizeof(double) * TOTAL;
+    // accumulator doubles per thread (phase B), padded to a multiple of 4 for the TMEM parking area
+    static constexpr int NACC = 2 * (MT0 * R1 + R1 + R1 * NT2 + R2 + R2 * NT3 + NT3), PKN = (NACC + 3) / 4 * 4;
     static_assert(K0 % 4 == 0 && H1 % 8 == 0 && H2 % 8 == 0 && AP % 8 == 0, "padded sizes");
-    static_assert(NT1 <= NW && NT2 <= NW && NT3 <= NW, "one output tile row per warp");
+    static_assert(NW % NG == 0 && NT3 <= WG, "group shape");
+    static_assert(NG == 1 || (2 * PKN * (NW / 4) <= 512), "TMEM columns: NW/4 warps share a 32-lane quadrant");
 };
 
 struct FusedArgs {
@@ -143,17 +158,26 @@ template <typename C, char ACT1, char ACT2, bool PG>
 __global__ void __launch_bounds__(C::NTHREADS, C::CTAS_PER_SM) k_fvp_fused(const FusedArgs p) {
     if (p.done && *p.done) return;
     extern __shared__ __align__(16) double sm[];
-    constexpr int K0 = C::K0, H1 = C::H1, H2 = C::H2, AP = C::AP, NW = C::NW, S = C::S, NT = C::NTHREADS;
+    constexpr int K0 = C::K0, H1 = C::H1, H2 = C::H2, AP = C::AP, NT = C::NTHREADS;
+    constexpr int NG = C::NG, WG = C::WG, SG = C::SG, GT = 32 * WG, R1 = C::R1, R2 = C::R2;
     constexpr int Q0 = C::Q0, MT0 = C::MT0, NT1 = C::NT1, NT2 = C::NT2, NT3 = C::NT3;
     constexpr int RS0 = C::RS0, RS1 = C::RS1, RS2 = C::RS2, RS3 = C::RS3, RSB = C::RSB;
+    constexpr bool PARK = NG > 1;
     double *W0f = sm + C::oW0, *VW0f = sm + C::oVW0, *W1s = sm + C::oW1, *VW1s = sm + C::oVW1;
     double *W2s = sm + C::oW2, *VW2s = sm + C::oVW2, *B0s = sm + C::oB0, *VB0s = sm + C::oVB0;
     double *B1s = sm + C::oB1, *VB1s = sm + C::oVB1, *VB2s = sm + C::oVB2, *IVs = sm + C::oIV;
-    double *Y0s = sm + C::oY0, *BufA = sm + C::oA, *BufC = sm + C::oC, *BufB = sm + C::oB, *BufD = sm + C::oD;
     double *Tab = sm + C::oTab;
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
+    const int grp = w / WG, wg = w % WG, tg = tid - grp * GT;      // warp group, warp and thread index inside the group
+    double *Y0s = sm + C::oY0 + grp * C::GSZ;                     // this group's observation double buffer + exchange buffers
+    double *BufA = Y0s + C::gA, *BufC = Y0s + C::gC, *BufB = Y0s + C::gB, *BufD = Y0s + C::gD;
     const int L0 = p.L0, L1 = p.L1, L2 = p.L2, L3 = p.L3;
+    // barrier over this group's warps only (named barrier 1 + grp); the whole CTA when there is one group
+    auto group_sync = [&]() {
+        if constexpr (NG == 1) __syncthreads();
+        else asm volatile("bar.sync %0, %1;" :: "r"(1 + grp), "n"(GT) : "memory");
+    };
 
     // ---------------- prologue: weights and direction into shared memory, in fragment order ----------------
     // A padded input column (K0 > L0) carries the layer-0 bias for free: the observation tile holds 1.0 in column L0 and
@@ -195,14 +219,27 @@ __global__ void __launch_bounds__(C::NTHREADS, C::CTAS_PER_SM) k_fvp_fused(const
         IVs[n]  = n < L3 ? p.inv_var[n] : 0.0;
     }
     load_exp2_table(Tab);
-    for (int i = tid; i < 2 * C::Y0SZ; i += NT) Y0s[i] = 0.0;
+    for (int i = tid; i < NG * C::GSZ; i += NT) sm[C::oY0 + i] = 0.0;
+    // Tensor Memory for the parked accumulators: 2 * PKN columns per warp, the NW / 4 warps of a quadrant side by side
+    __shared__ uint32_t tmem_slot;
+    constexpr uint32_t TM_COLS = (2 * C::PKN * (C::NW / 4) <= 32) ? 32 : (2 * C::PKN * (C::NW / 4) <= 64) ? 64
+                               : (2 * C::PKN * (C::NW / 4) <= 128) ? 128 : (2 * C::PKN * (C::NW / 4) <= 256) ? 256 : 512;
+    if constexpr (PARK) {
+        if (w == 0) tmem_alloc(&tmem_slot, TM_COLS);
+        tmem_fence_before_sync();
+    }
     __syncthreads();
-    // observation tile [S][K0] (zero padded / zero past the end of the batch), staged asynchronously one tile ahead
+    uint32_t tm = 0;
+    if constexpr (PARK) {
+        tmem_fence_after_sync();
+        tm = tmem_warp_addr(tmem_slot, w, (w >> 2) * 2 * C::PKN);
+    }
+    // observation tile [SG][K0] (zero padded / zero past the end of the batch), staged asynchronously one tile ahead
     auto stage_obs = [&](long long tile_idx, int buf) {
         double *dst = Y0s + buf * C::Y0SZ;
-        const long long s0n = tile_idx * S;
-        wait_samples(p, (s0n + S < p.nsamples ? s0n + S : p.nsamples) - 1);
-        for (int idx = tid; idx < S * K0; idx += NT) {
+        const long long s0n = tile_idx * SG;
+        wait_samples(p, (s0n + SG < p.nsamples ? s0n + SG : p.nsamples) - 1);
+        for (int idx = tg; idx < SG * K0; idx += GT) {
             const int row = idx / K0, col = idx % K0;
             const long long gs = s0n + row;
             const bool in = gs < p.nsamples && col < L0;
@@ -219,30 +256,97 @@ __global__ void __launch_bounds__(C::NTHREADS, C::CTAS_PER_SM) k_fvp_fused(const
     const double ones = (g == 0) ? 1.0 : 0.0;            // A fragment whose row 0 is all ones: column sums (bias gradients)
 
     // ---------------- persistent parameter-gradient accumulators (C-fragment layout) ----------------
-    double acc0[MT0][2], accb0[2];      // warp w < NT1: [Y0;1]^T * G1, output columns 8w..8w+7
-    double acc1[NT2][2], accb1[2];      // warp w < NT1: rows 8w..8w+7 of Y1^T * G2; warp w < NT2: bias tile w
-    double acc2[NT3][2], accb2[NT3][2]; // warp w < NT2: rows 8w..8w+7 of Y2^T * G3; last warp: bias
+    // Warp wg of a group owns R1 = ceil(NT1 / WG) row blocks of the layer-1 outer product and the same column blocks of the
+    // layer-0 one, R2 row blocks of the layer-2 one and R2 bias tiles of layer 1; the group's last warp the layer-2 bias.
+    double acc0[MT0][R1][2], accb0[R1][2];       // [Y0;1]^T * G1, output column blocks R1*wg + jj
+    double acc1[R1][NT2][2], accb1[R2][2];       // rows 8*(R1*wg+rr).. of Y1^T * G2; bias tiles R2*wg + jj of layer 1
+    double acc2[R2][NT3][2], accb2[NT3][2];      // rows 8*(R2*wg+rr).. of Y2^T * G3; last warp: bias of layer 2
 #pragma unroll
-    for (int i = 0; i < MT0; ++i) acc0[i][0] = acc0[i][1] = 0.0;
+    for (int i = 0; i < MT0; ++i)
 #pragma unroll
-    for (int i = 0; i < NT2; ++i) acc1[i][0] = acc1[i][1] = 0.0;
+        for (int j = 0; j < R1; ++j) acc0[i][j][0] = acc0[i][j][1] = 0.0;
 #pragma unroll
-    for (int i = 0; i < NT3; ++i) acc2[i][0] = acc2[i][1] = accb2[i][0] = accb2[i][1] = 0.0;
-    accb0[0] = accb0[1] = accb1[0] = accb1[1] = 0.0;
+    for (int i = 0; i < R1; ++i) {
+        accb0[i][0] = accb0[i][1] = 0.0;
+#pragma unroll
+        for (int j = 0; j < NT2; ++j) acc1[i][j][0] = acc1[i][j][1] = 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < R2; ++i) {
+        accb1[i][0] = accb1[i][1] = 0.0;
+#pragma unroll
+        for (int j = 0; j < NT3; ++j) acc2[i][j][0] = acc2[i][j][1] = 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < NT3; ++i) accb2[i][0] = accb2[i][1] = 0.0;
     double gl[NT3][2];                  // PG: this thread's share of the LogStd gradient (its row, its two columns per tile)
 #pragma unroll
     for (int i = 0; i < NT3; ++i) gl[i][0] = gl[i][1] = 0.0;
 
-    const long long ntiles = (p.nsamples + S - 1) / S;
-    const int rowA = 8 * w + g;                          // this lane's sample row inside the tile (phase A)
-    if ((long long)blockIdx.x < ntiles) stage_obs(blockIdx.x, 0);
+    // NG > 1: the accumulators live in Tensor Memory while phase A runs (tcgen05.st / tcgen05.ld, SASS STTM / LDTM)
+    auto park = [&]() {
+        double pk[C::PKN];
+        int k = 0;
+#pragma unroll
+        for (int i = 0; i < MT0; ++i)
+#pragma unroll
+            for (int j = 0; j < R1; ++j) { pk[k++] = acc0[i][j][0]; pk[k++] = acc0[i][j][1]; }
+#pragma unroll
+        for (int i = 0; i < R1; ++i) {
+            pk[k++] = accb0[i][0]; pk[k++] = accb0[i][1];
+#pragma unroll
+            for (int j = 0; j < NT2; ++j) { pk[k++] = acc1[i][j][0]; pk[k++] = acc1[i][j][1]; }
+        }
+#pragma unroll
+        for (int i = 0; i < R2; ++i) {
+            pk[k++] = accb1[i][0]; pk[k++] = accb1[i][1];
+#pragma unroll
+            for (int j = 0; j < NT3; ++j) { pk[k++] = acc2[i][j][0]; pk[k++] = acc2[i][j][1]; }
+        }
+#pragma unroll
+        for (int i = 0; i < NT3; ++i) { pk[k++] = accb2[i][0]; pk[k++] = accb2[i][1]; }
+#pragma unroll
+        for (; k < C::PKN; ++k) pk[k] = 0.0;
+        tmem_park<C::PKN>(tm, pk);
+    };
+    auto unpark = [&]() {
+        double pk[C::PKN];
+        tmem_wait_st();
+        tmem_fetch<C::PKN>(tm, pk);
+        int k = 0;
+#pragma unroll
+        for (int i = 0; i < MT0; ++i)
+#pragma unroll
+            for (int j = 0; j < R1; ++j) { acc0[i][j][0] = pk[k++]; acc0[i][j][1] = pk[k++]; }
+#pragma unroll
+        for (int i = 0; i < R1; ++i) {
+            accb0[i][0] = pk[k++]; accb0[i][1] = pk[k++];
+#pragma unroll
+            for (int j = 0; j < NT2; ++j) { acc1[i][j][0] = pk[k++]; acc1[i][j][1] = pk[k++]; }
+        }
+#pragma unroll
+        for (int i = 0; i < R2; ++i) {
+            accb1[i][0] = pk[k++]; accb1[i][1] = pk[k++];
+#pragma unroll
+            for (int j = 0; j < NT3; ++j) { acc2[i][j][0] = pk[k++]; acc2[i][j][1] = pk[k++]; }
+        }
+#pragma unroll
+        for (int i = 0; i < NT3; ++i) { accb2[i][0] = pk[k++]; accb2[i][1] = pk[k++]; }
+    };
+
+    const long long ntiles = (p.nsamples + SG - 1) / SG;
+    const long long tstride = (long long)gridDim.x * NG;
+    const int rowA = 8 * wg + g;                         // this lane's sample row inside the group's tile (phase A)
+    long long tile = (long long)blockIdx.x * NG + grp;
+    if (tile < ntiles) stage_obs(tile, 0);
     cp_async_wait_all();
-    __syncthreads();
+    group_sync();
     int buf = 0;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1) {
-        const long long s0 = tile * S;
+    for (; tile < ntiles; tile += tstride, buf ^= 1) {
+        const long long s0 = tile * SG;
         const double *Y0c = Y0s + buf * C::Y0SZ;
-        if (tile + gridDim.x < ntiles) stage_obs(tile + gridDim.x, buf ^ 1);     // lands during this tile's math
+        if (tile + tstride < ntiles) stage_obs(tile + tstride, buf ^ 1);         // lands during this tile's math
+        if constexpr (PARK) park();
 
         // ======================= phase A: this warp's 8 samples =======================
         double y1[NT1][2], ry1[NT1][2];
@@ -276,8 +380,6 @@ __global__ void __launch_bounds__(C::NTHREADS, C::CTAS_PER_SM) k_fvp_fused(const
         }
         // layer 1 in column groups of <= 4 output tiles (keeps the live register set small); each finished group is
         // consumed immediately by layer 2 (only Rx3 is needed: y3 does not enter the FVP when the last layer is linear).
-        // DMMAs that hit the same accumulator are issued GRP instructions apart: warps issue in order, so a
-        // back-to-back dependent pair would stall the warp for the full DMMA latency.
         constexpr int GRP = NT2 < 4 ? NT2 : 4;
         static_assert(NT2 % GRP == 0, "layer-2 width must split into equal column groups");
         double rx3p[GRP][NT3][2];            // GRP independent partial sums of Rx3
@@ -414,89 +516,125 @@ __global__ void __launch_bounds__(C::NTHREADS, C::CTAS_PER_SM) k_fvp_fused(const
             g1[b][0] *= act_deriv_y<ACT1>(p.act1, y.x);
             g1[b][1] *= act_deriv_y<ACT1>(p.act1, y.y);
         }
-        __syncthreads();
+        group_sync();
+        if constexpr (PARK) unpark();
 
-        // ======================= phase B1: W1 / B1 and W2 / B2 gradients over the whole tile =======================
-        if (w < NT1 || w < NT2 || w == NW - 1) {
+        // ======================= phase B1: W1 / B1 and W2 / B2 gradients over the group's tile =======================
+        if (R1 * wg < NT1 || R2 * wg < NT2 || wg == WG - 1) {
 #pragma unroll 4
-            for (int h = 0; h < S / 4; ++h) {
+            for (int h = 0; h < SG / 4; ++h) {
                 const int srow = 4 * h + t;
-                if (w < NT1) {            // rows 8w.. of Y1^T * G2
-                    const double a = BufA[srow * RS1 + 8 * w + g];
+                if (R1 * wg < NT1) {            // row blocks R1*wg + rr of Y1^T * G2
+                    double bg[NT2];
 #pragma unroll
-                    for (int j = 0; j < NT2; ++j) dmma(acc1[j], a, BufB[srow * RSB + 8 * j + g]);
-                }
-                if (w < NT2) {            // bias gradient tile w of layer 1, rows 8w.. of Y2^T * G3
-                    dmma(accb1, ones, BufB[srow * RSB + 8 * w + g]);
-                    const double a2 = BufC[srow * RS2 + 8 * w + g];
+                    for (int j = 0; j < NT2; ++j) bg[j] = BufB[srow * RSB + 8 * j + g];
 #pragma unroll
-                    for (int c = 0; c < NT3; ++c) dmma(acc2[c], a2, BufD[srow * RS3 + 8 * c + g]);
+                    for (int rr = 0; rr < R1; ++rr) {
+                        if (R1 * wg + rr < NT1) {
+                            const double a = BufA[srow * RS1 + 8 * (R1 * wg + rr) + g];
+#pragma unroll
+                            for (int j = 0; j < NT2; ++j) dmma(acc1[rr][j], a, bg[j]);
+                        }
+                    }
                 }
-                if (w == NW - 1) {
+                if (R2 * wg < NT2) {            // bias gradient tiles of layer 1, row blocks R2*wg + rr of Y2^T * G3
+                    double bd[NT3];
+#pragma unroll
+                    for (int c = 0; c < NT3; ++c) bd[c] = BufD[srow * RS3 + 8 * c + g];
+#pragma unroll
+                    for (int rr = 0; rr < R2; ++rr) {
+                        if (R2 * wg + rr < NT2) {
+                            dmma(accb1[rr], ones, BufB[srow * RSB + 8 * (R2 * wg + rr) + g]);
+                            const double a2 = BufC[srow * RS2 + 8 * (R2 * wg + rr) + g];
+#pragma unroll
+                            for (int c = 0; c < NT3; ++c) dmma(acc2[rr][c], a2, bd[c]);
+                        }
+                    }
+                }
+                if (wg == WG - 1) {
 #pragma unroll
                     for (int c = 0; c < NT3; ++c) dmma(accb2[c], ones, BufD[srow * RS3 + 8 * c + g]);
                 }
             }
         }
-        __syncthreads();
+        group_sync();
         // RG1 takes over BufB
 #pragma unroll
         for (int b = 0; b < NT1; ++b)
             *reinterpret_cast<double2 *>(&BufB[rowA * RSB + 8 * b + 2 * t]) = make_double2(g1[b][0], g1[b][1]);
-        __syncthreads();
+        group_sync();
         // ======================= phase B2: W0 / B0 gradients =======================
-        if (w < NT1) {
+        if (R1 * wg < NT1) {
 #pragma unroll 4
-            for (int h = 0; h < S / 4; ++h) {
+            for (int h = 0; h < SG / 4; ++h) {
                 const int srow = 4 * h + t;
-                const double bg = BufB[srow * RSB + 8 * w + g];
+                double ya[MT0];
 #pragma unroll
-                for (int m = 0; m < MT0; ++m) dmma(acc0[m], Y0c[srow * RS0 + 8 * m + g], bg);
-                if (!free_col) dmma(accb0, ones, bg);
+                for (int m = 0; m < MT0; ++m) ya[m] = Y0c[srow * RS0 + 8 * m + g];
+#pragma unroll
+                for (int jj = 0; jj < R1; ++jj) {
+                    if (R1 * wg + jj < NT1) {
+                        const double bg = BufB[srow * RSB + 8 * (R1 * wg + jj) + g];
+#pragma unroll
+                        for (int m = 0; m < MT0; ++m) dmma(acc0[m][jj], ya[m], bg);
+                        if (!free_col) dmma(accb0[jj], ones, bg);
+                    }
+                }
             }
         }
         cp_async_wait_all();
-        __syncthreads();
+        group_sync();
     }
 
-    // ---------------- epilogue: this CTA's partial row (only real, un-padded entries) ----------------
-    double *out = p.partial + (size_t)blockIdx.x * p.P;
-    if (w < NT1) {
+    if constexpr (PARK) {
+        tmem_fence_before_sync();
+        __syncthreads();                                     // every warp has fetched its accumulators for the last time
+        if (w == 0) tmem_dealloc(tmem_slot, TM_COLS);
+    }
+    // ---------------- epilogue: this group's partial row (only real, un-padded entries) ----------------
+    double *out = p.partial + ((size_t)blockIdx.x * NG + grp) * p.P;
+#pragma unroll
+    for (int jj = 0; jj < R1; ++jj) {
+        const int nb = R1 * wg + jj;                         // column block of layer 0 / row block of layer 1
+        if (nb >= NT1) continue;
 #pragma unroll
         for (int m = 0; m < MT0; ++m)
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
-                const int row = 8 * m + g, col = 8 * w + 2 * t + r;
-                if (row < rows0 && col < L1) out[p.w_off0 + row * L1 + col] = acc0[m][r];
+                const int row = 8 * m + g, col = 8 * nb + 2 * t + r;
+                if (row < rows0 && col < L1) out[p.w_off0 + row * L1 + col] = acc0[m][jj][r];
             }
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
-            const int col = 8 * w + 2 * t + r;
-            if (!free_col && g == 0 && col < L1) out[p.w_off0 + L0 * L1 + col] = accb0[r];
+            const int col = 8 * nb + 2 * t + r;
+            if (!free_col && g == 0 && col < L1) out[p.w_off0 + L0 * L1 + col] = accb0[jj][r];
         }
 #pragma unroll
         for (int j = 0; j < NT2; ++j)
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
-                const int row = 8 * w + g, col = 8 * j + 2 * t + r;
-                if (row < L1 && col < L2) out[p.w_off1 + row * L2 + col] = acc1[j][r];
+                const int row = 8 * nb + g, col = 8 * j + 2 * t + r;
+                if (row < L1 && col < L2) out[p.w_off1 + row * L2 + col] = acc1[jj][j][r];
             }
     }
-    if (w < NT2) {
+#pragma unroll
+    for (int jj = 0; jj < R2; ++jj) {
+        const int nb = R2 * wg + jj;
+        if (nb >= NT2) continue;
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
-            const int col = 8 * w + 2 * t + r;
-            if (g == 0 && col < L2) out[p.w_off1 + L1 * L2 + col] = accb1[r];
+            const int col = 8 * nb + 2 * t + r;
+            if (g == 0 && col < L2) out[p.w_off1 + L1 * L2 + col] = accb1[jj][r];
         }
 #pragma unroll
         for (int c = 0; c < NT3; ++c)
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
-                const int row = 8 * w + g, col = 8 * c + 2 * t + r;
-                if (row < L2 && col < L3) out[p.w_off2 + row * L3 + col] = acc2[c][r];
+                const int row = 8 * nb + g, col = 8 * c + 2 * t + r;
+                if (row < L2 && col < L3) out[p.w_off2 + row * L3 + col] = acc2[jj][c][r];
             }
     }
-    if (w == NW - 1) {
+    if (wg == WG - 1) {
 #pragma unroll
         for (int c = 0; c < NT3; ++c)
 #pragma unroll
@@ -506,9 +644,9 @@ __global__ void __launch_bounds__(C::NTHREADS, C::CTAS_PER_SM) k_fvp_fused(const
             }
     }
     if (PG) {
-        // LogStd gradient: fixed-order sum over the 8 rows of a warp (shuffle tree), then over the warps
-        __syncthreads();
-        double *red = BufD;                                  // NW * AP doubles
+        // LogStd gradient: fixed-order sum over the 8 rows of a warp (shuffle tree), then over the group's warps
+        group_sync();
+        double *red = BufD;                                  // WG * AP doubles
 #pragma unroll
         for (int c = 0; c < NT3; ++c)
 #pragma unroll
@@ -517,14 +655,14 @@ __global__ void __launch_bounds__(C::NTHREADS, C::CTAS_PER_SM) k_fvp_fused(const
                 vsum += __shfl_xor_sync(0xffffffffu, vsum, 4);
                 vsum += __shfl_xor_sync(0xffffffffu, vsum, 8);
                 vsum += __shfl_xor_sync(0xffffffffu, vsum, 16);
-                if (g == 0) red[w * AP + 8 * c + 2 * t + r] = vsum;
+                if (g == 0) red[wg * AP + 8 * c + 2 * t + r] = vsum;
             }
-        __syncthreads();
-        if (tid < L3) {
-            double vsum = red[tid];
+        group_sync();
+        if (tg < L3) {
+            double vsum = red[tg];
 #pragma unroll
-            for (int ww = 1; ww < NW; ++ww) vsum += red[ww * AP + tid];
-            out[p.logstd_off + tid] = vsum;
+            for (int ww = 1; ww < WG; ++ww) vsum += red[ww * AP + tg];
+            out[p.logstd_off + tg] = vsum;
         }
     }
 }
@@ -873,6 +1011,10 @@ using CfgArm4 = Cfg<16, 16, 16, 8, 4, 4>;
 using CfgH32  = Cfg<32, 32, 32, 8, 8>;     // hidden <= 32, up to 32 inputs (e.g. 11-32-32-3)
 using CfgP64  = Cfg<4, 64, 64, 8, 8>;      // InvertedPendulum-size: 4-64-64-1
 using CfgM64  = Cfg<20, 64, 64, 8, 8>;     // 17-64-64-6 (and anything with L0 <= 20, hidden <= 64, A <= 8)
+// two independent 4-warp groups per CTA (see Cfg): tiles of 32 samples, accumulators parked in Tensor Memory
+using CfgH32g = Cfg<32, 32, 32, 8, 8, 1, 2>;
+using CfgP64g = Cfg<4, 64, 64, 8, 8, 1, 2>;
+using CfgM64g = Cfg<20, 64, 64, 8, 8, 1, 2>;
 
 enum FusedShape { SHAPE_NONE = 0, SHAPE_ARM, SHAPE_H32, SHAPE_P64, SHAPE_M64 };
 
@@ -886,6 +1028,15 @@ FusedShape pick_shape(const NetDesc &net) {
     if (L0 <= 4 && L1 <= 64 && L2 <= 64) return SHAPE_P64;
     if (L0 <= 20 && L1 <= 64 && L2 <= 64) return SHAPE_M64;
     return SHAPE_NONE;
+}
+
+// Warp groups per CTA of the block-wide kernel. Measured at 1 M states (profiles/r02_summary.md): 17-32-32-6 0.963 -> 0.830 ms
+// with two groups, 17-64-64-6 2.082 -> 2.079 and 4-64-64-1 1.797 -> 1.794 (no gain: there every warp already owns a full row of
+// outer-product tiles and the kernel is bound by the LDS-fed DMMA stream itself). Default: two groups for hidden widths <= 32,
+// one for the 64-wide shapes (half as many partial rows to reduce); TRPO_FUSED_GROUPS = 1 | 2 overrides (read once).
+int fused_groups(int dflt) {
+    static const int forced = getenv("TRPO_FUSED_GROUPS") ? atoi(getenv("TRPO_FUSED_GROUPS")) : 0;
+    return forced == 1 || forced == 2 ? forced : dflt;
 }
 
 template <typename C, char A1, char A2, bool PG>
@@ -925,10 +1076,10 @@ int launch_warp_shape(const FusedArgs &a, cudaStream_t st, int *rows) {
 
 template <typename C, bool PG = false>
 int launch_shape(const FusedArgs &a, cudaStream_t st, int *rows) {
-    const long long ntiles = (a.nsamples + C::S - 1) / C::S;
+    const long long ntiles = (a.nsamples + C::SG - 1) / C::SG, nctas = (ntiles + C::NG - 1) / C::NG;
     const int max_grid = FUSED_SMS * C::CTAS_PER_SM;
-    const int grid = (int)(ntiles < max_grid ? ntiles : max_grid);
-    *rows = grid;
+    const int grid = (int)(nctas < max_grid ? nctas : max_grid);
+    *rows = grid * C::NG;                                  // every warp group writes its own partial row
     if (a.act1 == 't' && a.act2 == 't') return launch_cfg<C, 't', 't', PG>(a, grid, st);
     return launch_cfg<C, 0, 0, PG>(a, grid, st);
 }
@@ -963,9 +1114,9 @@ int fused_fvp_accumulate(const NetDesc &net, const double *d_theta, const double
                               : launch_warp_shape<CfgArm>(a, st, &rows);
             break;
         }
-        case SHAPE_H32: rc = launch_shape<CfgH32>(a, st, &rows); break;
-        case SHAPE_P64: rc = launch_shape<CfgP64>(a, st, &rows); break;
-        case SHAPE_M64: rc = launch_shape<CfgM64>(a, st, &rows); break;
+        case SHAPE_H32: rc = fused_groups(2) == 2 ? launch_shape<CfgH32g>(a, st, &rows) : launch_shape<CfgH32>(a, st, &rows); break;
+        case SHAPE_P64: rc = fused_groups(1) == 2 ? launch_shape<CfgP64g>(a, st, &rows) : launch_shape<CfgP64>(a, st, &rows); break;
+        case SHAPE_M64: rc = fused_groups(1) == 2 ? launch_shape<CfgM64g>(a, st, &rows) : launch_shape<CfgM64>(a, st, &rows); break;
         default: return 1;
     }
     if (rc) return -1;
@@ -993,9 +1144,9 @@ int fused_pg_accumulate(const NetDesc &net, const double *d_theta, const double 
     int rows = 0, rc = -1;
     switch (shape) {
         case SHAPE_ARM: rc = launch_shape<CfgArm, true>(a, st, &rows); break;
-        case SHAPE_H32: rc = launch_shape<CfgH32, true>(a, st, &rows); break;
-        case SHAPE_P64: rc = launch_shape<CfgP64, true>(a, st, &rows); break;
-        case SHAPE_M64: rc = launch_shape<CfgM64, true>(a, st, &rows); break;
+        case SHAPE_H32: rc = fused_groups(2) == 2 ? launch_shape<CfgH32g, true>(a, st, &rows) : launch_shape<CfgH32, true>(a, st, &rows); break;
+        case SHAPE_P64: rc = fused_groups(1) == 2 ? launch_shape<CfgP64g, true>(a, st, &rows) : launch_shape<CfgP64, true>(a, st, &rows); break;
+        case SHAPE_M64: rc = fused_groups(1) == 2 ? launch_shape<CfgM64g, true>(a, st, &rows) : launch_shape<CfgM64, true>(a, st, &rows); break;
         default: return 1;
     }
     if (rc) return -1;
