@@ -125,6 +125,10 @@ int    trpo_ctx_get_path(const trpo_ctx *ctx);      /* the path the last launch 
 int    trpo_ctx_set_chunk(trpo_ctx *ctx, size_t chunk_samples);
 size_t trpo_ctx_get_chunk(const trpo_ctx *ctx);     /* chunk of the last GEMM-chain launch (0 before the first) */
 int    trpo_ctx_sync(trpo_ctx *ctx);
+/* 1 if the last trpo_ctx_cg / _cg_device ran as the single persistent cooperative kernel (shapes the fused kernels take, one
+ * GPU or the peer-memory exchange), 0 if it ran as per-iteration launches. The environment variable TRPO_NO_FUSED_SOLVE
+ * forces the latter. */
+int    trpo_ctx_solve_kernel_used(const trpo_ctx *ctx);
 /* Number of kernels launched by this context since creation (bench.py's gpu_launches). */
 long long trpo_ctx_launch_count(const trpo_ctx *ctx);
 
@@ -269,6 +273,12 @@ int trpo_ctx_set_comm_mode(trpo_ctx *ctx, int mode);       /* P2P becomes the de
  * calls (trpo_ctx_fvp / _cg / _update / trpo_vf_evaluate) check the same flags themselves: they fail with -1, reset the flag, and
  * the device results of that call are poisoned (NaN) / the solve stopped. Callers of the asynchronous *_device calls poll this. */
 int trpo_ctx_comm_error(trpo_ctx *ctx);
+
+/* Roofline denominators measured on the device (< 0.1 s each; device < 0: the current one). MEASURED_PEAKS.json has no FP64 entry:
+ * the FP64 probe runs mma.sync.m8n8k4.f64 (DMMA, the pipe DFMA shares) with 16 independent accumulators per warp; the TF32 probe
+ * the legacy mma.sync.m16n8k8 path. TFLOP/s, or a negative value on failure. */
+double trpo_probe_fp64_peak_tflops(int device);
+double trpo_probe_tf32_mma_sync_tflops(int device);
 
 /* Total sample count over all ranks (the 1/N of TRPO_FVP.c:930). Computed by init_comm+set_batch via all-reduce. */
 size_t trpo_ctx_global_samples(const trpo_ctx *ctx);

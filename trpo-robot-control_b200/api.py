@@ -77,6 +77,7 @@ def lib():
         L.trpo_host_free_pinned.argtypes = [C.c_void_p]
         L.trpo_vf_failed.argtypes = [C.c_void_p]
         L.trpo_ctx_sync.argtypes = [C.c_void_p]
+        L.trpo_ctx_solve_kernel_used.argtypes = [C.c_void_p]
         L.trpo_ctx_launch_count.restype = C.c_longlong
         L.trpo_ctx_launch_count.argtypes = [C.c_void_p]
         L.trpo_ctx_kernel_timing.argtypes = [C.c_void_p, C.c_int]
@@ -117,6 +118,9 @@ def lib():
         L.trpo_ctx_p2p_attach.argtypes = [C.c_void_p, C.c_char_p]
         L.trpo_ctx_set_comm_mode.argtypes = [C.c_void_p, C.c_int]
         L.trpo_ctx_comm_error.argtypes = [C.c_void_p]
+        for name in ("trpo_probe_fp64_peak_tflops", "trpo_probe_tf32_mma_sync_tflops"):
+            getattr(L, name).restype = C.c_double
+            getattr(L, name).argtypes = [C.c_int]
         L.trpo_ctx_global_samples.restype = C.c_size_t
         L.trpo_ctx_global_samples.argtypes = [C.c_void_p]
         for name in ("FVP_GPU", "CG_GPU", "TRPO_Update_GPU", "TRPO_Lightweight_GPU", "TRPO_Lightweight_GPU_ex"):
@@ -261,6 +265,10 @@ class Context:
 
     def sync(self):
         _check(lib().trpo_ctx_sync(self.h))
+
+    def solve_kernel_used(self):
+        """True if the last CG ran as the single persistent cooperative kernel."""
+        return bool(lib().trpo_ctx_solve_kernel_used(self.h))
 
     def launch_count(self):
         return lib().trpo_ctx_launch_count(self.h)

@@ -154,10 +154,11 @@ __device__ __forceinline__ void wait_samples(const FusedArgs &p, long long last_
 // layer-2 forward at all: the seed uses the rollout's own Mean), seed g3 = A (a - mu) / sigma^2 * f', and the LogStd
 // gradient sum_n A (((a - mu)/sigma)^2 - 1) accumulated per thread; backward pass and outer products are shared.
 // In PG mode p.inv_var holds 1/sigma = exp(-LogStd) of the CURRENT parameters (TRPO_Update.c:298-300), p.v is unused.
+// stage: bit 0 = the parts that depend on the model and the batch header (W, B, 1/sigma^2, tables, zeroed buffers), bit 1 = the
+// parts that depend on the direction v (VW, VB). The stand-alone kernel stages both; the persistent solve kernel stages the
+// model once and the direction once per CG iteration (the direction is read with ld.global.cg: another CTA wrote it).
 template <typename C, char ACT1, char ACT2, bool PG>
-__global__ void __launch_bounds__(C::NTHREADS, C::CTAS_PER_SM) k_fvp_fused(const FusedArgs p) {
-    if (p.done && *p.done) return;
-    extern __shared__ __align__(16) double sm[];
+__device__ __forceinline__ void fused_pass(const FusedArgs &p, double *sm, const int stage) {
     constexpr int K0 = C::K0, H1 = C::H1, H2 = C::H2, AP = C::AP, NT = C::NTHREADS;
     constexpr int NG = C::NG, WG = C::WG, SG = C::SG, GT = 32 * WG, R1 = C::R1, R2 = C::R2;
     constexpr int Q0 = C::Q0, MT0 = C::MT0, NT1 = C::NT1, NT2 = C::NT2, NT3 = C::NT3;
@@ -185,41 +186,44 @@ __global__ void __launch_bounds__(C::NTHREADS, C::CTAS_PER_SM) k_fvp_fused(const
     // then needs neither an accumulator init nor its own gradient tile (row L0 of Y0^T * RG1 is the bias gradient).
     const bool free_col = L0 < K0;
     const int rows0 = L0 + (free_col ? 1 : 0);
+    const bool st_m = (stage & 1) != 0, st_v = (stage & 2) != 0;
     for (int idx = tid; idx < K0 * H1; idx += NT) {
         const int k = idx / H1, n = idx % H1;
         const bool in = k < rows0 && n < L1;
         const int dst = ((k >> 2) * NT1 + (n >> 3)) * 32 + (n & 7) * 4 + (k & 3);
-        W0f[dst]  = in ? p.theta[p.w_off0 + k * L1 + n] : 0.0;
-        if (!PG) VW0f[dst] = in ? p.v[p.w_off0 + k * L1 + n] : 0.0;
+        if (st_m) W0f[dst]  = in ? p.theta[p.w_off0 + k * L1 + n] : 0.0;
+        if (!PG && st_v) VW0f[dst] = in ? __ldcg(&p.v[p.w_off0 + k * L1 + n]) : 0.0;
     }
     for (int idx = tid; idx < H1 * H2; idx += NT) {
         const int j = idx / H2, n = idx % H2;
         const bool in = j < L1 && n < L2;
         const int dst = ((j >> 3) * NT2 + (n >> 3)) * 64 + swz(j & 7, n & 7);
-        W1s[dst]  = in ? p.theta[p.w_off1 + j * L2 + n] : 0.0;
-        if (!PG) VW1s[dst] = in ? p.v[p.w_off1 + j * L2 + n] : 0.0;
+        if (st_m) W1s[dst]  = in ? p.theta[p.w_off1 + j * L2 + n] : 0.0;
+        if (!PG && st_v) VW1s[dst] = in ? __ldcg(&p.v[p.w_off1 + j * L2 + n]) : 0.0;
     }
     for (int idx = tid; idx < H2 * AP; idx += NT) {
         const int j = idx / AP, n = idx % AP;
         const bool in = j < L2 && n < L3;
         const int dst = ((j >> 3) * NT3 + (n >> 3)) * 64 + swz(j & 7, n & 7);
-        W2s[dst]  = in ? p.theta[p.w_off2 + j * L3 + n] : 0.0;
-        if (!PG) VW2s[dst] = in ? p.v[p.w_off2 + j * L3 + n] : 0.0;
+        if (st_m) W2s[dst]  = in ? p.theta[p.w_off2 + j * L3 + n] : 0.0;
+        if (!PG && st_v) VW2s[dst] = in ? __ldcg(&p.v[p.w_off2 + j * L3 + n]) : 0.0;
     }
     for (int n = tid; n < H1; n += NT) {
-        B0s[n]  = n < L1 ? p.theta[p.w_off0 + L0 * L1 + n] : 0.0;
-        VB0s[n] = (!PG && n < L1) ? p.v[p.w_off0 + L0 * L1 + n] : 0.0;
+        if (st_m) B0s[n]  = n < L1 ? p.theta[p.w_off0 + L0 * L1 + n] : 0.0;
+        if (st_v) VB0s[n] = (!PG && n < L1) ? __ldcg(&p.v[p.w_off0 + L0 * L1 + n]) : 0.0;
     }
     for (int n = tid; n < H2; n += NT) {
-        B1s[n]  = n < L2 ? p.theta[p.w_off1 + L1 * L2 + n] : 0.0;
-        VB1s[n] = (!PG && n < L2) ? p.v[p.w_off1 + L1 * L2 + n] : 0.0;
+        if (st_m) B1s[n]  = n < L2 ? p.theta[p.w_off1 + L1 * L2 + n] : 0.0;
+        if (st_v) VB1s[n] = (!PG && n < L2) ? __ldcg(&p.v[p.w_off1 + L1 * L2 + n]) : 0.0;
     }
     for (int n = tid; n < AP; n += NT) {
-        VB2s[n] = n >= L3 ? 0.0 : (PG ? p.theta[p.w_off2 + L2 * L3 + n] : p.v[p.w_off2 + L2 * L3 + n]);   // PG: plain bias B2
-        IVs[n]  = n < L3 ? p.inv_var[n] : 0.0;
+        if (PG ? st_m : st_v) VB2s[n] = n >= L3 ? 0.0 : (PG ? p.theta[p.w_off2 + L2 * L3 + n] : __ldcg(&p.v[p.w_off2 + L2 * L3 + n]));   // PG: plain bias B2
+        if (st_m) IVs[n]  = n < L3 ? p.inv_var[n] : 0.0;
     }
-    load_exp2_table(Tab);
-    for (int i = tid; i < NG * C::GSZ; i += NT) sm[C::oY0 + i] = 0.0;
+    if (st_m) {
+        load_exp2_table(Tab);
+        for (int i = tid; i < NG * C::GSZ; i += NT) sm[C::oY0 + i] = 0.0;
+    }
     // Tensor Memory for the parked accumulators: 2 * PKN columns per warp, the NW / 4 warps of a quadrant side by side
     __shared__ uint32_t tmem_slot;
     constexpr uint32_t TM_COLS = (2 * C::PKN * (C::NW / 4) <= 32) ? 32 : (2 * C::PKN * (C::NW / 4) <= 64) ? 64
@@ -667,6 +671,13 @@ __global__ void __launch_bounds__(C::NTHREADS, C::CTAS_PER_SM) k_fvp_fused(const
     }
 }
 
+template <typename C, char ACT1, char ACT2, bool PG>
+__global__ void __launch_bounds__(C::NTHREADS, C::CTAS_PER_SM) k_fvp_fused(const FusedArgs p) {
+    if (p.done && *p.done) return;
+    extern __shared__ __align__(16) double sm[];
+    fused_pass<C, ACT1, ACT2, PG>(p, sm, 3);
+}
+
 
 // ---------------------------------------------------------------------------------------------------------------
 // Warp-private variant for very small nets (hidden <= 16, e.g. the reference's armDOF_0 policy 15-16-16-3): all
@@ -676,9 +687,7 @@ __global__ void __launch_bounds__(C::NTHREADS, C::CTAS_PER_SM) k_fvp_fused(const
 // units (50 k states over 1184 warps: 5.3 units each instead of 5.3 tiles of 64 per CTA with 2 of 8 warps doing the
 // outer products). The per-warp sums are added in fixed warp order at the end of the kernel.
 template <typename C, char ACT1, char ACT2>
-__global__ void __launch_bounds__(C::NTHREADS, 1) k_fvp_warp(const FusedArgs p) {
-    if (p.done && *p.done) return;
-    extern __shared__ __align__(16) double sm[];
+__device__ __forceinline__ void warp_pass(const FusedArgs &p, double *sm, const int stage) {
     constexpr int K0 = C::K0, H1 = C::H1, H2 = C::H2, AP = C::AP, NW = C::NW, NT = C::NTHREADS;
     constexpr int Q0 = C::Q0, MT0 = C::MT0, NT1 = C::NT1, NT2 = C::NT2, NT3 = C::NT3;
     constexpr int RS0 = C::RS0, RS1 = C::RS1, RS2 = C::RS2, RS3 = C::RS3, RSB = C::RSB;
@@ -693,41 +702,42 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_fvp_warp(const FusedArgs p) 
     const int L0 = p.L0, L1 = p.L1, L2 = p.L2, L3 = p.L3;
     const bool free_col = L0 < K0;
     const int rows0 = L0 + (free_col ? 1 : 0);
+    const bool st_m = (stage & 1) != 0, st_v = (stage & 2) != 0;
     for (int idx = tid; idx < K0 * H1; idx += NT) {
         const int k = idx / H1, n = idx % H1;
         const bool in = k < rows0 && n < L1;
         const int dst = ((k >> 2) * NT1 + (n >> 3)) * 32 + (n & 7) * 4 + (k & 3);
-        W0f[dst]  = in ? p.theta[p.w_off0 + k * L1 + n] : 0.0;
-        VW0f[dst] = in ? p.v[p.w_off0 + k * L1 + n] : 0.0;
+        if (st_m) W0f[dst]  = in ? p.theta[p.w_off0 + k * L1 + n] : 0.0;
+        if (st_v) VW0f[dst] = in ? __ldcg(&p.v[p.w_off0 + k * L1 + n]) : 0.0;
     }
     for (int idx = tid; idx < H1 * H2; idx += NT) {
         const int j = idx / H2, n = idx % H2;
         const bool in = j < L1 && n < L2;
         const int dst = ((j >> 3) * NT2 + (n >> 3)) * 64 + swz(j & 7, n & 7);
-        W1s[dst]  = in ? p.theta[p.w_off1 + j * L2 + n] : 0.0;
-        VW1s[dst] = in ? p.v[p.w_off1 + j * L2 + n] : 0.0;
+        if (st_m) W1s[dst]  = in ? p.theta[p.w_off1 + j * L2 + n] : 0.0;
+        if (st_v) VW1s[dst] = in ? __ldcg(&p.v[p.w_off1 + j * L2 + n]) : 0.0;
     }
     for (int idx = tid; idx < H2 * AP; idx += NT) {
         const int j = idx / AP, n = idx % AP;
         const bool in = j < L2 && n < L3;
         const int dst = ((j >> 3) * NT3 + (n >> 3)) * 64 + swz(j & 7, n & 7);
-        W2s[dst]  = in ? p.theta[p.w_off2 + j * L3 + n] : 0.0;
-        VW2s[dst] = in ? p.v[p.w_off2 + j * L3 + n] : 0.0;
+        if (st_m) W2s[dst]  = in ? p.theta[p.w_off2 + j * L3 + n] : 0.0;
+        if (st_v) VW2s[dst] = in ? __ldcg(&p.v[p.w_off2 + j * L3 + n]) : 0.0;
     }
     for (int n = tid; n < H1; n += NT) {
-        B0s[n]  = n < L1 ? p.theta[p.w_off0 + L0 * L1 + n] : 0.0;
-        VB0s[n] = n < L1 ? p.v[p.w_off0 + L0 * L1 + n] : 0.0;
+        if (st_m) B0s[n]  = n < L1 ? p.theta[p.w_off0 + L0 * L1 + n] : 0.0;
+        if (st_v) VB0s[n] = n < L1 ? __ldcg(&p.v[p.w_off0 + L0 * L1 + n]) : 0.0;
     }
     for (int n = tid; n < H2; n += NT) {
-        B1s[n]  = n < L2 ? p.theta[p.w_off1 + L1 * L2 + n] : 0.0;
-        VB1s[n] = n < L2 ? p.v[p.w_off1 + L1 * L2 + n] : 0.0;
+        if (st_m) B1s[n]  = n < L2 ? p.theta[p.w_off1 + L1 * L2 + n] : 0.0;
+        if (st_v) VB1s[n] = n < L2 ? __ldcg(&p.v[p.w_off1 + L1 * L2 + n]) : 0.0;
     }
     for (int n = tid; n < AP; n += NT) {
-        VB2s[n] = n < L3 ? p.v[p.w_off2 + L2 * L3 + n] : 0.0;
-        IVs[n]  = n < L3 ? p.inv_var[n] : 0.0;
+        if (st_v) VB2s[n] = n < L3 ? __ldcg(&p.v[p.w_off2 + L2 * L3 + n]) : 0.0;
+        if (st_m) IVs[n]  = n < L3 ? p.inv_var[n] : 0.0;
     }
-    load_exp2_table(Tab);
-    for (int i = tid; i < NW * WS; i += NT) scratch[i] = 0.0;
+    if (st_m) load_exp2_table(Tab);
+    for (int i = tid; i < NW * WS; i += NT) scratch[i] = 0.0;      // every pass: the per-warp sums below reuse this area
     __syncthreads();
 
     double *Y0w = scratch + w * WS;                         // [2][8*RS0 + 8]
@@ -991,6 +1001,228 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_fvp_warp(const FusedArgs p) 
     }
 }
 
+template <typename C, char ACT1, char ACT2>
+__global__ void __launch_bounds__(C::NTHREADS, 1) k_fvp_warp(const FusedArgs p) {
+    if (p.done && *p.done) return;
+    extern __shared__ __align__(16) double sm[];
+    warp_pass<C, ACT1, ACT2>(p, sm, 3);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// The whole conjugate-gradient solve (TRPO_CG.c:25-107) as ONE persistent cooperative kernel: one CTA per SM, the model
+// staged once, per iteration the FVP pass above (direction = the current p, re-staged from global memory), then
+//   grid barrier -> fixed-order sum of the per-CTA partial rows, every CTA a slice of columns
+//                -> multi-GPU: the slice is pushed into every peer's memory over NVLink and the peers' slices are summed
+//                   in rank order as they arrive (per-CTA flags: CTA b only waits for CTA b of each peer)
+//                -> z = sum / N + damping p, partial p.z        -> grid barrier -> v = r.r / p.z, x += v p, r -= v z
+//                -> partial r.r, x.x                            -> grid barrier -> mu, p = r + mu p -> grid barrier.
+// Every CTA forms the global scalars itself from the per-CTA partials in the same fixed order, so all CTAs (and, with the
+// fixed rank order of the exchange, all GPUs) take identical decisions and end with bitwise identical state: no broadcast.
+// Round 1 ran 3 - 4 launches per iteration (FVP, row reduction, all-reduce, single-CTA update): 44 us of serial tail per
+// iteration at 8 GPUs, a third of a 50 k-state solve of the arm policy.
+struct SolveArgs {
+    const double *b;             // right-hand side
+    double *x, *r, *pv, *z;      // CG vectors in global memory (P each); pv is the direction the FVP pass stages
+    double *zsum;                // reduced, un-normalised FVP sum (scratch, P)
+    double *dots;                // [4][DOT_STRIDE] per-CTA partials of b.b / p.z / r.r / x.x
+    unsigned int *gbar;          // grid barrier: [0] arrivals, [1] generation
+    CgState *st;
+    double *trace;
+    int trace_cap, max_iter, rows, logstd_off;
+    double residual_th, damping, n_total;
+    P2PComm comm;                // world <= 1: single GPU
+};
+constexpr int DOT_STRIDE = 160;
+
+__device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu_u32(unsigned int *p, unsigned int v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// All CTAs of the (co-resident: cooperative launch) grid. One release-acquire chain, no stand-alone fences: the block barrier
+// orders every thread's writes before thread 0's acq_rel arrival, the last arriver's release store of the new generation
+// publishes them, the acquire loads of the spinning CTAs (followed by their block barrier) make them visible.
+__device__ __forceinline__ void grid_sync(unsigned int *bar, unsigned int nblocks) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int gen, prev;
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(gen) : "l"(bar + 1) : "memory");    // cannot change before we arrive
+        asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(prev) : "l"(bar) : "memory");
+        if (prev == nblocks - 1) {
+            asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(bar), "r"(0u) : "memory");
+            st_release_gpu_u32(bar + 1, gen + 1);
+        } else {
+            while (ld_acquire_gpu_u32(bar + 1) == gen) { }
+        }
+    }
+    __syncthreads();
+}
+// fixed-order block sum of one value per thread (NT threads, NT / 32 <= 32 warps); result in every thread
+__device__ __forceinline__ double solve_block_sum(double v, double *red) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    double t = (threadIdx.x < nw) ? red[threadIdx.x] : 0.0;
+    if (w == 0) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+        if (lane == 0) red[32] = t;
+    }
+    __syncthreads();
+    return red[32];
+}
+// sum of the per-CTA partials of one dot product, identical in every thread of every CTA
+__device__ __forceinline__ double solve_global_sum(const double *part, int n, double *red) {
+    double v = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) v += __ldcg(&part[i]);
+    return solve_block_sum(v, red);
+}
+
+template <typename C, char ACT1, char ACT2, bool WARP>
+__global__ void __launch_bounds__(C::NTHREADS, 1) k_cg_solve(FusedArgs p, const SolveArgs s) {
+    extern __shared__ __align__(16) double sm[];
+    __shared__ double red[40];
+    __shared__ double colsh[8][32];
+    const int tid = threadIdx.x, NT = C::NTHREADS, G = gridDim.x, P = p.P;
+    const int cpb = (P + G - 1) / G, lo = blockIdx.x * cpb, hi = min(P, lo + cpb);
+    const bool multi = s.comm.world > 1;
+    unsigned long long seq = multi ? *s.comm.seq_dev : 0ull;
+    // ---- x = 0, r = p = b, r.r (TRPO_CG.c:25-42) ----
+    double acc = 0.0;
+    for (int e = lo + tid; e < hi; e += NT) {
+        const double bi = s.b[e];
+        s.x[e] = 0.0; s.r[e] = bi; s.pv[e] = bi;
+        acc += bi * bi;
+    }
+    acc = solve_block_sum(acc, red);
+    if (tid == 0) s.dots[0 * DOT_STRIDE + blockIdx.x] = acc;
+    grid_sync(s.gbar, G);
+    double rdotr = solve_global_sum(s.dots + 0 * DOT_STRIDE, G, red);
+    if (blockIdx.x == 0 && tid == 0) { s.trace[0] = rdotr; s.trace[s.trace_cap] = 0.0; }
+    int iters = 0, done = rdotr < s.residual_th ? 1 : 0;
+    double pdotz = 0.0, xnorm = 0.0;
+    p.v = s.pv;
+    int stage = 3;
+    for (int it = 0; it < s.max_iter && !done; ++it) {
+        // ---- FVP pass: this CTA's partial row of sum_n F_n p ----
+        if (WARP) warp_pass<C, ACT1, ACT2>(p, sm, stage);
+        else fused_pass<C, ACT1, ACT2, false>(p, sm, stage);
+        stage = 2;                                            // the model stays staged; only the direction changes
+        grid_sync(s.gbar, G);
+        // ---- column sums of this CTA's slice (fixed row order), exchange, z and p.z ----
+        const unsigned long long nseq = seq + 1;
+        const size_t slot = multi ? ((size_t)(nseq & 1) * s.comm.world + s.comm.rank) * P : 0;
+        for (int c0 = lo; c0 < hi; c0 += 32) {
+            const int e = c0 + (tid & 31), ry = tid >> 5;
+            const bool valid = e < hi && e < s.logstd_off;
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            if (valid && ry < 8) {
+                int rw = ry;
+                for (; rw + 24 < s.rows; rw += 32) {
+                    s0 += __ldcg(&p.partial[(size_t)rw * P + e]);
+                    s1 += __ldcg(&p.partial[(size_t)(rw + 8) * P + e]);
+                    s2 += __ldcg(&p.partial[(size_t)(rw + 16) * P + e]);
+                    s3 += __ldcg(&p.partial[(size_t)(rw + 24) * P + e]);
+                }
+                for (; rw < s.rows; rw += 8) s0 += __ldcg(&p.partial[(size_t)rw * P + e]);
+            }
+            __syncthreads();
+            if (ry < 8) colsh[ry][tid & 31] = (s0 + s1) + (s2 + s3);
+            __syncthreads();
+            if (ry == 0 && valid) {
+                double tsum = colsh[0][tid];
+#pragma unroll
+                for (int k = 1; k < 8; ++k) tsum += colsh[k][tid];
+                s.zsum[e] = tsum;
+                if (multi)
+                    for (int rk = 0; rk < s.comm.world; ++rk) s.comm.slots[rk][slot + e] = tsum;   // NVLink stores for the peers
+            }
+        }
+        if (multi) {
+            // publish: after the block barrier one system-scope fence covers the block's stores, then this CTA's flag on every
+            // rank; wait for CTA blockIdx.x of every rank (bounded spin), then sum the ranks in fixed order
+            __syncthreads();
+            if (tid == 0) {
+                __threadfence_system();
+                for (int rk = 0; rk < s.comm.world; ++rk)
+                    st_release_sys_u64(&s.comm.cflags[rk][((nseq & 1) * s.comm.world + s.comm.rank) * DOT_STRIDE + blockIdx.x], nseq);
+            }
+            if (tid < s.comm.world) {
+                const unsigned long long *f = &s.comm.cflags[s.comm.rank][((nseq & 1) * s.comm.world + tid) * DOT_STRIDE + blockIdx.x];
+                const long long t0 = clock64();
+                while (ld_acquire_sys_u64(f) < nseq) {
+                    if (clock64() - t0 > 40000000000LL) { *(volatile int *)s.comm.error = 1; break; }
+                }
+            }
+            __syncthreads();
+            seq = nseq;                                       // a timed-out wait is handled after the next grid barrier
+        }
+        acc = 0.0;
+        for (int e = lo + tid; e < hi; e += NT) {
+            const double pi = __ldcg(&s.pv[e]);
+            double mean;
+            if (e >= s.logstd_off) mean = 2.0 * pi;          // LogStd block: sum_n 2 v / N exactly (TRPO_FVP.c:918-921)
+            else if (multi) {
+                const double *base = s.comm.slots[s.comm.rank] + (size_t)(seq & 1) * s.comm.world * P;
+                double t2 = __ldcg(&base[e]);
+                for (int rk = 1; rk < s.comm.world; ++rk) t2 += __ldcg(&base[(size_t)rk * P + e]);
+                mean = t2 / s.n_total;
+            } else mean = s.zsum[e] / s.n_total;
+            const double zi = mean + s.damping * pi;
+            s.z[e] = zi;
+            acc += pi * zi;
+        }
+        acc = solve_block_sum(acc, red);
+        if (tid == 0) s.dots[1 * DOT_STRIDE + blockIdx.x] = acc;
+        grid_sync(s.gbar, G);
+        // a peer never arrived (flag set before the barrier, so every CTA sees it now): stop, poison, the host call fails
+        if (multi && *(volatile int *)s.comm.error) { done = 2; break; }
+        pdotz = solve_global_sum(s.dots + 1 * DOT_STRIDE, G, red);
+        const double v = rdotr / pdotz;
+        double acc_r = 0.0, acc_x = 0.0;
+        for (int e = lo + tid; e < hi; e += NT) {
+            const double xi = s.x[e] + v * s.pv[e];
+            const double ri = s.r[e] - v * s.z[e];
+            s.x[e] = xi; s.r[e] = ri;
+            acc_r += ri * ri;
+            acc_x += xi * xi;
+        }
+        acc_r = solve_block_sum(acc_r, red);
+        acc_x = solve_block_sum(acc_x, red);
+        if (tid == 0) { s.dots[2 * DOT_STRIDE + blockIdx.x] = acc_r; s.dots[3 * DOT_STRIDE + blockIdx.x] = acc_x; }
+        grid_sync(s.gbar, G);
+        const double newrdotr = solve_global_sum(s.dots + 2 * DOT_STRIDE, G, red);
+        const double xx = solve_global_sum(s.dots + 3 * DOT_STRIDE, G, red);
+        const double mu = newrdotr / rdotr;
+        for (int e = lo + tid; e < hi; e += NT) s.pv[e] = s.r[e] + mu * s.pv[e];
+        rdotr = newrdotr;
+        xnorm = sqrt(xx);
+        iters = it + 1;
+        if (blockIdx.x == 0 && tid == 0 && iters < s.trace_cap) { s.trace[iters] = newrdotr; s.trace[s.trace_cap + iters] = xnorm; }
+        if (newrdotr < s.residual_th) done = 1;
+        grid_sync(s.gbar, G);                                 // the new direction is complete before anyone stages it
+    }
+    if (blockIdx.x == 0 && tid == 0) {
+        s.st->rdotr = done == 2 ? __longlong_as_double(0x7ff8000000000000LL) : rdotr;
+        s.st->pdotz = pdotz; s.st->xnorm = xnorm; s.st->iters = iters; s.st->done = done ? 1 : 0;
+        if (multi) *s.comm.seq_dev = seq;
+    }
+}
+
 template <typename C>
 constexpr size_t warp_smem_bytes() {
     constexpr int WS = 2 * (8 * C::RS0 + 8) + 8 * C::RS1 + 8 * C::RS2 + 8 * C::RSB + 8 * C::RS3;
@@ -1122,6 +1354,72 @@ int fused_fvp_accumulate(const NetDesc &net, const double *d_theta, const double
     if (rc) return -1;
     ++*launches;
     launch_reduce_partials(d_partial, rows, net.P, d_zsum, d_done, p2p, st, launches);
+    return 0;
+}
+
+namespace {
+template <typename C, char A1, char A2, bool WARP>
+int launch_solve_cfg(const FusedArgs &a, const SolveArgs &sa, int grid, cudaStream_t st) {
+    const size_t smem = WARP ? warp_smem_bytes<C>() : C::SMEM_BYTES;
+    static DeviceOnce configured;
+    if (configured.pending()) {
+        if (cudaFuncSetAttribute(k_cg_solve<C, A1, A2, WARP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return -1;
+        configured.mark();
+    }
+    void *args[] = {(void *)&a, (void *)&sa};
+    // cooperative launch: the grid barriers need every CTA resident (one CTA per SM, grid <= number of SMs)
+    return cudaLaunchCooperativeKernel((const void *)k_cg_solve<C, A1, A2, WARP>, dim3(grid), dim3(C::NTHREADS), args, smem, st) == cudaSuccess ? 0 : -1;
+}
+template <typename C, bool WARP>
+int launch_solve_shape(FusedArgs &a, SolveArgs &sa, cudaStream_t st) {
+    int grid;
+    if (WARP) {
+        const long long nunits = (a.nsamples + 7) / 8, want = (nunits + C::NW - 1) / C::NW;
+        grid = (int)(want < FUSED_SMS ? want : FUSED_SMS);
+    } else {
+        const long long ntiles = (a.nsamples + C::SG - 1) / C::SG;
+        grid = (int)(ntiles < FUSED_SMS ? ntiles : FUSED_SMS);
+    }
+    sa.rows = grid;
+    if (a.act1 == 't' && a.act2 == 't') return launch_solve_cfg<C, 't', 't', WARP>(a, sa, grid, st);
+    return launch_solve_cfg<C, 0, 0, WARP>(a, sa, grid, st);
+}
+}  // namespace
+
+int fused_cg_solve(const NetDesc &net, const double *d_theta, const double *d_inv_var, const double *d_obs, size_t nsamples,
+                   double n_total, double *d_partial, const double *d_b, double *d_x, double *d_r, double *d_p, double *d_z,
+                   double *d_zsum, double *d_dots, unsigned int *d_gbar, CgState *d_state, double *d_trace, int trace_cap,
+                   size_t max_iter, double residual_th, double damping, const P2PComm *p2p, const int *stream_ready,
+                   size_t stream_chunk, int *stream_error, cudaStream_t st, long long *launches) {
+    const FusedShape shape = pick_shape(net);
+    if (shape == SHAPE_NONE) return 1;
+    static const bool disabled = getenv("TRPO_NO_FUSED_SOLVE") != nullptr;
+    if (disabled || max_iter > 0x7fffffff) return 1;
+    FusedArgs a;
+    a.theta = d_theta; a.v = d_p; a.inv_var = d_inv_var; a.obs = d_obs; a.partial = d_partial; a.done = nullptr;
+    a.nsamples = (long long)nsamples;
+    a.L0 = net.L[0]; a.L1 = net.L[1]; a.L2 = net.L[2]; a.L3 = net.L[3];
+    a.w_off0 = net.w_off[0]; a.w_off1 = net.w_off[1]; a.w_off2 = net.w_off[2];
+    a.P = net.P;
+    a.act1 = net.ac[1]; a.act2 = net.ac[2]; a.act3 = net.ac[3];
+    a.ready = stream_ready; a.chunk_samples = (long long)(stream_chunk ? stream_chunk : 1); a.error = stream_error;
+    a.mean = a.action = a.adv = nullptr; a.logstd_off = net.logstd_off; a.mean_out = nullptr;
+    SolveArgs sa;
+    sa.b = d_b; sa.x = d_x; sa.r = d_r; sa.pv = d_p; sa.z = d_z; sa.zsum = d_zsum; sa.dots = d_dots; sa.gbar = d_gbar;
+    sa.st = d_state; sa.trace = d_trace; sa.trace_cap = trace_cap; sa.max_iter = (int)max_iter; sa.rows = 0;
+    sa.logstd_off = net.logstd_off; sa.residual_th = residual_th; sa.damping = damping; sa.n_total = n_total;
+    if (p2p && p2p->world > 1) sa.comm = *p2p; else { sa.comm = P2PComm{}; }
+    int rc;
+    switch (shape) {
+        case SHAPE_ARM: rc = launch_solve_shape<CfgArm, true>(a, sa, st); break;
+        case SHAPE_H32: rc = launch_solve_shape<CfgH32, false>(a, sa, st); break;
+        case SHAPE_P64: rc = launch_solve_shape<CfgP64, false>(a, sa, st); break;
+        case SHAPE_M64: rc = launch_solve_shape<CfgM64, false>(a, sa, st); break;
+        default: return 1;
+    }
+    if (rc) return -1;
+    ++*launches;
     return 0;
 }
 

@@ -63,6 +63,7 @@ struct P2PComm {
     int world, rank;
     double *slots[TRPO_MAX_RANKS];               // slots[r]: base of rank r's slot area (peer-mapped; own for r == rank)
     unsigned long long *flags[TRPO_MAX_RANKS];   // flags[r]: base of rank r's flag area
+    unsigned long long *cflags[TRPO_MAX_RANKS];  // per-CTA flags [2][world][160] of the persistent solve kernel (same buffer)
     unsigned long long *seq_dev;                 // completed all-reduces (local, advanced by the consumer)
     unsigned int *block_counter;                 // last-block detection of the push kernel (local)
     int *error;                                  // set when a wait timed out (local)
@@ -110,6 +111,14 @@ int  fused_fvp_accumulate(const NetDesc &net, const double *d_theta, const doubl
 int  fused_pg_accumulate(const NetDesc &net, const double *d_theta, const double *d_inv_std, const double *d_obs,
                          const double *d_mean, const double *d_action, const double *d_adv, size_t nsamples,
                          double *d_partial, double *d_zsum, double *d_mean_out, cudaStream_t st, long long *launches);
+
+// Whole CG solve as one persistent cooperative kernel (fused-eligible shapes, single GPU or peer-memory exchange).
+// Returns 0 if enqueued, 1 if the shape / batch is not eligible (caller falls back to the per-iteration launches), -1 on error.
+int fused_cg_solve(const NetDesc &net, const double *d_theta, const double *d_inv_var, const double *d_obs, size_t nsamples,
+                   double n_total, double *d_partial, const double *d_b, double *d_x, double *d_r, double *d_p, double *d_z,
+                   double *d_zsum, double *d_dots, unsigned int *d_gbar, CgState *d_state, double *d_trace, int trace_cap,
+                   size_t max_iter, double residual_th, double damping, const P2PComm *p2p, const int *stream_ready,
+                   size_t stream_chunk, int *stream_error, cudaStream_t st, long long *launches);
 
 // ---- cg_kernels.cu ------------------------------------------------------------------------------------------------
 // p2p != NULL: the fixed-order row sum is pushed straight into every rank's slot (fused reduce + all-reduce send)

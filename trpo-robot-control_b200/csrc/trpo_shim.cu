@@ -90,6 +90,8 @@ struct trpo_ctx {
     CgState *h_state;          // pinned
     double *d_trace, *h_trace; // per-iteration CG trace: rdotr[0..trace_cap), xnorm[0..trace_cap) (h_trace pinned)
     int trace_cap;
+    double *d_dots;            // persistent solve kernel: per-CTA partial dot products [4][160]
+    unsigned int *d_gbar;      // ... and its grid-barrier state (arrivals, generation)
     int *h_flags;              // pinned: [0] peer-memory wait error, [1] streamed-staging wait error (read back after a sync)
     double *h_scal;            // pinned
     // gemm-chain scratch
@@ -130,6 +132,7 @@ struct trpo_ctx {
     // peer-memory all-reduce
     P2PComm p2p;               // world == 0 until attached
     bool p2p_on;
+    bool solve_kernel_used;    // the last CG ran as the single persistent kernel
     char *p2p_buf;             // own communication buffer (header + slots)
     void *p2p_peer[TRPO_MAX_RANKS];
     trpo_info info;
@@ -232,6 +235,9 @@ extern "C" trpo_ctx *trpo_ctx_create(const size_t *LayerSize, const char *AcFunc
     ok = ok && cudaMallocHost(&c->h_state, sizeof(CgState)) == cudaSuccess;
     ok = ok && cudaMallocHost(&c->h_scal, 16 * sizeof(double)) == cudaSuccess;
     ok = ok && cudaMallocHost(&c->h_flags, 2 * sizeof(int)) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->d_dots, 4 * 160 * sizeof(double)) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->d_gbar, 2 * sizeof(unsigned int)) == cudaSuccess;
+    ok = ok && cudaMemset(c->d_gbar, 0, 2 * sizeof(unsigned int)) == cudaSuccess;
     c->trace_cap = 64;
     ok = ok && cudaMalloc(&c->d_trace, 2 * (size_t)c->trace_cap * sizeof(double)) == cudaSuccess;
     ok = ok && cudaMallocHost(&c->h_trace, 2 * (size_t)c->trace_cap * sizeof(double)) == cudaSuccess;
@@ -281,6 +287,8 @@ extern "C" void trpo_ctx_destroy(trpo_ctx *c) {
     if (c->h_state) cudaFreeHost(c->h_state);
     if (c->h_scal) cudaFreeHost(c->h_scal);
     if (c->h_flags) cudaFreeHost(c->h_flags);
+    if (c->d_dots) cudaFree(c->d_dots);
+    if (c->d_gbar) cudaFree(c->d_gbar);
     if (c->d_trace) cudaFree(c->d_trace);
     if (c->h_trace) cudaFreeHost(c->h_trace);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
@@ -682,6 +690,33 @@ extern "C" int trpo_ctx_cg_device(trpo_ctx *c, const double *db, double *dResult
         CU(cudaMalloc(&c->d_trace, 2 * (size_t)cap * sizeof(double)));
         CU(cudaMallocHost(&c->h_trace, 2 * (size_t)cap * sizeof(double)));
         c->trace_cap = cap;
+    }
+    // Shapes the fused kernels take, on one GPU or with the peer-memory exchange attached: the whole solve is ONE persistent
+    // cooperative kernel (fvp_fused.cu, k_cg_solve). NCCL cannot be called from inside a kernel, so a communicator without
+    // peer buffers keeps the per-iteration launches below.
+    {
+        const int path0 = (c->path_req == TRPO_PATH_AUTO) ? (fused_eligible(c->net) ? TRPO_PATH_FUSED : TRPO_PATH_GEMM_CHAIN) : c->path_req;
+        const bool solo = !c->comm || active_p2p(c) != nullptr;
+        if (path0 == TRPO_PATH_FUSED && c->precision == TRPO_PRECISION_FP64 && solo && c->d_obs && c->n_local) {
+            const bool streaming = c->stream_first_fvp && c->copy_inflight;
+            const bool timed = c->ktime_on && c->ktime_n < KTIME_MAX;
+            if (timed) cudaEventRecord(c->ktime_ev[2 * c->ktime_n], c->stream);
+            const int rc = fused_cg_solve(c->net, c->d_theta, c->d_inv_var, c->d_obs, c->n_local, (double)c->n_total, c->d_fused_partial,
+                                          db, c->d_x, c->d_r, c->d_p, c->d_z, c->d_zsum, c->d_dots, c->d_gbar, c->d_state, c->d_trace,
+                                          c->trace_cap, MaxIter, ResidualTh, damping, active_p2p(c), streaming ? c->d_ready : nullptr,
+                                          c->stage_chunk, c->d_ready + 1, c->stream, &c->launches);
+            if (rc < 0) return fail("fused CG solve launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            if (rc == 0) {
+                if (timed) { cudaEventRecord(c->ktime_ev[2 * c->ktime_n + 1], c->stream); ++c->ktime_n; }
+                if (c->copy_inflight) { CU(cudaStreamWaitEvent(c->stream, c->ev_copy, 0)); c->copy_inflight = false; }
+                c->stream_first_fvp = false;
+                c->path_used = TRPO_PATH_FUSED;
+                c->solve_kernel_used = true;
+                CU(cudaMemcpyAsync(dResult, c->d_x, c->net.P * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+                return 0;
+            }
+        }
+        c->solve_kernel_used = false;
     }
     // A solve is 3 launches per iteration; for small batches (armDOF_0 x 50 k states: a whole FVP is ~30 us) the launch
     // gaps are a fifth of the solve, so an identical repeated solve is captured once into a CUDA graph and replayed.
@@ -1239,7 +1274,7 @@ extern "C" int trpo_ctx_init_comm(trpo_ctx *c, const char id[128], int rank, int
 
 // ---- peer-memory all-reduce plumbing ------------------------------------------------------------------------
 // buffer layout: [0,256) flags[2][8] u64 | 256: seq_dev u64 | 264: block_counter u32 | 268: error i32 | 1024: slots[2][world][P]
-#define P2P_HDR 1024
+#define P2P_HDR 24576        // [1024, 21504): per-CTA flags [2][8][160] u64 of the persistent solve kernel
 extern "C" int trpo_ctx_p2p_export(trpo_ctx *c, char handle_out[64]) {
     if (!c || !handle_out) return fail("null argument");
     if (c->world < 2) return fail("trpo_ctx_init_comm with world_size >= 2 first");
@@ -1275,6 +1310,7 @@ extern "C" int trpo_ctx_p2p_attach(trpo_ctx *c, const char *handles) {
             base = (char *)ptr;
         }
         c->p2p.flags[r] = (unsigned long long *)base;
+        c->p2p.cflags[r] = (unsigned long long *)(base + 1024);
         c->p2p.slots[r] = (double *)(base + P2P_HDR);
     }
     c->p2p.seq_dev = (unsigned long long *)(c->p2p_buf + 256);
@@ -1305,3 +1341,4 @@ extern "C" int trpo_ctx_comm_error(trpo_ctx *c) {
 }
 
 extern "C" size_t trpo_ctx_global_samples(const trpo_ctx *c) { return c ? c->n_total : 0; }
+extern "C" int trpo_ctx_solve_kernel_used(const trpo_ctx *c) { return c && c->solve_kernel_used ? 1 : 0; }
