@@ -129,6 +129,10 @@ int    trpo_ctx_sync(trpo_ctx *ctx);
  * GPU or the peer-memory exchange), 0 if it ran as per-iteration launches. The environment variable TRPO_NO_FUSED_SOLVE
  * forces the latter. */
 int    trpo_ctx_solve_kernel_used(const trpo_ctx *ctx);
+/* Diagnostics: phase time stamps of the persistent solve kernel. Call with max_iters > 0 and out == NULL to enable (0 disables);
+ * after a solve call with out != NULL to read max_iters x 8 nanosecond stamps of CTA 0 per CG iteration: pass start, own pass
+ * done, all passes done, slice sums formed, peers' slices arrived, p.z complete, r.r complete, new direction published. */
+int    trpo_ctx_solve_timeline(trpo_ctx *ctx, size_t max_iters, unsigned long long *out);
 /* Number of kernels launched by this context since creation (bench.py's gpu_launches). */
 long long trpo_ctx_launch_count(const trpo_ctx *ctx);
 

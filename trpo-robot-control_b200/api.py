@@ -78,6 +78,7 @@ def lib():
         L.trpo_vf_failed.argtypes = [C.c_void_p]
         L.trpo_ctx_sync.argtypes = [C.c_void_p]
         L.trpo_ctx_solve_kernel_used.argtypes = [C.c_void_p]
+        L.trpo_ctx_solve_timeline.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_ulonglong)]
         L.trpo_ctx_launch_count.restype = C.c_longlong
         L.trpo_ctx_launch_count.argtypes = [C.c_void_p]
         L.trpo_ctx_kernel_timing.argtypes = [C.c_void_p, C.c_int]
@@ -265,6 +266,15 @@ class Context:
 
     def sync(self):
         _check(lib().trpo_ctx_sync(self.h))
+
+    def solve_timeline(self, max_iters, read=False):
+        """Enable (read=False) or read (read=True -> array [max_iters, 8] of ns stamps) the solve kernel's phase timeline."""
+        if not read:
+            _check(lib().trpo_ctx_solve_timeline(self.h, max_iters, None))
+            return None
+        out = np.zeros((max_iters, 8), dtype=np.uint64)
+        _check(lib().trpo_ctx_solve_timeline(self.h, max_iters, out.ctypes.data_as(C.POINTER(C.c_ulonglong))))
+        return out
 
     def solve_kernel_used(self):
         """True if the last CG ran as the single persistent cooperative kernel."""

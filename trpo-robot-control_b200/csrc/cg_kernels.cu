@@ -105,7 +105,9 @@ __global__ void __launch_bounds__(RED_COLS * RED_GROUPS) k_reduce_partials_push(
         if (prev == gridDim.x - 1) {
             *c.block_counter = 0;
             __threadfence_system();
-            for (int r = 0; r < c.world; ++r) st_release_sys(&c.flags[r][(seq & 1) * c.world + c.rank], seq);
+            // relaxed stores after the one fence above: a st.release.sys per peer would be a system fence per peer
+            for (int r = 0; r < c.world; ++r)
+                asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(&c.flags[r][(seq & 1) * c.world + c.rank]), "l"(seq) : "memory");
         }
     }
 }

@@ -238,16 +238,30 @@ __device__ __forceinline__ void fused_pass(const FusedArgs &p, double *sm, const
         tmem_fence_after_sync();
         tm = tmem_warp_addr(tmem_slot, w, (w >> 2) * 2 * C::PKN);
     }
-    // observation tile [SG][K0] (zero padded / zero past the end of the batch), staged asynchronously one tile ahead
-    auto stage_obs = [&](long long tile_idx, int buf) {
+    // Work split over the Wk = gridDim.x * NG warp groups: F full rounds of round-robin tiles (tile wid + r * Wk: the batch is
+    // consumed front to back, which is what the streamed staging needs), then the remaining < Wk * SG samples are dealt out in
+    // 8-sample units, contiguous and as evenly as possible, ONE partial tile per group. A partial tile costs the active warps'
+    // phase A plus a phase B over its rows only, so 13.2 tiles per group take 13.4 tile times instead of 14 (the 8-GPU shard of
+    // the headline batch: 125 k states over 148 CTAs).
+    const long long Wk = (long long)gridDim.x * NG, wid = (long long)blockIdx.x * NG + grp;
+    const long long F = p.nsamples / (Wk * SG), sT = F * Wk * SG;
+    const long long Ut = (p.nsamples - sT + 7) / 8, ubase = Ut / Wk, uextra = Ut % Wk;
+    const long long tail_lo = sT + 8 * (wid * ubase + (wid < uextra ? wid : uextra));
+    const long long tail_hi0 = tail_lo + 8 * (ubase + (wid < uextra ? 1 : 0));
+    const long long tail_hi = tail_hi0 < p.nsamples ? tail_hi0 : p.nsamples;
+    const int nk = (int)F + (tail_hi > tail_lo ? 1 : 0);            // tiles of this group
+    auto tile_begin = [&](int k) { return k < F ? (wid + (long long)k * Wk) * SG : tail_lo; };
+    auto tile_end = [&](int k) { return k < F ? (wid + (long long)k * Wk) * SG + SG : tail_hi; };
+    // observation tile [SG][K0] (zero padded / zero past the end of the tile), staged asynchronously one tile ahead
+    auto stage_obs = [&](int k, int buf) {
         double *dst = Y0s + buf * C::Y0SZ;
-        const long long s0n = tile_idx * SG;
-        wait_samples(p, (s0n + SG < p.nsamples ? s0n + SG : p.nsamples) - 1);
+        const long long s0n = tile_begin(k), s1n = tile_end(k);
+        wait_samples(p, s1n - 1);
         for (int idx = tg; idx < SG * K0; idx += GT) {
             const int row = idx / K0, col = idx % K0;
             const long long gs = s0n + row;
-            const bool in = gs < p.nsamples && col < L0;
-            if (free_col && col == L0) dst[row * RS0 + col] = (gs < p.nsamples) ? 1.0 : 0.0;
+            const bool in = gs < s1n && col < L0;
+            if (free_col && col == L0) dst[row * RS0 + col] = (gs < s1n) ? 1.0 : 0.0;
             else cp_async8(&dst[row * RS0 + col], in ? &p.obs[gs * L0 + col] : p.obs, in ? 8 : 0);
         }
     };
@@ -338,21 +352,22 @@ __device__ __forceinline__ void fused_pass(const FusedArgs &p, double *sm, const
         for (int i = 0; i < NT3; ++i) { accb2[i][0] = pk[k++]; accb2[i][1] = pk[k++]; }
     };
 
-    const long long ntiles = (p.nsamples + SG - 1) / SG;
-    const long long tstride = (long long)gridDim.x * NG;
     const int rowA = 8 * wg + g;                         // this lane's sample row inside the group's tile (phase A)
-    long long tile = (long long)blockIdx.x * NG + grp;
-    if (tile < ntiles) stage_obs(tile, 0);
+    if (nk > 0) stage_obs(0, 0);
     cp_async_wait_all();
     group_sync();
     int buf = 0;
-    for (; tile < ntiles; tile += tstride, buf ^= 1) {
-        const long long s0 = tile * SG;
+    for (int k = 0; k < nk; ++k, buf ^= 1) {
+        const long long s0 = tile_begin(k), s1 = tile_end(k);
+        const int hmax = (int)((s1 - s0 + 7) / 8) * 2;   // phase-B k-steps (4 rows each) that hold samples; SG / 4 for a full tile
+        const bool warp_active = s0 + 8 * wg < s1;       // a partial tile leaves the upper warps without samples
         const double *Y0c = Y0s + buf * C::Y0SZ;
-        if (tile + tstride < ntiles) stage_obs(tile + tstride, buf ^ 1);         // lands during this tile's math
+        if (k + 1 < nk) stage_obs(k + 1, buf ^ 1);       // lands during this tile's math
         if constexpr (PARK) park();
 
         // ======================= phase A: this warp's 8 samples =======================
+        double g1[NT1][2];
+        if (warp_active) {
         double y1[NT1][2], ry1[NT1][2];
         {   // layer 0: x1 = [y0,1]*[W0;B0], Rx1 = [y0,1]*[VW0;VB0]   (Ry0 = 0)
 #pragma unroll
@@ -453,7 +468,7 @@ __device__ __forceinline__ void fused_pass(const FusedArgs &p, double *sm, const
                 rx3[c][r] = sum;
             }
         // R-gradient seed: RG3 = Ry3 / sigma^2 (times the constant f' of the last layer, twice: Ry3 = f' Rx3, RG3 *= f')
-        const bool valid = (s0 + rowA) < p.nsamples;     // rows past the end of the batch contribute nothing
+        const bool valid = (s0 + rowA) < s1;             // rows past the end of the tile contribute nothing
         double g3[NT3][2];
         if (PG) {
             // surrogate-loss seed (TRPO_Update.c:297-301,310-324): t = (a - mu)/sigma, g = A t / sigma * f', dLogStd = A (t^2 - 1)
@@ -505,7 +520,6 @@ __device__ __forceinline__ void fused_pass(const FusedArgs &p, double *sm, const
             *reinterpret_cast<double2 *>(&BufB[rowA * RSB + 8 * b + 2 * t]) = make_double2(g2[b][0], g2[b][1]);
         }
         // backward through layer 1: RG1 = (RG2 * W1^T) .* f'(y1); stays in registers until BufB is free again
-        double g1[NT1][2];
 #pragma unroll
         for (int b = 0; b < NT1; ++b) g1[b][0] = g1[b][1] = 0.0;
 #pragma unroll
@@ -520,13 +534,17 @@ __device__ __forceinline__ void fused_pass(const FusedArgs &p, double *sm, const
             g1[b][0] *= act_deriv_y<ACT1>(p.act1, y.x);
             g1[b][1] *= act_deriv_y<ACT1>(p.act1, y.y);
         }
+        } else {
+#pragma unroll
+            for (int b = 0; b < NT1; ++b) g1[b][0] = g1[b][1] = 0.0;
+        }
         group_sync();
         if constexpr (PARK) unpark();
 
         // ======================= phase B1: W1 / B1 and W2 / B2 gradients over the group's tile =======================
         if (R1 * wg < NT1 || R2 * wg < NT2 || wg == WG - 1) {
 #pragma unroll 4
-            for (int h = 0; h < SG / 4; ++h) {
+            for (int h = 0; h < hmax; ++h) {
                 const int srow = 4 * h + t;
                 if (R1 * wg < NT1) {            // row blocks R1*wg + rr of Y1^T * G2
                     double bg[NT2];
@@ -570,7 +588,7 @@ __device__ __forceinline__ void fused_pass(const FusedArgs &p, double *sm, const
         // ======================= phase B2: W0 / B0 gradients =======================
         if (R1 * wg < NT1) {
 #pragma unroll 4
-            for (int h = 0; h < SG / 4; ++h) {
+            for (int h = 0; h < hmax; ++h) {
                 const int srow = 4 * h + t;
                 double ya[MT0];
 #pragma unroll
@@ -1031,8 +1049,14 @@ struct SolveArgs {
     int trace_cap, max_iter, rows, logstd_off;
     double residual_th, damping, n_total;
     P2PComm comm;                // world <= 1: single GPU
+    unsigned long long *timeline;   // optional [max_iter][8] globaltimer stamps of CTA 0 (nullptr: off), see trpo_ctx_solve_timeline
 };
 constexpr int DOT_STRIDE = 160;
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 
 __device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int *p) {
     unsigned int v;
@@ -1050,24 +1074,6 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned 
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-// All CTAs of the (co-resident: cooperative launch) grid. One release-acquire chain, no stand-alone fences: the block barrier
-// orders every thread's writes before thread 0's acq_rel arrival, the last arriver's release store of the new generation
-// publishes them, the acquire loads of the spinning CTAs (followed by their block barrier) make them visible.
-__device__ __forceinline__ void grid_sync(unsigned int *bar, unsigned int nblocks) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned int gen, prev;
-        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(gen) : "l"(bar + 1) : "memory");    // cannot change before we arrive
-        asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(prev) : "l"(bar) : "memory");
-        if (prev == nblocks - 1) {
-            asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(bar), "r"(0u) : "memory");
-            st_release_gpu_u32(bar + 1, gen + 1);
-        } else {
-            while (ld_acquire_gpu_u32(bar + 1) == gen) { }
-        }
-    }
-    __syncthreads();
-}
 // fixed-order block sum of one value per thread (NT threads, NT / 32 <= 32 warps); result in every thread
 __device__ __forceinline__ double solve_block_sum(double v, double *red) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -1084,6 +1090,29 @@ __device__ __forceinline__ double solve_block_sum(double v, double *red) {
     }
     __syncthreads();
     return red[32];
+}
+// All CTAs of the (co-resident: cooperative launch) grid. One release-acquire chain, no stand-alone fences: the block barrier
+// orders every thread's writes before thread 0's acq_rel arrival, the last arriver's release store of the new generation
+// publishes them, the acquire loads of the spinning CTAs (followed by their block barrier) make them visible. 2.5 - 3.5 us on
+// 148 SMs. (A flag-per-CTA variant in which every CTA polls all 148 flags and picks up the partial sums in the same round
+// trip measured SLOWER -- 4.6 - 7.5 us: 148 x 148 polling acquire loads -- and was dropped, profiles/r02_summary.md.)
+__device__ __forceinline__ void grid_sync(unsigned int *bar, unsigned int nblocks) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int gen, prev;
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(gen) : "l"(bar + 1) : "memory");    // cannot change before we arrive
+        asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(prev) : "l"(bar) : "memory");
+        if (prev == nblocks - 1) {
+            asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(bar), "r"(0u) : "memory");
+            st_release_gpu_u32(bar + 1, gen + 1);
+        } else {
+            const long long t0 = clock64();
+            while (ld_acquire_gpu_u32(bar + 1) == gen) {
+                if (clock64() - t0 > 20000000000LL) __trap();      // ~10 s: a CTA is missing (not co-resident?): abort, do not hang
+            }
+        }
+    }
+    __syncthreads();
 }
 // sum of the per-CTA partials of one dot product, identical in every thread of every CTA
 __device__ __forceinline__ double solve_global_sum(const double *part, int n, double *red) {
@@ -1119,10 +1148,15 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cg_solve(FusedArgs p, const 
     int stage = 3;
     for (int it = 0; it < s.max_iter && !done; ++it) {
         // ---- FVP pass: this CTA's partial row of sum_n F_n p ----
+        const bool stamp = s.timeline != nullptr && blockIdx.x == 0 && tid == 0;
+        unsigned long long *tl = s.timeline + (size_t)it * 8;
+        if (stamp) tl[0] = globaltimer_ns();
         if (WARP) warp_pass<C, ACT1, ACT2>(p, sm, stage);
         else fused_pass<C, ACT1, ACT2, false>(p, sm, stage);
         stage = 2;                                            // the model stays staged; only the direction changes
+        if (stamp) tl[1] = globaltimer_ns();                  // this CTA's pass done
         grid_sync(s.gbar, G);
+        if (stamp) tl[2] = globaltimer_ns();                  // every CTA's pass done
         // ---- column sums of this CTA's slice (fixed row order), exchange, z and p.z ----
         const unsigned long long nseq = seq + 1;
         const size_t slot = multi ? ((size_t)(nseq & 1) * s.comm.world + s.comm.rank) * P : 0;
@@ -1152,14 +1186,19 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cg_solve(FusedArgs p, const 
                     for (int rk = 0; rk < s.comm.world; ++rk) s.comm.slots[rk][slot + e] = tsum;   // NVLink stores for the peers
             }
         }
+        if (stamp) tl[3] = globaltimer_ns();                  // slice column sums formed (and pushed)
         if (multi) {
             // publish: after the block barrier one system-scope fence covers the block's stores, then this CTA's flag on every
             // rank; wait for CTA blockIdx.x of every rank (bounded spin), then sum the ranks in fixed order
             __syncthreads();
             if (tid == 0) {
+                // ONE system-scope fence, then relaxed flag stores: a st.release.sys per peer is a fence per peer, and each waits
+                // for the NVLink stores in flight (8 of them cost 29 us per iteration, profiles/r02_summary.md)
                 __threadfence_system();
-                for (int rk = 0; rk < s.comm.world; ++rk)
-                    st_release_sys_u64(&s.comm.cflags[rk][((nseq & 1) * s.comm.world + s.comm.rank) * DOT_STRIDE + blockIdx.x], nseq);
+                for (int rk = 0; rk < s.comm.world; ++rk) {
+                    unsigned long long *f = &s.comm.cflags[rk][((nseq & 1) * s.comm.world + s.comm.rank) * DOT_STRIDE + blockIdx.x];
+                    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(f), "l"(nseq) : "memory");
+                }
             }
             if (tid < s.comm.world) {
                 const unsigned long long *f = &s.comm.cflags[s.comm.rank][((nseq & 1) * s.comm.world + tid) * DOT_STRIDE + blockIdx.x];
@@ -1171,6 +1210,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cg_solve(FusedArgs p, const 
             __syncthreads();
             seq = nseq;                                       // a timed-out wait is handled after the next grid barrier
         }
+        if (stamp) tl[4] = globaltimer_ns();                  // peers' slices have arrived
         acc = 0.0;
         for (int e = lo + tid; e < hi; e += NT) {
             const double pi = __ldcg(&s.pv[e]);
@@ -1191,6 +1231,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cg_solve(FusedArgs p, const 
         grid_sync(s.gbar, G);
         // a peer never arrived (flag set before the barrier, so every CTA sees it now): stop, poison, the host call fails
         if (multi && *(volatile int *)s.comm.error) { done = 2; break; }
+        if (stamp) tl[5] = globaltimer_ns();
         pdotz = solve_global_sum(s.dots + 1 * DOT_STRIDE, G, red);
         const double v = rdotr / pdotz;
         double acc_r = 0.0, acc_x = 0.0;
@@ -1205,6 +1246,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cg_solve(FusedArgs p, const 
         acc_x = solve_block_sum(acc_x, red);
         if (tid == 0) { s.dots[2 * DOT_STRIDE + blockIdx.x] = acc_r; s.dots[3 * DOT_STRIDE + blockIdx.x] = acc_x; }
         grid_sync(s.gbar, G);
+        if (stamp) tl[6] = globaltimer_ns();
         const double newrdotr = solve_global_sum(s.dots + 2 * DOT_STRIDE, G, red);
         const double xx = solve_global_sum(s.dots + 3 * DOT_STRIDE, G, red);
         const double mu = newrdotr / rdotr;
@@ -1215,6 +1257,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cg_solve(FusedArgs p, const 
         if (blockIdx.x == 0 && tid == 0 && iters < s.trace_cap) { s.trace[iters] = newrdotr; s.trace[s.trace_cap + iters] = xnorm; }
         if (newrdotr < s.residual_th) done = 1;
         grid_sync(s.gbar, G);                                 // the new direction is complete before anyone stages it
+        if (stamp) tl[7] = globaltimer_ns();
     }
     if (blockIdx.x == 0 && tid == 0) {
         s.st->rdotr = done == 2 ? __longlong_as_double(0x7ff8000000000000LL) : rdotr;
@@ -1300,6 +1343,8 @@ template <typename C>
 int launch_warp_shape(const FusedArgs &a, cudaStream_t st, int *rows) {
     const long long nunits = (a.nsamples + 7) / 8;
     const long long want = (nunits + C::NW - 1) / C::NW;
+    // one 8-warp CTA per SM: a 128-register build with two CTAs per SM measured 7 % slower at 50 k states and 2 % slower at 1 M
+    // (profiles/r02_summary.md) -- the kernel is not short of warps
     const int grid = (int)(want < FUSED_SMS ? want : FUSED_SMS);
     *rows = grid;
     if (a.act1 == 't' && a.act2 == 't') return launch_warp_cfg<C, 't', 't'>(a, grid, st);
@@ -1391,11 +1436,20 @@ int fused_cg_solve(const NetDesc &net, const double *d_theta, const double *d_in
                    double n_total, double *d_partial, const double *d_b, double *d_x, double *d_r, double *d_p, double *d_z,
                    double *d_zsum, double *d_dots, unsigned int *d_gbar, CgState *d_state, double *d_trace, int trace_cap,
                    size_t max_iter, double residual_th, double damping, const P2PComm *p2p, const int *stream_ready,
-                   size_t stream_chunk, int *stream_error, cudaStream_t st, long long *launches) {
+                   size_t stream_chunk, int *stream_error, unsigned long long *d_timeline, cudaStream_t st, long long *launches) {
     const FusedShape shape = pick_shape(net);
     if (shape == SHAPE_NONE) return 1;
     static const bool disabled = getenv("TRPO_NO_FUSED_SOLVE") != nullptr;
+    static const bool forced = getenv("TRPO_FUSED_SOLVE") != nullptr;
     if (disabled || max_iter > 0x7fffffff) return 1;
+    // Single GPU, tiny batch (armDOF_0 x 50 k: a pass is 20 us): the 4 grid synchronisations per iteration (13 us) cost more than
+    // the three short launches of the per-iteration path replayed from a CUDA graph (0.355 against 0.31 ms per solve, measured);
+    // the persistent kernel wins from about 2 GFLOP per pass on, and always when the FVP sums cross GPUs.
+    {
+        double flops = 6.0 * net.L[0] * net.L[1];
+        for (int i = 1; i < net.K; ++i) flops += 10.0 * net.L[i] * net.L[i + 1];
+        if (!forced && !(p2p && p2p->world > 1) && flops * (double)nsamples < 2e9) return 1;
+    }
     FusedArgs a;
     a.theta = d_theta; a.v = d_p; a.inv_var = d_inv_var; a.obs = d_obs; a.partial = d_partial; a.done = nullptr;
     a.nsamples = (long long)nsamples;
@@ -1410,6 +1464,7 @@ int fused_cg_solve(const NetDesc &net, const double *d_theta, const double *d_in
     sa.st = d_state; sa.trace = d_trace; sa.trace_cap = trace_cap; sa.max_iter = (int)max_iter; sa.rows = 0;
     sa.logstd_off = net.logstd_off; sa.residual_th = residual_th; sa.damping = damping; sa.n_total = n_total;
     if (p2p && p2p->world > 1) sa.comm = *p2p; else { sa.comm = P2PComm{}; }
+    sa.timeline = d_timeline;
     int rc;
     switch (shape) {
         case SHAPE_ARM: rc = launch_solve_shape<CfgArm, true>(a, sa, st); break;

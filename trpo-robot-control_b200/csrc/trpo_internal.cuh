@@ -118,7 +118,7 @@ int fused_cg_solve(const NetDesc &net, const double *d_theta, const double *d_in
                    double n_total, double *d_partial, const double *d_b, double *d_x, double *d_r, double *d_p, double *d_z,
                    double *d_zsum, double *d_dots, unsigned int *d_gbar, CgState *d_state, double *d_trace, int trace_cap,
                    size_t max_iter, double residual_th, double damping, const P2PComm *p2p, const int *stream_ready,
-                   size_t stream_chunk, int *stream_error, cudaStream_t st, long long *launches);
+                   size_t stream_chunk, int *stream_error, unsigned long long *d_timeline, cudaStream_t st, long long *launches);
 
 // ---- cg_kernels.cu ------------------------------------------------------------------------------------------------
 // p2p != NULL: the fixed-order row sum is pushed straight into every rank's slot (fused reduce + all-reduce send)

@@ -92,6 +92,8 @@ struct trpo_ctx {
     int trace_cap;
     double *d_dots;            // persistent solve kernel: per-CTA partial dot products [4][160]
     unsigned int *d_gbar;      // ... and its grid-barrier state (arrivals, generation)
+    unsigned long long *d_timeline;   // optional per-iteration phase stamps of the solve kernel (trpo_ctx_solve_timeline)
+    size_t timeline_iters;
     int *h_flags;              // pinned: [0] peer-memory wait error, [1] streamed-staging wait error (read back after a sync)
     double *h_scal;            // pinned
     // gemm-chain scratch
@@ -289,6 +291,7 @@ extern "C" void trpo_ctx_destroy(trpo_ctx *c) {
     if (c->h_flags) cudaFreeHost(c->h_flags);
     if (c->d_dots) cudaFree(c->d_dots);
     if (c->d_gbar) cudaFree(c->d_gbar);
+    if (c->d_timeline) cudaFree(c->d_timeline);
     if (c->d_trace) cudaFree(c->d_trace);
     if (c->h_trace) cudaFreeHost(c->h_trace);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
@@ -704,7 +707,8 @@ extern "C" int trpo_ctx_cg_device(trpo_ctx *c, const double *db, double *dResult
             const int rc = fused_cg_solve(c->net, c->d_theta, c->d_inv_var, c->d_obs, c->n_local, (double)c->n_total, c->d_fused_partial,
                                           db, c->d_x, c->d_r, c->d_p, c->d_z, c->d_zsum, c->d_dots, c->d_gbar, c->d_state, c->d_trace,
                                           c->trace_cap, MaxIter, ResidualTh, damping, active_p2p(c), streaming ? c->d_ready : nullptr,
-                                          c->stage_chunk, c->d_ready + 1, c->stream, &c->launches);
+                                          c->stage_chunk, c->d_ready + 1,
+                                          (c->d_timeline && MaxIter <= c->timeline_iters) ? c->d_timeline : nullptr, c->stream, &c->launches);
             if (rc < 0) return fail("fused CG solve launch failed: %s", cudaGetErrorString(cudaGetLastError()));
             if (rc == 0) {
                 if (timed) { cudaEventRecord(c->ktime_ev[2 * c->ktime_n + 1], c->stream); ++c->ktime_n; }
@@ -1342,3 +1346,23 @@ extern "C" int trpo_ctx_comm_error(trpo_ctx *c) {
 
 extern "C" size_t trpo_ctx_global_samples(const trpo_ctx *c) { return c ? c->n_total : 0; }
 extern "C" int trpo_ctx_solve_kernel_used(const trpo_ctx *c) { return c && c->solve_kernel_used ? 1 : 0; }
+// Phase stamps of the persistent solve kernel (CTA 0, %globaltimer, nanoseconds): enable with max_iters > 0, then after a solve
+// and a sync read max_iters x 8 values: [0] pass start, [1] own pass done, [2] all CTAs' passes done, [3] slice sums formed,
+// [4] peers' slices arrived, [5] p.z complete, [6] r.r complete, [7] new direction published.
+extern "C" int trpo_ctx_solve_timeline(trpo_ctx *c, size_t max_iters, unsigned long long *out) {
+    if (!c) return fail("null context");
+    CU(cudaSetDevice(c->device));
+    if (out && c->d_timeline) {
+        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaMemcpy(out, c->d_timeline, (max_iters < c->timeline_iters ? max_iters : c->timeline_iters) * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        return 0;
+    }
+    if (c->d_timeline) { cudaFree(c->d_timeline); c->d_timeline = nullptr; }
+    c->timeline_iters = 0;
+    if (max_iters) {
+        CU(cudaMalloc(&c->d_timeline, max_iters * 8 * sizeof(unsigned long long)));
+        CU(cudaMemset(c->d_timeline, 0, max_iters * 8 * sizeof(unsigned long long)));
+        c->timeline_iters = max_iters;
+    }
+    return 0;
+}
