@@ -31,7 +31,8 @@ std = np.exp(theta[-layers[-1]:])
 v = rng.uniform(0, 1, theta.size)
 flops = 6 * layers[0] * layers[1] + 10 * sum(layers[i] * layers[i + 1] for i in range(1, len(layers) - 1))
 out = {"workload": name, "n": n, "env": {k: v_ for k, v_ in os.environ.items() if k.startswith("TRPO_")}}
-with pkg.Context(layers, ac) as ctx:
+fp32 = "--fp32" in sys.argv
+with pkg.Context(layers, ac, precision=1 if fp32 else 0) as ctx:
     ctx.set_model(theta)
     ctx.set_batch(obs, std)
     for _ in range(3):

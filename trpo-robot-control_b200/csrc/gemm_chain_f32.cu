@@ -427,9 +427,11 @@ inline int layer_slices(int tiles, int max_slices) {
 }  // namespace
 
 size_t chain_f32_scratch_floats(const NetDesc &net, int chunk, int nslices) {
-    size_t maxL = 1, sumL = 0;
+    size_t maxL = 1, sumL = 0, wts = 0;
     for (int i = 1; i <= net.K; ++i) { sumL += net.L[i]; if ((size_t)net.L[i] > maxL) maxL = net.L[i]; }
-    return (size_t)chunk * (sumL + 4 * maxL) + (size_t)nslices * net.P + 2 * (size_t)net.P + 64;
+    for (int i = 0; i + 1 < net.K; ++i) wts += 4 * (size_t)net.L[i] * net.L[i + 1] + 64;      // transposed hi / lo weights
+    // activations + ping-pong buffers, the same again for the TF32 remainders (Ylo, RYlo), slices, weights
+    return (size_t)chunk * (2 * sumL + 6 * maxL) + (size_t)nslices * net.P + 2 * (size_t)net.P + wts + 1024;
 }
 
 void chain_f32_convert(const double *d_src, float *d_dst, size_t n, cudaStream_t st, long long *launches) {
@@ -446,6 +448,12 @@ int chain_f32_accumulate(const NetDesc &net, const ChainScratchF32 &sc, const fl
                          const int *d_done, const P2PComm *p2p, cudaStream_t st, long long *launches) {
     if (!configure()) return -1;
     const int K = net.K;
+    // hidden layers that run on tcgen05 (tc_fwd_f32.cu): their transposed hi / lo weights are rebuilt once per FVP (v changes)
+    bool tc[TRPO_MAX_LAYERS] = {};
+    for (int i = 0; i + 1 < K; ++i) {
+        tc[i] = tc_fwd_eligible(net.L[i], net.L[i + 1]) && (i > 0 || sc.obs_lo != nullptr);
+        if (tc[i]) tc_prep_weights(f_theta + net.w_off[i], f_v + net.w_off[i], net.L[i], net.L[i + 1], sc.wt[i], st, launches);
+    }
     int chunk_idx = 0;
     for (size_t c0 = 0; c0 < nsamples; c0 += sc.chunk, ++chunk_idx) {
         const int rows = (int)((nsamples - c0 < (size_t)sc.chunk) ? nsamples - c0 : sc.chunk);
@@ -453,6 +461,22 @@ int chain_f32_accumulate(const NetDesc &net, const ChainScratchF32 &sc, const fl
         for (int i = 0; i < K; ++i) {
             const float *Yin = (i == 0) ? f_obs + c0 * net.L[0] : sc.Y[i];
             const bool last = (i == K - 1);
+            if (tc[i]) {
+                const int Kd = net.L[i], N = net.L[i + 1];
+                const float *Ylo_in = (i == 0) ? sc.obs_lo + c0 * net.L[0] : sc.Ylo[i];
+                const float *RYin = (i == 0) ? nullptr : sc.RY[i & 1], *RYlo_in = (i == 0) ? nullptr : sc.RYlo[i & 1];
+                if (i > 0 && !tc[i - 1]) {          // the previous layer ran on the legacy kernels: split its outputs here
+                    tc_lo_split(sc.Y[i], sc.Ylo[i], (size_t)rows * Kd, st, launches);
+                    tc_lo_split(sc.RY[i & 1], sc.RYlo[i & 1], (size_t)rows * Kd, st, launches);
+                }
+                const bool next_tc = tc[i + 1];
+                if (tc_fwd_layer(Yin, Ylo_in, RYin, RYlo_in, sc.wt[i], f_theta + net.w_off[i] + (size_t)Kd * N,
+                                 f_v + net.w_off[i] + (size_t)Kd * N, rows, Kd, N, net.ac[i + 1], sc.Y[i + 1],
+                                 next_tc ? sc.Ylo[i + 1] : nullptr, sc.RY[(i + 1) & 1], next_tc ? sc.RYlo[(i + 1) & 1] : nullptr,
+                                 d_done, st, launches))
+                    return -1;
+                continue;
+            }
             const bool needY = !last || net.ac[K] == 't' || net.ac[K] == 's';
             dim3 grid(cdiv(net.L[i + 1], BN), cdiv(rows, BM));
             // two 64-row CTAs per SM by default (TRPO_CHAIN_FWD_TM=128: one 128-row CTA), as in the FP64 chain

@@ -1,0 +1,348 @@
+// tc_fwd_f32.cu -- FP32 mode, forward R-op layer on the 5th-generation tensor cores (tcgen05 / TMEM / TMA).
+//
+// One hidden layer of the combined forward pass of the Fisher-vector product (TRPO_FVP.c:783-836) for a 128-row block of
+// samples and ALL N <= 256 outputs of the layer:
+//     X  = Y W + B                      Y_out  = f(X)
+//     RX = RY W + Y VW + VB             RY_out = RX f'(X)
+// as 3xTF32 products with FP32 accumulation: every FP32 operand is x = hi + lo with hi = x truncated to TF32 (what the
+// tensor core reads from the FP32 bits) and lo = x - hi kept in a second array, and a product a*b is issued as
+// a_hi*b_hi + a_hi*b_lo + a_lo*b_hi. The lo arrays are produced where the data is produced (this kernel's epilogue for the
+// activations, one small kernel per FVP for the transposed weights, one pass per batch for the observations), so the main
+// loop is pure data movement + MMA:
+//   warp 0   TMA producer: cp.async.bulk.tensor (SASS UTMALDG) of the operand tiles of one k-block (16 columns = 64 bytes,
+//            SWIZZLE_64B) into a ring of shared-memory stages, completion on an mbarrier (complete_tx)
+//   warp 1   MMA issuer: one thread issues tcgen05.mma.cta_group::1.kind::tf32 (SASS UTCHMMA / UTCMMA), M = 128, N = BN, K = 8,
+//            9 per k-step (6 for layer 0, where RY = 0) into two TMEM accumulators (X and RX, BN columns each);
+//            tcgen05.commit releases the stage to the producer and finally hands the accumulators to the epilogue
+//   warps 2-5  epilogue: tcgen05.ld (SASS LDTM) of 32 rows x 32 columns per warp and step, bias, activation, R-op scaling,
+//            hi/lo split, 128-byte row segments straight to global memory.
+// Edges need no code: TMA zero-fills rows past the chunk, columns past Kd (376 is not a multiple of 16) and weight rows past N.
+// The legacy path (gemm_chain_f32.cu: mma.sync HMMA.1688, 278 TFLOP/s) stays for the layers this kernel does not take
+// (last layer, Kd not a multiple of 4, N > 256) and for the backward / outer-product GEMMs.
+#include <cuda.h>
+#include <stdint.h>
+#include <stdlib.h>
+
+#include "trpo_internal.cuh"
+#include "tmem_scratch.cuh"
+
+namespace {
+
+constexpr int TC_BM = 128, TC_BK = 16, TC_THREADS = 192;
+
+// ---- PTX helpers ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// bounded wait: a pipeline bug must end as a trapped kernel, not as a hung GPU
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    const uint32_t a = smem_u32(bar);
+    const long long t0 = clock64();
+    for (;;) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+        if (ok) return;
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 :: "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
+    asm volatile("prefetch.tensormap [%0];" :: "l"(map) : "memory");
+}
+// K-major operand tile, rows of 64 bytes, SWIZZLE_64B: 8-row groups 512 bytes apart (SBO), LBO unused (1), descriptor version 1
+__device__ __forceinline__ uint64_t umma_desc_k_sw64(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);            // start address
+    d |= (uint64_t)1 << 16;                             // leading byte offset (ignored for swizzled K-major)
+    d |= (uint64_t)(512 >> 4) << 32;                    // stride byte offset
+    d |= (uint64_t)1 << 46;                             // version = 1 (sm_100)
+    d |= (uint64_t)4 << 61;                             // layout type SWIZZLE_64B
+    return d;
+}
+// D (TMEM) (+)= A (smem) * B (smem), kind::tf32; accumulate == 0 overwrites D
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}"
+                 :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ float tc_act(char a, float x, float &d) {
+    if (a == 't') {                                     // tanh = 1 - 2 / (exp(2x) + 1): ex2.approx + rcp.approx, ~1e-7 absolute
+        const float e = __expf(2.0f * x);
+        const float y = 1.0f - __fdividef(2.0f, e + 1.0f);
+        d = 1.0f - y * y;
+        return y;
+    }
+    if (a == 's') { const float y = __fdividef(1.0f, 1.0f + __expf(-x)); d = y * (1.0f - y); return y; }
+    if (a == 'o') { d = 0.1f; return 0.1f * x; }
+    d = 1.0f;
+    return x;
+}
+__device__ __forceinline__ float tf32_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+
+template <int BN, bool HAS_RA>
+struct TcCfg {
+    static constexpr int NA = HAS_RA ? 4 : 2;                                    // Y, Ylo [, RY, RYlo]
+    static constexpr int A_BYTES = TC_BM * TC_BK * 4, B_BYTES = BN * TC_BK * 4;   // 8 KB, BN * 64 B
+    static constexpr int STAGE_BYTES = NA * A_BYTES + 4 * B_BYTES;               // + W, Wlo, VW, VWlo
+    static constexpr int STAGES = (200 * 1024 / STAGE_BYTES) > 4 ? 4 : (200 * 1024 / STAGE_BYTES);
+    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
+    static constexpr uint32_t TM_COLS = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
+    static_assert(STAGES >= 2, "pipeline depth");
+    static_assert(BN % 32 == 0 && BN <= 256, "tile width");
+};
+
+struct TcMaps { CUtensorMap y, ylo, ry, rylo, w, wlo, vw, vwlo; };
+
+template <int BN, bool HAS_RA>
+__global__ void __launch_bounds__(TC_THREADS, 1) k_tc_fwd(const __grid_constant__ TcMaps maps, const float *__restrict__ bias,
+                                                          const float *__restrict__ vbias, int rows, int Kd, int N, char act,
+                                                          float *__restrict__ Yout, float *__restrict__ Ylo_out,
+                                                          float *__restrict__ RYout, float *__restrict__ RYlo_out,
+                                                          const int *__restrict__ done) {
+    if (done && *done) return;
+    using C = TcCfg<BN, HAS_RA>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);       // swizzled tiles: 1024-byte aligned
+    uint64_t *full = (uint64_t *)(smem + (size_t)C::STAGES * C::STAGE_BYTES);            // [STAGES] TMA -> MMA
+    uint64_t *empty = full + C::STAGES;                                                  // [STAGES] MMA -> TMA
+    uint64_t *acc_ready = empty + C::STAGES;                                             // MMA -> epilogue
+    uint32_t *tmem_slot = (uint32_t *)(acc_ready + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * TC_BM;
+    const int nkb = (Kd + TC_BK - 1) / TC_BK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&maps.y); tma_prefetch_desc(&maps.ylo); tma_prefetch_desc(&maps.w); tma_prefetch_desc(&maps.wlo);
+        tma_prefetch_desc(&maps.vw); tma_prefetch_desc(&maps.vwlo);
+        if (HAS_RA) { tma_prefetch_desc(&maps.ry); tma_prefetch_desc(&maps.rylo); }
+        for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(acc_ready, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, C::TM_COLS);
+    tmem_fence_before_sync();
+    __syncthreads();
+    tmem_fence_after_sync();
+    const uint32_t tm = *tmem_slot;                       // X at columns [0, BN), RX at [BN, 2 BN)
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % C::STAGES, it = kb / C::STAGES;
+                if (it > 0) mbar_wait(&empty[s], (it - 1) & 1);                // the MMAs that read this stage have completed
+                uint8_t *st = smem + (size_t)s * C::STAGE_BYTES;
+                mbar_expect_tx(&full[s], C::STAGE_BYTES);
+                const int k0 = kb * TC_BK;
+                tma_load_2d(st + 0 * C::A_BYTES, &maps.y, &full[s], k0, m0);
+                tma_load_2d(st + 1 * C::A_BYTES, &maps.ylo, &full[s], k0, m0);
+                if (HAS_RA) {
+                    tma_load_2d(st + 2 * C::A_BYTES, &maps.ry, &full[s], k0, m0);
+                    tma_load_2d(st + 3 * C::A_BYTES, &maps.rylo, &full[s], k0, m0);
+                }
+                uint8_t *sb = st + C::NA * C::A_BYTES;
+                tma_load_2d(sb + 0 * C::B_BYTES, &maps.w, &full[s], k0, 0);
+                tma_load_2d(sb + 1 * C::B_BYTES, &maps.wlo, &full[s], k0, 0);
+                tma_load_2d(sb + 2 * C::B_BYTES, &maps.vw, &full[s], k0, 0);
+                tma_load_2d(sb + 3 * C::B_BYTES, &maps.vwlo, &full[s], k0, 0);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            // instruction descriptor: D = F32 (1 << 4), A = B = TF32 (2 << 7, 2 << 10), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+            constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+            const uint32_t tmX = tm, tmRX = tm + BN;
+            uint32_t accX = 0, accRX = 0;
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % C::STAGES, it = kb / C::STAGES;
+                mbar_wait(&full[s], it & 1);
+                tmem_fence_after_sync();
+                const uint32_t sa = smem_u32(smem + (size_t)s * C::STAGE_BYTES), sbb = sa + C::NA * C::A_BYTES;
+#pragma unroll
+                for (int kk = 0; kk < TC_BK / 8; ++kk) {
+                    const uint32_t ko = kk * 32;                               // 8 TF32 = 32 bytes along K inside the 64-byte rows
+                    const uint64_t dY = umma_desc_k_sw64(sa + 0 * C::A_BYTES + ko), dYl = umma_desc_k_sw64(sa + 1 * C::A_BYTES + ko);
+                    const uint64_t dW = umma_desc_k_sw64(sbb + 0 * C::B_BYTES + ko), dWl = umma_desc_k_sw64(sbb + 1 * C::B_BYTES + ko);
+                    const uint64_t dV = umma_desc_k_sw64(sbb + 2 * C::B_BYTES + ko), dVl = umma_desc_k_sw64(sbb + 3 * C::B_BYTES + ko);
+                    // X = Y W: compensation terms first
+                    umma_tf32(tmX, dYl, dW, idesc, accX); accX = 1;
+                    umma_tf32(tmX, dY, dWl, idesc, 1);
+                    umma_tf32(tmX, dY, dW, idesc, 1);
+                    // RX = Y VW (+ RY W)
+                    umma_tf32(tmRX, dYl, dV, idesc, accRX); accRX = 1;
+                    umma_tf32(tmRX, dY, dVl, idesc, 1);
+                    umma_tf32(tmRX, dY, dV, idesc, 1);
+                    if (HAS_RA) {
+                        const uint64_t dR = umma_desc_k_sw64(sa + 2 * C::A_BYTES + ko), dRl = umma_desc_k_sw64(sa + 3 * C::A_BYTES + ko);
+                        umma_tf32(tmRX, dRl, dW, idesc, 1);
+                        umma_tf32(tmRX, dR, dWl, idesc, 1);
+                        umma_tf32(tmRX, dR, dW, idesc, 1);
+                    }
+                }
+                umma_commit(&empty[s]);                                        // arrives when the MMAs above have read the stage
+            }
+            umma_commit(acc_ready);                                            // ... and when every MMA of the tile has completed
+        }
+    } else {
+        // ===================== epilogue: warps 2..5, TMEM lane quadrant = warp % 4 =====================
+        const int q = warp & 3, row = m0 + 32 * q + lane;
+        mbar_wait(acc_ready, 0);
+        tmem_fence_after_sync();
+        const uint32_t tq = tm + ((uint32_t)(32 * q) << 16);
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t xr[32], rr[32];
+            tmem_ld32(tq + c0, xr);
+            tmem_ld32(tq + BN + c0, rr);
+            if (row < rows && c0 < N) {
+                float y[32], ry[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int n = c0 + j;
+                    const float b = n < N ? bias[n] : 0.0f, vb = n < N ? vbias[n] : 0.0f;
+                    float d;
+                    y[j] = tc_act(act, __uint_as_float(xr[j]) + b, d);
+                    ry[j] = (__uint_as_float(rr[j]) + vb) * d;
+                }
+                const size_t o = (size_t)row * N + c0;
+                if (c0 + 32 <= N && (N & 3) == 0) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        *reinterpret_cast<float4 *>(Yout + o + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+                        *reinterpret_cast<float4 *>(RYout + o + j) = make_float4(ry[j], ry[j + 1], ry[j + 2], ry[j + 3]);
+                        if (Ylo_out) {
+                            *reinterpret_cast<float4 *>(Ylo_out + o + j) = make_float4(tf32_lo(y[j]), tf32_lo(y[j + 1]), tf32_lo(y[j + 2]), tf32_lo(y[j + 3]));
+                            *reinterpret_cast<float4 *>(RYlo_out + o + j) = make_float4(tf32_lo(ry[j]), tf32_lo(ry[j + 1]), tf32_lo(ry[j + 2]), tf32_lo(ry[j + 3]));
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if (c0 + j < N) {
+                            Yout[o + j] = y[j]; RYout[o + j] = ry[j];
+                            if (Ylo_out) { Ylo_out[o + j] = tf32_lo(y[j]); RYlo_out[o + j] = tf32_lo(ry[j]); }
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tmem_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tm, C::TM_COLS);
+}
+
+// Wt[n][k] = W[k][n] (hi: truncated to TF32, lo: the remainder), for the weight matrix and the direction of one layer
+__global__ void k_tc_prep_weights(const float *__restrict__ W, const float *__restrict__ VW, int Kd, int N,
+                                  float *__restrict__ Wt, float *__restrict__ Wtlo, float *__restrict__ VWt, float *__restrict__ VWtlo) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= Kd * N) return;
+    const int n = idx / Kd, k = idx % Kd;
+    const float w = W[(size_t)k * N + n], v = VW[(size_t)k * N + n];
+    const float wh = __uint_as_float(__float_as_uint(w) & 0xffffe000u), vh = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+    Wt[idx] = wh; Wtlo[idx] = w - wh; VWt[idx] = vh; VWtlo[idx] = v - vh;
+}
+__global__ void k_tc_lo(const float *__restrict__ x, float *__restrict__ lo, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) lo[i] = tf32_lo(x[i]);
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+        cudaGetLastError();
+    }
+    return fn;
+}
+// row-major FP32 matrix [nrows x ncols] (row stride ld floats), box = box_rows x 16 columns, SWIZZLE_64B, zero fill
+bool make_map(CUtensorMap *m, const float *base, int nrows, int ncols, int ld, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)ncols, (cuuint64_t)nrows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int BN, bool HAS_RA>
+int launch_tc(const TcMaps &maps, const float *bias, const float *vbias, int rows, int Kd, int N, char act, float *Yout,
+              float *Ylo_out, float *RYout, float *RYlo_out, const int *done, cudaStream_t st) {
+    using C = TcCfg<BN, HAS_RA>;
+    static DeviceOnce once;
+    if (once.pending()) {
+        if (cudaFuncSetAttribute(k_tc_fwd<BN, HAS_RA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM) != cudaSuccess) return -1;
+        once.mark();
+    }
+    k_tc_fwd<BN, HAS_RA><<<(rows + TC_BM - 1) / TC_BM, TC_THREADS, C::SMEM, st>>>(maps, bias, vbias, rows, Kd, N, act, Yout, Ylo_out,
+                                                                                RYout, RYlo_out, done);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+}  // namespace
+
+bool tc_fwd_eligible(int Kd, int N) {
+    static const bool off = getenv("TRPO_NO_TCGEN05") != nullptr;
+    return !off && encode_fn() != nullptr && (Kd % 4) == 0 && Kd >= 16 && (N % 32) == 0 && N >= 32 && N <= 256;
+}
+
+void tc_lo_split(const float *x, float *lo, size_t n, cudaStream_t st, long long *launches) {
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
+    k_tc_lo<<<blocks, 256, 0, st>>>(x, lo, n);
+    ++*launches;
+}
+
+void tc_prep_weights(const float *W, const float *VW, int Kd, int N, float *wt4, cudaStream_t st, long long *launches) {
+    const size_t sz = (size_t)Kd * N;
+    k_tc_prep_weights<<<(int)((sz + 255) / 256), 256, 0, st>>>(W, VW, Kd, N, wt4, wt4 + sz, wt4 + 2 * sz, wt4 + 3 * sz);
+    ++*launches;
+}
+
+// One forward layer. Yin / Ylo_in: [rows x Kd]; RYin / RYlo_in: the same or NULL (layer 0); wt4: the four transposed weight
+// arrays of tc_prep_weights; bias / vbias: row Kd of W and VW (N floats). Ylo_out / RYlo_out may be NULL (next layer is not ours).
+int tc_fwd_layer(const float *Yin, const float *Ylo_in, const float *RYin, const float *RYlo_in, const float *wt4, const float *bias,
+                 const float *vbias, int rows, int Kd, int N, char act, float *Yout, float *Ylo_out, float *RYout, float *RYlo_out,
+                 const int *done, cudaStream_t st, long long *launches) {
+    const int BN = N <= 64 ? 64 : N <= 128 ? 128 : 256;
+    const size_t sz = (size_t)Kd * N;
+    TcMaps maps;
+    bool ok = make_map(&maps.y, Yin, rows, Kd, Kd, TC_BM) && make_map(&maps.ylo, Ylo_in, rows, Kd, Kd, TC_BM) &&
+              make_map(&maps.w, wt4, N, Kd, Kd, BN) && make_map(&maps.wlo, wt4 + sz, N, Kd, Kd, BN) &&
+              make_map(&maps.vw, wt4 + 2 * sz, N, Kd, Kd, BN) && make_map(&maps.vwlo, wt4 + 3 * sz, N, Kd, Kd, BN);
+    if (RYin) ok = ok && make_map(&maps.ry, RYin, rows, Kd, Kd, TC_BM) && make_map(&maps.rylo, RYlo_in, rows, Kd, Kd, TC_BM);
+    else { maps.ry = maps.y; maps.rylo = maps.ylo; }
+    if (!ok) return -1;
+    int rc;
+    if (RYin) rc = BN == 64 ? launch_tc<64, true>(maps, bias, vbias, rows, Kd, N, act, Yout, Ylo_out, RYout, RYlo_out, done, st)
+                : BN == 128 ? launch_tc<128, true>(maps, bias, vbias, rows, Kd, N, act, Yout, Ylo_out, RYout, RYlo_out, done, st)
+                            : launch_tc<256, true>(maps, bias, vbias, rows, Kd, N, act, Yout, Ylo_out, RYout, RYlo_out, done, st);
+    else rc = BN == 64 ? launch_tc<64, false>(maps, bias, vbias, rows, Kd, N, act, Yout, Ylo_out, RYout, RYlo_out, done, st)
+            : BN == 128 ? launch_tc<128, false>(maps, bias, vbias, rows, Kd, N, act, Yout, Ylo_out, RYout, RYlo_out, done, st)
+                        : launch_tc<256, false>(maps, bias, vbias, rows, Kd, N, act, Yout, Ylo_out, RYout, RYlo_out, done, st);
+    if (rc == 0) ++*launches;
+    return rc;
+}

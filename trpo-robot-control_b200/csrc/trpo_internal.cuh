@@ -90,12 +90,26 @@ struct ChainScratchF32 {
     float *G[2];
     int chunk, nslices;
     float *partial;                  // [nslices x P] FP32 partial sums
+    // tcgen05 forward layers (tc_fwd_f32.cu): TF32 remainders (x - trunc_tf32(x)) of the activations, and per layer the
+    // transposed weights / directions [hi, lo, V hi, V lo] x [N x Kd]
+    float *Ylo[TRPO_MAX_LAYERS];
+    float *RYlo[2];
+    float *wt[TRPO_MAX_LAYERS];
+    const float *obs_lo;             // remainders of the observation matrix (whole shard), or NULL
 };
 size_t chain_f32_scratch_floats(const NetDesc &net, int chunk, int nslices);
 void chain_f32_convert(const double *d_src, float *d_dst, size_t n, cudaStream_t st, long long *launches);
 int chain_f32_accumulate(const NetDesc &net, const ChainScratchF32 &sc, const float *f_theta, const float *f_v,
                          const float *f_inv_var, const float *f_obs, size_t nsamples, double *d_zsum,
                          const int *d_done, const P2PComm *p2p, cudaStream_t st, long long *launches);
+
+// ---- tc_fwd_f32.cu (FP32 mode: forward R-op layer on tcgen05 / TMEM / TMA) --------------------------------------------
+bool tc_fwd_eligible(int Kd, int N);
+void tc_lo_split(const float *x, float *lo, size_t n, cudaStream_t st, long long *launches);
+void tc_prep_weights(const float *W, const float *VW, int Kd, int N, float *wt4, cudaStream_t st, long long *launches);
+int tc_fwd_layer(const float *Yin, const float *Ylo_in, const float *RYin, const float *RYlo_in, const float *wt4, const float *bias,
+                 const float *vbias, int rows, int Kd, int N, char act, float *Yout, float *Ylo_out, float *RYout, float *RYlo_out,
+                 const int *done, cudaStream_t st, long long *launches);
 
 // ---- fvp_fused.cu -------------------------------------------------------------------------------------------------
 // Fused DMMA kernel for 4-layer nets whose padded weights fit in shared memory. Returns 0 if it handled the launch,

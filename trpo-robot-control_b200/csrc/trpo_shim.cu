@@ -105,6 +105,7 @@ struct trpo_ctx {
     // optional FP32 mode (FVP inside CG): FP32 copies of the model, direction and observations + FP32 scratch
     int precision;
     float *f_theta, *f_v, *f_inv_var, *f_obs;
+    float *f_obs_lo;           // TF32 remainders of f_obs for the tcgen05 forward layer (NULL: layer 0 stays on the legacy kernel)
     size_t cap_fobs;
     ChainScratchF32 scf;
     float *scf_base;
@@ -281,7 +282,7 @@ extern "C" void trpo_ctx_destroy(trpo_ctx *c) {
                       c->d_inv_var, c->d_std, c->d_inv_std_model, c->d_scal, c->d_blockpart, c->d_mean_new, c->sc_base, c->d_fused_partial,
                       c->d_reward};
     for (double *v : vecs) if (v) cudaFree(v);
-    float *fvecs[] = {c->f_theta, c->f_v, c->f_inv_var, c->f_obs, c->scf_base};
+    float *fvecs[] = {c->f_theta, c->f_v, c->f_inv_var, c->f_obs, c->f_obs_lo, c->scf_base};
     for (float *v : fvecs) if (v) cudaFree(v);
     if (c->d_draws) cudaFree(c->d_draws);
     free(c->h_logstd);
@@ -371,13 +372,18 @@ static int set_std(trpo_ctx *c, const double *Std) {
         chain_f32_convert(c->d_inv_var, c->f_inv_var, A, c->stream, &c->launches);
         // FP32 copy of the observations (they are already on the stream: set_std runs after the batch copy / adoption)
         const size_t n = c->n_local * (size_t)c->net.L[0];
-        if (n > c->cap_fobs) {
+        const bool want_lo = c->net.K >= 2 && tc_fwd_eligible(c->net.L[0], c->net.L[1]);
+        if (n > c->cap_fobs || (want_lo && !c->f_obs_lo)) {
             if (c->f_obs) cudaFree(c->f_obs);
-            c->f_obs = nullptr;
+            if (c->f_obs_lo) cudaFree(c->f_obs_lo);
+            c->f_obs = c->f_obs_lo = nullptr;
+            c->cap_fobs = 0;
             CU(cudaMalloc(&c->f_obs, n * sizeof(float)));
+            if (want_lo) CU(cudaMalloc(&c->f_obs_lo, n * sizeof(float)));
             c->cap_fobs = n;
         }
         chain_f32_convert(c->d_obs, c->f_obs, n, c->stream, &c->launches);
+        if (c->f_obs_lo) tc_lo_split(c->f_obs, c->f_obs_lo, n, c->stream, &c->launches);
     }
     CU(cudaStreamSynchronize(c->stream));
     return 0;
@@ -604,9 +610,13 @@ static int ensure_f32_scratch(trpo_ctx *c) {
     CU(cudaMemsetAsync(c->scf_base, 0, floats * sizeof(float), c->stream));
     c->scf_floats = floats;
     float *p = c->scf_base;
-    for (int i = 1; i <= c->net.K; ++i) { c->scf.Y[i] = p; p += chunk * c->net.L[i]; }
-    for (int j = 0; j < 2; ++j) { c->scf.RY[j] = p; p += chunk * maxL; }
-    for (int j = 0; j < 2; ++j) { c->scf.G[j] = p; p += chunk * maxL; }
+    auto align64 = [](float *q) { return (float *)(((uintptr_t)q + 255) & ~(uintptr_t)255); };     // TMA bases: 16-byte aligned at least
+    for (int i = 1; i <= c->net.K; ++i) { c->scf.Y[i] = p; p = align64(p + chunk * c->net.L[i]); }
+    for (int j = 0; j < 2; ++j) { c->scf.RY[j] = p; p = align64(p + chunk * maxL); }
+    for (int j = 0; j < 2; ++j) { c->scf.G[j] = p; p = align64(p + chunk * maxL); }
+    for (int i = 1; i <= c->net.K; ++i) { c->scf.Ylo[i] = p; p = align64(p + chunk * c->net.L[i]); }
+    for (int j = 0; j < 2; ++j) { c->scf.RYlo[j] = p; p = align64(p + chunk * maxL); }
+    for (int i = 0; i + 1 < c->net.K; ++i) { c->scf.wt[i] = p; p = align64(p + 4 * (size_t)c->net.L[i] * c->net.L[i + 1]); }
     c->scf.partial = p;
     c->scf.chunk = (int)chunk;
     c->scf.nslices = nslices;
@@ -622,6 +632,7 @@ static int fvp_sum(trpo_ctx *c, const double *d_v, const int *d_done) {
         const bool timed32 = c->ktime_on && c->ktime_n < KTIME_MAX;
         if (timed32) cudaEventRecord(c->ktime_ev[2 * c->ktime_n], c->stream);
         chain_f32_convert(d_v, c->f_v, c->net.P, c->stream, &c->launches);
+        c->scf.obs_lo = c->f_obs_lo;
         if (chain_f32_accumulate(c->net, c->scf, c->f_theta, c->f_v, c->f_inv_var, c->f_obs, c->n_local, c->d_zsum, d_done,
                                  nullptr, c->stream, &c->launches))
             return fail("FP32 gemm-chain FVP launch failed: %s", cudaGetErrorString(cudaGetLastError()));
