@@ -28,7 +28,8 @@
 
 namespace {
 
-constexpr int TC_BM = 128, TC_BK = 16, TC_THREADS = 192;
+constexpr int TC_BM = 128, TC_BK = 16;
+constexpr int TC_EPI_WARPS = 16, TC_THREADS = 64 + 32 * TC_EPI_WARPS;       // warp 0: TMA, warp 1: MMA, 16 epilogue warps
 
 // ---- PTX helpers ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -53,6 +54,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  :: "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+// the same load delivered to the same shared-memory offset (and signalled on the same mbarrier offset) of every CTA in cta_mask
+__device__ __forceinline__ void tma_load_2d_mc(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, uint16_t cta_mask) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;"
+                 :: "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "h"(cta_mask), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t *bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 :: "r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
     asm volatile("prefetch.tensormap [%0];" :: "l"(map) : "memory");
@@ -96,8 +110,10 @@ struct TcCfg {
     static constexpr int NA = HAS_RA ? 4 : 2;                                    // Y, Ylo [, RY, RYlo]
     static constexpr int A_BYTES = TC_BM * TC_BK * 4, B_BYTES = BN * TC_BK * 4;   // 8 KB, BN * 64 B
     static constexpr int STAGE_BYTES = NA * A_BYTES + 4 * B_BYTES;               // + W, Wlo, VW, VWlo
-    static constexpr int STAGES = (200 * 1024 / STAGE_BYTES) > 4 ? 4 : (200 * 1024 / STAGE_BYTES);
-    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
+    static constexpr int STAGES = (200 * 1024 / STAGE_BYTES) > 6 ? 6 : (200 * 1024 / STAGE_BYTES);
+    static constexpr int EPI_BYTES = TC_EPI_WARPS * 2 * 32 * 33 * 4;            // epilogue staging tiles reuse the operand ring
+    static constexpr int RING_BYTES = STAGES * STAGE_BYTES > EPI_BYTES ? STAGES * STAGE_BYTES : EPI_BYTES;
+    static constexpr size_t SMEM = (size_t)RING_BYTES + 1024 /* alignment slack */ + 128 /* barriers */ + 2048 /* bias rows */;
     static constexpr uint32_t TM_COLS = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
     static_assert(STAGES >= 2, "pipeline depth");
     static_assert(BN % 32 == 0 && BN <= 256, "tile width");
@@ -105,17 +121,21 @@ struct TcCfg {
 
 struct TcMaps { CUtensorMap y, ylo, ry, rylo, w, wlo, vw, vwlo; };
 
-template <int BN, bool HAS_RA>
+// CL > 1: thread-block cluster of CL CTAs (consecutive 128-row blocks). Every CTA needs the SAME weight tiles, and with one CTA
+// per SM all 148 of them ask the L2 for the same few cache lines at the same time (measured: 3.4 TB/s of TMA traffic, two thirds
+// of it weights, the tensor pipe 29 % busy): each CTA loads 1/CL of every weight tile and TMA multicasts it to the whole cluster.
+// A stage may be refilled only when the MMAs of ALL CTAs of the cluster have read it: the empty barriers count CL commits.
+template <int BN, bool HAS_RA, int CL>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_fwd(const __grid_constant__ TcMaps maps, const float *__restrict__ bias,
                                                           const float *__restrict__ vbias, int rows, int Kd, int N, char act,
                                                           float *__restrict__ Yout, float *__restrict__ Ylo_out,
                                                           float *__restrict__ RYout, float *__restrict__ RYlo_out,
-                                                          const int *__restrict__ done) {
+                                                          const int *__restrict__ done, int dbg) {
     if (done && *done) return;
     using C = TcCfg<BN, HAS_RA>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);       // swizzled tiles: 1024-byte aligned
-    uint64_t *full = (uint64_t *)(smem + (size_t)C::STAGES * C::STAGE_BYTES);            // [STAGES] TMA -> MMA
+    uint64_t *full = (uint64_t *)(smem + (size_t)C::RING_BYTES);                         // [STAGES] TMA -> MMA
     uint64_t *empty = full + C::STAGES;                                                  // [STAGES] MMA -> TMA
     uint64_t *acc_ready = empty + C::STAGES;                                             // MMA -> epilogue
     uint32_t *tmem_slot = (uint32_t *)(acc_ready + 1);
@@ -123,17 +143,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_fwd(const __grid_constant_
     const int m0 = blockIdx.x * TC_BM;
     const int nkb = (Kd + TC_BK - 1) / TC_BK;
 
+    const uint32_t crank = CL > 1 ? cluster_ctarank() : 0;
+    constexpr uint16_t CMASK = (uint16_t)((1u << CL) - 1);
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&maps.y); tma_prefetch_desc(&maps.ylo); tma_prefetch_desc(&maps.w); tma_prefetch_desc(&maps.wlo);
         tma_prefetch_desc(&maps.vw); tma_prefetch_desc(&maps.vwlo);
         if (HAS_RA) { tma_prefetch_desc(&maps.ry); tma_prefetch_desc(&maps.rylo); }
-        for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL); }
         mbar_init(acc_ready, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(tmem_slot, C::TM_COLS);
+    {   // bias rows of W and VW, read by every epilogue thread: shared memory, zero past N
+        float *sb = reinterpret_cast<float *>(smem + (size_t)C::RING_BYTES + 128);
+        for (int i = threadIdx.x; i < 512; i += TC_THREADS) {
+            const int n = i & 255;
+            sb[i] = n < N ? (i < 256 ? bias[n] : vbias[n]) : 0.0f;
+        }
+    }
     tmem_fence_before_sync();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();                       // every CTA's barriers exist before a peer's TMA / commit can reach them
     tmem_fence_after_sync();
     const uint32_t tm = *tmem_slot;                       // X at columns [0, BN), RX at [BN, 2 BN)
 
@@ -153,10 +183,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_fwd(const __grid_constant_
                     tma_load_2d(st + 3 * C::A_BYTES, &maps.rylo, &full[s], k0, m0);
                 }
                 uint8_t *sb = st + C::NA * C::A_BYTES;
-                tma_load_2d(sb + 0 * C::B_BYTES, &maps.w, &full[s], k0, 0);
-                tma_load_2d(sb + 1 * C::B_BYTES, &maps.wlo, &full[s], k0, 0);
-                tma_load_2d(sb + 2 * C::B_BYTES, &maps.vw, &full[s], k0, 0);
-                tma_load_2d(sb + 3 * C::B_BYTES, &maps.vwlo, &full[s], k0, 0);
+                if (CL == 1) {
+                    tma_load_2d(sb + 0 * C::B_BYTES, &maps.w, &full[s], k0, 0);
+                    tma_load_2d(sb + 1 * C::B_BYTES, &maps.wlo, &full[s], k0, 0);
+                    tma_load_2d(sb + 2 * C::B_BYTES, &maps.vw, &full[s], k0, 0);
+                    tma_load_2d(sb + 3 * C::B_BYTES, &maps.vwlo, &full[s], k0, 0);
+                } else {
+                    // this CTA's slice (BN / CL weight rows) of each of the four tiles, delivered to every CTA of the cluster
+                    constexpr int SL = BN / CL;
+                    const int n0 = (int)crank * SL;
+                    uint8_t *sl = sb + (size_t)n0 * TC_BK * 4;
+                    tma_load_2d_mc(sl + 0 * C::B_BYTES, &maps.w, &full[s], k0, n0, CMASK);
+                    tma_load_2d_mc(sl + 1 * C::B_BYTES, &maps.wlo, &full[s], k0, n0, CMASK);
+                    tma_load_2d_mc(sl + 2 * C::B_BYTES, &maps.vw, &full[s], k0, n0, CMASK);
+                    tma_load_2d_mc(sl + 3 * C::B_BYTES, &maps.vwlo, &full[s], k0, n0, CMASK);
+                }
             }
         }
     } else if (warp == 1) {
@@ -178,6 +219,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_fwd(const __grid_constant_
                     const uint64_t dW = umma_desc_k_sw64(sbb + 0 * C::B_BYTES + ko), dWl = umma_desc_k_sw64(sbb + 1 * C::B_BYTES + ko);
                     const uint64_t dV = umma_desc_k_sw64(sbb + 2 * C::B_BYTES + ko), dVl = umma_desc_k_sw64(sbb + 3 * C::B_BYTES + ko);
                     // X = Y W: compensation terms first
+                    if (dbg & 8) continue;
                     umma_tf32(tmX, dYl, dW, idesc, accX); accX = 1;
                     umma_tf32(tmX, dY, dWl, idesc, 1);
                     umma_tf32(tmX, dY, dW, idesc, 1);
@@ -192,55 +234,54 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_fwd(const __grid_constant_
                         umma_tf32(tmRX, dR, dW, idesc, 1);
                     }
                 }
-                umma_commit(&empty[s]);                                        // arrives when the MMAs above have read the stage
+                if (CL == 1) umma_commit(&empty[s]);                           // arrives when the MMAs above have read the stage
+                else umma_commit_mc(&empty[s], CMASK);                         // ... on the empty barrier of every CTA of the cluster
             }
             umma_commit(acc_ready);                                            // ... and when every MMA of the tile has completed
         }
     } else {
-        // ===================== epilogue: warps 2..5, TMEM lane quadrant = warp % 4 =====================
-        const int q = warp & 3, row = m0 + 32 * q + lane;
+        // ===================== epilogue: 16 warps; TMEM lane quadrant = warp % 4, column group = (warp - 2) / 4 =====================
+        // tcgen05.ld hands every thread ONE ROW of the accumulator tile (32 consecutive columns per step). Stored from there a
+        // warp's store instruction would touch 32 different 128-byte lines, so each 32 x 32 block goes through a padded per-warp
+        // shared-memory tile (the operand ring is free by now) and leaves as whole 128-byte rows; the TF32 remainders are formed
+        // on the way out. Measured with 4 epilogue warps: 1.0 of the 1.6 ms the two hidden layers took at 200 k states was this
+        // epilogue, one warp per scheduler exposing every latency -- hence 16 warps (4 per scheduler).
+        const int q = warp & 3, cg = (warp - 2) >> 2;
+        float *sbias = reinterpret_cast<float *>(smem + (size_t)C::RING_BYTES + 128);   // [2][256], after the barriers
         mbar_wait(acc_ready, 0);
         tmem_fence_after_sync();
         const uint32_t tq = tm + ((uint32_t)(32 * q) << 16);
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        float *tile = reinterpret_cast<float *>(smem) + (size_t)(warp - 2) * (2 * 32 * 33);         // [y, ry][32 rows][33]
+        const int rows_here = min(32, rows - (m0 + 32 * q));                             // rows of this warp inside the chunk (may be <= 0)
+        for (int c0 = 32 * cg; c0 < BN && c0 < N; c0 += 32 * (TC_EPI_WARPS / 4)) {
+            if (dbg & 4) break;
             uint32_t xr[32], rr[32];
             tmem_ld32(tq + c0, xr);
             tmem_ld32(tq + BN + c0, rr);
-            if (row < rows && c0 < N) {
-                float y[32], ry[32];
+            if (dbg & 2) continue;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int n = c0 + j;
-                    const float b = n < N ? bias[n] : 0.0f, vb = n < N ? vbias[n] : 0.0f;
-                    float d;
-                    y[j] = tc_act(act, __uint_as_float(xr[j]) + b, d);
-                    ry[j] = (__uint_as_float(rr[j]) + vb) * d;
-                }
-                const size_t o = (size_t)row * N + c0;
-                if (c0 + 32 <= N && (N & 3) == 0) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        *reinterpret_cast<float4 *>(Yout + o + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
-                        *reinterpret_cast<float4 *>(RYout + o + j) = make_float4(ry[j], ry[j + 1], ry[j + 2], ry[j + 3]);
-                        if (Ylo_out) {
-                            *reinterpret_cast<float4 *>(Ylo_out + o + j) = make_float4(tf32_lo(y[j]), tf32_lo(y[j + 1]), tf32_lo(y[j + 2]), tf32_lo(y[j + 3]));
-                            *reinterpret_cast<float4 *>(RYlo_out + o + j) = make_float4(tf32_lo(ry[j]), tf32_lo(ry[j + 1]), tf32_lo(ry[j + 2]), tf32_lo(ry[j + 3]));
-                        }
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        if (c0 + j < N) {
-                            Yout[o + j] = y[j]; RYout[o + j] = ry[j];
-                            if (Ylo_out) { Ylo_out[o + j] = tf32_lo(y[j]); RYlo_out[o + j] = tf32_lo(ry[j]); }
-                        }
-                    }
+            for (int j = 0; j < 32; ++j) {
+                float d;
+                const float y = tc_act(act, __uint_as_float(xr[j]) + sbias[c0 + j], d);
+                tile[(0 * 32 + lane) * 33 + j] = y;
+                tile[(1 * 32 + lane) * 33 + j] = (__uint_as_float(rr[j]) + sbias[256 + c0 + j]) * d;
+            }
+            __syncwarp();
+            if (c0 + lane < N && !(dbg & 1)) {
+                for (int r = 0; r < rows_here; ++r) {
+                    const size_t o = (size_t)(m0 + 32 * q + r) * N + c0 + lane;
+                    const float y = tile[(0 * 32 + r) * 33 + lane], ry = tile[(1 * 32 + r) * 33 + lane];
+                    Yout[o] = y;
+                    RYout[o] = ry;
+                    if (Ylo_out) { Ylo_out[o] = tf32_lo(y); RYlo_out[o] = tf32_lo(ry); }
                 }
             }
+            __syncwarp();
         }
     }
     tmem_fence_before_sync();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();                       // no CTA leaves while a peer may still multicast into it or signal it
     if (warp == 1) tmem_dealloc(tm, C::TM_COLS);
 }
 
@@ -287,18 +328,34 @@ bool make_map(CUtensorMap *m, const float *base, int nrows, int ncols, int ld, i
               CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int BN, bool HAS_RA>
+template <int BN, bool HAS_RA, int CL>
 int launch_tc(const TcMaps &maps, const float *bias, const float *vbias, int rows, int Kd, int N, char act, float *Yout,
               float *Ylo_out, float *RYout, float *RYlo_out, const int *done, cudaStream_t st) {
     using C = TcCfg<BN, HAS_RA>;
     static DeviceOnce once;
     if (once.pending()) {
-        if (cudaFuncSetAttribute(k_tc_fwd<BN, HAS_RA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM) != cudaSuccess) return -1;
+        if (cudaFuncSetAttribute(k_tc_fwd<BN, HAS_RA, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM) != cudaSuccess) return -1;
         once.mark();
     }
-    k_tc_fwd<BN, HAS_RA><<<(rows + TC_BM - 1) / TC_BM, TC_THREADS, C::SMEM, st>>>(maps, bias, vbias, rows, Kd, N, act, Yout, Ylo_out,
-                                                                                RYout, RYlo_out, done);
-    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+    const int tiles = (rows + TC_BM - 1) / TC_BM;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((tiles + CL - 1) / CL * CL);       // whole clusters: surplus CTAs see only zero-filled rows and store nothing
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = C::SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = CL > 1 ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, k_tc_fwd<BN, HAS_RA, CL>, maps, bias, vbias, rows, Kd, N, act, Yout, Ylo_out, RYout, RYlo_out, done, getenv("TRPO_TC_DEBUG") ? atoi(getenv("TRPO_TC_DEBUG")) : 0) == cudaSuccess ? 0 : -1;
+}
+template <int BN, bool HAS_RA>
+int launch_tc_cl(int cl, const TcMaps &maps, const float *bias, const float *vbias, int rows, int Kd, int N, char act, float *Yout,
+                 float *Ylo_out, float *RYout, float *RYlo_out, const int *done, cudaStream_t st) {
+    if (cl == 4) return launch_tc<BN, HAS_RA, 4>(maps, bias, vbias, rows, Kd, N, act, Yout, Ylo_out, RYout, RYlo_out, done, st);
+    if (cl == 2) return launch_tc<BN, HAS_RA, 2>(maps, bias, vbias, rows, Kd, N, act, Yout, Ylo_out, RYout, RYlo_out, done, st);
+    return launch_tc<BN, HAS_RA, 1>(maps, bias, vbias, rows, Kd, N, act, Yout, Ylo_out, RYout, RYlo_out, done, st);
 }
 
 }  // namespace
@@ -328,21 +385,25 @@ int tc_fwd_layer(const float *Yin, const float *Ylo_in, const float *RYin, const
                  const float *vbias, int rows, int Kd, int N, char act, float *Yout, float *Ylo_out, float *RYout, float *RYlo_out,
                  const int *done, cudaStream_t st, long long *launches) {
     const int BN = N <= 64 ? 64 : N <= 128 ? 128 : 256;
+    // cluster size: weight tiles are multicast over CL consecutive row blocks (TRPO_TC_CLUSTER = 1 | 2 | 4 overrides)
+    static const int cl_env = getenv("TRPO_TC_CLUSTER") ? atoi(getenv("TRPO_TC_CLUSTER")) : 0;
+    int cl = (cl_env == 1 || cl_env == 2 || cl_env == 4) ? cl_env : 4;
+    if ((rows + TC_BM - 1) / TC_BM < 2 * cl) cl = 1;
     const size_t sz = (size_t)Kd * N;
     TcMaps maps;
     bool ok = make_map(&maps.y, Yin, rows, Kd, Kd, TC_BM) && make_map(&maps.ylo, Ylo_in, rows, Kd, Kd, TC_BM) &&
-              make_map(&maps.w, wt4, N, Kd, Kd, BN) && make_map(&maps.wlo, wt4 + sz, N, Kd, Kd, BN) &&
-              make_map(&maps.vw, wt4 + 2 * sz, N, Kd, Kd, BN) && make_map(&maps.vwlo, wt4 + 3 * sz, N, Kd, Kd, BN);
+              make_map(&maps.w, wt4, N, Kd, Kd, BN / cl) && make_map(&maps.wlo, wt4 + sz, N, Kd, Kd, BN / cl) &&
+              make_map(&maps.vw, wt4 + 2 * sz, N, Kd, Kd, BN / cl) && make_map(&maps.vwlo, wt4 + 3 * sz, N, Kd, Kd, BN / cl);
     if (RYin) ok = ok && make_map(&maps.ry, RYin, rows, Kd, Kd, TC_BM) && make_map(&maps.rylo, RYlo_in, rows, Kd, Kd, TC_BM);
     else { maps.ry = maps.y; maps.rylo = maps.ylo; }
     if (!ok) return -1;
     int rc;
-    if (RYin) rc = BN == 64 ? launch_tc<64, true>(maps, bias, vbias, rows, Kd, N, act, Yout, Ylo_out, RYout, RYlo_out, done, st)
-                : BN == 128 ? launch_tc<128, true>(maps, bias, vbias, rows, Kd, N, act, Yout, Ylo_out, RYout, RYlo_out, done, st)
-                            : launch_tc<256, true>(maps, bias, vbias, rows, Kd, N, act, Yout, Ylo_out, RYout, RYlo_out, done, st);
-    else rc = BN == 64 ? launch_tc<64, false>(maps, bias, vbias, rows, Kd, N, act, Yout, Ylo_out, RYout, RYlo_out, done, st)
-            : BN == 128 ? launch_tc<128, false>(maps, bias, vbias, rows, Kd, N, act, Yout, Ylo_out, RYout, RYlo_out, done, st)
-                        : launch_tc<256, false>(maps, bias, vbias, rows, Kd, N, act, Yout, Ylo_out, RYout, RYlo_out, done, st);
+    if (RYin) rc = BN == 64 ? launch_tc_cl<64, true>(cl, maps, bias, vbias, rows, Kd, N, act, Yout, Ylo_out, RYout, RYlo_out, done, st)
+                : BN == 128 ? launch_tc_cl<128, true>(cl, maps, bias, vbias, rows, Kd, N, act, Yout, Ylo_out, RYout, RYlo_out, done, st)
+                            : launch_tc_cl<256, true>(cl, maps, bias, vbias, rows, Kd, N, act, Yout, Ylo_out, RYout, RYlo_out, done, st);
+    else rc = BN == 64 ? launch_tc_cl<64, false>(cl, maps, bias, vbias, rows, Kd, N, act, Yout, Ylo_out, RYout, RYlo_out, done, st)
+            : BN == 128 ? launch_tc_cl<128, false>(cl, maps, bias, vbias, rows, Kd, N, act, Yout, Ylo_out, RYout, RYlo_out, done, st)
+                        : launch_tc_cl<256, false>(cl, maps, bias, vbias, rows, Kd, N, act, Yout, Ylo_out, RYout, RYlo_out, done, st);
     if (rc == 0) ++*launches;
     return rc;
 }
