@@ -377,6 +377,110 @@ __global__ void k_to_float(const double *__restrict__ src, float *__restrict__ d
         dst[i] = (float)src[i];
 }
 
+// tail: the LAST weight layer when the action dimension is small (A <= 32) and the output activation is linear / 0.1x -- the
+// FP32 counterpart of k_chain_tail (gemm_chain.cu). One kernel replaces forward(K-1) + seed + backward(K), which as two
+// 128 x 64-tile tensor-core GEMMs padded a 17-column layer to 64 columns and took 0.81 of the 3.56 ms of a 200 k-state FVP:
+//   Rx_K = Ry_{K-1} W + y_{K-1} VW + VB   (TRPO_FVP.c:795-803),   RG_K = Rx_K f'^2 / sigma^2   (:852-854, :869-882),
+//   RG_{K-1} = (RG_K W^T) .* f'(y_{K-1})  (:890-899).
+// Plain FP32 FMAs: 13 k per sample is nothing against the 2 KB of activations it has to read (memory bound). A warp takes
+// 4 rows at a time; lane l owns the hidden units l, l + 32, ...; the weights sit in shared memory at an odd row stride
+// (conflict-free for lane-strided rows) and every weight read feeds 8 (forward) / 4 (backward) FMAs.
+constexpr int TAIL_ROWS = 4, TAIL_AS = 33;
+template <int JJ>      // JJ = H / 32 hidden units per lane
+__global__ void __launch_bounds__(256) k_tail_f32(const float *__restrict__ Y, const float *__restrict__ RY,
+                                                  const float *__restrict__ W, const float *__restrict__ VW, int rows, int A,
+                                                  char act_prev, float d3, const float *__restrict__ inv_var,
+                                                  float *__restrict__ GK, float *__restrict__ Gprev, float *__restrict__ Gprev_lo,
+                                                  const int *__restrict__ done) {
+    if (done && *done) return;
+    constexpr int H = 32 * JJ;
+    extern __shared__ __align__(16) float smem_f[];
+    float *Ws = smem_f, *VWs = Ws + H * TAIL_AS, *vbs = VWs + H * TAIL_AS, *ivs = vbs + 32;
+    for (int idx = threadIdx.x; idx < H * A; idx += blockDim.x) {
+        const int j = idx / A, a = idx % A;
+        Ws[j * TAIL_AS + a] = W[idx];
+        VWs[j * TAIL_AS + a] = VW[idx];
+    }
+    for (int a = threadIdx.x; a < 32; a += blockDim.x) { vbs[a] = a < A ? VW[(size_t)H * A + a] : 0.0f; ivs[a] = a < A ? inv_var[a] : 0.0f; }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = gridDim.x * (blockDim.x >> 5);
+    for (long long r0 = (long long)(blockIdx.x * (blockDim.x >> 5) + warp) * TAIL_ROWS; r0 < rows; r0 += (long long)nwarp * TAIL_ROWS) {
+        float y[TAIL_ROWS][JJ], ry[TAIL_ROWS][JJ];
+#pragma unroll
+        for (int r = 0; r < TAIL_ROWS; ++r)
+#pragma unroll
+            for (int jj = 0; jj < JJ; ++jj) {
+                const bool in = r0 + r < rows;
+                y[r][jj] = in ? Y[(size_t)(r0 + r) * H + lane + 32 * jj] : 0.0f;
+                ry[r][jj] = in ? RY[(size_t)(r0 + r) * H + lane + 32 * jj] : 0.0f;
+            }
+        float g3[TAIL_ROWS];                                   // after the reduction lane a holds RG_K[r][a]
+#pragma unroll
+        for (int r = 0; r < TAIL_ROWS; ++r) g3[r] = 0.0f;
+        for (int a = 0; a < A; ++a) {
+            float acc[TAIL_ROWS];
+#pragma unroll
+            for (int r = 0; r < TAIL_ROWS; ++r) acc[r] = 0.0f;
+#pragma unroll
+            for (int jj = 0; jj < JJ; ++jj) {
+                const float w = Ws[(lane + 32 * jj) * TAIL_AS + a], v = VWs[(lane + 32 * jj) * TAIL_AS + a];
+#pragma unroll
+                for (int r = 0; r < TAIL_ROWS; ++r) acc[r] = fmaf(ry[r][jj], w, fmaf(y[r][jj], v, acc[r]));
+            }
+#pragma unroll
+            for (int r = 0; r < TAIL_ROWS; ++r) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
+                if (lane == a) g3[r] = (acc[r] + vbs[a]) * d3 * ivs[a] * d3;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < TAIL_ROWS; ++r)
+            if (lane < A && r0 + r < rows) GK[(size_t)(r0 + r) * A + lane] = g3[r];
+        // RG_{K-1}[r][j] = f'(y[r][j]) * sum_a RG_K[r][a] W[j][a]
+        float g2[TAIL_ROWS][JJ];
+#pragma unroll
+        for (int r = 0; r < TAIL_ROWS; ++r)
+#pragma unroll
+            for (int jj = 0; jj < JJ; ++jj) g2[r][jj] = 0.0f;
+        for (int a = 0; a < A; ++a) {
+            float ga[TAIL_ROWS];
+#pragma unroll
+            for (int r = 0; r < TAIL_ROWS; ++r) ga[r] = __shfl_sync(0xffffffffu, g3[r], a);
+#pragma unroll
+            for (int jj = 0; jj < JJ; ++jj) {
+                const float w = Ws[(lane + 32 * jj) * TAIL_AS + a];
+#pragma unroll
+                for (int r = 0; r < TAIL_ROWS; ++r) g2[r][jj] = fmaf(ga[r], w, g2[r][jj]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < TAIL_ROWS; ++r) {
+            if (r0 + r >= rows) continue;
+#pragma unroll
+            for (int jj = 0; jj < JJ; ++jj) {
+                const float gv = g2[r][jj] * act_deriv(act_prev, y[r][jj]);
+                Gprev[(size_t)(r0 + r) * H + lane + 32 * jj] = gv;
+                if (Gprev_lo) Gprev_lo[(size_t)(r0 + r) * H + lane + 32 * jj] = gv - __uint_as_float(__float_as_uint(gv) & 0xffffe000u);
+            }
+        }
+    }
+}
+template <int JJ>
+int launch_tail_f32(const float *Y, const float *RY, const float *W, const float *VW, int rows, int A, char act_prev, float d3,
+                    const float *inv_var, float *GK, float *Gprev, float *Gprev_lo, const int *done, cudaStream_t st) {
+    const size_t smem = sizeof(float) * (2 * 32 * JJ * TAIL_AS + 64);
+    static DeviceOnce once;
+    if (once.pending()) {
+        if (cudaFuncSetAttribute(k_tail_f32<JJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+        once.mark();
+    }
+    int grid = (rows + 8 * TAIL_ROWS - 1) / (8 * TAIL_ROWS);
+    if (grid > 148 * 2) grid = 148 * 2;
+    k_tail_f32<JJ><<<grid, 256, smem, st>>>(Y, RY, W, VW, rows, A, act_prev, d3, inv_var, GK, Gprev, Gprev_lo, done);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
 // zsum[e] (FP64) = fixed-order sum over slices of the FP32 partial rows
 __global__ void __launch_bounds__(256) k_reduce_f32(const float *__restrict__ partial, int rows, int P,
                                                     double *__restrict__ zsum, const int *__restrict__ done) {
@@ -454,11 +558,15 @@ int chain_f32_accumulate(const NetDesc &net, const ChainScratchF32 &sc, const fl
         tc[i] = tc_fwd_eligible(net.L[i], net.L[i + 1]) && (i > 0 || sc.obs_lo != nullptr);
         if (tc[i]) tc_prep_weights(f_theta + net.w_off[i], f_v + net.w_off[i], net.L[i], net.L[i + 1], sc.wt[i], st, launches);
     }
+    // the last layer of a narrow-action FVP goes through the fused FP32 tail kernel (forward(K-1) + seed + backward(K))
+    const int Hl = K >= 2 ? net.L[K - 1] : 0, Al = net.L[K];
+    static const bool no_tail = getenv("TRPO_NO_F32_TAIL") != nullptr;
+    const bool tail = !no_tail && K >= 2 && Al <= 32 && (net.ac[K] == 'l' || net.ac[K] == 'o') && (Hl % 32) == 0 && Hl >= 32 && Hl <= 256;
     int chunk_idx = 0;
     for (size_t c0 = 0; c0 < nsamples; c0 += sc.chunk, ++chunk_idx) {
         const int rows = (int)((nsamples - c0 < (size_t)sc.chunk) ? nsamples - c0 : sc.chunk);
         const int accumulate = chunk_idx > 0;
-        for (int i = 0; i < K; ++i) {
+        for (int i = 0; i < (tail ? K - 1 : K); ++i) {
             const float *Yin = (i == 0) ? f_obs + c0 * net.L[0] : sc.Y[i];
             const bool last = (i == K - 1);
             if (tc[i]) {
@@ -498,6 +606,24 @@ int chain_f32_accumulate(const NetDesc &net, const ChainScratchF32 &sc, const fl
                                                                  Yo, RYo, Go, f_inv_var, d_done);
             ++*launches;
         }
+        if (tail) {
+            const float d3 = net.ac[K] == 'o' ? 0.1f : 1.0f;
+            const float *Wl = f_theta + net.w_off[K - 1], *VWl = f_v + net.w_off[K - 1];
+            float *GK = sc.G[K & 1], *Gp = sc.G[(K - 1) & 1];
+            int rc;
+            switch (Hl / 32) {
+                case 1: rc = launch_tail_f32<1>(sc.Y[K - 1], sc.RY[(K - 1) & 1], Wl, VWl, rows, Al, net.ac[K - 1], d3, f_inv_var, GK, Gp, nullptr, d_done, st); break;
+                case 2: rc = launch_tail_f32<2>(sc.Y[K - 1], sc.RY[(K - 1) & 1], Wl, VWl, rows, Al, net.ac[K - 1], d3, f_inv_var, GK, Gp, nullptr, d_done, st); break;
+                case 3: rc = launch_tail_f32<3>(sc.Y[K - 1], sc.RY[(K - 1) & 1], Wl, VWl, rows, Al, net.ac[K - 1], d3, f_inv_var, GK, Gp, nullptr, d_done, st); break;
+                case 4: rc = launch_tail_f32<4>(sc.Y[K - 1], sc.RY[(K - 1) & 1], Wl, VWl, rows, Al, net.ac[K - 1], d3, f_inv_var, GK, Gp, nullptr, d_done, st); break;
+                case 5: rc = launch_tail_f32<5>(sc.Y[K - 1], sc.RY[(K - 1) & 1], Wl, VWl, rows, Al, net.ac[K - 1], d3, f_inv_var, GK, Gp, nullptr, d_done, st); break;
+                case 6: rc = launch_tail_f32<6>(sc.Y[K - 1], sc.RY[(K - 1) & 1], Wl, VWl, rows, Al, net.ac[K - 1], d3, f_inv_var, GK, Gp, nullptr, d_done, st); break;
+                case 7: rc = launch_tail_f32<7>(sc.Y[K - 1], sc.RY[(K - 1) & 1], Wl, VWl, rows, Al, net.ac[K - 1], d3, f_inv_var, GK, Gp, nullptr, d_done, st); break;
+                default: rc = launch_tail_f32<8>(sc.Y[K - 1], sc.RY[(K - 1) & 1], Wl, VWl, rows, Al, net.ac[K - 1], d3, f_inv_var, GK, Gp, nullptr, d_done, st); break;
+            }
+            if (rc) return -1;
+            ++*launches;
+        }
         for (int i = K; i >= 1; --i) {
             const float *Yprev = (i == 1) ? f_obs + c0 * net.L[0] : sc.Y[i - 1];
             const int M0 = net.L[i - 1], N = net.L[i];
@@ -508,7 +634,7 @@ int chain_f32_accumulate(const NetDesc &net, const ChainScratchF32 &sc, const fl
             k_outer<<<go, NT, SMEM_SINGLE, st>>>(Yprev, sc.G[i & 1], rows, M0, N, cdiv(cdiv(rows, ns), BK) * BK, tiles_n,
                                                 sc.partial, net.P, net.w_off[i - 1], accumulate, bias_colsum, d_done);
             ++*launches;
-            if (i > 1) {
+            if (i > 1 && !(tail && i == K)) {
                 dim3 gb(cdiv(M0, BN), cdiv(rows, BM));
                 k_bwd<<<gb, NT, SMEM_SINGLE, st>>>(sc.G[i & 1], f_theta + net.w_off[i - 1], sc.Y[i - 1], rows, N, M0,
                                                   net.ac[i - 1], sc.G[(i - 1) & 1], d_done);
