@@ -538,3 +538,127 @@ def test_reference_own_harness_against_the_dropin(pkg, armtest, tmp_path):
     assert "Difference" not in out.stdout                           # no element off by more than 1 %
     # both CG traces were printed: the GPU's (from CG_FPGA) and the reference's (from CG)
     assert out.stdout.count("CG Iter[8] Residual Norm=") == 2
+
+
+def _run_with_env(code, env_extra, timeout=600):
+    """Kernel-selection switches are read once per process: run a snippet in a subprocess with the given environment."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    prelude = ("import sys, json, numpy as np\n"
+               f"sys.path.insert(0, {root!r}); sys.path.insert(0, {os.path.join(root, 'tests')!r})\n"
+               "from __graft_entry__ import load_package\n"
+               "from conftest import load_synth\n"
+               "pkg = load_package()\n")
+    out = subprocess.run([sys.executable, "-c", prelude + code], env=dict(os.environ, **env_extra), capture_output=True, text=True,
+                         timeout=timeout)
+    assert out.returncode == 0, out.stdout[-800:] + out.stderr[-2000:]
+    return out.stdout
+
+
+SOLVE_SNIPPET = (
+    "res = {}\n"
+    "for name in ('mlp64', 'arm_sigma', 'pendulum64'):\n"
+    "    s = load_synth(name)\n"
+    "    with pkg.Context(s['layers'], s['acfunc']) as ctx:\n"
+    "        ctx.set_model(s['theta']); ctx.set_batch(s['Observ'], s['Std'], s['Mean'], s['Action'], s['Advantage'])\n"
+    "        x, info = ctx.cg(s['b'], 10, 1e-10, 0.1)\n"
+    "        x0, info0 = ctx.cg(s['b'], 10, 0.0, 0.1)\n"
+    "        u, _ = ctx.update(0.1)\n"
+    "        res[name] = dict(x=x.tolist(), iters=info.cg_iters, rd=list(info.cg_rdotr[:11]), x0=x0.tolist(), iters0=info0.cg_iters,\n"
+    "                         u=u.tolist(), solve_kernel=ctx.solve_kernel_used(),\n"
+    "                         e=float(np.abs(x - s['ref_cg']).max() / np.abs(s['ref_cg']).max()),\n"
+    "                         eu=float(np.abs(u - s['ref_update']).max() / np.abs(s['ref_update']).max()))\n"
+    "print('RESULT' + json.dumps(res))\n")
+
+
+def test_persistent_solve_kernel_against_per_iteration_launches():
+    """The whole CG as ONE cooperative kernel (in-kernel row reduction, grid barriers, CG update) and as per-iteration launches
+    (FVP kernel, row reduction, single-CTA update): same iteration counts, same early exit, both within tolerance of the
+    compiled reference, and within rounding of each other (the dot products are summed in different fixed orders)."""
+    import json
+    a = json.loads(_run_with_env(SOLVE_SNIPPET, {"TRPO_FUSED_SOLVE": "1"}).split("RESULT")[1])
+    b = json.loads(_run_with_env(SOLVE_SNIPPET, {"TRPO_NO_FUSED_SOLVE": "1"}).split("RESULT")[1])
+    for name in a:
+        assert a[name]["solve_kernel"] is True and b[name]["solve_kernel"] is False
+        assert a[name]["iters"] == b[name]["iters"] and a[name]["iters0"] == b[name]["iters0"] == 10
+        assert a[name]["e"] < CG_TOL and b[name]["e"] < CG_TOL and a[name]["eu"] < CG_TOL and b[name]["eu"] < CG_TOL
+        xa, xb = np.array(a[name]["x"]), np.array(b[name]["x"])
+        assert rel_err(xa, xb)[0] < 1e-10
+        n = a[name]["iters"] + 1
+        assert np.allclose(a[name]["rd"][:n], b[name]["rd"][:n], rtol=1e-9)
+
+
+def test_warp_group_variants_of_the_fused_kernel():
+    """TRPO_FUSED_GROUPS = 1 | 2: one 8-warp group per CTA (block barriers) or two independent 4-warp groups with the
+    accumulators parked in Tensor Memory (tcgen05.st / tcgen05.ld): same results within rounding, both within tolerance."""
+    import json
+    snippet = (
+        "res = {}\n"
+        "for name in ('mlp64', 'pendulum64'):\n"
+        "    s = load_synth(name)\n"
+        "    with pkg.Context(s['layers'], s['acfunc']) as ctx:\n"
+        "        ctx.set_model(s['theta']); ctx.set_batch(s['Observ'], s['Std'], s['Mean'], s['Action'], s['Advantage'])\n"
+        "        z = ctx.fvp(s['v'], 0.1); pg = ctx.policy_gradient()\n"
+        "        res[name] = dict(z=z.tolist(), pg=pg.tolist(), e=float(np.abs(z - s['ref_fvpfast']).max() / np.abs(s['ref_fvpfast']).max()))\n"
+        "layers, ac = [11, 32, 32, 3], 'lttl'\n"
+        "theta = pkg.synth.make_model(layers, 3); b = pkg.synth.make_batch(layers, ac, theta, 5000, 3); v = pkg.synth.make_vectors(layers, 3)\n"
+        "with pkg.Context(layers, ac) as ctx:\n"
+        "    ctx.set_model(theta); ctx.set_batch(b['Observ'], b['Std'], b['Mean'], b['Action'], b['Advantage'])\n"
+        "    res['h32'] = dict(z=ctx.fvp(v['v'], 0.1).tolist(), pg=ctx.policy_gradient().tolist(), e=0.0)\n"
+        "print('RESULT' + json.dumps(res))\n")
+    one = json.loads(_run_with_env(snippet, {"TRPO_FUSED_GROUPS": "1"}).split("RESULT")[1])
+    two = json.loads(_run_with_env(snippet, {"TRPO_FUSED_GROUPS": "2"}).split("RESULT")[1])
+    for name in one:
+        assert one[name]["e"] < FVP_TOL and two[name]["e"] < FVP_TOL
+        assert rel_err(np.array(one[name]["z"]), np.array(two[name]["z"]))[0] < 1e-12
+        assert rel_err(np.array(one[name]["pg"]), np.array(two[name]["pg"]))[0] < 1e-12
+
+
+def test_tail_of_the_batch_is_split_in_eight_sample_units(pkg, oracle):
+    """The last, partial round of tiles is dealt out in 8-sample units (one partial tile per warp group): sizes around the
+    full-round boundary of 148 CTAs x 64 samples, with tails that are not multiples of 8."""
+    layers, ac = [17, 64, 64, 6], "lttl"
+    theta = pkg.synth.make_model(layers, 21)
+    vec = pkg.synth.make_vectors(layers, 21)
+    for n in (9472 - 3, 9472, 9472 + 5, 2 * 9472 + 8 * 148 + 1, 20001):
+        batch = pkg.synth.make_batch(layers, ac, theta, n, 21)
+        ref = oracle.fvp(layers, ac, theta, batch["Std"], batch["Observ"], 0.1, vec["v"])
+        pg_ref = oracle.policy_gradient(layers, ac, theta, batch["Observ"], batch["Mean"], batch["Action"], batch["Advantage"])
+        with pkg.Context(layers, ac) as ctx:
+            ctx.set_model(theta)
+            ctx.set_batch(batch["Observ"], batch["Std"], batch["Mean"], batch["Action"], batch["Advantage"])
+            z = ctx.fvp(vec["v"], 0.1)
+            pg = ctx.policy_gradient()
+        assert rel_err(z, ref)[0] < FVP_TOL, (n, rel_err(z, ref))
+        assert rel_err(pg, pg_ref)[0] < FVP_TOL, (n, rel_err(pg, pg_ref))
+
+
+def test_fp32_tcgen05_layers_against_the_legacy_tensor_path():
+    """FP32 mode at Humanoid width: the forward layers on tcgen05 (TMA-fed, TMEM accumulators) and the fused tail kernel against the
+    mma.sync kernels they replace (TRPO_NO_TCGEN05 / TRPO_NO_F32_TAIL): both within the stated 1e-4 of the FP64 oracle, and
+    within 3xTF32 rounding of each other; ragged row counts and a 376-wide (not a multiple of 16) first layer included."""
+    import json
+    snippet = (
+        "sys.path.insert(0, 'tests')\n"
+        "from oracle_lib import Oracle\n"
+        "res = {}\n"
+        "for layers, n in (([376, 256, 256, 17], 1000), ([376, 64, 64, 17], 777), ([40, 96, 32, 5], 300)):\n"
+        "    ac = 'lttl'\n"
+        "    theta = pkg.synth.make_model(layers, 4); b = pkg.synth.make_batch(layers, ac, theta, n, 4); v = pkg.synth.make_vectors(layers, 4)\n"
+        "    ref = Oracle(fast=True).fvp(layers, ac, theta, b['Std'], b['Observ'], 0.1, v['v'])\n"
+        "    with pkg.Context(layers, ac, precision=pkg.api.PRECISION_FP32) as ctx:\n"
+        "        ctx.set_model(theta); ctx.set_batch(b['Observ'], b['Std'])\n"
+        "        z = ctx.fvp(v['v'], 0.1)\n"
+        "        ctx.set_chunk(256)\n"
+        "        z2 = ctx.fvp(v['v'], 0.1)\n"
+        "    res[str(layers)] = dict(z=z.tolist(), e=float(np.linalg.norm(z - ref) / np.linalg.norm(ref)),\n"
+        "                            e2=float(np.linalg.norm(z2 - ref) / np.linalg.norm(ref)))\n"
+        "print('RESULT' + json.dumps(res))\n")
+    new = json.loads(_run_with_env(snippet, {}).split("RESULT")[1])
+    old = json.loads(_run_with_env(snippet, {"TRPO_NO_TCGEN05": "1", "TRPO_NO_F32_TAIL": "1"}).split("RESULT")[1])
+    for k in new:
+        assert new[k]["e"] < FP32_TOL and new[k]["e2"] < FP32_TOL and old[k]["e"] < FP32_TOL, (k, new[k]["e"], new[k]["e2"], old[k]["e"])
+        assert new[k]["e"] > 1e-12
+        assert rel_err(np.array(new[k]["z"]), np.array(old[k]["z"]))[1] < FP32_TOL
