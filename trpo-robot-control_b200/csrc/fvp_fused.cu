@@ -131,7 +131,24 @@ struct FusedArgs {
     // mean == NULL: the kernel forms the network output itself (one more DMMA step per sample) and, when mean_out is
     // set, stores it -- the baseline objective's Predict (TRPO_Baseline.c:134) and its gradient in ONE pass
     double *mean_out;
+    // persistent solve kernel: the grid barrier that publishes the direction v is split -- the CTA arrived before calling the
+    // pass and waits (thread 0 on the generation word, then a block barrier) only right before it reads v, with the first
+    // observation tile already on its way
+    unsigned int *wait_bar;
+    unsigned int wait_gen;
 };
+__device__ __forceinline__ void pass_grid_wait(const FusedArgs &p) {
+    if (p.wait_bar == nullptr) return;
+    if (threadIdx.x == 0) {
+        unsigned int g;
+        const long long t0 = clock64();
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(g) : "l"(p.wait_bar + 1) : "memory");
+            if (g == p.wait_gen && clock64() - t0 > 20000000000LL) __trap();
+        } while (g == p.wait_gen);
+    }
+    __syncthreads();
+}
 
 __device__ __forceinline__ int ld_volatile_i32(const int *p) {
     int v;
@@ -187,6 +204,38 @@ __device__ __forceinline__ void fused_pass(const FusedArgs &p, double *sm, const
     const bool free_col = L0 < K0;
     const int rows0 = L0 + (free_col ? 1 : 0);
     const bool st_m = (stage & 1) != 0, st_v = (stage & 2) != 0;
+    // Work split over the Wk = gridDim.x * NG warp groups: F full rounds of round-robin tiles (tile wid + r * Wk: the batch is
+    // consumed front to back, which is what the streamed staging needs), then the remaining < Wk * SG samples are dealt out in
+    // 8-sample units, contiguous and as evenly as possible, ONE partial tile per group. A partial tile costs the active warps'
+    // phase A plus a phase B over its rows only, so 13.2 tiles per group take 13.4 tile times instead of 14 (the 8-GPU shard of
+    // the headline batch: 125 k states over 148 CTAs).
+    const long long Wk = (long long)gridDim.x * NG, wid = (long long)blockIdx.x * NG + grp;
+    const long long F = p.nsamples / (Wk * SG), sT = F * Wk * SG;
+    const long long Ut = (p.nsamples - sT + 7) / 8, ubase = Ut / Wk, uextra = Ut % Wk;
+    const long long tail_lo = sT + 8 * (wid * ubase + (wid < uextra ? wid : uextra));
+    const long long tail_hi0 = tail_lo + 8 * (ubase + (wid < uextra ? 1 : 0));
+    const long long tail_hi = tail_hi0 < p.nsamples ? tail_hi0 : p.nsamples;
+    const int nk = (int)F + (tail_hi > tail_lo ? 1 : 0);            // tiles of this group
+    auto tile_begin = [&](int k) { return k < F ? (wid + (long long)k * Wk) * SG : tail_lo; };
+    auto tile_end = [&](int k) { return k < F ? (wid + (long long)k * Wk) * SG + SG : tail_hi; };
+    // observation tile [SG][K0] (zero padded / zero past the end of the tile), staged asynchronously one tile ahead
+    auto stage_obs = [&](int k, int buf) {
+        double *dst = Y0s + buf * C::Y0SZ;
+        const long long s0n = tile_begin(k), s1n = tile_end(k);
+        wait_samples(p, s1n - 1);
+        for (int idx = tg; idx < SG * K0; idx += GT) {
+            const int row = idx / K0, col = idx % K0;
+            const long long gs = s0n + row;
+            const bool in = gs < s1n && col < L0;
+            if (free_col && col == L0) dst[row * RS0 + col] = (gs < s1n) ? 1.0 : 0.0;
+            else cp_async8(&dst[row * RS0 + col], in ? &p.obs[gs * L0 + col] : p.obs, in ? 8 : 0);
+        }
+    };
+
+    // later passes of the persistent solve: the buffers are already clean, so the first observation tile is requested before
+    // anything else and lands while the CTA waits for the new direction and stages it
+    if (!st_m && nk > 0) stage_obs(0, 0);
+    pass_grid_wait(p);
     for (int idx = tid; idx < K0 * H1; idx += NT) {
         const int k = idx / H1, n = idx % H1;
         const bool in = k < rows0 && n < L1;
@@ -238,34 +287,6 @@ __device__ __forceinline__ void fused_pass(const FusedArgs &p, double *sm, const
         tmem_fence_after_sync();
         tm = tmem_warp_addr(tmem_slot, w, (w >> 2) * 2 * C::PKN);
     }
-    // Work split over the Wk = gridDim.x * NG warp groups: F full rounds of round-robin tiles (tile wid + r * Wk: the batch is
-    // consumed front to back, which is what the streamed staging needs), then the remaining < Wk * SG samples are dealt out in
-    // 8-sample units, contiguous and as evenly as possible, ONE partial tile per group. A partial tile costs the active warps'
-    // phase A plus a phase B over its rows only, so 13.2 tiles per group take 13.4 tile times instead of 14 (the 8-GPU shard of
-    // the headline batch: 125 k states over 148 CTAs).
-    const long long Wk = (long long)gridDim.x * NG, wid = (long long)blockIdx.x * NG + grp;
-    const long long F = p.nsamples / (Wk * SG), sT = F * Wk * SG;
-    const long long Ut = (p.nsamples - sT + 7) / 8, ubase = Ut / Wk, uextra = Ut % Wk;
-    const long long tail_lo = sT + 8 * (wid * ubase + (wid < uextra ? wid : uextra));
-    const long long tail_hi0 = tail_lo + 8 * (ubase + (wid < uextra ? 1 : 0));
-    const long long tail_hi = tail_hi0 < p.nsamples ? tail_hi0 : p.nsamples;
-    const int nk = (int)F + (tail_hi > tail_lo ? 1 : 0);            // tiles of this group
-    auto tile_begin = [&](int k) { return k < F ? (wid + (long long)k * Wk) * SG : tail_lo; };
-    auto tile_end = [&](int k) { return k < F ? (wid + (long long)k * Wk) * SG + SG : tail_hi; };
-    // observation tile [SG][K0] (zero padded / zero past the end of the tile), staged asynchronously one tile ahead
-    auto stage_obs = [&](int k, int buf) {
-        double *dst = Y0s + buf * C::Y0SZ;
-        const long long s0n = tile_begin(k), s1n = tile_end(k);
-        wait_samples(p, s1n - 1);
-        for (int idx = tg; idx < SG * K0; idx += GT) {
-            const int row = idx / K0, col = idx % K0;
-            const long long gs = s0n + row;
-            const bool in = gs < s1n && col < L0;
-            if (free_col && col == L0) dst[row * RS0 + col] = (gs < s1n) ? 1.0 : 0.0;
-            else cp_async8(&dst[row * RS0 + col], in ? &p.obs[gs * L0 + col] : p.obs, in ? 8 : 0);
-        }
-    };
-
     // per-lane offsets into a swizzled block: forward fragment (row 2t+r, col g), transposed fragment (row g, col 2t+r)
     int sf[2], sb[2];
 #pragma unroll
@@ -353,7 +374,7 @@ __device__ __forceinline__ void fused_pass(const FusedArgs &p, double *sm, const
     };
 
     const int rowA = 8 * wg + g;                         // this lane's sample row inside the group's tile (phase A)
-    if (nk > 0) stage_obs(0, 0);
+    if (st_m && nk > 0) stage_obs(0, 0);
     cp_async_wait_all();
     group_sync();
     int buf = 0;
@@ -1151,7 +1172,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cg_solve(FusedArgs p, const 
         const bool stamp = s.timeline != nullptr && blockIdx.x == 0 && tid == 0;
         unsigned long long *tl = s.timeline + (size_t)it * 8;
         if (stamp) tl[0] = globaltimer_ns();
-        if (WARP) warp_pass<C, ACT1, ACT2>(p, sm, stage);
+        if (WARP) { pass_grid_wait(p); warp_pass<C, ACT1, ACT2>(p, sm, stage); }
         else fused_pass<C, ACT1, ACT2, false>(p, sm, stage);
         stage = 2;                                            // the model stays staged; only the direction changes
         if (stamp) tl[1] = globaltimer_ns();                  // this CTA's pass done
@@ -1165,46 +1186,68 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cg_solve(FusedArgs p, const 
             const bool valid = e < hi && e < s.logstd_off;
             double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
             if (valid && ry < 8) {
-                int rw = ry;
-                for (; rw + 24 < s.rows; rw += 32) {
-                    s0 += __ldcg(&p.partial[(size_t)rw * P + e]);
-                    s1 += __ldcg(&p.partial[(size_t)(rw + 8) * P + e]);
-                    s2 += __ldcg(&p.partial[(size_t)(rw + 16) * P + e]);
-                    s3 += __ldcg(&p.partial[(size_t)(rw + 24) * P + e]);
+                // all of this thread's rows in flight at once (the loads are independent; four at a time cost five L2 round
+                // trips per chunk), summed afterwards in the order of k_reduce_partials
+                for (int rb = ry; rb < s.rows; rb += 8 * 20) {
+                    double v[20];
+#pragma unroll
+                    for (int k = 0; k < 20; ++k) v[k] = rb + 8 * k < s.rows ? __ldcg(&p.partial[(size_t)(rb + 8 * k) * P + e]) : 0.0;
+#pragma unroll
+                    for (int k = 0; k < 20; k += 4) { s0 += v[k]; s1 += v[k + 1]; s2 += v[k + 2]; s3 += v[k + 3]; }
                 }
-                for (; rw < s.rows; rw += 8) s0 += __ldcg(&p.partial[(size_t)rw * P + e]);
             }
             __syncthreads();
             if (ry < 8) colsh[ry][tid & 31] = (s0 + s1) + (s2 + s3);
             __syncthreads();
-            if (ry == 0 && valid) {
+            if (ry == 0) {
                 double tsum = colsh[0][tid];
 #pragma unroll
                 for (int k = 1; k < 8; ++k) tsum += colsh[k][tid];
-                s.zsum[e] = tsum;
-                if (multi)
-                    for (int rk = 0; rk < s.comm.world; ++rk) s.comm.slots[rk][slot + e] = tsum;   // NVLink stores for the peers
+                if (valid) s.zsum[e] = tsum;
+                colsh[0][tid] = tsum;
             }
-        }
-        if (stamp) tl[3] = globaltimer_ns();                  // slice column sums formed (and pushed)
-        if (multi) {
-            // publish: after the block barrier one system-scope fence covers the block's stores, then this CTA's flag on every
-            // rank; wait for CTA blockIdx.x of every rank (bounded spin), then sum the ranks in fixed order
-            __syncthreads();
-            if (tid == 0) {
-                // ONE system-scope fence, then relaxed flag stores: a st.release.sys per peer is a fence per peer, and each waits
-                // for the NVLink stores in flight (8 of them cost 29 us per iteration, profiles/r02_summary.md)
-                __threadfence_system();
-                for (int rk = 0; rk < s.comm.world; ++rk) {
-                    unsigned long long *f = &s.comm.cflags[rk][((nseq & 1) * s.comm.world + s.comm.rank) * DOT_STRIDE + blockIdx.x];
-                    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(f), "l"(nseq) : "memory");
+            if (multi) {
+                // low-latency exchange (the NCCL "LL" idea): every 8-byte word carries 4 bytes of payload and the 32-bit sequence
+                // number, so the receiver needs no flag and the sender no fence -- a word is valid when its tag matches. Warp w
+                // stores this chunk's sums into rank w's memory (two tagged words per double, one 16-byte NVLink store).
+                __syncthreads();
+                if (ry < s.comm.world && valid) {
+                    const unsigned long long bits = (unsigned long long)__double_as_longlong(colsh[0][tid & 31]);
+                    const unsigned long long tag = (nseq & 0xffffffffull) << 32;
+                    unsigned long long *dst = s.comm.ll[ry] + 2 * (slot + e);
+                    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" :: "l"(dst), "l"(tag | (bits & 0xffffffffull)), "l"(tag | (bits >> 32)) : "memory");
                 }
             }
-            if (tid < s.comm.world) {
-                const unsigned long long *f = &s.comm.cflags[s.comm.rank][((nseq & 1) * s.comm.world + tid) * DOT_STRIDE + blockIdx.x];
-                const long long t0 = clock64();
-                while (ld_acquire_sys_u64(f) < nseq) {
-                    if (clock64() - t0 > 40000000000LL) { *(volatile int *)s.comm.error = 1; break; }
+        }
+        __syncthreads();                                      // zsum of this slice was written by warp 0, every warp reads it below
+        if (stamp) tl[3] = globaltimer_ns();                  // slice column sums formed (and pushed)
+        if (multi) {
+            // receive: thread (rank r, column c) of each 32-column chunk spins on its two tagged words, then the ranks are summed
+            // in fixed order (bounded spin: a peer that never arrives poisons the solve instead of hanging the GPU)
+            const unsigned long long want = nseq & 0xffffffffull;
+            const unsigned long long *mine = s.comm.ll[s.comm.rank] + 2 * ((size_t)(nseq & 1) * s.comm.world * P);
+            for (int c0 = lo; c0 < hi; c0 += 32) {
+                const int e = c0 + (tid & 31), rk = tid >> 5;
+                const bool valid = e < hi && e < s.logstd_off;
+                double val = 0.0;
+                if (valid && rk < s.comm.world) {
+                    const unsigned long long *src = mine + 2 * ((size_t)rk * P + e);
+                    unsigned long long w0, w1;
+                    const long long t0 = clock64();
+                    for (;;) {
+                        asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(src) : "memory");
+                        if ((w0 >> 32) == want && (w1 >> 32) == want) break;
+                        if (clock64() - t0 > 40000000000LL) { *(volatile int *)s.comm.error = 1; break; }
+                    }
+                    val = __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+                }
+                __syncthreads();
+                if (rk < 8) colsh[rk][tid & 31] = val;
+                __syncthreads();
+                if (rk == 0 && valid) {
+                    double t2 = colsh[0][tid];
+                    for (int r2 = 1; r2 < s.comm.world; ++r2) t2 += colsh[r2][tid];
+                    s.zsum[e] = t2;
                 }
             }
             __syncthreads();
@@ -1216,12 +1259,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cg_solve(FusedArgs p, const 
             const double pi = __ldcg(&s.pv[e]);
             double mean;
             if (e >= s.logstd_off) mean = 2.0 * pi;          // LogStd block: sum_n 2 v / N exactly (TRPO_FVP.c:918-921)
-            else if (multi) {
-                const double *base = s.comm.slots[s.comm.rank] + (size_t)(seq & 1) * s.comm.world * P;
-                double t2 = __ldcg(&base[e]);
-                for (int rk = 1; rk < s.comm.world; ++rk) t2 += __ldcg(&base[(size_t)rk * P + e]);
-                mean = t2 / s.n_total;
-            } else mean = s.zsum[e] / s.n_total;
+            else mean = s.zsum[e] / s.n_total;          // single GPU: this CTA's column sums; several: the sum over the ranks
             const double zi = mean + s.damping * pi;
             s.z[e] = zi;
             acc += pi * zi;
@@ -1256,7 +1294,22 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cg_solve(FusedArgs p, const 
         iters = it + 1;
         if (blockIdx.x == 0 && tid == 0 && iters < s.trace_cap) { s.trace[iters] = newrdotr; s.trace[s.trace_cap + iters] = xnorm; }
         if (newrdotr < s.residual_th) done = 1;
-        grid_sync(s.gbar, G);                                 // the new direction is complete before anyone stages it
+        // the new direction must be complete before anyone stages it: arrive here, wait inside the next pass (pass_grid_wait)
+        {
+            __syncthreads();
+            unsigned int gen = 0;
+            if (tid == 0) {
+                unsigned int prev;
+                asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(gen) : "l"(s.gbar + 1) : "memory");
+                asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(prev) : "l"(s.gbar) : "memory");
+                if (prev == (unsigned int)G - 1) {
+                    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(s.gbar), "r"(0u) : "memory");
+                    st_release_gpu_u32(s.gbar + 1, gen + 1);
+                }
+            }
+            p.wait_bar = s.gbar;
+            p.wait_gen = gen;                                 // meaningful in thread 0, the only reader
+        }
         if (stamp) tl[7] = globaltimer_ns();
     }
     if (blockIdx.x == 0 && tid == 0) {
@@ -1381,6 +1434,7 @@ int fused_fvp_accumulate(const NetDesc &net, const double *d_theta, const double
     a.act1 = net.ac[1]; a.act2 = net.ac[2]; a.act3 = net.ac[3];
     a.ready = stream_ready; a.chunk_samples = (long long)(stream_chunk ? stream_chunk : 1); a.error = stream_error;
     a.mean = a.action = a.adv = nullptr; a.logstd_off = net.logstd_off; a.mean_out = nullptr;
+    a.wait_bar = nullptr; a.wait_gen = 0;
     int rows = 0, rc = -1;
     switch (shape) {
         case SHAPE_ARM: {
@@ -1459,6 +1513,7 @@ int fused_cg_solve(const NetDesc &net, const double *d_theta, const double *d_in
     a.act1 = net.ac[1]; a.act2 = net.ac[2]; a.act3 = net.ac[3];
     a.ready = stream_ready; a.chunk_samples = (long long)(stream_chunk ? stream_chunk : 1); a.error = stream_error;
     a.mean = a.action = a.adv = nullptr; a.logstd_off = net.logstd_off; a.mean_out = nullptr;
+    a.wait_bar = nullptr; a.wait_gen = 0;
     SolveArgs sa;
     sa.b = d_b; sa.x = d_x; sa.r = d_r; sa.pv = d_p; sa.z = d_z; sa.zsum = d_zsum; sa.dots = d_dots; sa.gbar = d_gbar;
     sa.st = d_state; sa.trace = d_trace; sa.trace_cap = trace_cap; sa.max_iter = (int)max_iter; sa.rows = 0;
@@ -1494,6 +1549,7 @@ int fused_pg_accumulate(const NetDesc &net, const double *d_theta, const double 
     a.act1 = net.ac[1]; a.act2 = net.ac[2]; a.act3 = net.ac[3];
     a.ready = nullptr; a.chunk_samples = 1; a.error = nullptr;
     a.mean = d_mean; a.action = d_action; a.adv = d_adv; a.logstd_off = net.logstd_off; a.mean_out = d_mean_out;
+    a.wait_bar = nullptr; a.wait_gen = 0;
     int rows = 0, rc = -1;
     switch (shape) {
         case SHAPE_ARM: rc = launch_shape<CfgArm, true>(a, st, &rows); break;

@@ -63,7 +63,7 @@ struct P2PComm {
     int world, rank;
     double *slots[TRPO_MAX_RANKS];               // slots[r]: base of rank r's slot area (peer-mapped; own for r == rank)
     unsigned long long *flags[TRPO_MAX_RANKS];   // flags[r]: base of rank r's flag area
-    unsigned long long *cflags[TRPO_MAX_RANKS];  // per-CTA flags [2][world][160] of the persistent solve kernel (same buffer)
+    unsigned long long *ll[TRPO_MAX_RANKS];      // persistent solve kernel: tagged words [2][world][P][2] (low-latency exchange), or NULL
     unsigned long long *seq_dev;                 // completed all-reduces (local, advanced by the consumer)
     unsigned int *block_counter;                 // last-block detection of the push kernel (local)
     int *error;                                  // set when a wait timed out (local)

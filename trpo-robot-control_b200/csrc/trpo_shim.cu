@@ -1289,14 +1289,16 @@ extern "C" int trpo_ctx_init_comm(trpo_ctx *c, const char id[128], int rank, int
 
 // ---- peer-memory all-reduce plumbing ------------------------------------------------------------------------
 // buffer layout: [0,256) flags[2][8] u64 | 256: seq_dev u64 | 264: block_counter u32 | 268: error i32 | 1024: slots[2][world][P]
-#define P2P_HDR 24576        // [1024, 21504): per-CTA flags [2][8][160] u64 of the persistent solve kernel
+#define P2P_HDR 1024
 extern "C" int trpo_ctx_p2p_export(trpo_ctx *c, char handle_out[64]) {
     if (!c || !handle_out) return fail("null argument");
     if (c->world < 2) return fail("trpo_ctx_init_comm with world_size >= 2 first");
     if (c->world > TRPO_MAX_RANKS) return fail("peer-memory all-reduce supports at most %d ranks", TRPO_MAX_RANKS);
     CU(cudaSetDevice(c->device));
     if (!c->p2p_buf) {
-        const size_t bytes = P2P_HDR + sizeof(double) * 2 * (size_t)c->world * c->net.P;
+        // header | slots[2][world][P] doubles | (fused shapes) tagged words [2][world][P][2] of the persistent solve kernel
+        const size_t slot_bytes = sizeof(double) * 2 * (size_t)c->world * c->net.P;
+        const size_t bytes = P2P_HDR + slot_bytes + (fused_eligible(c->net) ? 2 * slot_bytes : 0);
         CU(cudaMalloc(&c->p2p_buf, bytes));
         CU(cudaMemset(c->p2p_buf, 0, bytes));
         CU(cudaDeviceSynchronize());
@@ -1325,7 +1327,7 @@ extern "C" int trpo_ctx_p2p_attach(trpo_ctx *c, const char *handles) {
             base = (char *)ptr;
         }
         c->p2p.flags[r] = (unsigned long long *)base;
-        c->p2p.cflags[r] = (unsigned long long *)(base + 1024);
+        c->p2p.ll[r] = fused_eligible(c->net) ? (unsigned long long *)(base + P2P_HDR + sizeof(double) * 2 * (size_t)c->world * c->net.P) : nullptr;
         c->p2p.slots[r] = (double *)(base + P2P_HDR);
     }
     c->p2p.seq_dev = (unsigned long long *)(c->p2p_buf + 256);
