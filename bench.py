@@ -6,14 +6,18 @@
 A "step" is one 10-iteration conjugate-gradient solve (ResidualTh = 0, so exactly 10 Fisher-vector products,
 TRPO_CG.c:45-107) over the whole rollout batch. Default workload = BASELINE.json configs[2], the configuration the
 metric is quoted on: the 17-64-64-6 tanh Gaussian policy over 1M synthetic states, sharded over the N ranks
-(total work fixed => "strong" scaling; one NCCL all-reduce of the P-length FVP sum per CG iteration).
+(total work fixed => "strong" scaling; one all-reduce of the P-length FVP sum per CG iteration -- by default the NVLink
+peer-memory exchange inside the persistent solve kernel, `--comm nccl` for ncclAllReduce between per-iteration launches).
 
 value    FVP samples/s with the batch already resident in HBM (10 * N_states / step time; CUDA events on the
          launching stream, L2 flushed between steps, max over ranks)
 e2e      the same metric through the C-ABI with HOST buffers (trpo_ctx_set_batch + trpo_ctx_cg from pinned memory:
          H2D of the batch and b, D2H of x every step)
-roofline the dominant kernel (per-sample FVP sum) against the measured FP64 DMMA peak
+roofline the dominant kernel (the persistent solve kernel: 10 FVP passes per launch) timed live with CUDA events, against the
+         FP64 DMMA peak measured in this process right before; traffic from the committed ncu capture (profiles/ncu_traffic.json)
+parity   driver-visible correctness: sharded vs single-GPU solve (N > 1), a prefix through the unmodified reference CG() vs the GPU
 cpu_baseline / --impl reference: the reference's own CPU CG (oracle/_ref, unmodified sources) on a bounded sample.
+also     BASELINE configs 2, 4, 5 and the file-based drop-ins, measured in the same run (single GPU).
 """
 import argparse
 import json

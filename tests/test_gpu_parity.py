@@ -662,3 +662,32 @@ def test_fp32_tcgen05_layers_against_the_legacy_tensor_path():
         assert new[k]["e"] < FP32_TOL and new[k]["e2"] < FP32_TOL and old[k]["e"] < FP32_TOL, (k, new[k]["e"], new[k]["e2"], old[k]["e"])
         assert new[k]["e"] > 1e-12
         assert rel_err(np.array(new[k]["z"]), np.array(old[k]["z"]))[1] < FP32_TOL
+
+
+def test_piecewise_staging_of_a_large_pinned_batch_on_the_gemm_chain(pkg):
+    """GEMM-chain path, pinned source >= 256 MB: the observation matrix crosses PCIe in pieces with an event each and the first
+    FVP's chunk loop waits per piece. The result must be bitwise the one of a fully resident batch, on the first and later FVPs."""
+    import torch
+    layers, ac = [376, 64, 64, 17], "lttl"
+    n = 200_000
+    theta = pkg.synth.make_model(layers, 8)
+    rng = np.random.default_rng(8)
+    obs = rng.standard_normal((n, layers[0]))
+    std = np.exp(theta[-layers[-1]:])
+    v = rng.uniform(0, 1, theta.size)
+    pinned = torch.from_numpy(obs).pin_memory()
+    with pkg.Context(layers, ac) as ctx:
+        ctx.set_model(theta)
+        ctx.set_chunk(50_000)                                  # 4 chunks, pieces of ~89 k rows: chunks straddle pieces
+        ctx.set_batch(obs, std)                                # pageable: plain synchronous copy
+        z_ref = ctx.fvp(v, 0.1)
+        for _ in range(2):
+            ctx.set_batch(pinned.numpy(), std)                 # pinned: piecewise, the FVP below starts before the copy ends
+            z1 = ctx.fvp(v, 0.1)
+            z2 = ctx.fvp(v, 0.1)
+            assert np.array_equal(z1, z_ref) and np.array_equal(z2, z_ref)
+        ctx.set_batch(pinned.numpy(), std)
+        x, info = ctx.cg(0.01 * v, 3, 0.0, 0.1)
+        ctx.set_batch(obs, std)
+        x_ref, _ = ctx.cg(0.01 * v, 3, 0.0, 0.1)
+        assert info.cg_iters == 3 and np.array_equal(x, x_ref)

@@ -645,6 +645,10 @@ int chain_accumulate(const NetDesc &net, const ChainScratch &sc, ChainMode mode,
     for (size_t c0 = 0; c0 < nsamples; c0 += sc.chunk, ++chunk_idx) {
         const int rows = (int)((nsamples - c0 < (size_t)sc.chunk) ? nsamples - c0 : sc.chunk);
         const int accumulate = chunk_idx > 0;
+        if (sc.piece_events && sc.piece_rows) {          // host-to-device copy still in flight: wait for this chunk's rows only
+            for (size_t pi = c0 / sc.piece_rows; pi * sc.piece_rows < c0 + rows && pi < (size_t)sc.n_pieces; ++pi)
+                if (cudaStreamWaitEvent(st, sc.piece_events[pi], 0) != cudaSuccess) return -1;
+        }
         // the last layer of a narrow-action FVP goes through the fused tail kernel (forward(K-1) + seed + backward(K))
         const bool tail = fvp && K >= 2 && A <= 24 && (net.ac[K] == 'l' || net.ac[K] == 'o') &&
                           tail_smem_bytes<3>(net.L[K - 1]) <= 200 * 1024;

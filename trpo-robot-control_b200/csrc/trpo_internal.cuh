@@ -49,6 +49,11 @@ struct ChainScratch {
     int chunk;                       // samples per chunk
     int nslices;                     // split-K slices of the outer-product GEMM
     double *partial;                 // [nslices x P] un-normalised partial sums, fixed-order reduced
+    // streamed staging of the observation matrix: piece i of piece_rows rows has landed when piece_events[i] has completed
+    // (recorded on the copy stream); the chunk loop makes the compute stream wait only for the pieces a chunk touches
+    const cudaEvent_t *piece_events;
+    int n_pieces;
+    size_t piece_rows;
 };
 
 enum ChainMode { CHAIN_FVP = 0, CHAIN_PG = 1 };

@@ -96,6 +96,7 @@ struct trpo_ctx {
     size_t timeline_iters;
     int *h_flags;              // pinned: [0] peer-memory wait error, [1] streamed-staging wait error (read back after a sync)
     double *h_scal;            // pinned
+    double *h_vec;             // pinned, P doubles: host vectors go through here while a batch copy occupies the copy engine
     // gemm-chain scratch
     ChainScratch sc;
     double *sc_base;
@@ -127,6 +128,12 @@ struct trpo_ctx {
     bool copy_inflight;        // an asynchronous batch copy has been issued and not yet joined into c->stream
     bool stream_first_fvp;     // the next fused FVP may start before the copy has finished
     size_t stage_chunk;        // samples per staged chunk
+    // GEMM-chain path: the pinned observation matrix is copied in pieces with an event each; the first FVP's chunk loop waits
+    // per piece, so chunk k computes while chunk k + 1 is still crossing PCIe (Humanoid-size batch: 3 GB, 55 ms)
+    cudaEvent_t ev_piece[64];
+    int n_pieces;
+    size_t piece_rows;
+    bool pieces_pending;
     // CUDA graph of a whole CG solve (single GPU, fused path): captured on the second identical call, replayed afterwards
     struct CgKey { const double *db; double *dres; size_t iters; double th, damping; const double *obs; size_t n; cudaStream_t st; int path; } cg_key;
     int cg_key_seen;
@@ -237,6 +244,7 @@ extern "C" trpo_ctx *trpo_ctx_create(const size_t *LayerSize, const char *AcFunc
     ok = ok && cudaMalloc(&c->d_state, sizeof(CgState)) == cudaSuccess;
     ok = ok && cudaMallocHost(&c->h_state, sizeof(CgState)) == cudaSuccess;
     ok = ok && cudaMallocHost(&c->h_scal, 16 * sizeof(double)) == cudaSuccess;
+    ok = ok && cudaMallocHost(&c->h_vec, P * sizeof(double)) == cudaSuccess;
     ok = ok && cudaMallocHost(&c->h_flags, 2 * sizeof(int)) == cudaSuccess;
     ok = ok && cudaMalloc(&c->d_dots, 4 * 160 * sizeof(double)) == cudaSuccess;
     ok = ok && cudaMalloc(&c->d_gbar, 2 * sizeof(unsigned int)) == cudaSuccess;
@@ -247,6 +255,7 @@ extern "C" trpo_ctx *trpo_ctx_create(const size_t *LayerSize, const char *AcFunc
     ok = ok && cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&c->ev_compute, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < 64 && ok; ++i) ok = cudaEventCreateWithFlags(&c->ev_piece[i], cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaMalloc(&c->d_ready, 2 * sizeof(int)) == cudaSuccess;
     ok = ok && cudaMemset(c->d_ready, 0, 2 * sizeof(int)) == cudaSuccess;
     ok = ok && cudaMallocHost(&c->h_ready_vals, (STAGE_CHUNKS + 1) * sizeof(int)) == cudaSuccess;
@@ -289,6 +298,7 @@ extern "C" void trpo_ctx_destroy(trpo_ctx *c) {
     if (c->d_state) cudaFree(c->d_state);
     if (c->h_state) cudaFreeHost(c->h_state);
     if (c->h_scal) cudaFreeHost(c->h_scal);
+    if (c->h_vec) cudaFreeHost(c->h_vec);
     if (c->h_flags) cudaFreeHost(c->h_flags);
     if (c->d_dots) cudaFree(c->d_dots);
     if (c->d_gbar) cudaFree(c->d_gbar);
@@ -298,6 +308,7 @@ extern "C" void trpo_ctx_destroy(trpo_ctx *c) {
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     if (c->ev_compute) cudaEventDestroy(c->ev_compute);
     if (c->ev_copy) cudaEventDestroy(c->ev_copy);
+    for (int i = 0; i < 64; ++i) if (c->ev_piece[i]) cudaEventDestroy(c->ev_piece[i]);
     if (c->d_ready) cudaFree(c->d_ready);
     if (c->h_ready_vals) cudaFreeHost(c->h_ready_vals);
     if (c->cg_exec) cudaGraphExecDestroy(c->cg_exec);
@@ -414,6 +425,7 @@ extern "C" int trpo_ctx_set_batch(trpo_ctx *c, size_t N, const double *Observ, c
     // join any copy still in flight, then decide how to stage the observations
     if (c->copy_inflight) { CU(cudaStreamWaitEvent(c->stream, c->ev_copy, 0)); c->copy_inflight = false; }
     c->stream_first_fvp = false;
+    c->pieces_pending = false;
     cudaPointerAttributes attr;
     const bool pinned = cudaPointerGetAttributes(&attr, Observ) == cudaSuccess && attr.type == cudaMemoryTypeHost;
     cudaGetLastError();
@@ -437,6 +449,23 @@ extern "C" int trpo_ctx_set_batch(trpo_ctx *c, size_t N, const double *Observ, c
         CU(cudaEventRecord(c->ev_copy, c->copy_stream));
         c->copy_inflight = true;
         c->stream_first_fvp = true;
+    } else if (pinned && N >= 65536 && c->precision == TRPO_PRECISION_FP64 && N * O * sizeof(double) >= ((size_t)256 << 20)) {
+        // GEMM-chain path, large pinned batch: pieces of about 256 MB on the copy stream, one event each
+        size_t pr = ((((size_t)256 << 20) / (O * sizeof(double))) + 127) / 128 * 128;
+        if ((N + pr - 1) / pr > 64) pr = ((N + 63) / 64 + 127) / 128 * 128;
+        c->piece_rows = pr;
+        c->n_pieces = (int)((N + pr - 1) / pr);
+        CU(cudaEventRecord(c->ev_compute, c->stream));
+        CU(cudaStreamWaitEvent(c->copy_stream, c->ev_compute, 0));          // do not overwrite rows still being read
+        for (int i = 0; i < c->n_pieces; ++i) {
+            const size_t s0 = (size_t)i * pr, n = (N - s0 < pr) ? N - s0 : pr;
+            CU(cudaMemcpyAsync(c->d_obs + s0 * O, Observ + s0 * O, n * O * sizeof(double), cudaMemcpyHostToDevice, c->copy_stream));
+            CU(cudaEventRecord(c->ev_piece[i], c->copy_stream));
+        }
+        CU(cudaEventRecord(c->ev_copy, c->copy_stream));
+        c->copy_inflight = true;
+        c->pieces_pending = true;
+        if (getenv("TRPO_DEBUG_STAGING")) fprintf(stderr, "[staging] piecewise: %d pieces of %zu rows\n", c->n_pieces, c->piece_rows);
     } else {
         CU(cudaMemcpyAsync(c->d_obs, Observ, N * O * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     }
@@ -657,11 +686,23 @@ static int fvp_sum(trpo_ctx *c, const double *d_v, const int *d_done) {
         }
         c->stream_first_fvp = false;
     } else {
-        if (c->copy_inflight) { CU(cudaStreamWaitEvent(c->stream, c->ev_copy, 0)); c->copy_inflight = false; }
+        const bool piecewise = c->copy_inflight && c->pieces_pending;
+        if (getenv("TRPO_DEBUG_STAGING")) fprintf(stderr, "[staging] chain fvp: inflight %d pending %d\n", (int)c->copy_inflight, (int)c->pieces_pending);
+        if (c->copy_inflight && !piecewise) { CU(cudaStreamWaitEvent(c->stream, c->ev_copy, 0)); c->copy_inflight = false; }
         c->stream_first_fvp = false;
         if (ensure_chain_scratch(c)) return -1;
-        if (chain_accumulate(c->net, c->sc, CHAIN_FVP, c->d_theta, d_v, c->d_inv_var, c->d_obs, nullptr, nullptr, nullptr,
-                             c->n_local, c->d_zsum, d_done, active_p2p(c), c->stream, &c->launches))
+        c->sc.piece_events = piecewise ? c->ev_piece : nullptr;
+        c->sc.n_pieces = piecewise ? c->n_pieces : 0;
+        c->sc.piece_rows = piecewise ? c->piece_rows : 0;
+        const int rc_chain = chain_accumulate(c->net, c->sc, CHAIN_FVP, c->d_theta, d_v, c->d_inv_var, c->d_obs, nullptr, nullptr, nullptr,
+                                              c->n_local, c->d_zsum, d_done, active_p2p(c), c->stream, &c->launches);
+        c->sc.piece_events = nullptr; c->sc.n_pieces = 0; c->sc.piece_rows = 0;
+        if (piecewise) {             // everything enqueued after this FVP sees a fully resident batch
+            CU(cudaStreamWaitEvent(c->stream, c->ev_copy, 0));
+            c->copy_inflight = false;
+            c->pieces_pending = false;
+        }
+        if (rc_chain)
             return fail("gemm-chain FVP launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
     if (timed) { cudaEventRecord(c->ktime_ev[2 * c->ktime_n + 1], c->stream); ++c->ktime_n; }
@@ -831,11 +872,32 @@ static int p2p_align_ranks(trpo_ctx *c) {
     return 0;
 }
 
+// P-length host vector -> device. While a streamed batch copy is in flight the host-to-device copy engine is busy with it for
+// tens of milliseconds, and a cudaMemcpyAsync of the direction / right-hand side queues behind it: the solve would start only
+// when the whole batch has landed (measured: first Humanoid-size FVP 100.7 ms = 54 ms copy + 46 ms compute, no overlap).
+// So the vector goes through a pinned buffer that a kernel reads over PCIe (UVA: page-locked host memory is device-visible).
+__global__ void k_pull_vector(double *__restrict__ dst, const double *__restrict__ src_host, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src_host[i];
+}
+static int upload_vector(trpo_ctx *c, double *d_dst, const double *src_host) {
+    const size_t bytes = c->net.P * sizeof(double);
+    if (!c->copy_inflight) {
+        CU(cudaMemcpyAsync(d_dst, src_host, bytes, cudaMemcpyHostToDevice, c->stream));
+        return 0;
+    }
+    memcpy(c->h_vec, src_host, bytes);
+    k_pull_vector<<<(c->net.P + 255) / 256, 256, 0, c->stream>>>(d_dst, c->h_vec, c->net.P);
+    ++c->launches;
+    CU(cudaGetLastError());
+    return 0;
+}
+
 extern "C" int trpo_ctx_fvp(trpo_ctx *c, const double *Input, double *Result, double damping) {
     if (!c || !Input || !Result) return fail("null argument");
     CU(cudaSetDevice(c->device));
     const size_t bytes = c->net.P * sizeof(double);
-    CU(cudaMemcpyAsync(c->d_in, Input, bytes, cudaMemcpyHostToDevice, c->stream));
+    if (upload_vector(c, c->d_in, Input)) return -1;
     if (p2p_align_ranks(c)) return -1;
     if (trpo_ctx_fvp_device(c, c->d_in, c->d_out, damping)) return -1;
     CU(cudaMemcpyAsync(Result, c->d_out, bytes, cudaMemcpyDeviceToHost, c->stream));
@@ -846,7 +908,7 @@ extern "C" int trpo_ctx_cg(trpo_ctx *c, const double *b, double *Result, size_t 
     if (!c || !b || !Result) return fail("null argument");
     CU(cudaSetDevice(c->device));
     const size_t bytes = c->net.P * sizeof(double);
-    CU(cudaMemcpyAsync(c->d_b, b, bytes, cudaMemcpyHostToDevice, c->stream));
+    if (upload_vector(c, c->d_b, b)) return -1;
     if (p2p_align_ranks(c)) return -1;
     if (trpo_ctx_cg_device(c, c->d_b, c->d_out, MaxIter, ResidualTh, damping)) return -1;
     CU(cudaMemcpyAsync(Result, c->d_out, bytes, cudaMemcpyDeviceToHost, c->stream));
