@@ -666,7 +666,9 @@ def test_fp32_tcgen05_layers_against_the_legacy_tensor_path():
 
 def test_piecewise_staging_of_a_large_pinned_batch_on_the_gemm_chain(pkg):
     """GEMM-chain path, pinned source >= 256 MB: the observation matrix crosses PCIe in pieces with an event each and the first
-    FVP's chunk loop waits per piece. The result must be bitwise the one of a fully resident batch, on the first and later FVPs."""
+    FVP's chunk loop waits per piece. With chunks no larger than a piece the chunking is the resident one and the result is
+    bitwise the resident batch's, on the first and later FVPs; with the automatic (larger) chunk the streamed FVP walks the batch
+    piece by piece -- same sums grouped differently, equal to rounding -- and every later FVP is bitwise the resident one again."""
     import torch
     layers, ac = [376, 64, 64, 17], "lttl"
     n = 200_000
@@ -691,3 +693,10 @@ def test_piecewise_staging_of_a_large_pinned_batch_on_the_gemm_chain(pkg):
         ctx.set_batch(obs, std)
         x_ref, _ = ctx.cg(0.01 * v, 3, 0.0, 0.1)
         assert info.cg_iters == 3 and np.array_equal(x, x_ref)
+        ctx.set_chunk(0)                                       # automatic chunk (the whole batch): the streamed FVP steps by piece
+        ctx.set_batch(obs, std)
+        z_ref = ctx.fvp(v, 0.1)
+        ctx.set_batch(pinned.numpy(), std)
+        z1 = ctx.fvp(v, 0.1)
+        z2 = ctx.fvp(v, 0.1)
+        assert rel_err(z1, z_ref)[0] < 1e-13 and np.array_equal(z2, z_ref)
