@@ -700,3 +700,41 @@ def test_piecewise_staging_of_a_large_pinned_batch_on_the_gemm_chain(pkg):
         z1 = ctx.fvp(v, 0.1)
         z2 = ctx.fvp(v, 0.1)
         assert rel_err(z1, z_ref)[0] < 1e-13 and np.array_equal(z2, z_ref)
+
+
+@pytest.mark.parametrize("layers,ac,n", [([376, 256, 256, 17], "lttl", 1500),      # Humanoid width: ragged 128-row tiles, 376 = 23.5 boxes
+                                          ([40, 64, 48, 6], "lttl", 2100),          # widths that are not multiples of the 64-column tile
+                                          ([18, 34, 22, 4], "ltsl", 900),           # boxes cut by the matrix edge in both directions
+                                          ([17, 64, 64, 6], "lttl", 1300)])         # odd input width: layer 0 stays on the cp.async kernel
+def test_tma_fed_chain_kernels_match_the_cp_async_ones(pkg, oracle, layers, ac, n):
+    """gemm_chain_tma.cu: the outer-product and backward GEMMs fetch their tiles by TMA into swizzled boxes and walk the
+    contraction index in a permuted order. Same sums as the cp.async kernels (TRPO_NO_CHAIN_TMA=1), grouped differently inside a
+    32-wide k-step: equal to rounding, and both within the FP64 tolerance of the oracle; several chunks accumulate in place."""
+    import os
+    seed = 900 + sum(layers)
+    theta = pkg.synth.make_model(layers, seed)
+    batch = pkg.synth.make_batch(layers, ac, theta, n, seed)
+    batch["Mean"] = oracle.forward(layers, ac, theta, batch["Observ"])
+    vec = pkg.synth.make_vectors(layers, seed)
+    z_ref = oracle.fvp(layers, ac, theta, batch["Std"], batch["Observ"], 0.1, vec["v"])
+    pg_ref = oracle.policy_gradient(layers, ac, theta, batch["Observ"], batch["Mean"], batch["Action"], batch["Advantage"])
+    out = {}
+    try:
+        for tag in ("tma", "cp_async"):
+            if tag == "cp_async":
+                os.environ["TRPO_NO_CHAIN_TMA"] = "1"
+            for chunk in (0, 512):
+                with pkg.Context(layers, ac) as ctx:
+                    ctx.set_path(pkg.api.PATH_GEMM_CHAIN)
+                    ctx.set_chunk(chunk)
+                    ctx.set_model(theta)
+                    ctx.set_batch(batch["Observ"], batch["Std"], batch["Mean"], batch["Action"], batch["Advantage"])
+                    out[tag, chunk] = (ctx.fvp(vec["v"], 0.1), ctx.policy_gradient())
+    finally:
+        os.environ.pop("TRPO_NO_CHAIN_TMA", None)
+    for key, (z, pg) in out.items():
+        assert rel_err(z, z_ref)[0] < FVP_TOL and rel_err(z, z_ref)[1] < FVP_TOL, (key, rel_err(z, z_ref))
+        assert rel_err(pg, pg_ref)[0] < FVP_TOL, (key, rel_err(pg, pg_ref))
+    for chunk in (0, 512):
+        assert rel_err(out["tma", chunk][0], out["cp_async", chunk][0])[0] < 1e-13
+        assert rel_err(out["tma", chunk][1], out["cp_async", chunk][1])[0] < 1e-13

@@ -718,16 +718,29 @@ int chain_accumulate(const NetDesc &net, const ChainScratch &sc, ChainMode mode,
             const int M0 = net.L[i - 1], N = net.L[i];
             // the bias row would open a 32-row warp tile (or a whole 128-row CTA tile) of its own: column sums instead
             const int bias_colsum = (M0 % 32) == 0;
-            const int tiles_m = bias_colsum ? cdiv(M0, BM) : cdiv(M0 + 1, BM), tiles_n = cdiv(N, BN);
-            const int ns = layer_slices(tiles_m * tiles_n, sc.nslices);
-            dim3 go(tiles_m * tiles_n, ns);
-            k_chain_outer<<<go, NT, SMEM_SINGLE, st>>>(Yprev, sc.G[i & 1], rows, M0, N, cdiv(cdiv(rows, ns), BK_SINGLE) * BK_SINGLE, tiles_n,
-                                             sc.partial, net.P, net.w_off[i - 1], accumulate, bias_colsum, d_done);
+            const int tiles_n = cdiv(N, BN);
+            if (chain_tma_outer_eligible(Yprev, sc.G[i & 1], M0, N)) {
+                // operands by TMA (gemm_chain_tma.cu); the bias-gradient row always comes from the column sums there
+                const int ns = layer_slices(chain_tma_tiles_m(M0) * tiles_n, sc.nslices);
+                if (chain_tma_outer(Yprev, sc.G[i & 1], rows, M0, N, cdiv(cdiv(rows, ns), BK_SINGLE) * BK_SINGLE, tiles_n, ns, sc.partial,
+                                    net.P, net.w_off[i - 1], accumulate, d_done, st)) return -1;
+            } else {
+                const int tiles_m = bias_colsum ? cdiv(M0, BM) : cdiv(M0 + 1, BM);
+                const int ns = layer_slices(tiles_m * tiles_n, sc.nslices);
+                dim3 go(tiles_m * tiles_n, ns);
+                k_chain_outer<<<go, NT, SMEM_SINGLE, st>>>(Yprev, sc.G[i & 1], rows, M0, N, cdiv(cdiv(rows, ns), BK_SINGLE) * BK_SINGLE, tiles_n,
+                                                 sc.partial, net.P, net.w_off[i - 1], accumulate, bias_colsum, d_done);
+            }
             ++*launches;
             if (i > 1 && !(tail && i == K)) {
-                dim3 gb(cdiv(M0, BN), cdiv(rows, BM));
-                k_chain_bwd<<<gb, NT, SMEM_SINGLE, st>>>(sc.G[i & 1], d_theta + net.w_off[i - 1], sc.Y[i - 1], rows, N, M0,
-                                               net.ac[i - 1], sc.G[(i - 1) & 1], d_done);
+                const double *Wb = d_theta + net.w_off[i - 1];
+                if (chain_tma_bwd_eligible(sc.G[i & 1], Wb, sc.Y[i - 1], sc.G[(i - 1) & 1], N, M0)) {
+                    if (chain_tma_bwd(sc.G[i & 1], Wb, sc.Y[i - 1], rows, N, M0, net.ac[i - 1], sc.G[(i - 1) & 1], d_done, st)) return -1;
+                } else {
+                    dim3 gb(cdiv(M0, BN), cdiv(rows, BM));
+                    k_chain_bwd<<<gb, NT, SMEM_SINGLE, st>>>(sc.G[i & 1], Wb, sc.Y[i - 1], rows, N, M0,
+                                                   net.ac[i - 1], sc.G[(i - 1) & 1], d_done);
+                }
                 ++*launches;
             }
         }

@@ -1,0 +1,276 @@
+// gemm_chain_tma.cu -- TMA-fed variants of the FP64 GEMM-chain kernels (sm_100a).
+//
+// The cp.async loaders of gemm_chain.cu cost the DMMA main loop 8 - 10 % on their own (12 LDGSTS per thread and k-step plus their
+// index arithmetic; tools/dmma_gemm_loop.cu: fragments + DMMA 37.1 TFLOP/s, + block barrier 36.5, + cp.async double buffer 33.0,
+// tiles by TMA instead 35.4). Here one thread issues a handful of cp.async.bulk.tensor.2d copies per k-step, the tiles land in
+// SWIZZLE_128B boxes of 16 FP64 columns (128-byte rows) and complete on an mbarrier; out-of-range rows / columns are zero-filled by
+// the copy engine, so the kernels carry no bounds logic in the main loop.
+//
+// Fragment reads go through the swizzle, byte (row, col) of a box = row*128 + (((col >> 1) ^ (row & 7)) << 4) + (col & 1)*8, with
+// the contraction index PERMUTED so that the 16 lanes of a half warp hit 16 distinct 8-byte bank pairs (both operands of a DMMA use
+// the same permutation, the sum over k does not care):
+//   operand whose box ROWS are k (outer product: Y[s][m], G[s][n]):  lane t of step q takes row 8*(q/2) + 2t + (q&1)
+//   operand whose box COLUMNS are k (backward: G[s][k], W[n][k]):    lane t of step q takes column 16*(q/4) + 2*(q&3) + 8*(t/2) + (t&1)
+// Results agree with the cp.async kernels to rounding (different order inside a k-step), not bitwise.
+#include <cuda.h>
+#include <stdint.h>
+#include <stdlib.h>
+
+#include "trpo_internal.cuh"
+#include "dmma_common.cuh"
+#include "tma_common.cuh"
+
+namespace {
+using namespace tma;
+
+constexpr int BM = 128, BN = 64, BK = 32, NT = 256;
+constexpr int BOX_K_BYTES = BK * 128;                     // a [32 k-rows x 16 columns] box (outer product operands)
+constexpr int STAGE_BYTES = (BM / 16 + BN / 16) * BOX_K_BYTES;      // 48 KB
+constexpr int SMEM_BYTES = 2 * STAGE_BYTES + 1024;        // + slack to align the stages to the 1 KB swizzle atom
+
+__device__ __forceinline__ double act_deriv(char a, double y) {   // f'(x) expressed through y = f(x)
+    switch (a) {
+        case 't': return 1.0 - y * y;
+        case 'o': return 0.1;
+        case 's': return y * (1.0 - y);
+        default:  return 1.0;
+    }
+}
+__device__ __forceinline__ unsigned char *align_1k(unsigned char *p) { return p + ((1024u - (smem_u32(p) & 1023u)) & 1023u); }
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap *map, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" :: "l"(map), "r"(c0), "r"(c1) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// outer: out[slice][m*N + n] (+)= sum_{s in slice} Yprev[s][m] * G[s][n] for m < M0; row M0 (bias gradient) = column sums of G,
+// formed by the m-tile-0 CTAs from the B boxes they stage anyway (TRPO_FVP.c:890-899 summed over the samples, :903-921).
+__global__ void __launch_bounds__(NT, 2) k_outer_tma(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CUtensorMap mapG,
+                                                     int rows, int M0, int N, int per_slice, int tiles_n,
+                                                     double *__restrict__ partial, int P, int out_off, int accumulate,
+                                                     const int *__restrict__ done) {
+    if (done && *done) return;
+    extern __shared__ __align__(1024) unsigned char smem_dyn[];
+    __shared__ __align__(8) uint64_t full[2];
+    unsigned char *smem = align_1k(smem_dyn);
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3, wm = w >> 1, wn = w & 1;
+    const int m0 = (blockIdx.x / tiles_n) * BM, n0 = (blockIdx.x % tiles_n) * BN;
+    const int slice = blockIdx.y, s0 = slice * per_slice, s1 = min(rows, s0 + per_slice);
+    const int nk = s1 > s0 ? (s1 - s0 + BK - 1) / BK : 0;        // per_slice is a multiple of BK: a k-step never straddles two slices
+    if (tid == 0) {
+        mbar_init(&full[0], 1); mbar_init(&full[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    double acc[4][4][2] = {};
+    const bool colsum = m0 == 0;
+    double bsum = 0.0;
+    const bool active = m0 + 32 * wm < M0 && n0 + 32 * wn < N;   // sub-tiles outside the matrix issue no DMMAs
+    int off[2][2];                                        // lane offsets through the swizzle: [q & 1][8-column half of a box]
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int ib = 0; ib < 2; ++ib) off[c][ib] = (2 * t + c) * 128 + (((4 * ib + (g >> 1)) ^ (2 * t + c)) << 4) + (g & 1) * 8;
+    auto issue = [&](int st, int ks) {
+        unsigned char *base = smem + st * STAGE_BYTES;
+        mbar_expect_tx(&full[st], STAGE_BYTES);
+#pragma unroll
+        for (int mb = 0; mb < BM / 16; ++mb) tma_load_2d(base + mb * BOX_K_BYTES, &mapY, &full[st], m0 + 16 * mb, ks);
+#pragma unroll
+        for (int nb = 0; nb < BN / 16; ++nb) tma_load_2d(base + (BM / 16 + nb) * BOX_K_BYTES, &mapG, &full[st], n0 + 16 * nb, ks);
+    };
+    if (tid == 0 && nk) issue(0, s0);
+    // column sums: thread (column n, k-phase) adds its 8 rows of every k-step; box byte of (k, n) as above
+    const int cn = tid & 63, cph = tid >> 6;
+    const unsigned char *cs_base = smem + (BM / 16 + (cn >> 4)) * BOX_K_BYTES + cph * 1024 + ((cn & 15) & 1) * 8;
+    for (int it = 0; it < nk; ++it) {
+        __syncthreads();                                   // everybody is done with the other stage
+        if (tid == 0 && it + 1 < nk) issue((it + 1) & 1, s0 + (it + 1) * BK);
+        mbar_wait(&full[it & 1], (it >> 1) & 1);
+        const unsigned char *A = smem + (it & 1) * STAGE_BYTES + 2 * wm * BOX_K_BYTES;
+        const unsigned char *B = smem + (it & 1) * STAGE_BYTES + (BM / 16 + 2 * wn) * BOX_K_BYTES;
+        if (active) {
+#pragma unroll
+            for (int q = 0; q < BK / 4; ++q) {
+                double a[4], b[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const double *>(A + (i >> 1) * BOX_K_BYTES + (q >> 1) * 1024 + off[q & 1][i & 1]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) b[j] = *reinterpret_cast<const double *>(B + (j >> 1) * BOX_K_BYTES + (q >> 1) * 1024 + off[q & 1][j & 1]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) dmma(acc[i][j], a[i], b[j]);
+            }
+        }
+        if (colsum) {
+            const unsigned char *cb = cs_base + (it & 1) * STAGE_BYTES;
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) bsum += *reinterpret_cast<const double *>(cb + kk * 128 + ((((cn & 15) >> 1) ^ kk) << 4));
+        }
+    }
+    double *out = partial + (size_t)slice * P + out_off;
+    if (colsum) {
+        __syncthreads();                                   // everybody is done with the stage buffers
+        double *red = reinterpret_cast<double *>(smem);
+        red[tid] = bsum;
+        __syncthreads();
+        const int gn = n0 + tid;
+        if (tid < BN && gn < N) {
+            const double sum = ((red[tid] + red[tid + 64]) + red[tid + 128]) + red[tid + 192];
+            const size_t o = (size_t)M0 * N + gn;
+            out[o] = accumulate ? out[o] + sum : sum;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int gm = m0 + 32 * wm + 8 * i + g;
+        if (gm >= M0) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {                  // scalar: slice * P + out_off need not be even
+                const int gn = n0 + 32 * wn + 8 * j + 2 * t + r;
+                if (gn >= N) continue;
+                const size_t o = (size_t)gm * N + gn;
+                out[o] = accumulate ? out[o] + acc[i][j][r] : acc[i][j][r];
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// backward: Gout[s][n] = f'(Yprev[s][n]) * sum_k Gin[s][k] * W[n][k]   (W is [N x Kd] row-major: already K-major for this product)
+// Boxes: Gin [128 rows x 16 k], W [64 rows x 16 k], two of each per 32-wide k-step; after the main loop the Yprev tile
+// [128 rows x 64 columns] arrives in the then idle stage memory by TMA as well (its L2 prefetch is issued at kernel start).
+constexpr int BWD_A_BOX = BM * 128, BWD_B_BOX = BN * 128;         // 16 KB, 8 KB
+static_assert(2 * BWD_A_BOX + 2 * BWD_B_BOX == STAGE_BYTES, "backward stage = outer stage");
+__global__ void __launch_bounds__(NT, 2) k_bwd_tma(const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CUtensorMap mapW,
+                                                   const __grid_constant__ CUtensorMap mapY, int rows, int Kd, int N, char act_prev,
+                                                   double *__restrict__ Gout, const int *__restrict__ done) {
+    if (done && *done) return;
+    extern __shared__ __align__(1024) unsigned char smem_dyn[];
+    __shared__ __align__(8) uint64_t full[3];
+    unsigned char *smem = align_1k(smem_dyn);
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3, wm = w >> 1, wn = w & 1;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;     // the n-tiles of one row block run together: its A boxes are read from L2 once
+    const int nk = (Kd + BK - 1) / BK;
+    if (tid == 0) {
+        mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_init(&full[2], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#pragma unroll
+        for (int nb = 0; nb < BN / 16; ++nb) tma_prefetch_l2_2d(&mapY, n0 + 16 * nb, m0);
+    }
+    __syncthreads();
+    double acc[4][4][2] = {};
+    int off[4];                                           // lane offsets through the swizzle for c0 = q & 3
+#pragma unroll
+    for (int c0 = 0; c0 < 4; ++c0) off[c0] = g * 128 + (((c0 + 4 * (t >> 1)) ^ g) << 4) + (t & 1) * 8;
+    auto issue = [&](int st, int k0) {
+        unsigned char *base = smem + st * STAGE_BYTES;
+        mbar_expect_tx(&full[st], STAGE_BYTES);
+        tma_load_2d(base, &mapG, &full[st], k0, m0);
+        tma_load_2d(base + BWD_A_BOX, &mapG, &full[st], k0 + 16, m0);
+        tma_load_2d(base + 2 * BWD_A_BOX, &mapW, &full[st], k0, n0);
+        tma_load_2d(base + 2 * BWD_A_BOX + BWD_B_BOX, &mapW, &full[st], k0 + 16, n0);
+    };
+    if (tid == 0) issue(0, 0);
+    for (int it = 0; it < nk; ++it) {
+        __syncthreads();
+        if (tid == 0 && it + 1 < nk) issue((it + 1) & 1, (it + 1) * BK);
+        mbar_wait(&full[it & 1], (it >> 1) & 1);
+        const unsigned char *A = smem + (it & 1) * STAGE_BYTES + 32 * wm * 128;
+        const unsigned char *B = smem + (it & 1) * STAGE_BYTES + 2 * BWD_A_BOX + 32 * wn * 128;
+#pragma unroll
+        for (int q = 0; q < BK / 4; ++q) {
+            double a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const double *>(A + (q >> 2) * BWD_A_BOX + i * 1024 + off[q & 3]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = *reinterpret_cast<const double *>(B + (q >> 2) * BWD_B_BOX + j * 1024 + off[q & 3]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma(acc[i][j], a[i], b[j]);
+        }
+    }
+    // the Yprev tile: 4 boxes of [128 rows x 16 columns] over both (now idle) stages
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(&full[2], 4 * BWD_A_BOX);
+#pragma unroll
+        for (int nb = 0; nb < BN / 16; ++nb) tma_load_2d(smem + nb * BWD_A_BOX, &mapY, &full[2], n0 + 16 * nb, m0);
+    }
+    mbar_wait(&full[2], 0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = 32 * wm + 8 * i + g, gm = m0 + r;
+        if (gm >= rows) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int gn = n0 + 32 * wn + 8 * j + 2 * t;        // N is even
+            if (gn >= N) continue;
+            // columns 8(j&1) + 2t, +1 of box 2wn + (j>>1): one 16-byte chunk, index 4(j&1) + t, swizzled by the row
+            const double2 y = *reinterpret_cast<const double2 *>(smem + (2 * wn + (j >> 1)) * BWD_A_BOX + r * 128 + (((4 * (j & 1) + t) ^ g) << 4));
+            *reinterpret_cast<double2 *>(&Gout[(size_t)gm * N + gn]) =
+                make_double2(acc[i][j][0] * act_deriv(act_prev, y.x), acc[i][j][1] * act_deriv(act_prev, y.y));
+        }
+    }
+}
+
+// row-major FP64 matrix [nrows x ncols] (contiguous rows), boxes of 16 columns x box_rows rows, SWIZZLE_128B, zero fill
+bool make_map(CUtensorMap *m, const double *base, size_t nrows, int ncols, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)ncols, (cuuint64_t)nrows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ncols * sizeof(double)};
+    const cuuint32_t box[2] = {16, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void *)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+bool configure() {
+    static DeviceOnce once;
+    if (!once.pending()) return true;
+    bool r = cudaFuncSetAttribute(k_outer_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess &&
+             cudaFuncSetAttribute(k_bwd_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess;
+    if (r) once.mark();
+    return r;
+}
+inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace
+
+// TRPO_NO_CHAIN_TMA=1 keeps the cp.async kernels (A/B timing, tests of both)
+bool chain_tma_enabled() {
+    const char *e = getenv("TRPO_NO_CHAIN_TMA");
+    return !(e && atoi(e)) && tma::encode_fn() != nullptr;
+}
+// tensor-map rows are 16-byte multiples: even widths, 16-byte aligned bases
+bool chain_tma_outer_eligible(const double *Yprev, const double *G, int M0, int N) {
+    return chain_tma_enabled() && (M0 & 1) == 0 && (N & 1) == 0 && M0 >= 16 && N >= 16 && aligned16(Yprev) && aligned16(G);
+}
+bool chain_tma_bwd_eligible(const double *Gin, const double *W, const double *Yprev, const double *Gout, int Kd, int N) {
+    return chain_tma_enabled() && (Kd & 1) == 0 && (N & 1) == 0 && Kd >= 16 && N >= 16 && aligned16(Gin) && aligned16(W) &&
+           aligned16(Yprev) && aligned16(Gout);
+}
+int chain_tma_tiles_m(int M0) { return (M0 + BM - 1) / BM; }
+
+int chain_tma_outer(const double *Yprev, const double *G, int rows, int M0, int N, int per_slice, int tiles_n, int nslices,
+                    double *partial, int P, int out_off, int accumulate, const int *done, cudaStream_t st) {
+    CUtensorMap mY, mG;
+    if (!configure() || !make_map(&mY, Yprev, (size_t)rows, M0, BK) || !make_map(&mG, G, (size_t)rows, N, BK)) return -1;
+    dim3 grid(chain_tma_tiles_m(M0) * tiles_n, nslices);
+    k_outer_tma<<<grid, NT, SMEM_BYTES, st>>>(mY, mG, rows, M0, N, per_slice, tiles_n, partial, P, out_off, accumulate, done);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+int chain_tma_bwd(const double *Gin, const double *W, const double *Yprev, int rows, int Kd, int N, char act_prev, double *Gout,
+                  const int *done, cudaStream_t st) {
+    CUtensorMap mG, mW, mY;
+    if (!configure() || !make_map(&mG, Gin, (size_t)rows, Kd, BM) || !make_map(&mW, W, (size_t)N, Kd, BN) ||
+        !make_map(&mY, Yprev, (size_t)rows, N, BM)) return -1;
+    dim3 grid((N + BN - 1) / BN, (rows + BM - 1) / BM);
+    k_bwd_tma<<<grid, NT, SMEM_BYTES, st>>>(mG, mW, mY, rows, Kd, N, act_prev, Gout, done);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}

@@ -25,41 +25,15 @@
 
 #include "trpo_internal.cuh"
 #include "tmem_scratch.cuh"
+#include "tma_common.cuh"
 
 namespace {
+using namespace tma;
 
 constexpr int TC_BM = 128, TC_BK = 16;
 constexpr int TC_EPI_WARPS = 16, TC_THREADS = 64 + 32 * TC_EPI_WARPS;       // warp 0: TMA, warp 1: MMA, 16 epilogue warps
 
-// ---- PTX helpers ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-// bounded wait: a pipeline bug must end as a trapped kernel, not as a hung GPU
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    const uint32_t a = smem_u32(bar);
-    const long long t0 = clock64();
-    for (;;) {
-        uint32_t ok;
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
-        if (ok) return;
-        if (clock64() - t0 > 4000000000LL) __trap();
-    }
-}
-__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                 :: "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
-}
-// the same load delivered to the same shared-memory offset (and signalled on the same mbarrier offset) of every CTA in cta_mask
-__device__ __forceinline__ void tma_load_2d_mc(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, uint16_t cta_mask) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;"
-                 :: "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "h"(cta_mask), "r"(c0), "r"(c1) : "memory");
-}
+// ---- PTX helpers (TMA / mbarrier ones in tma_common.cuh) -------------------------------------------------------------
 __device__ __forceinline__ void umma_commit_mc(uint64_t *bar, uint16_t cta_mask) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  :: "r"(smem_u32(bar)), "h"(cta_mask) : "memory");
@@ -299,23 +273,6 @@ __global__ void k_tc_lo(const float *__restrict__ x, float *__restrict__ lo, siz
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) lo[i] = tf32_lo(x[i]);
 }
 
-// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency)
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void *p = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
-            fn = (EncodeTiledFn)p;
-        cudaGetLastError();
-    }
-    return fn;
-}
 // row-major FP32 matrix [nrows x ncols] (row stride ld floats), box = box_rows x 16 columns, SWIZZLE_64B, zero fill
 bool make_map(CUtensorMap *m, const float *base, int nrows, int ncols, int ld, int box_rows) {
     EncodeTiledFn fn = encode_fn();

@@ -88,6 +88,16 @@ int chain_forward(const NetDesc &net, const ChainScratch &sc, const double *d_th
                   size_t nsamples, double *d_mean_out, cudaStream_t st, long long *launches);
 size_t chain_scratch_bytes(const NetDesc &net, int chunk, int nslices);
 
+// gemm_chain_tma.cu: TMA-fed variants of the single-product GEMM-chain kernels (operands in SWIZZLE_128B boxes, mbarrier completion)
+bool chain_tma_enabled();
+bool chain_tma_outer_eligible(const double *Yprev, const double *G, int M0, int N);
+bool chain_tma_bwd_eligible(const double *Gin, const double *W, const double *Yprev, const double *Gout, int Kd, int N);
+int chain_tma_tiles_m(int M0);
+int chain_tma_outer(const double *Yprev, const double *G, int rows, int M0, int N, int per_slice, int tiles_n, int nslices,
+                    double *partial, int P, int out_off, int accumulate, const int *done, cudaStream_t st);
+int chain_tma_bwd(const double *Gin, const double *W, const double *Yprev, int rows, int Kd, int N, char act_prev, double *Gout,
+                  const int *done, cudaStream_t st);
+
 // ---- gemm_chain_f32.cu (optional FP32 mode) ------------------------------------------------------------------------
 struct ChainScratchF32 {
     float *Y[TRPO_MAX_LAYERS];
