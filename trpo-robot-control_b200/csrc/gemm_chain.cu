@@ -630,7 +630,8 @@ inline int layer_slices(int tiles, int max_slices) {
 size_t chain_scratch_bytes(const NetDesc &net, int chunk, int nslices) {
     size_t maxL = 0, sumL = 0;
     for (int i = 1; i <= net.K; ++i) { sumL += net.L[i]; if ((size_t)net.L[i] > maxL) maxL = net.L[i]; }
-    return sizeof(double) * ((size_t)chunk * (sumL + 4 * maxL) + (size_t)nslices * net.P);
+    // + the row-permuted weight / direction copies of the TMA-fed forward kernel (2 doubles of slack keep them 16-byte aligned)
+    return sizeof(double) * ((size_t)chunk * (sumL + 4 * maxL) + (size_t)nslices * net.P + 2 + 2 * chain_tma_perm_offset(net, net.K));
 }
 
 int chain_accumulate(const NetDesc &net, const ChainScratch &sc, ChainMode mode,
@@ -647,6 +648,8 @@ int chain_accumulate(const NetDesc &net, const ChainScratch &sc, ChainMode mode,
     // worth of arithmetic after the last byte lands -- with 300 k-row chunks that tail was 14 + 4 ms, with 89 k-row pieces 1 - 4 ms.
     // Same sums, grouped differently: the streamed FVP agrees with a resident one to rounding (1e-15), not bitwise.
     const size_t step = (sc.piece_events && sc.piece_rows && sc.piece_rows < (size_t)sc.chunk) ? sc.piece_rows : (size_t)sc.chunk;
+    // TMA-fed forward layers read the weights and the direction from row-permuted copies (gemm_chain_tma.cu), rebuilt per FVP
+    bool perm_ready[TRPO_MAX_LAYERS] = {};
     for (size_t c0 = 0; c0 < nsamples; c0 += step, ++chunk_idx) {
         const int rows = (int)((nsamples - c0 < step) ? nsamples - c0 : step);
         const int accumulate = chunk_idx > 0;
@@ -670,6 +673,17 @@ int chain_accumulate(const NetDesc &net, const ChainScratch &sc, ChainMode mode,
                 dim3 grid_h(cdiv(net.L[i + 1], BN), cdiv(rows, TM_HALF));
                 double *Yo = needY ? sc.Y[i + 1] : nullptr, *RYo = last ? nullptr : sc.RY[(i + 1) & 1], *Go = last ? sc.G[K & 1] : nullptr;
                 const double *Wl = d_theta + net.w_off[i], *VWl = d_v + net.w_off[i];
+                if (sc.wperm && chain_tma_fwd_eligible(Yin, RYin, Yo, RYo, Go, net.L[i], net.L[i + 1])) {
+                    double *Wp = sc.wperm + chain_tma_perm_offset(net, i), *Vp = sc.vperm + chain_tma_perm_offset(net, i);
+                    if (!perm_ready[i]) {
+                        chain_tma_permute_rows(Wl, Wp, net.L[i], net.L[i + 1], st);
+                        chain_tma_permute_rows(VWl, Vp, net.L[i], net.L[i + 1], st);
+                        *launches += 2;
+                        perm_ready[i] = true;
+                    }
+                    if (chain_tma_fwd(Yin, RYin, Wp, Vp, Wl, VWl, rows, net.L[i], net.L[i + 1], net.ac[i + 1], Yo, RYo, Go, d_inv_var, d_done, st))
+                        return -1;
+                } else
                 if (i == 0 && half_tiles)
                     k_chain_fwd<true, false, TM_HALF><<<grid_h, 256, SMEM_FWD_L0_H, st>>>(Yin, nullptr, Wl, VWl, rows, net.L[i], net.L[i + 1],
                                                                                      net.ac[i + 1], Yo, RYo, Go, d_inv_var, d_done);

@@ -217,6 +217,163 @@ __global__ void __launch_bounds__(NT, 2) k_bwd_tma(const __grid_constant__ CUten
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// forward R-op layer (TRPO_FVP.c:795-834): [Y | RY] = f([Yin | RYin] W, RYin W + Yin VW) with both biases as the accumulators'
+// start values. 64 x 64 CTA tile, 8 warps of 32 x 16, k-step 16, two CTAs per SM (as k_chain_fwd<.., .., 64>).
+// Yin / RYin boxes are [64 rows x 16 k] (k along the 128-byte box row). The weights' box rows ARE k, and the k order the
+// activations' layout dictates (lane t of step c0 holds k = 2 c0 + 8 (t/2) + (t&1)) would put lanes t and t + 2 on rows 8 apart --
+// the same swizzle phase, a 2-way conflict. So the weights are staged from a copy whose rows are permuted inside every group of
+// 16 (k_permute_rows16: bit 0 <-> bit 1, bit 2 <-> bit 3 of the row index): lane t then reads row 8 (c0/2) + 2t + (c0&1), four
+// distinct swizzle phases. The copy is rebuilt per FVP for W and the direction (2 P elements, microseconds).
+constexpr int FWD_TM = 64, FWD_BK = 16;
+constexpr int FWD_A_BOX = FWD_TM * 128;                   // 8 KB
+constexpr int FWD_B_BOX = FWD_BK * 128;                   // 2 KB: [16 k-rows x 16 columns]
+template <bool HAS_RA> struct FwdCfg {
+    static constexpr int STAGE = FWD_A_BOX * (HAS_RA ? 2 : 1) + 2 * (BN / 16) * FWD_B_BOX;       // 32 KB / 24 KB
+    static constexpr int NS = HAS_RA ? 3 : 4;
+    static constexpr int SMEM = NS * STAGE + 1024;
+};
+
+__global__ void k_permute_rows16(const double *__restrict__ W, double *__restrict__ Wp, int Kd, int N, int Kpad) {
+    const size_t total = (size_t)Kpad * N;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int row = (int)(idx / N), n = (int)(idx % N), rho = row & 15;
+        const int kp = ((rho & 1) << 1) | ((rho & 2) >> 1) | ((rho & 4) << 1) | ((rho & 8) >> 1);
+        const int k = (row & ~15) + kp;
+        Wp[idx] = k < Kd ? W[(size_t)k * N + n] : 0.0;
+    }
+}
+
+template <bool HAS_RA>
+__global__ void __launch_bounds__(NT, 2) k_fwd_tma(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CUtensorMap mapRY,
+                                                   const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapV,
+                                                   const double *__restrict__ W, const double *__restrict__ VW,
+                                                   int rows, int Kd, int N, char act,
+                                                   double *__restrict__ Yout, double *__restrict__ RYout, double *__restrict__ Gout,
+                                                   const double *__restrict__ inv_var, const int *__restrict__ done) {
+    if (done && *done) return;
+    using C = FwdCfg<HAS_RA>;
+    extern __shared__ __align__(1024) unsigned char smem_dyn[];
+    __shared__ __align__(8) uint64_t full[C::NS];
+    __shared__ double exp2_tab[64];
+    unsigned char *smem = align_1k(smem_dyn);
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3, wm = w >> 2, wn = w & 3;
+    const int m0 = blockIdx.y * FWD_TM, n0 = blockIdx.x * BN;   // the n-tiles of one row block run together: its A boxes are read from L2 once
+    const int nk = (Kd + FWD_BK - 1) / FWD_BK;
+    load_exp2_table(exp2_tab);                            // visible after the first barrier
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < C::NS; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int st, int k0) {
+        unsigned char *base = smem + st * C::STAGE;
+        mbar_expect_tx(&full[st], C::STAGE);
+        tma_load_2d(base, &mapY, &full[st], k0, m0);
+        if (HAS_RA) tma_load_2d(base + FWD_A_BOX, &mapRY, &full[st], k0, m0);
+        unsigned char *bw = base + (HAS_RA ? 2 : 1) * FWD_A_BOX;
+#pragma unroll
+        for (int nb = 0; nb < BN / 16; ++nb) {
+            tma_load_2d(bw + nb * FWD_B_BOX, &mapW, &full[st], n0 + 16 * nb, k0);
+            tma_load_2d(bw + (BN / 16 + nb) * FWD_B_BOX, &mapV, &full[st], n0 + 16 * nb, k0);
+        }
+    };
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < C::NS - 1; ++s) if (s < nk) issue(s, s * FWD_BK);
+    }
+    // both biases are the accumulators' start values (the contraction runs over Kd, no augmented row)
+    double acc[4][2][2], racc[4][2][2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int gn = n0 + 16 * wn + 8 * j + 2 * t + r;
+            const double bw = gn < N ? W[(size_t)Kd * N + gn] : 0.0, bv = gn < N ? VW[(size_t)Kd * N + gn] : 0.0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { acc[i][j][r] = bw; racc[i][j][r] = bv; }
+        }
+    const bool active = n0 + 16 * wn < N;                 // a warp whose 16 columns lie outside the matrix issues no DMMAs
+    int offA[4], offB[2][2];
+#pragma unroll
+    for (int c0 = 0; c0 < 4; ++c0) offA[c0] = (32 * wm + g) * 128 + (((c0 + 4 * (t >> 1)) ^ g) << 4) + (t & 1) * 8;
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) offB[c][j] = wn * FWD_B_BOX + (2 * t + c) * 128 + (((4 * j + (g >> 1)) ^ (2 * t + c)) << 4) + (g & 1) * 8;
+    for (int it = 0; it < nk; ++it) {
+        __syncthreads();                                   // everybody is done with the stage of step it - 1
+        if (tid == 0 && it + C::NS - 1 < nk) issue((it + C::NS - 1) % C::NS, (it + C::NS - 1) * FWD_BK);
+        mbar_wait(&full[it % C::NS], (it / C::NS) & 1);
+        if (!active) continue;
+        const unsigned char *A = smem + (it % C::NS) * C::STAGE, *RA = A + FWD_A_BOX;
+        const unsigned char *B = A + (HAS_RA ? 2 : 1) * FWD_A_BOX, *VB = B + (BN / 16) * FWD_B_BOX;
+#pragma unroll
+        for (int q = 0; q < FWD_BK / 4; ++q) {
+            double a[4], ra[4], b[2], vb[2];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                a[i] = *reinterpret_cast<const double *>(A + i * 1024 + offA[q]);
+                if (HAS_RA) ra[i] = *reinterpret_cast<const double *>(RA + i * 1024 + offA[q]);
+            }
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                b[j] = *reinterpret_cast<const double *>(B + (q >> 1) * 1024 + offB[q & 1][j]);
+                vb[j] = *reinterpret_cast<const double *>(VB + (q >> 1) * 1024 + offB[q & 1][j]);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    if (HAS_RA) dmma(racc[i][j], ra[i], b[j]);
+                    dmma(acc[i][j], a[i], b[j]);
+                    dmma(racc[i][j], a[i], vb[j]);
+                }
+        }
+    }
+    if (!active) return;
+    // epilogue: activation, R{y} = R{x} f'(x), last layer: R-gradient seed RG_K = Ry_K / sigma^2 * f' (TRPO_FVP.c:852-882)
+#pragma unroll
+    for (int i0 = 0; i0 < 4; i0 += 2) {
+        double xv[8], dv[8];                               // 8 values per lock-step tanh: 2 row blocks x 2 tiles x 2 columns
+#pragma unroll
+        for (int ii = 0; ii < 2; ++ii)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) { xv[(ii * 2 + j) * 2] = acc[i0 + ii][j][0]; xv[(ii * 2 + j) * 2 + 1] = acc[i0 + ii][j][1]; }
+        if (act == 't') tanh_vec<8>(xv, dv, exp2_tab);
+        else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const double x = xv[e];
+                switch (act) {
+                    case 'o': xv[e] = 0.1 * x; break;
+                    case 's': xv[e] = 1.0 / (1.0 + exp(-x)); break;
+                    default: break;
+                }
+                dv[e] = act_deriv(act, xv[e]);
+            }
+        }
+#pragma unroll
+        for (int ii = 0; ii < 2; ++ii) {
+            const int i = i0 + ii, gm = m0 + 32 * wm + 8 * i + g;
+            if (gm >= rows) continue;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int gn = n0 + 16 * wn + 8 * j + 2 * t;    // N is even: both columns of the pair are inside or outside
+                if (gn >= N) continue;
+                const double y0 = xv[(ii * 2 + j) * 2], y1 = xv[(ii * 2 + j) * 2 + 1], d0 = dv[(ii * 2 + j) * 2], d1 = dv[(ii * 2 + j) * 2 + 1];
+                const size_t o = (size_t)gm * N + gn;
+                if (Yout) *reinterpret_cast<double2 *>(&Yout[o]) = make_double2(y0, y1);
+                const double r0 = racc[i][j][0] * d0, r1 = racc[i][j][1] * d1;
+                if (RYout) *reinterpret_cast<double2 *>(&RYout[o]) = make_double2(r0, r1);
+                if (Gout) *reinterpret_cast<double2 *>(&Gout[o]) = make_double2(r0 * inv_var[gn] * d0, r1 * inv_var[gn + 1] * d1);
+            }
+        }
+    }
+}
+
 // row-major FP64 matrix [nrows x ncols] (contiguous rows), boxes of 16 columns x box_rows rows, SWIZZLE_128B, zero fill
 bool make_map(CUtensorMap *m, const double *base, size_t nrows, int ncols, int box_rows) {
     EncodeTiledFn fn = encode_fn();
@@ -233,7 +390,9 @@ bool configure() {
     static DeviceOnce once;
     if (!once.pending()) return true;
     bool r = cudaFuncSetAttribute(k_outer_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess &&
-             cudaFuncSetAttribute(k_bwd_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess;
+             cudaFuncSetAttribute(k_bwd_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess &&
+             cudaFuncSetAttribute(k_fwd_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdCfg<true>::SMEM) == cudaSuccess &&
+             cudaFuncSetAttribute(k_fwd_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdCfg<false>::SMEM) == cudaSuccess;
     if (r) once.mark();
     return r;
 }
@@ -272,5 +431,38 @@ int chain_tma_bwd(const double *Gin, const double *W, const double *Yprev, int r
         !make_map(&mY, Yprev, (size_t)rows, N, BM)) return -1;
     dim3 grid((N + BN - 1) / BN, (rows + BM - 1) / BM);
     k_bwd_tma<<<grid, NT, SMEM_BYTES, st>>>(mG, mW, mY, rows, Kd, N, act_prev, Gout, done);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+// ---- forward ----
+bool chain_tma_fwd_eligible(const double *Yin, const double *RYin, const double *Yout, const double *RYout, const double *Gout, int Kd, int N) {
+    static const bool off = getenv("TRPO_NO_CHAIN_TMA_FWD") && atoi(getenv("TRPO_NO_CHAIN_TMA_FWD"));
+    return !off && chain_tma_enabled() && (Kd & 1) == 0 && (N & 1) == 0 && Kd >= 16 && N >= 16 && aligned16(Yin) && aligned16(RYin) &&
+           aligned16(Yout) && aligned16(RYout) && aligned16(Gout);
+}
+size_t chain_tma_perm_doubles(int Kd, int N) { return ((size_t)((Kd + 15) / 16 * 16) * N + 1) & ~(size_t)1; }
+size_t chain_tma_perm_offset(const NetDesc &net, int layer) {
+    size_t o = 0;
+    for (int i = 0; i < layer && i < net.K; ++i) o += chain_tma_perm_doubles(net.L[i], net.L[i + 1]);
+    return o;
+}
+void chain_tma_permute_rows(const double *W, double *Wp, int Kd, int N, cudaStream_t st) {
+    const int Kpad = (Kd + 15) / 16 * 16;
+    const size_t total = (size_t)Kpad * N;
+    k_permute_rows16<<<(int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184), 256, 0, st>>>(W, Wp, Kd, N, Kpad);
+}
+// Wp / Vp: the row-permuted copies of W[Kd x N] / VW[Kd x N] (chain_tma_permute_rows); W / VW: the originals (bias rows)
+int chain_tma_fwd(const double *Yin, const double *RYin, const double *Wp, const double *Vp, const double *W, const double *VW,
+                  int rows, int Kd, int N, char act, double *Yout, double *RYout, double *Gout, const double *inv_var,
+                  const int *done, cudaStream_t st) {
+    const int Kpad = (Kd + 15) / 16 * 16;
+    CUtensorMap mY, mRY, mW, mV;
+    if (!configure() || !make_map(&mY, Yin, (size_t)rows, Kd, FWD_TM) || !make_map(&mW, Wp, (size_t)Kpad, N, FWD_BK) ||
+        !make_map(&mV, Vp, (size_t)Kpad, N, FWD_BK)) return -1;
+    if (RYin) { if (!make_map(&mRY, RYin, (size_t)rows, Kd, FWD_TM)) return -1; }
+    else mRY = mY;
+    dim3 grid((N + BN - 1) / BN, (rows + FWD_TM - 1) / FWD_TM);
+    if (RYin) k_fwd_tma<true><<<grid, NT, FwdCfg<true>::SMEM, st>>>(mY, mRY, mW, mV, W, VW, rows, Kd, N, act, Yout, RYout, Gout, inv_var, done);
+    else k_fwd_tma<false><<<grid, NT, FwdCfg<false>::SMEM, st>>>(mY, mRY, mW, mV, W, VW, rows, Kd, N, act, Yout, RYout, Gout, inv_var, done);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }

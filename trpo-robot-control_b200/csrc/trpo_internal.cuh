@@ -49,6 +49,7 @@ struct ChainScratch {
     int chunk;                       // samples per chunk
     int nslices;                     // split-K slices of the outer-product GEMM
     double *partial;                 // [nslices x P] un-normalised partial sums, fixed-order reduced
+    double *wperm, *vperm;           // row-permuted copies of the weights / the direction for the TMA-fed forward kernel (chain_tma_perm_total)
     // streamed staging of the observation matrix: piece i of piece_rows rows has landed when piece_events[i] has completed
     // (recorded on the copy stream); the chunk loop makes the compute stream wait only for the pieces a chunk touches
     const cudaEvent_t *piece_events;
@@ -96,6 +97,13 @@ int chain_tma_tiles_m(int M0);
 int chain_tma_outer(const double *Yprev, const double *G, int rows, int M0, int N, int per_slice, int tiles_n, int nslices,
                     double *partial, int P, int out_off, int accumulate, const int *done, cudaStream_t st);
 int chain_tma_bwd(const double *Gin, const double *W, const double *Yprev, int rows, int Kd, int N, char act_prev, double *Gout,
+                  const int *done, cudaStream_t st);
+bool chain_tma_fwd_eligible(const double *Yin, const double *RYin, const double *Yout, const double *RYout, const double *Gout, int Kd, int N);
+size_t chain_tma_perm_doubles(int Kd, int N);         // one layer's permuted copy: Kd rounded up to 16 rows
+size_t chain_tma_perm_offset(const NetDesc &net, int layer);     // layer == K: the total
+void chain_tma_permute_rows(const double *W, double *Wp, int Kd, int N, cudaStream_t st);
+int chain_tma_fwd(const double *Yin, const double *RYin, const double *Wp, const double *Vp, const double *W, const double *VW,
+                  int rows, int Kd, int N, char act, double *Yout, double *RYout, double *Gout, const double *inv_var,
                   const int *done, cudaStream_t st);
 
 // ---- gemm_chain_f32.cu (optional FP32 mode) ------------------------------------------------------------------------

@@ -195,6 +195,10 @@ static int ensure_chain_scratch(trpo_ctx *c) {
     for (int j = 0; j < 2; ++j) { c->sc.RY[j] = p; p += chunk * maxL; }
     for (int j = 0; j < 2; ++j) { c->sc.G[j] = p; p += chunk * maxL; }
     c->sc.partial = p;
+    p += (size_t)nslices * c->net.P;
+    if ((p - c->sc_base) & 1) ++p;                       // 16-byte alignment for the tensor maps
+    c->sc.wperm = p;
+    c->sc.vperm = p + chain_tma_perm_offset(c->net, c->net.K);
     c->sc.chunk = (int)chunk;
     c->sc.nslices = nslices;
     return 0;
