@@ -457,8 +457,11 @@ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 // A warp owns 16 rows; RG_K stays in its accumulator registers and is used directly as the A fragment of the second
 // product (contraction-index permutation, as in fvp_fused.cu), with W^T staged once per CTA in shared memory at a row
 // stride of HP + 2 doubles (2*stride % 16 == 4: conflict-free fragment reads).
-template <int NTA>
-__global__ void __launch_bounds__(NT, 1) k_chain_tail(const double *__restrict__ Y, const double *__restrict__ RY,
+// TMT rows per CTA, 16 per warp. 64-row CTAs of 4 warps (two per SM, 104 KB of shared memory each at H = 256) let one CTA's
+// W^T staging, first loads and store epilogue overlap the other's DMMA phases; the 128-row shape (one CTA per SM) ran the phases
+// back to back: 35 % DMMA-pipe activity, long-scoreboard stalls on top (profiles/r02_summary.md).
+template <int NTA, int TMT>
+__global__ void __launch_bounds__(2 * TMT, TMT == 64 ? 2 : 1) k_chain_tail(const double *__restrict__ Y, const double *__restrict__ RY,
                                                       const double *__restrict__ W, const double *__restrict__ VW,
                                                       int rows, int H, int A, char act_prev, double d3,
                                                       const double *__restrict__ inv_var,
@@ -467,23 +470,21 @@ __global__ void __launch_bounds__(NT, 1) k_chain_tail(const double *__restrict__
     if (done && *done) return;
     extern __shared__ __align__(16) double smem[];
     constexpr int BK = 16, RSA = Tile<BK>::RSA, AP = 8 * NTA, RSBT = AP + 4;
-    constexpr int A_TILE = BM * RSA, B_TILE = BK * RSBT, STAGE = 2 * A_TILE + 2 * B_TILE;
+    constexpr int NTT = 2 * TMT;
+    constexpr int A_TILE = TMT * RSA, B_TILE = BK * RSBT, STAGE = 2 * A_TILE + 2 * B_TILE;
     const int HP = (H + 7) & ~7, RST = HP + 2;
-    double *WT = smem + 2 * STAGE;                              // [AP][RST]
+    constexpr int NS = 3;                                       // cp.async ring: two k-steps of look-ahead cover a DRAM round trip
+    double *WT = smem;                                          // [AP][RST], staged over the ring once the forward loop is done
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
-    const int m0 = blockIdx.x * BM;
-    // W^T, zero padded: WT[k][j] = W[j][k]
-    for (int idx = tid; idx < AP * RST; idx += NT) WT[idx] = 0.0;
-    __syncthreads();
-    for (int idx = tid; idx < H * A; idx += NT) { const int j = idx / A, k = idx % A; WT[k * RST + j] = W[idx]; }
+    const int m0 = blockIdx.x * TMT;
 
     double rxa[2][NTA][2] = {}, rxb[2][NTA][2] = {};
     const int nk = (H + 1 + BK - 1) / BK;
     auto load = [&](int st, int k0) {
         double *As = smem + st * STAGE, *RAs = As + A_TILE, *Bs = RAs + A_TILE, *VBs = Bs + B_TILE;
-        load_a_rowmajor<BK, NT>(As, Y, rows, H, m0, k0, true, 1.0, tid);
-        load_a_rowmajor<BK, NT>(RAs, RY, rows, H, m0, k0, false, 0.0, tid);
-        for (int idx = tid; idx < BK * AP; idx += NT) {
+        load_a_rowmajor<BK, NTT, TMT>(As, Y, rows, H, m0, k0, true, 1.0, tid);
+        load_a_rowmajor<BK, NTT, TMT>(RAs, RY, rows, H, m0, k0, false, 0.0, tid);
+        for (int idx = tid; idx < BK * AP; idx += NTT) {
             const int k = idx / AP, n = idx % AP, gk = k0 + k;
             const bool in = gk <= H && n < A;
             cp_async8(&Bs[k * RSBT + n], in ? &W[(size_t)gk * A + n] : W, in ? 8 : 0);
@@ -491,12 +492,13 @@ __global__ void __launch_bounds__(NT, 1) k_chain_tail(const double *__restrict__
         }
         cp_async_commit();
     };
-    load(0, 0);
+#pragma unroll
+    for (int s0 = 0; s0 < NS - 1; ++s0) { if (s0 < nk) load(s0, s0 * BK); else cp_async_commit(); }
     for (int it = 0; it < nk; ++it) {
-        if (it + 1 < nk) { load((it + 1) & 1, (it + 1) * BK); cp_async_wait_group<1>(); }
-        else cp_async_wait_group<0>();
-        __syncthreads();
-        const double *As = smem + (it & 1) * STAGE, *RAs = As + A_TILE, *Bs = RAs + A_TILE, *VBs = Bs + B_TILE;
+        cp_async_wait_group<NS - 2>();
+        __syncthreads();                                        // publishes stage `it`, frees the buffer of step it - 1
+        if (it + NS - 1 < nk) load((it + NS - 1) % NS, (it + NS - 1) * BK); else cp_async_commit();
+        const double *As = smem + (it % NS) * STAGE, *RAs = As + A_TILE, *Bs = RAs + A_TILE, *VBs = Bs + B_TILE;
 #pragma unroll
         for (int q = 0; q < BK / 4; ++q) {
             double a[2], ra[2], b[NTA], vb[NTA];
@@ -512,8 +514,14 @@ __global__ void __launch_bounds__(NT, 1) k_chain_tail(const double *__restrict__
 #pragma unroll
                 for (int j = 0; j < NTA; ++j) { dmma(rxa[i][j], ra[i], b[j]); dmma(rxb[i][j], a[i], vb[j]); }
         }
-        __syncthreads();
     }
+    cp_async_wait_group<0>();
+    __syncthreads();                                            // the ring is idle: W^T takes its place
+    // W^T, zero padded: WT[k][j] = W[j][k]
+    for (int idx = tid; idx < AP * RST; idx += NTT) WT[idx] = 0.0;
+    __syncthreads();
+    for (int idx = tid; idx < H * A; idx += NTT) { const int j = idx / A, k = idx % A; WT[k * RST + j] = W[idx]; }
+    __syncthreads();
     // RG_K in accumulator layout; rows past the end of the chunk contribute nothing
     double gk[2][NTA][2];
 #pragma unroll
@@ -529,16 +537,34 @@ __global__ void __launch_bounds__(NT, 1) k_chain_tail(const double *__restrict__
                 if (gm < rows && col < A) GK[(size_t)gm * A + col] = v;
             }
     }
-    // RG_{K-1} = (RG_K W^T) .* f'(y_{K-1}), 64 columns at a time
-    for (int n0 = 0; n0 < HP; n0 += 64) {
-        double acc[2][8][2] = {};
+    // RG_{K-1} = (RG_K W^T) .* f'(y_{K-1}), 32 columns at a time. The y_{K-1} values the epilogue multiplies with are fetched
+    // BEFORE the block's DMMAs (16 registers of double2): issued after them, every f' waited a full global-load latency
+    // (long-scoreboard stalls on the 1 - y^2 DFMAs were the kernel's top stall, profiles/r02_summary.md).
+    const bool pair_ok = (H & 1) == 0 && (reinterpret_cast<uintptr_t>(Y) & 15) == 0 && (reinterpret_cast<uintptr_t>(Gprev) & 15) == 0;
+    for (int n0 = 0; n0 < HP; n0 += 32) {
+        double2 yv[2][4];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int gm = m0 + 16 * w + 8 * i + g;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int col = n0 + 8 * j + 2 * t;
+                yv[i][j] = make_double2(0.0, 0.0);
+                if (gm < rows && col < H) {
+                    const size_t o = (size_t)gm * H + col;
+                    if (pair_ok) yv[i][j] = *reinterpret_cast<const double2 *>(&Y[o]);
+                    else { yv[i][j].x = Y[o]; if (col + 1 < H) yv[i][j].y = Y[o + 1]; }
+                }
+            }
+        }
+        double acc[2][4][2] = {};
 #pragma unroll
         for (int b = 0; b < NTA; ++b)
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
                 const double *wrow = WT + (8 * b + 2 * t + r) * RST + n0 + g;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
+                for (int j = 0; j < 4; ++j) {
                     const double bf = (n0 + 8 * j < HP) ? wrow[8 * j] : 0.0;
 #pragma unroll
                     for (int i = 0; i < 2; ++i) dmma(acc[i][j], gk[i][b][r], bf);
@@ -549,32 +575,41 @@ __global__ void __launch_bounds__(NT, 1) k_chain_tail(const double *__restrict__
             const int gm = m0 + 16 * w + 8 * i + g;
             if (gm >= rows) continue;
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-#pragma unroll
-                for (int r = 0; r < 2; ++r) {
-                    const int col = n0 + 8 * j + 2 * t + r;
-                    if (col >= H) continue;
-                    const size_t o = (size_t)gm * H + col;
-                    Gprev[o] = acc[i][j][r] * act_deriv(act_prev, Y[o]);
-                }
+            for (int j = 0; j < 4; ++j) {
+                const int col = n0 + 8 * j + 2 * t;
+                if (col >= H) continue;
+                const size_t o = (size_t)gm * H + col;
+                const double g0 = acc[i][j][0] * act_deriv(act_prev, yv[i][j].x), g1 = acc[i][j][1] * act_deriv(act_prev, yv[i][j].y);
+                if (pair_ok) *reinterpret_cast<double2 *>(&Gprev[o]) = make_double2(g0, g1);
+                else { Gprev[o] = g0; if (col + 1 < H) Gprev[o + 1] = g1; }
+            }
         }
     }
 }
 
-template <int NTA>
+template <int NTA, int TMT = BM>
 size_t tail_smem_bytes(int H) {
     constexpr int BK = 16, AP = 8 * NTA;
     const int HP = (H + 7) & ~7;
-    return sizeof(double) * (2 * (2 * BM * Tile<BK>::RSA + 2 * BK * (AP + 4)) + (size_t)AP * (HP + 2));
+    const size_t ring = 3 * (size_t)(2 * TMT * Tile<BK>::RSA + 2 * BK * (AP + 4)), wt = (size_t)AP * (HP + 2);     // W^T reuses the ring
+    return sizeof(double) * (ring > wt ? ring : wt);
 }
 
 template <int NTA>
 int launch_tail(const double *Y, const double *RY, const double *W, const double *VW, int rows, int H, int A, char act_prev,
                 double d3, const double *inv_var, double *GK, double *Gprev, const int *done, cudaStream_t st) {
+    // two 64-row CTAs per SM when both fit (113 KB each); TRPO_CHAIN_TAIL_TM=128 keeps the one-CTA shape
+    static const bool want_half = !(getenv("TRPO_CHAIN_TAIL_TM") && atoi(getenv("TRPO_CHAIN_TAIL_TM")) == 128);
+    if (want_half && tail_smem_bytes<NTA, 64>(H) <= 113 * 1024) {
+        const size_t bytes = tail_smem_bytes<NTA, 64>(H);
+        if (cudaFuncSetAttribute(k_chain_tail<NTA, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return -1;
+        k_chain_tail<NTA, 64><<<cdiv(rows, 64), 128, bytes, st>>>(Y, RY, W, VW, rows, H, A, act_prev, d3, inv_var, GK, Gprev, done);
+        return 0;
+    }
     const size_t bytes = tail_smem_bytes<NTA>(H);
     // size depends on the layer width and the attribute is per device: set it on every launch (host-side only, ~1 us)
-    if (cudaFuncSetAttribute(k_chain_tail<NTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return -1;
-    k_chain_tail<NTA><<<cdiv(rows, BM), NT, bytes, st>>>(Y, RY, W, VW, rows, H, A, act_prev, d3, inv_var, GK, Gprev, done);
+    if (cudaFuncSetAttribute(k_chain_tail<NTA, BM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return -1;
+    k_chain_tail<NTA, BM><<<cdiv(rows, BM), NT, bytes, st>>>(Y, RY, W, VW, rows, H, A, act_prev, d3, inv_var, GK, Gprev, done);
     return 0;
 }
 
