@@ -469,7 +469,6 @@ extern "C" int trpo_ctx_set_batch(trpo_ctx *c, size_t N, const double *Observ, c
         CU(cudaEventRecord(c->ev_copy, c->copy_stream));
         c->copy_inflight = true;
         c->pieces_pending = true;
-        if (getenv("TRPO_DEBUG_STAGING")) fprintf(stderr, "[staging] piecewise: %d pieces of %zu rows\n", c->n_pieces, c->piece_rows);
     } else {
         CU(cudaMemcpyAsync(c->d_obs, Observ, N * O * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     }
@@ -691,7 +690,6 @@ static int fvp_sum(trpo_ctx *c, const double *d_v, const int *d_done) {
         c->stream_first_fvp = false;
     } else {
         const bool piecewise = c->copy_inflight && c->pieces_pending;
-        if (getenv("TRPO_DEBUG_STAGING")) fprintf(stderr, "[staging] chain fvp: inflight %d pending %d\n", (int)c->copy_inflight, (int)c->pieces_pending);
         if (c->copy_inflight && !piecewise) { CU(cudaStreamWaitEvent(c->stream, c->ev_copy, 0)); c->copy_inflight = false; }
         c->stream_first_fvp = false;
         if (ensure_chain_scratch(c)) return -1;
