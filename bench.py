@@ -532,7 +532,7 @@ def run_gpu_arm(args, pkg):
         # dominant kernel: the persistent solve kernel runs all CG_ITERS FVP passes in one launch, otherwise one FVP per launch
         fvps_per_launch = CG_ITERS if solve_kernel else 1
         kernel_name = "k_cg_solve (persistent: %d FVP passes + reductions + CG update per launch)" % CG_ITERS if solve_kernel \
-            else ("k_fvp_fused / k_fvp_warp" if path_used == "fused_dmma" else "GEMM chain (k_chain_fwd/bwd/outer/tail), one FVP")
+            else ("k_fvp_fused / k_fvp_warp" if path_used == "fused_dmma" else "GEMM chain (TMA-fed k_fwd_tma / k_bwd_tma / k_outer_tma + k_chain_tail), all launches of one FVP")
         k_avg_ms = k_ms / max(k_n, 1)
         achieved = fvps_per_launch * fl * n_local / (k_avg_ms * 1e-3) / 1e12 if k_n else None
         if precision == "fp32":

@@ -134,3 +134,50 @@ def test_chunked_scan_of_the_return_and_advantage_recurrences(oracle):
             r_ref, a_ref = oracle.gae(reward, base, num_ep, ep_len, gamma, lam)
             assert np.abs(ret - r_ref).max() < 1e-12 * max(1.0, np.abs(r_ref).max())
             assert np.abs(adv - a_ref).max() < 1e-11
+
+
+def _sw128(row, col):
+    """Byte offset of FP64 element (row, col) inside a SWIZZLE_128B box of 16 columns (gemm_chain_tma.cu)."""
+    return row * 128 + (((col >> 1) ^ (row & 7)) << 4) + (col & 1) * 8
+
+
+def _conflict_free(offsets):
+    """An LDS.64 is served per half warp: its 16 lanes must hit 16 distinct 8-byte words of the 128-byte bank window."""
+    for half in (offsets[:16], offsets[16:]):
+        assert len({(o % 128) // 8 for o in half}) == 16, sorted((o % 128) // 8 for o in half)
+
+
+def test_tma_fragment_addressing_is_a_conflict_free_permutation_of_k():
+    """The TMA-fed GEMM kernels read their m8n8k4 fragments through the 128-byte swizzle with the contraction index permuted
+    (gemm_chain_tma.cu header). Restated here lane by lane: every k of a k-step is visited exactly once, both operands of a DMMA
+    see the same k in the same lane, and no half warp has a shared-memory bank conflict."""
+    lanes = [(l >> 2, l & 3) for l in range(32)]                      # (g, t)
+    # operands whose box rows are k (outer product): lane t of step q reads row 8*(q/2) + 2t + (q&1), column 8*ib + g
+    seen = set()
+    for q in range(8):
+        ks = [8 * (q >> 1) + 2 * t + (q & 1) for t in range(4)]
+        seen.update(ks)
+        for ib in range(2):
+            _conflict_free([_sw128(8 * (q >> 1) + 2 * t + (q & 1), 8 * ib + g) for g, t in lanes])
+    assert seen == set(range(32))
+    # operands whose box columns are k (backward GEMM, forward activations): lane t of step c0 reads column 2c0 + 8(t/2) + (t&1)
+    seen = set()
+    for c0 in range(4):
+        cols = [2 * c0 + 8 * (t >> 1) + (t & 1) for t in range(4)]
+        seen.update(cols)
+        for i in range(4):
+            _conflict_free([_sw128(8 * i + g, 2 * c0 + 8 * (t >> 1) + (t & 1)) for g, t in lanes])
+    assert seen == set(range(16))
+    # forward layer: the weights' box rows are k, stored through the row permutation of k_permute_rows16 (bit 0 <-> 1, 2 <-> 3)
+    perm = [((r & 1) << 1) | ((r & 2) >> 1) | ((r & 4) << 1) | ((r & 8) >> 1) for r in range(16)]
+    assert sorted(perm) == list(range(16)) and all(perm[perm[r]] == r for r in range(16))
+    for c0 in range(4):
+        for t in range(4):
+            k_act = 2 * c0 + 8 * (t >> 1) + (t & 1)                   # the k the activation fragment of lane t holds
+            rho = 8 * (c0 >> 1) + 2 * t + (c0 & 1)                    # the stored weight row that lane reads
+            assert perm[rho] == k_act                                 # ... holds the same k
+        for j in range(2):
+            _conflict_free([_sw128(8 * (c0 >> 1) + 2 * t + (c0 & 1), 8 * j + g) for g, t in lanes])
+    # un-permuted, lanes t and t + 2 would read rows 8 apart: same swizzle phase, same banks
+    bad = [_sw128(2 * 0 + 8 * (t >> 1) + (t & 1), g) for g, t in lanes]
+    assert len({(o % 128) // 8 for o in bad[:16]}) < 16
