@@ -666,7 +666,8 @@ size_t chain_scratch_bytes(const NetDesc &net, int chunk, int nslices) {
     size_t maxL = 0, sumL = 0;
     for (int i = 1; i <= net.K; ++i) { sumL += net.L[i]; if ((size_t)net.L[i] > maxL) maxL = net.L[i]; }
     // + the row-permuted weight / direction copies of the TMA-fed forward kernel (2 doubles of slack keep them 16-byte aligned)
-    return sizeof(double) * ((size_t)chunk * (sumL + 4 * maxL) + (size_t)nslices * net.P + 2 + 2 * chain_tma_perm_offset(net, net.K));
+    return sizeof(double) * ((size_t)chunk * (sumL + 4 * maxL) + (size_t)nslices * net.P + 2 + 2 * chain_tma_perm_offset(net, net.K) +
+                             chain_tma_tail_doubles(net.K >= 1 ? net.L[net.K - 1] : 0));
 }
 
 int chain_accumulate(const NetDesc &net, const ChainScratch &sc, ChainMode mode,
@@ -684,7 +685,7 @@ int chain_accumulate(const NetDesc &net, const ChainScratch &sc, ChainMode mode,
     // Same sums, grouped differently: the streamed FVP agrees with a resident one to rounding (1e-15), not bitwise.
     const size_t step = (sc.piece_events && sc.piece_rows && sc.piece_rows < (size_t)sc.chunk) ? sc.piece_rows : (size_t)sc.chunk;
     // TMA-fed forward layers read the weights and the direction from row-permuted copies (gemm_chain_tma.cu), rebuilt per FVP
-    bool perm_ready[TRPO_MAX_LAYERS] = {};
+    bool perm_ready[TRPO_MAX_LAYERS] = {}, tail_ready = false;
     for (size_t c0 = 0; c0 < nsamples; c0 += step, ++chunk_idx) {
         const int rows = (int)((nsamples - c0 < step) ? nsamples - c0 : step);
         const int accumulate = chunk_idx > 0;
@@ -755,6 +756,11 @@ int chain_accumulate(const NetDesc &net, const ChainScratch &sc, ChainMode mode,
             const double d3 = net.ac[K] == 'o' ? 0.1 : 1.0;
             const double *W = d_theta + net.w_off[K - 1], *VW = d_v + net.w_off[K - 1];
             int rc;
+            if (sc.tailw && chain_tma_tail_eligible(sc.Y[K - 1], sc.RY[(K - 1) & 1], sc.G[(K - 1) & 1], H, A)) {
+                if (!tail_ready) { chain_tma_tail_prepare(W, VW, sc.tailw, H, A, st); *launches += 3; tail_ready = true; }
+                rc = chain_tma_tail(sc.Y[K - 1], sc.RY[(K - 1) & 1], VW, sc.tailw, rows, H, A, net.ac[K - 1], d3, d_inv_var, sc.G[K & 1],
+                                    sc.G[(K - 1) & 1], d_done, st);
+            } else
             if (A <= 8) rc = launch_tail<1>(sc.Y[K - 1], sc.RY[(K - 1) & 1], W, VW, rows, H, A, net.ac[K - 1], d3, d_inv_var, sc.G[K & 1], sc.G[(K - 1) & 1], d_done, st);
             else if (A <= 16) rc = launch_tail<2>(sc.Y[K - 1], sc.RY[(K - 1) & 1], W, VW, rows, H, A, net.ac[K - 1], d3, d_inv_var, sc.G[K & 1], sc.G[(K - 1) & 1], d_done, st);
             else rc = launch_tail<3>(sc.Y[K - 1], sc.RY[(K - 1) & 1], W, VW, rows, H, A, net.ac[K - 1], d3, d_inv_var, sc.G[K & 1], sc.G[(K - 1) & 1], d_done, st);

@@ -374,6 +374,179 @@ __global__ void __launch_bounds__(NT, 2) k_fwd_tma(const __grid_constant__ CUten
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// tail: the last weight layer of the FVP for a narrow action layer (A <= 24, linear / 0.1x output) -- what k_chain_tail does, with
+// the operands of the forward product by TMA. That kernel issued 14 LDGSTS per thread for 48 DMMAs per warp and k-step (the big
+// GEMMs: 12 for 128), so its forward loop was bound by the copy instructions, not by the tensor pipe.
+//   Rx_K = Ry_{K-1} W + y_{K-1} VW + VB (TRPO_FVP.c:795-803): y / Ry boxes [64 rows x 16 k]; W / VW from row-permuted copies
+//        padded to 32 columns (two boxes of [16 k-rows x 16]); VB is the start value of the second accumulator set
+//   RG_K = Rx_K f'^2 / sigma^2 (:809-823, :852-854, :869-882);  RG_{K-1} = (RG_K W^T) .* f'(y_{K-1}) (:890-899)
+// W^T (zero padded [8 NTA][HP + 2], built once per FVP by k_tail_wt_image) arrives as ONE bulk copy over the idle ring.
+constexpr int TAIL_TM = 64, TAIL_NT = 128, TAIL_NS = 3;
+constexpr int TAIL_STAGE = 2 * FWD_A_BOX + 4 * FWD_B_BOX;         // y, Ry, 2 W boxes, 2 VW boxes: 24 KB
+
+__global__ void k_permute_rows16_pad(const double *__restrict__ W, double *__restrict__ Wp, int Kd, int Nin, int Nout, int Kpad) {
+    const size_t total = (size_t)Kpad * Nout;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int row = (int)(idx / Nout), n = (int)(idx % Nout), rho = row & 15;
+        const int kp = ((rho & 1) << 1) | ((rho & 2) >> 1) | ((rho & 4) << 1) | ((rho & 8) >> 1);
+        const int k = (row & ~15) + kp;
+        Wp[idx] = (k < Kd && n < Nin) ? W[(size_t)k * Nin + n] : 0.0;
+    }
+}
+// WT[k][j] = W[j][k] for k < A, j < H, zero elsewhere; row stride RST
+__global__ void k_tail_wt_image(const double *__restrict__ W, double *__restrict__ WT, int H, int A, int AP, int RST) {
+    const int total = AP * RST;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int k = idx / RST, j = idx % RST;
+        WT[idx] = (k < A && j < H) ? W[(size_t)j * A + k] : 0.0;
+    }
+}
+
+template <int NTA>
+__global__ void __launch_bounds__(TAIL_NT, 3) k_tail_tma(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CUtensorMap mapRY,
+                                                         const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapV,
+                                                         const double *__restrict__ Y, const double *__restrict__ VW,
+                                                         const double *__restrict__ WTg, int rows, int H, int A, char act_prev, double d3,
+                                                         const double *__restrict__ inv_var,
+                                                         double *__restrict__ GK, double *__restrict__ Gprev,
+                                                         const int *__restrict__ done) {
+    if (done && *done) return;
+    extern __shared__ __align__(1024) unsigned char smem_dyn[];
+    __shared__ __align__(8) uint64_t full[TAIL_NS + 1];
+    unsigned char *smem = align_1k(smem_dyn);
+    constexpr int AP = 8 * NTA;
+    const int HP = (H + 7) & ~7, RST = HP + 2;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
+    const int m0 = blockIdx.x * TAIL_TM;
+    const int nk = (H + FWD_BK - 1) / FWD_BK;
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s <= TAIL_NS; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int st, int k0) {
+        unsigned char *base = smem + st * TAIL_STAGE;
+        mbar_expect_tx(&full[st], TAIL_STAGE);
+        tma_load_2d(base, &mapY, &full[st], k0, m0);
+        tma_load_2d(base + FWD_A_BOX, &mapRY, &full[st], k0, m0);
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb) {
+            tma_load_2d(base + 2 * FWD_A_BOX + nb * FWD_B_BOX, &mapW, &full[st], 16 * nb, k0);
+            tma_load_2d(base + 2 * FWD_A_BOX + (2 + nb) * FWD_B_BOX, &mapV, &full[st], 16 * nb, k0);
+        }
+    };
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < TAIL_NS - 1; ++s) if (s < nk) issue(s, s * FWD_BK);
+    }
+    double rxa[2][NTA][2] = {}, rxb[2][NTA][2];
+#pragma unroll
+    for (int j = 0; j < NTA; ++j)
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int col = 8 * j + 2 * t + r;
+            const double vb = col < A ? VW[(size_t)H * A + col] : 0.0;         // VB: the bias row of the direction
+            rxb[0][j][r] = vb; rxb[1][j][r] = vb;
+        }
+    int offA[4], offB[2][2];
+#pragma unroll
+    for (int c0 = 0; c0 < 4; ++c0) offA[c0] = (16 * w + g) * 128 + (((c0 + 4 * (t >> 1)) ^ g) << 4) + (t & 1) * 8;
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int jb = 0; jb < 2; ++jb) offB[c][jb] = (2 * t + c) * 128 + (((4 * jb + (g >> 1)) ^ (2 * t + c)) << 4) + (g & 1) * 8;
+    for (int it = 0; it < nk; ++it) {
+        __syncthreads();                                   // everybody is done with the stage of step it - 1
+        if (tid == 0 && it + TAIL_NS - 1 < nk) issue((it + TAIL_NS - 1) % TAIL_NS, (it + TAIL_NS - 1) * FWD_BK);
+        mbar_wait(&full[it % TAIL_NS], (it / TAIL_NS) & 1);
+        const unsigned char *As = smem + (it % TAIL_NS) * TAIL_STAGE, *RAs = As + FWD_A_BOX;
+        const unsigned char *Bs = As + 2 * FWD_A_BOX, *VBs = Bs + 2 * FWD_B_BOX;
+#pragma unroll
+        for (int q = 0; q < FWD_BK / 4; ++q) {
+            double a[2], ra[2], b[NTA], vb[NTA];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                a[i] = *reinterpret_cast<const double *>(As + i * 1024 + offA[q]);
+                ra[i] = *reinterpret_cast<const double *>(RAs + i * 1024 + offA[q]);
+            }
+#pragma unroll
+            for (int j = 0; j < NTA; ++j) {
+                b[j] = *reinterpret_cast<const double *>(Bs + (j >> 1) * FWD_B_BOX + (q >> 1) * 1024 + offB[q & 1][j & 1]);
+                vb[j] = *reinterpret_cast<const double *>(VBs + (j >> 1) * FWD_B_BOX + (q >> 1) * 1024 + offB[q & 1][j & 1]);
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < NTA; ++j) { dmma(rxa[i][j], ra[i], b[j]); dmma(rxb[i][j], a[i], vb[j]); }
+        }
+    }
+    __syncthreads();                                            // the ring is idle: W^T takes its place, one bulk copy
+    const double *WT = reinterpret_cast<const double *>(smem);
+    if (tid == 0) {
+        const uint32_t bytes = (uint32_t)(AP * RST * sizeof(double));
+        mbar_expect_tx(&full[TAIL_NS], bytes);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"(smem_u32(smem)), "l"(WTg), "r"(bytes), "r"(smem_u32(&full[TAIL_NS])) : "memory");
+    }
+    // RG_K in accumulator layout; rows past the end of the chunk contribute nothing
+    double gk[2][NTA][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int gm = m0 + 16 * w + 8 * i + g;
+#pragma unroll
+        for (int j = 0; j < NTA; ++j)
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int col = 8 * j + 2 * t + r;
+                const double v = (gm < rows && col < A) ? (rxa[i][j][r] + rxb[i][j][r]) * d3 * inv_var[col] * d3 : 0.0;
+                gk[i][j][r] = v;
+                if (gm < rows && col < A) GK[(size_t)gm * A + col] = v;
+            }
+    }
+    mbar_wait(&full[TAIL_NS], 0);
+    // RG_{K-1} = (RG_K W^T) .* f'(y_{K-1}), 32 columns at a time; the y values are fetched before the block's DMMAs
+    for (int n0 = 0; n0 < HP; n0 += 32) {
+        double2 yv[2][4];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int gm = m0 + 16 * w + 8 * i + g;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int col = n0 + 8 * j + 2 * t;
+                yv[i][j] = (gm < rows && col < H) ? *reinterpret_cast<const double2 *>(&Y[(size_t)gm * H + col]) : make_double2(0.0, 0.0);
+            }
+        }
+        double acc[2][4][2] = {};
+#pragma unroll
+        for (int b = 0; b < NTA; ++b)
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const double *wrow = WT + (8 * b + 2 * t + r) * RST + n0 + g;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const double bf = (n0 + 8 * j < HP) ? wrow[8 * j] : 0.0;
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) dmma(acc[i][j], gk[i][b][r], bf);
+                }
+            }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int gm = m0 + 16 * w + 8 * i + g;
+            if (gm >= rows) continue;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int col = n0 + 8 * j + 2 * t;
+                if (col >= H) continue;                    // H is even: the pair is inside or outside
+                *reinterpret_cast<double2 *>(&Gprev[(size_t)gm * H + col]) =
+                    make_double2(acc[i][j][0] * act_deriv(act_prev, yv[i][j].x), acc[i][j][1] * act_deriv(act_prev, yv[i][j].y));
+            }
+        }
+    }
+}
+
 // row-major FP64 matrix [nrows x ncols] (contiguous rows), boxes of 16 columns x box_rows rows, SWIZZLE_128B, zero fill
 bool make_map(CUtensorMap *m, const double *base, size_t nrows, int ncols, int box_rows) {
     EncodeTiledFn fn = encode_fn();
@@ -464,5 +637,46 @@ int chain_tma_fwd(const double *Yin, const double *RYin, const double *Wp, const
     dim3 grid((N + BN - 1) / BN, (rows + FWD_TM - 1) / FWD_TM);
     if (RYin) k_fwd_tma<true><<<grid, NT, FwdCfg<true>::SMEM, st>>>(mY, mRY, mW, mV, W, VW, rows, Kd, N, act, Yout, RYout, Gout, inv_var, done);
     else k_fwd_tma<false><<<grid, NT, FwdCfg<false>::SMEM, st>>>(mY, mRY, mW, mV, W, VW, rows, Kd, N, act, Yout, RYout, Gout, inv_var, done);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+// ---- tail ----
+// scratch behind the forward layers' permuted copies: W', VW' [ceil16(H) x 32] and the W^T image [24 x (HP + 2)]
+size_t chain_tma_tail_doubles(int H) {
+    const size_t Hpad = (H + 15) / 16 * 16, HP = (H + 7) & ~7;
+    return 2 * Hpad * 32 + 24 * (HP + 2);
+}
+bool chain_tma_tail_eligible(const double *Y, const double *RY, const double *Gprev, int H, int A) {
+    static const bool off = getenv("TRPO_NO_CHAIN_TMA_TAIL") && atoi(getenv("TRPO_NO_CHAIN_TMA_TAIL"));
+    const size_t HP = (H + 7) & ~7;
+    return !off && chain_tma_enabled() && (H & 1) == 0 && H >= 16 && A <= 24 && aligned16(Y) && aligned16(RY) && aligned16(Gprev) &&
+           24 * (HP + 2) * sizeof(double) <= (size_t)TAIL_NS * TAIL_STAGE;
+}
+void chain_tma_tail_prepare(const double *W, const double *VW, double *scratch, int H, int A, cudaStream_t st) {
+    const int Hpad = (H + 15) / 16 * 16, HP = (H + 7) & ~7, RST = HP + 2, AP = A <= 8 ? 8 : A <= 16 ? 16 : 24;
+    double *Wp = scratch, *Vp = scratch + (size_t)Hpad * 32, *WT = Vp + (size_t)Hpad * 32;
+    k_permute_rows16_pad<<<(Hpad * 32 + 255) / 256, 256, 0, st>>>(W, Wp, H, A, 32, Hpad);
+    k_permute_rows16_pad<<<(Hpad * 32 + 255) / 256, 256, 0, st>>>(VW, Vp, H, A, 32, Hpad);
+    k_tail_wt_image<<<(AP * RST + 255) / 256, 256, 0, st>>>(W, WT, H, A, AP, RST);
+}
+int chain_tma_tail(const double *Y, const double *RY, const double *VW, const double *scratch, int rows, int H, int A, char act_prev,
+                   double d3, const double *inv_var, double *GK, double *Gprev, const int *done, cudaStream_t st) {
+    const int Hpad = (H + 15) / 16 * 16;
+    const double *Wp = scratch, *Vp = scratch + (size_t)Hpad * 32, *WT = Vp + (size_t)Hpad * 32;
+    CUtensorMap mY, mRY, mW, mV;
+    if (!make_map(&mY, Y, (size_t)rows, H, TAIL_TM) || !make_map(&mRY, RY, (size_t)rows, H, TAIL_TM) ||
+        !make_map(&mW, Wp, (size_t)Hpad, 32, FWD_BK) || !make_map(&mV, Vp, (size_t)Hpad, 32, FWD_BK)) return -1;
+    constexpr int SMEM = TAIL_NS * TAIL_STAGE + 1024;
+    static DeviceOnce once;
+    if (once.pending()) {
+        if (cudaFuncSetAttribute(k_tail_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess ||
+            cudaFuncSetAttribute(k_tail_tma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess ||
+            cudaFuncSetAttribute(k_tail_tma<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess) return -1;
+        once.mark();
+    }
+    const int grid = (rows + TAIL_TM - 1) / TAIL_TM;
+    if (A <= 8) k_tail_tma<1><<<grid, TAIL_NT, SMEM, st>>>(mY, mRY, mW, mV, Y, VW, WT, rows, H, A, act_prev, d3, inv_var, GK, Gprev, done);
+    else if (A <= 16) k_tail_tma<2><<<grid, TAIL_NT, SMEM, st>>>(mY, mRY, mW, mV, Y, VW, WT, rows, H, A, act_prev, d3, inv_var, GK, Gprev, done);
+    else k_tail_tma<3><<<grid, TAIL_NT, SMEM, st>>>(mY, mRY, mW, mV, Y, VW, WT, rows, H, A, act_prev, d3, inv_var, GK, Gprev, done);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }

@@ -50,6 +50,7 @@ struct ChainScratch {
     int nslices;                     // split-K slices of the outer-product GEMM
     double *partial;                 // [nslices x P] un-normalised partial sums, fixed-order reduced
     double *wperm, *vperm;           // row-permuted copies of the weights / the direction for the TMA-fed forward kernel (chain_tma_perm_total)
+    double *tailw;                   // TMA-fed tail kernel: permuted, padded W / VW of the last layer and the W^T image (chain_tma_tail_doubles)
     // streamed staging of the observation matrix: piece i of piece_rows rows has landed when piece_events[i] has completed
     // (recorded on the copy stream); the chunk loop makes the compute stream wait only for the pieces a chunk touches
     const cudaEvent_t *piece_events;
@@ -102,6 +103,11 @@ bool chain_tma_fwd_eligible(const double *Yin, const double *RYin, const double 
 size_t chain_tma_perm_doubles(int Kd, int N);         // one layer's permuted copy: Kd rounded up to 16 rows
 size_t chain_tma_perm_offset(const NetDesc &net, int layer);     // layer == K: the total
 void chain_tma_permute_rows(const double *W, double *Wp, int Kd, int N, cudaStream_t st);
+size_t chain_tma_tail_doubles(int H);
+bool chain_tma_tail_eligible(const double *Y, const double *RY, const double *Gprev, int H, int A);
+void chain_tma_tail_prepare(const double *W, const double *VW, double *scratch, int H, int A, cudaStream_t st);
+int chain_tma_tail(const double *Y, const double *RY, const double *VW, const double *scratch, int rows, int H, int A, char act_prev,
+                   double d3, const double *inv_var, double *GK, double *Gprev, const int *done, cudaStream_t st);
 int chain_tma_fwd(const double *Yin, const double *RYin, const double *Wp, const double *Vp, const double *W, const double *VW,
                   int rows, int Kd, int N, char act, double *Yout, double *RYout, double *Gout, const double *inv_var,
                   const int *done, cudaStream_t st);

@@ -199,6 +199,7 @@ static int ensure_chain_scratch(trpo_ctx *c) {
     if ((p - c->sc_base) & 1) ++p;                       // 16-byte alignment for the tensor maps
     c->sc.wperm = p;
     c->sc.vperm = p + chain_tma_perm_offset(c->net, c->net.K);
+    c->sc.tailw = c->sc.vperm + chain_tma_perm_offset(c->net, c->net.K);
     c->sc.chunk = (int)chunk;
     c->sc.nslices = nslices;
     return 0;
