@@ -696,6 +696,7 @@ int chain_accumulate(const NetDesc &net, const ChainScratch &sc, ChainMode mode,
         // the last layer of a narrow-action FVP goes through the fused tail kernel (forward(K-1) + seed + backward(K))
         const bool tail = fvp && K >= 2 && A <= 24 && (net.ac[K] == 'l' || net.ac[K] == 'o') &&
                           tail_smem_bytes<3>(net.L[K - 1]) <= 200 * 1024;
+        int ldgK = A;                                          // row stride of G_K (padded to even by the TMA-fed tail when A >= 16 is odd)
         // ---- forward ----
         for (int i = 0; i < (tail ? K - 1 : K); ++i) {
             const double *Yin = (i == 0) ? d_obs + c0 * net.L[0] : sc.Y[i];
@@ -758,8 +759,9 @@ int chain_accumulate(const NetDesc &net, const ChainScratch &sc, ChainMode mode,
             int rc;
             if (sc.tailw && chain_tma_tail_eligible(sc.Y[K - 1], sc.RY[(K - 1) & 1], sc.G[(K - 1) & 1], H, A)) {
                 if (!tail_ready) { chain_tma_tail_prepare(W, VW, sc.tailw, H, A, st); *launches += 3; tail_ready = true; }
+                if (A >= 16) ldgK = (A + 1) & ~1;               // even row stride: RG_K becomes a TMA operand of the layer's outer product
                 rc = chain_tma_tail(sc.Y[K - 1], sc.RY[(K - 1) & 1], VW, sc.tailw, rows, H, A, net.ac[K - 1], d3, d_inv_var, sc.G[K & 1],
-                                    sc.G[(K - 1) & 1], d_done, st);
+                                    ldgK, sc.G[(K - 1) & 1], d_done, st);
             } else
             if (A <= 8) rc = launch_tail<1>(sc.Y[K - 1], sc.RY[(K - 1) & 1], W, VW, rows, H, A, net.ac[K - 1], d3, d_inv_var, sc.G[K & 1], sc.G[(K - 1) & 1], d_done, st);
             else if (A <= 16) rc = launch_tail<2>(sc.Y[K - 1], sc.RY[(K - 1) & 1], W, VW, rows, H, A, net.ac[K - 1], d3, d_inv_var, sc.G[K & 1], sc.G[(K - 1) & 1], d_done, st);
@@ -774,10 +776,11 @@ int chain_accumulate(const NetDesc &net, const ChainScratch &sc, ChainMode mode,
             // the bias row would open a 32-row warp tile (or a whole 128-row CTA tile) of its own: column sums instead
             const int bias_colsum = (M0 % 32) == 0;
             const int tiles_n = cdiv(N, BN);
-            if (chain_tma_outer_eligible(Yprev, sc.G[i & 1], M0, N)) {
+            const int ldg = (i == K) ? ldgK : N;               // row stride of G_i
+            if (chain_tma_outer_eligible(Yprev, sc.G[i & 1], M0, N, ldg)) {
                 // operands by TMA (gemm_chain_tma.cu); the bias-gradient row always comes from the column sums there
                 const int ns = layer_slices(chain_tma_tiles_m(M0) * tiles_n, sc.nslices);
-                if (chain_tma_outer(Yprev, sc.G[i & 1], rows, M0, N, cdiv(cdiv(rows, ns), BK_SINGLE) * BK_SINGLE, tiles_n, ns, sc.partial,
+                if (chain_tma_outer(Yprev, sc.G[i & 1], ldg, rows, M0, N, cdiv(cdiv(rows, ns), BK_SINGLE) * BK_SINGLE, tiles_n, ns, sc.partial,
                                     net.P, net.w_off[i - 1], accumulate, d_done, st)) return -1;
             } else {
                 const int tiles_m = bias_colsum ? cdiv(M0, BM) : cdiv(M0 + 1, BM);

@@ -410,7 +410,7 @@ __global__ void __launch_bounds__(TAIL_NT, 3) k_tail_tma(const __grid_constant__
                                                          const double *__restrict__ Y, const double *__restrict__ VW,
                                                          const double *__restrict__ WTg, int rows, int H, int A, char act_prev, double d3,
                                                          const double *__restrict__ inv_var,
-                                                         double *__restrict__ GK, double *__restrict__ Gprev,
+                                                         double *__restrict__ GK, int ldgk, double *__restrict__ Gprev,
                                                          const int *__restrict__ done) {
     if (done && *done) return;
     extern __shared__ __align__(1024) unsigned char smem_dyn[];
@@ -503,7 +503,7 @@ __global__ void __launch_bounds__(TAIL_NT, 3) k_tail_tma(const __grid_constant__
                 const int col = 8 * j + 2 * t + r;
                 const double v = (gm < rows && col < A) ? (rxa[i][j][r] + rxb[i][j][r]) * d3 * inv_var[col] * d3 : 0.0;
                 gk[i][j][r] = v;
-                if (gm < rows && col < A) GK[(size_t)gm * A + col] = v;
+                if (gm < rows && col < ldgk) GK[(size_t)gm * ldgk + col] = v;      // column A of an odd-width RG_K is padding: zero
             }
     }
     mbar_wait(&full[TAIL_NS], 0);
@@ -548,11 +548,11 @@ __global__ void __launch_bounds__(TAIL_NT, 3) k_tail_tma(const __grid_constant__
 }
 
 // row-major FP64 matrix [nrows x ncols] (contiguous rows), boxes of 16 columns x box_rows rows, SWIZZLE_128B, zero fill
-bool make_map(CUtensorMap *m, const double *base, size_t nrows, int ncols, int box_rows) {
+bool make_map(CUtensorMap *m, const double *base, size_t nrows, int ncols, int box_rows, int ld = 0) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return false;
     const cuuint64_t dims[2] = {(cuuint64_t)ncols, (cuuint64_t)nrows};
-    const cuuint64_t strides[1] = {(cuuint64_t)ncols * sizeof(double)};
+    const cuuint64_t strides[1] = {(cuuint64_t)(ld ? ld : ncols) * sizeof(double)};      // ld: row stride in doubles (even), default dense
     const cuuint32_t box[2] = {16, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void *)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -579,8 +579,9 @@ bool chain_tma_enabled() {
     return !(e && atoi(e)) && tma::encode_fn() != nullptr;
 }
 // tensor-map rows are 16-byte multiples: even widths, 16-byte aligned bases
-bool chain_tma_outer_eligible(const double *Yprev, const double *G, int M0, int N) {
-    return chain_tma_enabled() && (M0 & 1) == 0 && (N & 1) == 0 && M0 >= 16 && N >= 16 && aligned16(Yprev) && aligned16(G);
+// ldg: row stride of G in doubles (the TMA-fed tail writes a 17-column RG_K with stride 18 so that it qualifies)
+bool chain_tma_outer_eligible(const double *Yprev, const double *G, int M0, int N, int ldg) {
+    return chain_tma_enabled() && (M0 & 1) == 0 && (ldg & 1) == 0 && M0 >= 16 && N >= 16 && aligned16(Yprev) && aligned16(G);
 }
 bool chain_tma_bwd_eligible(const double *Gin, const double *W, const double *Yprev, const double *Gout, int Kd, int N) {
     return chain_tma_enabled() && (Kd & 1) == 0 && (N & 1) == 0 && Kd >= 16 && N >= 16 && aligned16(Gin) && aligned16(W) &&
@@ -588,10 +589,10 @@ bool chain_tma_bwd_eligible(const double *Gin, const double *W, const double *Yp
 }
 int chain_tma_tiles_m(int M0) { return (M0 + BM - 1) / BM; }
 
-int chain_tma_outer(const double *Yprev, const double *G, int rows, int M0, int N, int per_slice, int tiles_n, int nslices,
+int chain_tma_outer(const double *Yprev, const double *G, int ldg, int rows, int M0, int N, int per_slice, int tiles_n, int nslices,
                     double *partial, int P, int out_off, int accumulate, const int *done, cudaStream_t st) {
     CUtensorMap mY, mG;
-    if (!configure() || !make_map(&mY, Yprev, (size_t)rows, M0, BK) || !make_map(&mG, G, (size_t)rows, N, BK)) return -1;
+    if (!configure() || !make_map(&mY, Yprev, (size_t)rows, M0, BK) || !make_map(&mG, G, (size_t)rows, N, BK, ldg)) return -1;
     dim3 grid(chain_tma_tiles_m(M0) * tiles_n, nslices);
     k_outer_tma<<<grid, NT, SMEM_BYTES, st>>>(mY, mG, rows, M0, N, per_slice, tiles_n, partial, P, out_off, accumulate, done);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
@@ -660,7 +661,7 @@ void chain_tma_tail_prepare(const double *W, const double *VW, double *scratch, 
     k_tail_wt_image<<<(AP * RST + 255) / 256, 256, 0, st>>>(W, WT, H, A, AP, RST);
 }
 int chain_tma_tail(const double *Y, const double *RY, const double *VW, const double *scratch, int rows, int H, int A, char act_prev,
-                   double d3, const double *inv_var, double *GK, double *Gprev, const int *done, cudaStream_t st) {
+                   double d3, const double *inv_var, double *GK, int ldgk, double *Gprev, const int *done, cudaStream_t st) {
     const int Hpad = (H + 15) / 16 * 16;
     const double *Wp = scratch, *Vp = scratch + (size_t)Hpad * 32, *WT = Vp + (size_t)Hpad * 32;
     CUtensorMap mY, mRY, mW, mV;
@@ -675,8 +676,8 @@ int chain_tma_tail(const double *Y, const double *RY, const double *VW, const do
         once.mark();
     }
     const int grid = (rows + TAIL_TM - 1) / TAIL_TM;
-    if (A <= 8) k_tail_tma<1><<<grid, TAIL_NT, SMEM, st>>>(mY, mRY, mW, mV, Y, VW, WT, rows, H, A, act_prev, d3, inv_var, GK, Gprev, done);
-    else if (A <= 16) k_tail_tma<2><<<grid, TAIL_NT, SMEM, st>>>(mY, mRY, mW, mV, Y, VW, WT, rows, H, A, act_prev, d3, inv_var, GK, Gprev, done);
-    else k_tail_tma<3><<<grid, TAIL_NT, SMEM, st>>>(mY, mRY, mW, mV, Y, VW, WT, rows, H, A, act_prev, d3, inv_var, GK, Gprev, done);
+    if (A <= 8) k_tail_tma<1><<<grid, TAIL_NT, SMEM, st>>>(mY, mRY, mW, mV, Y, VW, WT, rows, H, A, act_prev, d3, inv_var, GK, ldgk, Gprev, done);
+    else if (A <= 16) k_tail_tma<2><<<grid, TAIL_NT, SMEM, st>>>(mY, mRY, mW, mV, Y, VW, WT, rows, H, A, act_prev, d3, inv_var, GK, ldgk, Gprev, done);
+    else k_tail_tma<3><<<grid, TAIL_NT, SMEM, st>>>(mY, mRY, mW, mV, Y, VW, WT, rows, H, A, act_prev, d3, inv_var, GK, ldgk, Gprev, done);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }

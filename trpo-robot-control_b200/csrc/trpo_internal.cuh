@@ -92,10 +92,10 @@ size_t chain_scratch_bytes(const NetDesc &net, int chunk, int nslices);
 
 // gemm_chain_tma.cu: TMA-fed variants of the single-product GEMM-chain kernels (operands in SWIZZLE_128B boxes, mbarrier completion)
 bool chain_tma_enabled();
-bool chain_tma_outer_eligible(const double *Yprev, const double *G, int M0, int N);
+bool chain_tma_outer_eligible(const double *Yprev, const double *G, int M0, int N, int ldg);
 bool chain_tma_bwd_eligible(const double *Gin, const double *W, const double *Yprev, const double *Gout, int Kd, int N);
 int chain_tma_tiles_m(int M0);
-int chain_tma_outer(const double *Yprev, const double *G, int rows, int M0, int N, int per_slice, int tiles_n, int nslices,
+int chain_tma_outer(const double *Yprev, const double *G, int ldg, int rows, int M0, int N, int per_slice, int tiles_n, int nslices,
                     double *partial, int P, int out_off, int accumulate, const int *done, cudaStream_t st);
 int chain_tma_bwd(const double *Gin, const double *W, const double *Yprev, int rows, int Kd, int N, char act_prev, double *Gout,
                   const int *done, cudaStream_t st);
@@ -107,7 +107,7 @@ size_t chain_tma_tail_doubles(int H);
 bool chain_tma_tail_eligible(const double *Y, const double *RY, const double *Gprev, int H, int A);
 void chain_tma_tail_prepare(const double *W, const double *VW, double *scratch, int H, int A, cudaStream_t st);
 int chain_tma_tail(const double *Y, const double *RY, const double *VW, const double *scratch, int rows, int H, int A, char act_prev,
-                   double d3, const double *inv_var, double *GK, double *Gprev, const int *done, cudaStream_t st);
+                   double d3, const double *inv_var, double *GK, int ldgk, double *Gprev, const int *done, cudaStream_t st);
 int chain_tma_fwd(const double *Yin, const double *RYin, const double *Wp, const double *Vp, const double *W, const double *VW,
                   int rows, int Kd, int N, char act, double *Yout, double *RYout, double *Gout, const double *inv_var,
                   const int *done, cudaStream_t st);
