@@ -1,4 +1,6 @@
-// gemm_chain_tma.cu -- TMA-fed variants of the FP64 GEMM-chain kernels (sm_100a).
+// gemm_chain_tma.cu -- TMA-fed variants of the FP64 GEMM-chain kernels (sm_100a): forward R-op layer (k_fwd_tma), backward GEMM
+// (k_bwd_tma), split-K outer product (k_outer_tma) and the fused tail of a narrow action layer (k_tail_tma). Same arithmetic as
+// the cp.async kernels of gemm_chain.cu (TRPO_FVP.c:771-924 batched over the samples), which remain for odd widths.
 //
 // The cp.async loaders of gemm_chain.cu cost the DMMA main loop 8 - 10 % on their own (12 LDGSTS per thread and k-step plus their
 // index arithmetic; tools/dmma_gemm_loop.cu: fragments + DMMA 37.1 TFLOP/s, + block barrier 36.5, + cp.async double buffer 33.0,
@@ -8,9 +10,10 @@
 //
 // Fragment reads go through the swizzle, byte (row, col) of a box = row*128 + (((col >> 1) ^ (row & 7)) << 4) + (col & 1)*8, with
 // the contraction index PERMUTED so that the 16 lanes of a half warp hit 16 distinct 8-byte bank pairs (both operands of a DMMA use
-// the same permutation, the sum over k does not care):
+// the same permutation, the sum over k does not care; tests/test_host_logic.py restates the addressing lane by lane):
 //   operand whose box ROWS are k (outer product: Y[s][m], G[s][n]):  lane t of step q takes row 8*(q/2) + 2t + (q&1)
-//   operand whose box COLUMNS are k (backward: G[s][k], W[n][k]):    lane t of step q takes column 16*(q/4) + 2*(q&3) + 8*(t/2) + (t&1)
+//   operand whose box COLUMNS are k (backward: G[s][k], W[n][k]; forward / tail activations): lane t of step q takes column
+//   16*(q/4) + 2*(q&3) + 8*(t/2) + (t&1); the forward weights are then read from a copy with rows permuted inside groups of 16
 // Results agree with the cp.async kernels to rounding (different order inside a k-step), not bitwise.
 #include <cuda.h>
 #include <stdint.h>
