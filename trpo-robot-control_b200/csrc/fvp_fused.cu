@@ -1503,6 +1503,9 @@ int fused_cg_solve(const NetDesc &net, const double *d_theta, const double *d_in
         double flops = 6.0 * net.L[0] * net.L[1];
         for (int i = 1; i < net.K; ++i) flops += 10.0 * net.L[i] * net.L[i + 1];
         if (!forced && !(p2p && p2p->world > 1) && flops * (double)nsamples < 2e9) return 1;
+        // 4-64-64-1 (one input k-step, one action): on one GPU the pass compiled into the solve kernel is 2.4 % slower than the
+        // stand-alone kernel replayed from a graph (18.44 against 18.01 ms per 1 M-state solve, tools/time_solve.py); 17-64-64-6 gains 1.5 %
+        if (!forced && !(p2p && p2p->world > 1) && shape == SHAPE_P64) return 1;
     }
     FusedArgs a;
     a.theta = d_theta; a.v = d_p; a.inv_var = d_inv_var; a.obs = d_obs; a.partial = d_partial; a.done = nullptr;
